@@ -1,0 +1,83 @@
+/* b200det.h — C ABI of libb200det.so: the B200 (sm_100a) detection post-network hot path.
+ *
+ * Drop-in boundary for tfwcn/tensorflow2-machine-vision.  The reference has no FFI/plugin layer
+ * (grep for load_op_library / ctypes / dlpack: 0 hits), so each entry point replaces one Python
+ * function of the reference's L2 utilities; the citation beside each declaration names it
+ * (paths relative to AIServer/ai_api/ai_models/).  INTEGRATION.md shows the ctypes/DLPack stub a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer unless the name ends in _host; fp32, NHWC, C-contiguous;
+ *   - the caller owns every buffer (inputs, outputs, workspace); nothing is allocated or freed here;
+ *   - `stream` is a cudaStream_t passed as void*; calls enqueue work and return without synchronising;
+ *   - return 0 on success, negative on error (B200_ERR_*), message via b200_last_error() (thread-local);
+ *   - no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef B200DET_H_
+#define B200DET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200DET_VERSION 100
+
+#define B200_OK 0
+#define B200_ERR_BAD_ARG (-1)
+#define B200_ERR_WORKSPACE (-2)
+#define B200_ERR_CUDA (-3)
+#define B200_ERR_UNSUPPORTED (-4)
+
+/* Pairwise metric selector.  Two families exist in the reference and both are reproduced bit-for-bit:
+ * YOLO (utils/tf_iou_utils.py:5-65, boxes x1,y1,x2,y2) and EfficientDet (efficientnet/utils/iou.py:26-100,
+ * boxes y1,x1,y2,x2, NaN-free). */
+enum {
+  B200_METRIC_YOLO_IOU = 0,
+  B200_METRIC_YOLO_DIOU = 1, /* iou - (u/c)^0.6, tf_iou_utils.py:50 */
+  B200_METRIC_YOLO_CIOU = 2, /* iou - (u/c + alpha*v), tf_iou_utils.py:55-61 */
+  B200_METRIC_EFF_IOU = 3,
+  B200_METRIC_EFF_GIOU = 4,
+  B200_METRIC_EFF_DIOU = 5,
+  B200_METRIC_EFF_CIOU = 6,
+  B200_METRIC_COUNT = 7
+};
+
+/* NMS survivor predicate. */
+enum {
+  B200_NMS_AGNOSTIC = 0, /* survivor iff metric < thr (NaN drops): GetIOUNMS tiu:98, get_nms enms:51 */
+  B200_NMS_BY_CLASS = 1  /* suppressed iff metric >= thr and same class (NaN stays): GetIOUNMSByClasses tiu:146 */
+};
+
+const char* b200_last_error(void);
+int b200_version(void);
+/* 0 if a CUDA device is usable, else B200_ERR_CUDA (the library has no CPU path). */
+int b200_device_ok(void);
+
+/* detmath self-test hook: out[i] = f(x[i]) evaluated on the device with csrc/detmath.h. */
+enum {
+  B200_DM_EXP = 0, B200_DM_SIGMOID = 1, B200_DM_LOG = 2, B200_DM_LOG1P = 3, B200_DM_ATAN = 4,
+  B200_DM_POW06 = 5, B200_DM_POW15 = 6, B200_DM_BCE = 7 /* bce_with_logits(label=y, logit=x) */, B200_DM_COUNT = 8
+};
+int b200_detmath_eval(int op, const float* x, const float* y, float* out, size_t n, void* stream);
+
+/* GetIOU (utils/tf_iou_utils.py:5-65) / get_iou (efficientnet/utils/iou.py:26-100).
+ * pairwise: out[n1,n2] = metric(b1[i], b2[j]);  elementwise: out[n] = metric(b1[i], b2[i]). */
+int b200_pairwise_iou(const float* b1, int n1, const float* b2, int n2, int metric, float* out, void* stream);
+int b200_elementwise_iou(const float* b1, const float* b2, size_t n, int metric, float* out, void* stream);
+
+/* GetIOUNMS tiu:67-108, GetIOUNMSByClasses tiu:110-157, get_nms enms:5-61 — batched over segments.
+ * boxes [total,4] (16-byte aligned), scores [total], classes [total] int32 or NULL, order_id [total] or NULL
+ * (unique ids giving the tie order; NULL = position), seg_offsets [num_segments+1] int32 (device).
+ * out_idx [num_segments, max_out]: positions local to the segment, in emit order; out_count [num_segments].
+ * use_score_thr != 0 stops at the first top score < score_thr (enms:44).  max_out <= 4096. */
+int b200_nms(const float* boxes, const float* scores, const int32_t* classes, const uint32_t* order_id,
+             const int32_t* seg_offsets, int num_segments, int metric, int mode, float iou_thr,
+             int use_score_thr, float score_thr, int max_out, int32_t* out_idx, int32_t* out_count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DET_H_ */

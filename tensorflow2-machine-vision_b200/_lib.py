@@ -1,0 +1,52 @@
+"""ctypes binding of libb200det.so (declared in include/b200det.h)."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200det.so")
+_lib = None
+
+c_f = ctypes.c_float
+c_i = ctypes.c_int
+c_p = ctypes.c_void_p
+c_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes); every symbol include/b200det.h declares
+SIGNATURES = {
+    "b200_last_error": (ctypes.c_char_p, []),
+    "b200_version": (c_i, []),
+    "b200_device_ok": (c_i, []),
+    "b200_detmath_eval": (c_i, [c_i, c_p, c_p, c_p, c_sz, c_p]),
+    "b200_pairwise_iou": (c_i, [c_p, c_i, c_p, c_i, c_i, c_p, c_p]),
+    "b200_elementwise_iou": (c_i, [c_p, c_p, c_sz, c_i, c_p, c_p]),
+    "b200_nms": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_i, c_f, c_i, c_p, c_p, c_p]),
+}
+
+METRIC_YOLO = {"iou": 0, "diou": 1, "ciou": 2}
+METRIC_EFF = {"iou": 3, "giou": 4, "diou": 5, "ciou": 6}
+NMS_AGNOSTIC, NMS_BY_CLASS = 0, 1
+
+
+def load():
+    """Load the library once.  Raises RuntimeError (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libb200det.so not found at %s - build it with `python tensorflow2-machine-vision_b200/build.py` "
+                "(or __graft_entry__.build()); this package has no CPU fallback" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().b200_last_error().decode("utf-8", "replace")
+        if status == -1:
+            raise ValueError("%s: %s" % (what, msg))
+        raise RuntimeError("%s failed (%d): %s" % (what, status, msg))
