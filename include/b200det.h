@@ -77,6 +77,31 @@ int b200_nms(const float* boxes, const float* scores, const int32_t* classes, co
              const int32_t* seg_offsets, int num_segments, int metric, int mode, float iou_thr,
              int use_score_thr, float score_thr, int max_out, int32_t* out_idx, int32_t* out_count, void* stream);
 
+/* GetNMSBoxes (utils/tf_yolo_utils.py:169-269) for a batch, B==1 semantics per image:
+ * GetBoxes decode (:129-167), strict thresholds conf > conf_thr and max_c sigmoid(cls) > score_thr (:191-192),
+ * score = max_c sigmoid(cls), class_id = argmax (:199-203), per-class NMS capped at max_out (:255-261; the
+ * reference hard-codes 500), gather (:262-266).
+ * heads[l]: device (B,H_l,W_l,A*(5+C)), 16-byte aligned; hw = {H0,W0,H1,W1,H2,W2}; anchors_wh_host [3][A][2]
+ * pixels (layer 0 = coarsest head); image_wh_host [2]; metric in YOLO_IOU/DIOU/CIOU.
+ * Outputs are padded to max_out rows per image, `out_count[B]` gives the valid rows:
+ *   out_boxes [B,max_out,4] x1,y1,x2,y2 normalised; out_class_id [B,max_out] int32; out_score [B,max_out];
+ *   out_classes [B,max_out,C] (may be NULL); out_conf [B,max_out];
+ *   out_sel_idx [B,max_out] position in the reference's compacted candidate list (may be NULL);
+ *   out_sel_anchor [B,max_out] flat anchor index level-major/h/w/a (may be NULL). */
+size_t b200_yolo_decode_nms_workspace_bytes(const int32_t hw[6], int B, int A, int max_out);
+int b200_yolo_decode_nms(const float* const heads[3], const int32_t hw[6], int B, int A, int C,
+                         const float* anchors_wh_host, const float* image_wh_host, float conf_thr, float score_thr,
+                         float iou_thr, int metric, int max_out, float* out_boxes, int32_t* out_class_id,
+                         float* out_score, float* out_classes, float* out_conf, int32_t* out_sel_idx,
+                         int32_t* out_sel_anchor, int32_t* out_count, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* GetBoxes (utils/tf_yolo_utils.py:129-167) without the final boolean_mask: dense decode of one level.
+ * head (B,H,W,A*(5+C)); anchors_wh_norm_dev [A][2] = anchors/image_wh (device); outputs for all B*H*W*A
+ * anchors in row-major order: boxes [N,4], conf [N], classes [N,C] (sigmoid), valid [N] (x2>x1 && y2>y1). */
+int b200_yolo_decode_dense(const float* head, int B, int H, int W, int A, int C, const float* anchors_wh_norm_dev,
+                           float* boxes, float* conf, float* classes, unsigned char* valid, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

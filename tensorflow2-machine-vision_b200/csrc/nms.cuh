@@ -71,7 +71,7 @@ __device__ __forceinline__ bool nms_suppresses(const BoxT& kept, int kept_cls, c
 
 // Runs NMS for one segment with the whole CTA (blockDim.x == NMS_THREADS).  out_pos receives the local
 // positions (0..n-1) of emitted candidates in emit order; returns the number emitted (uniform across threads).
-__device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cfg, int32_t* __restrict__ out_pos,
+static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cfg, int32_t* __restrict__ out_pos,
                                unsigned char* smem_raw) {
   const int tid = threadIdx.x;
   const int lane = tid & 31;

@@ -8,6 +8,20 @@ pytestmark = pytest.mark.gpu
 F = np.float32
 
 
+def assert_bits_equal(got, want):
+    """Bit-for-bit equality of fp32 arrays; NaNs must coincide but their payload/sign bits are not compared."""
+    got = np.asarray(got, F)
+    want = np.asarray(want, F)
+    assert got.shape == want.shape
+    gn, wn = np.isnan(got), np.isnan(want)
+    assert np.array_equal(gn, wn), "NaN positions differ"
+    ok = np.array_equal(got.view(np.uint32)[~gn], want.view(np.uint32)[~wn])
+    if not ok:
+        bad = np.flatnonzero((got.view(np.uint32) != want.view(np.uint32)).reshape(-1) & ~gn.reshape(-1))
+        raise AssertionError("%d of %d values differ, first at %d: got %r want %r" % (
+            bad.size, got.size, bad[0], got.reshape(-1)[bad[0]], want.reshape(-1)[bad[0]]))
+
+
 def _t(x, cuda, dtype=None):
     import torch
     t = torch.from_numpy(np.ascontiguousarray(x))
@@ -74,11 +88,11 @@ def test_get_iou_yolo_bitwise(lib, cuda, iou_type):
     want = oy.get_iou(b1, b2, iou_type)
     got = GetIOU(_t(b1, cuda), _t(b2, cuda), iou_type).cpu().numpy()
     assert got.shape == want.shape == (6, 5, 3, 37)
-    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert_bits_equal(got, want)
     # elementwise broadcast form used inside the NMS loops: (1,4) x (n,4)
     w2 = oy.get_iou(b1.reshape(-1, 4)[0:1], b2[0], iou_type)
     g2 = GetIOU(_t(b1.reshape(-1, 4)[0:1], cuda), _t(b2[0], cuda), iou_type).cpu().numpy()
-    assert np.array_equal(g2.view(np.uint32), w2.view(np.uint32))
+    assert_bits_equal(g2, w2)
     with pytest.raises(AssertionError):
         GetIOU(_t(b1, cuda), _t(b2, cuda), "giou")
 
@@ -95,7 +109,7 @@ def test_get_iou_effdet_bitwise(lib, cuda, iou_type):
     b2[7] = [9, 9, 3, 3]  # inverted -> clamped to zero area
     want = oe.get_iou(b1, b2, iou_type)
     got = get_iou(_t(b1, cuda), _t(b2, cuda), iou_type).cpu().numpy()
-    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert_bits_equal(got, want)
 
 
 NMS_CASES = [
