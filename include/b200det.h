@@ -102,6 +102,28 @@ int b200_yolo_decode_nms(const float* const heads[3], const int32_t hw[6], int B
 int b200_yolo_decode_dense(const float* head, int B, int H, int W, int A, int C, const float* anchors_wh_norm_dev,
                            float* boxes, float* conf, float* classes, unsigned char* valid, void* stream);
 
+/* GetLoss (utils/tf_yolo_utils.py:6-127) / Yolov4Loss.call (losses/yolo_loss.py:85-159).
+ * y_true[l]: (B,H_l,W_l,A,5+C) dense targets (xy,wh normalised, obj, one-hot); y_pred[l]: (B,H_l,W_l,A*(5+C)) logits.
+ * anchors_wh_host [3][A][2] pixels, layer 0 = coarsest head; metric selects the ignore-mask IoU (iou|diou|ciou);
+ * variant 0 = tf_yolo_utils.GetLoss (+1e-8 in the log, raw_xy multiplied by obj), 1 = Yolov4Loss / unit-test copy.
+ * batch_divisor: the batch size the sums are divided by (pass the GLOBAL batch when sharding images over ranks;
+ * the 12 partial terms are then summed across ranks by one all-reduce).
+ * out_parts [3][4] = per level {xy, wh, obj, cls} / batch_divisor (may be NULL); out_loss: scalar. */
+enum { B200_YOLO_LOSS_TF_YOLO_UTILS = 0, B200_YOLO_LOSS_KERAS_YOLO3 = 1 };
+size_t b200_yolo_loss_workspace_bytes(const int32_t hw[6], int B, int A);
+int b200_yolo_loss(const float* const y_true[3], const float* const y_pred[3], const int32_t hw[6], int B, int A,
+                   int C, const float* anchors_wh_host, const float* image_wh_host, float iou_thresh, int metric,
+                   int variant, float batch_divisor, float* out_parts, float* out_loss, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* DataGenerator.GetTargets (datasets/coco_dataset.py:185-285), batched: boxes [total,4] pixel corners
+ * x1,y1,x2,y2, classes [total] int32, offsets [B+1] int32 (all device).  targets[l]: (B,H_l,W_l,A,5+C), zeroed
+ * here when zero_fill != 0.  Boxes whose cell falls outside the grid are skipped (tf.scatter_nd would raise). */
+int b200_yolo_assign_targets(const float* boxes, const int32_t* classes, const int32_t* offsets, int B,
+                             int total_boxes, const float* anchors_wh_host, int A, const float* image_wh_host, int C,
+                             const int32_t hw[6], float* const targets[3], int zero_fill, void* stream);
+int b200_fill_zero(float* dst, size_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

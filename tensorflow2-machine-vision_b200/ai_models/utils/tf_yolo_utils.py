@@ -120,3 +120,73 @@ def GetNMSBoxes(y1, y2, y3, anchors_wh, image_wh, classes_num,
   cnt = r['count'].cpu().tolist()
   pick = lambda t: torch.cat([t[b, :cnt[b]] for b in range(len(cnt))], dim=0) if len(cnt) != 1 else t[0, :cnt[0]]
   return pick(r['boxes']), pick(r['classes_id']), pick(r['scores']), pick(r['classes']), pick(r['confidence'])
+
+
+def _loss_call(y_true, y_pred, image_wh, anchors_wh, iou_thresh, iou_type, variant, batch_divisor=None,
+               return_parts=False, workspace=None):
+  lib = _lib.load()
+  if len(y_true) != 3 or len(y_pred) != 3:
+    raise ValueError('y_true and y_pred must each hold 3 levels')
+  yt = [T.to_cuda(t) for t in y_true]
+  yp = [T.to_cuda(t) for t in y_pred]
+  anc = T.host_floats(anchors_wh)
+  if anc.size % 6 != 0:
+    raise ValueError('anchors_wh must be (3, anchors_num, 2)')
+  A = anc.size // 6
+  B = yt[0].shape[0]
+  RF = yt[0].shape[-1]
+  for l in range(3):
+    if yt[l].dim() != 5 or yt[l].shape[3] != A:
+      raise ValueError('y_true[%d] must be (B,H,W,%d,5+C)' % (l, A))
+    if yp[l].numel() != yt[l].numel():
+      raise ValueError('y_pred[%d] cannot be reshaped to y_true[%d]' % (l, l))
+  img = T.host_floats(image_wh, 2)
+  dev = yt[0].device
+  hw = (ctypes.c_int32 * 6)(*[d for t in yt for d in (t.shape[1], t.shape[2])])
+  tp = (ctypes.c_void_p * 3)(*[t.data_ptr() for t in yt])
+  pp = (ctypes.c_void_p * 3)(*[t.data_ptr() for t in yp])
+  parts = torch.empty((3, 4), dtype=torch.float32, device=dev)
+  loss = torch.empty((), dtype=torch.float32, device=dev)
+  ws_bytes = lib.b200_yolo_loss_workspace_bytes(hw, B, A)
+  if workspace is None or workspace.numel() < ws_bytes:
+    workspace = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+  div = float(B if batch_divisor is None else batch_divisor)
+  _lib.check(lib.b200_yolo_loss(tp, pp, hw, B, A, RF - 5, anc.ctypes.data_as(ctypes.c_void_p),
+                                img.ctypes.data_as(ctypes.c_void_p), float(iou_thresh), _lib.METRIC_YOLO[iou_type],
+                                variant, div, T.ptr(parts), T.ptr(loss), T.ptr(workspace), ws_bytes, T.stream_ptr()),
+             'GetLoss')
+  return (loss, parts) if return_parts else loss
+
+
+def GetLoss(y_true, y_pred, image_wh, anchors_wh, iou_thresh=0.5, iou_type='iou'):
+  '''
+  YOLO loss (forward value).
+
+  Args:
+    y_true: [(batch, 13, 13, 3, 5+num_classes), (batch, 26, 26, 3, ...), (batch, 52, 52, 3, ...)]
+    y_pred: same three levels, (batch, H, W, 3*(5+num_classes)) or already split per anchor
+    image_wh: (w, h) pixels; anchors_wh: (3, 3, 2) pixels, layer 0 = coarsest head
+    iou_type: metric of the ignore mask only ('iou' for YOLOv3, 'ciou' for YOLOv4 call sites)
+  Returns:
+    scalar fp32 tensor (device)
+  '''
+  assert iou_type in ['iou','diou','ciou']
+  return _loss_call(y_true, y_pred, image_wh, anchors_wh, iou_thresh, iou_type, 0)
+
+
+def GetLossSharded(y_true, y_pred, image_wh, anchors_wh, iou_thresh=0.5, iou_type='iou', global_batch=None,
+                   group=None):
+  '''Data-parallel GetLoss: every rank passes its own images; the 12 per-level terms (already divided by the
+  global batch) are summed with ONE NCCL all-reduce and re-added in the reference's order (tyu:120-125).'''
+  import torch.distributed as dist
+  assert iou_type in ['iou','diou','ciou']
+  world = dist.get_world_size(group) if dist.is_initialized() else 1
+  if global_batch is None:
+    global_batch = T.to_cuda(y_true[0]).shape[0] * world
+  loss, parts = _loss_call(y_true, y_pred, image_wh, anchors_wh, iou_thresh, iou_type, 0,
+                           batch_divisor=global_batch, return_parts=True)
+  if world > 1:
+    dist.all_reduce(parts, op=dist.ReduceOp.SUM, group=group)
+    loss = ((parts[:, 0] + parts[:, 1]) + parts[:, 2]) + parts[:, 3]
+    loss = (loss[0] + loss[1]) + loss[2]
+  return loss

@@ -1,0 +1,150 @@
+// yolo_targets.cu — best-anchor target assignment: DataGenerator.GetTargets (datasets/coco_dataset.py:185-285),
+// batched over images (the reference maps it per image inside tf.data, cds:328).
+//
+//   K5a fill_zero_kernel        dense targets start as zeros (tf.scatter_nd into a zero tensor, cds:265-276):
+//                               128-bit streaming stores, persistent grid — the HBM-write-bound part (7.7 MB/img
+//                               at 608x608).
+//   K5b yolo_scatter_targets    one thread per ground-truth box: floor-div centre (cds:193), normalise (:196-197),
+//                               IoU of the origin-centred box against the 9 origin-centred anchors with GetIOU
+//                               exactly as written — normalised box vs *pixel* anchors (cds:200-219, quirk Q8) —
+//                               first-max argmax (:222), layer = idx // layers_num, anchor = idx % layers_num
+//                               (:237,241), cell = floor(xy[::-1] * layer_hw) (:244).  The obj channel is bumped
+//                               with atomicAdd; the thread that saw 0 writes the record.
+//   K5c yolo_fix_collisions     scatter_nd sums duplicates, then every record with obj > 1 is zeroed (cds:279-284):
+//                               each box re-derives its record and clears it when obj > 1.
+#include "boxmath.cuh"
+#include "common.cuh"
+
+#define YT_LEVELS 3
+
+__global__ void fill_zero_kernel(float4* __restrict__ dst, size_t n_vec, float* __restrict__ tail, int n_tail) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+#pragma unroll 4
+  for (; i < n_vec; i += stride) __stcs(dst + i, z);
+  if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) tail[threadIdx.x] = 0.0f;
+}
+
+struct YtParams {
+  const float* boxes;       // [total,4] pixel corners x1,y1,x2,y2
+  const int32_t* classes;   // [total]
+  const int32_t* offsets;   // [B+1]
+  int B, total, A, C, RF, layers_num;
+  float img_w, img_h;
+  float* target[YT_LEVELS];
+  int h[YT_LEVELS], w[YT_LEVELS];
+  float anc_w[YT_LEVELS * 8], anc_h[YT_LEVELS * 8];  // flattened (layers*A) in reshape(-1,2) order, pixels
+};
+
+// returns the record pointer for box i (nullptr when the cell falls outside the grid) and the update fields
+__device__ __forceinline__ float* yt_locate(const YtParams& p, int i, float& nx, float& ny, float& nw, float& nh) {
+  // image index: binary search in offsets
+  int lo = 0, hi = p.B;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (p.offsets[mid] <= i) lo = mid; else hi = mid;
+  }
+  const int img = lo;
+  const float x1 = p.boxes[4 * (size_t)i], y1 = p.boxes[4 * (size_t)i + 1];
+  const float x2 = p.boxes[4 * (size_t)i + 2], y2 = p.boxes[4 * (size_t)i + 3];
+  // (x2y2 + x1y1) // 2 : float floor division
+  const float cx = floorf(DM_DIV(DM_ADD(x2, x1), 2.0f)), cy = floorf(DM_DIV(DM_ADD(y2, y1), 2.0f));
+  const float bw = DM_SUB(x2, x1), bh = DM_SUB(y2, y1);
+  nx = DM_DIV(cx, p.img_w); ny = DM_DIV(cy, p.img_h);
+  nw = DM_DIV(bw, p.img_w); nh = DM_DIV(bh, p.img_h);
+  const float mx = DM_DIV(nw, 2.0f), my = DM_DIV(nh, 2.0f);
+  const BoxT b = bm_prep(-mx, -my, mx, my, B200_METRIC_YOLO_IOU);
+  int best = 0;
+  float best_v = 0.f;
+  const int n_anchor = YT_LEVELS * p.A;
+  for (int k = 0; k < n_anchor; ++k) {
+    const float ax = DM_DIV(p.anc_w[k], 2.0f), ay = DM_DIV(p.anc_h[k], 2.0f);
+    const BoxT a = bm_prep(-ax, -ay, ax, ay, B200_METRIC_YOLO_IOU);
+    const float v = bm_metric(b, a, B200_METRIC_YOLO_IOU);
+    if (k == 0 || v > best_v) { best = k; best_v = v; }  // tf.argmax: first maximal index
+  }
+  const int layer = best / p.layers_num;
+  const int anchor = best % p.layers_num;
+  if (layer >= YT_LEVELS || anchor >= p.A) return nullptr;
+  const int yy = (int)floorf(DM_MUL(ny, (float)p.h[layer]));
+  const int xx = (int)floorf(DM_MUL(nx, (float)p.w[layer]));
+  if (yy < 0 || yy >= p.h[layer] || xx < 0 || xx >= p.w[layer]) return nullptr;
+  return p.target[layer] + ((((size_t)img * p.h[layer] + yy) * p.w[layer] + xx) * p.A + anchor) * p.RF;
+}
+
+__global__ void yolo_scatter_targets_kernel(YtParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.total) return;
+  float nx, ny, nw, nh;
+  float* rec = yt_locate(p, i, nx, ny, nw, nh);
+  if (!rec) return;
+  const float old = atomicAdd(rec + 4, 1.0f);
+  if (old == 0.0f) {
+    rec[0] = nx; rec[1] = ny; rec[2] = nw; rec[3] = nh;
+    const int c = p.classes[i];
+    if (c >= 0 && c < p.C) rec[5 + c] = 1.0f;  // tf.one_hot: out of range -> all zeros
+  }
+}
+
+__global__ void yolo_fix_collisions_kernel(YtParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.total) return;
+  float nx, ny, nw, nh;
+  float* rec = yt_locate(p, i, nx, ny, nw, nh);
+  if (!rec) return;
+  // obj is a small integer count here; any writer clearing it concurrently also clears the whole record
+  if (rec[4] > 1.0f) {
+    for (int c = 0; c < p.RF; ++c) if (c != 4) rec[c] = 0.0f;
+    __threadfence();
+    rec[4] = 0.0f;
+  }
+}
+
+extern "C" int b200_fill_zero(float* dst, size_t n, void* stream) {
+  if (n == 0) return B200_OK;
+  B200_REQUIRE(dst, B200_ERR_BAD_ARG, "b200_fill_zero: null pointer");
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 15) == 0, B200_ERR_BAD_ARG, "b200_fill_zero: destination not 16-byte aligned");
+  const size_t n_vec = n / 4;
+  const int n_tail = (int)(n - n_vec * 4);
+  size_t blocks = (n_vec + 255) / 256;
+  const size_t cap = (size_t)b200_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  fill_zero_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(dst), n_vec, dst + n_vec * 4, n_tail);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" int b200_yolo_assign_targets(const float* boxes, const int32_t* classes, const int32_t* offsets, int B,
+                                        int total_boxes, const float* anchors_wh_host, int A, const float* image_wh_host,
+                                        int C, const int32_t hw[6], float* const targets[3], int zero_fill, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B200_REQUIRE(B >= 0 && total_boxes >= 0 && A >= 1 && A <= 8 && C >= 0, B200_ERR_BAD_ARG, "b200_yolo_assign_targets: bad sizes");
+  B200_REQUIRE(anchors_wh_host && image_wh_host && hw && targets, B200_ERR_BAD_ARG, "b200_yolo_assign_targets: null argument");
+  if (B == 0) return B200_OK;
+  YtParams p;
+  p.boxes = boxes; p.classes = classes; p.offsets = offsets; p.B = B; p.total = total_boxes; p.A = A; p.C = C; p.RF = 5 + C;
+  p.layers_num = YT_LEVELS;  // tf.shape(anchors_wh)[0], cds:191
+  p.img_w = image_wh_host[0]; p.img_h = image_wh_host[1];
+  for (int l = 0; l < YT_LEVELS; ++l) {
+    B200_REQUIRE(targets[l] && hw[2 * l] > 0 && hw[2 * l + 1] > 0, B200_ERR_BAD_ARG, "b200_yolo_assign_targets: bad level %d", l);
+    p.target[l] = targets[l]; p.h[l] = hw[2 * l]; p.w[l] = hw[2 * l + 1];
+  }
+  for (int k = 0; k < YT_LEVELS * A; ++k) { p.anc_w[k] = anchors_wh_host[2 * k]; p.anc_h[k] = anchors_wh_host[2 * k + 1]; }
+  if (zero_fill) {
+    for (int l = 0; l < YT_LEVELS; ++l) {
+      int st = b200_fill_zero(targets[l], (size_t)B * p.h[l] * p.w[l] * A * p.RF, stream_);
+      if (st != B200_OK) return st;
+    }
+  }
+  if (total_boxes > 0) {
+    B200_REQUIRE(boxes && classes && offsets, B200_ERR_BAD_ARG, "b200_yolo_assign_targets: null box arrays");
+    const int blocks = (total_boxes + 127) / 128;
+    yolo_scatter_targets_kernel<<<blocks, 128, 0, stream>>>(p);
+    B200_LAUNCH_CHECK();
+    yolo_fix_collisions_kernel<<<blocks, 128, 0, stream>>>(p);
+    B200_LAUNCH_CHECK();
+  }
+  return B200_OK;
+}

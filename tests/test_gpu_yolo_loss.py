@@ -1,0 +1,98 @@
+"""GPU parity: GetTargets (bit-exact) and GetLoss / Yolov4Loss (<= 1e-4 relative) vs the oracle."""
+import numpy as np
+import pytest
+
+from test_gpu_core import _t, assert_bits_equal
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+LOSS_RTOL = 1e-4
+
+
+def _dense_targets(rng, batch, image, anc, max_boxes=100, normalised_anchors=False):
+    from oracle import yolo as oy
+    from tfmv_b200 import synth
+    boxes, classes, off = synth.gt_batch(rng, batch, (image, image), max_boxes=max_boxes)
+    a = anc / F(image) if normalised_anchors else anc
+    per = [oy.get_targets(boxes[off[b]:off[b + 1]], classes[off[b]:off[b + 1]], a, (image, image), 80) for b in range(batch)]
+    return boxes, classes, off, [np.stack([p[l] for p in per], 0) for l in range(3)]
+
+
+@pytest.mark.parametrize("image,batch,normalised", [(416, 3, False), (608, 2, False), (416, 4, True), (96, 6, True)])
+def test_get_targets_bit_exact(lib, cuda, image, batch, normalised):
+    from tfmv_b200 import synth
+    from tfmv_b200.ai_models.datasets.coco_dataset import DataGenerator
+    rng = np.random.default_rng(20261018 + 2 + image)
+    anc = synth.yolo_anchors().astype(F)
+    boxes, classes, off, want = _dense_targets(rng, batch, image, anc, normalised_anchors=normalised)
+    if batch >= 3:  # force collisions: duplicate the first boxes of image 0 inside image 0
+        n0 = off[1]
+        boxes[1:min(3, n0)] = boxes[0]
+        a = anc / F(image) if normalised else anc
+        from oracle import yolo as oy
+        p0 = oy.get_targets(boxes[:n0], classes[:n0], a, (image, image), 80)
+        for l in range(3):
+            want[l][0] = p0[l]
+    gen = DataGenerator(80, anc / F(image) if normalised else anc, (image, image))
+    got = gen.GetTargetsBatch(_t(classes, cuda), _t(boxes, cuda), _t(off, cuda))
+    for l in range(3):
+        assert tuple(got[l].shape) == want[l].shape
+        assert_bits_equal(got[l].cpu().numpy(), want[l])
+    if normalised:
+        assert sum(float(w[..., 4].sum()) for w in want[:2]) > 0  # real argmax spreads over the layers
+    # single-image reference signature, including the empty image
+    img, t1 = gen.GetTargets("img", classes[:off[1]], _t(boxes[:off[1]], cuda))
+    assert img == "img"
+    assert_bits_equal(t1[2].cpu().numpy(), want[2][0])
+    _, te = gen.GetTargets(None, np.zeros((0,), np.int32), np.zeros((0, 4), F))
+    assert all(float(x.abs().sum()) == 0.0 for x in te)
+
+
+@pytest.mark.parametrize("image,batch,iou_type,normalised", [
+    (416, 2, "iou", False), (416, 2, "ciou", True), (608, 2, "ciou", False), (416, 3, "diou", True), (96, 5, "ciou", True)])
+def test_get_loss_matches_oracle(lib, cuda, image, batch, iou_type, normalised):
+    from oracle import yolo as oy
+    from tfmv_b200 import synth
+    from tfmv_b200.ai_models.utils.tf_yolo_utils import GetLoss, _loss_call
+    rng = np.random.default_rng(20261018 + 2 + batch)
+    anc = synth.yolo_anchors().astype(F)
+    _, _, _, y_true = _dense_targets(rng, batch, image, anc, normalised_anchors=normalised)
+    if batch > 2:
+        for l in range(3):
+            y_true[l][batch - 1] = 0  # an image without ground truth: ignore mask all ones (reduce_max of empty)
+    y_pred = synth.yolo_heads(rng, batch, image)
+    # make some predictions overlap their targets so the ignore mask has zeros
+    for l in range(3):
+        yt = y_true[l]
+        yp = y_pred[l].reshape(yt.shape)
+        m = yt[..., 4] > 0
+        yp[m, 2:4] = np.log(np.maximum(yt[m, 2:4] * image, 1e-3) / anc[l][np.nonzero(m)[3]]) + rng.normal(0, 0.1, (int(m.sum()), 2))
+    want, want_parts = oy.get_loss(y_true, y_pred, (image, image), anc, 0.5, iou_type, return_parts=True)
+    got, parts = _loss_call([_t(t, cuda) for t in y_true], [_t(t, cuda) for t in y_pred], (image, image), anc, 0.5, iou_type, 0,
+                            return_parts=True)
+    np.testing.assert_allclose(parts.cpu().numpy(), want_parts, rtol=LOSS_RTOL, atol=1e-6)
+    assert abs(float(got) - float(want)) <= LOSS_RTOL * abs(float(want))
+    got2 = GetLoss([_t(t, cuda) for t in y_true], [_t(t, cuda) for t in y_pred], image_wh=(image, image), anchors_wh=anc,
+                   iou_thresh=0.5, iou_type=iou_type)
+    assert float(got2) == float(got)  # deterministic reduction: bit-identical run to run
+
+
+def test_reference_unit_test_relation_on_gpu(lib, cuda):
+    """yolo_v3/unit_test/loss_test.py:152-172 on the GPU: GetLoss-copy == Yolov4Loss on uniform-random tensors."""
+    from oracle import yolo as oy
+    from tfmv_b200.ai_models.losses.yolo_loss import Yolov4Loss
+    from tfmv_b200.ai_models.utils.tf_yolo_utils import _loss_call
+    rng = np.random.default_rng(5)
+    grids = (2, 4, 8)
+    yt = [rng.random((2, g, g, 3, 85), dtype=F) for g in grids]
+    yp = [rng.random((2, g, g, 255), dtype=F) for g in grids]
+    anc = oy.load_anchors_order(oy.COCO_ANCHORS_FLAT.reshape(-1))
+    a = Yolov4Loss(oy.COCO_ANCHORS_FLAT, 80)([_t(t, cuda) for t in yt], [_t(t, cuda) for t in yp])
+    b = _loss_call([_t(t, cuda) for t in yt], [_t(t, cuda) for t in yp], (64, 64), anc, 0.5, "iou", 1)
+    assert float(a) == float(b)
+    want = oy.yolov4_loss(oy.COCO_ANCHORS_FLAT, 80, yt, yp)
+    assert abs(float(a) - float(want)) <= LOSS_RTOL * abs(float(want))
+    # the tf_yolo_utils variant differs on non-binary obj (Q10, Q11) and must follow the oracle too
+    c = _loss_call([_t(t, cuda) for t in yt], [_t(t, cuda) for t in yp], (64, 64), anc, 0.5, "ciou", 0)
+    want_c = oy.get_loss(yt, yp, (64, 64), anc, 0.5, "ciou")
+    assert abs(float(c) - float(want_c)) <= LOSS_RTOL * abs(float(want_c))
