@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (0 = workload default)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--l2-fetch", type=int, default=0, help="set cudaLimitMaxL2FetchGranularity (32/64/128), 0 = leave")
+    ap.add_argument("--no-graph", action="store_true", help="issue the step launch by launch instead of replaying a CUDA graph")
+    ap.add_argument("--only-step", action="store_true", help="skip phase timing / e2e / cpu baseline (profiling runs)")
     return ap.parse_args()
 
 
@@ -183,6 +186,8 @@ def run_b200(args, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    if args.l2_fetch:
+        _lib.check(lib.b200_set_l2_fetch_granularity(args.l2_fetch), "set_l2_fetch_granularity")
     batch = args.batch or wl["batch"]
     image = wl["image"]
     anc = synth.yolo_anchors().astype(F)
@@ -240,10 +245,19 @@ def run_b200(args, wl):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev = timed(lambda: step(heads_d, boxes_d, classes_d, off_d), args.steps, max(args.warmup, 3))
+    from tfmv_b200 import runtime
+    if args.no_graph:
+        dev_step = lambda: step(heads_d, boxes_d, classes_d, off_d)
+    else:
+        dev_step = runtime.capture(lambda: step(heads_d, boxes_d, classes_d, off_d))
+    ms_dev = timed(dev_step, args.steps, max(args.warmup, 3))
     clocks = sampler.stop() if rank == 0 else None
     loss_val = float(parts_buf["loss"].item())
 
+    if args.only_step:
+        if rank == 0:
+            print(json.dumps({"value": global_batch * args.steps / (ms_dev / 1e3), "ms_per_step": ms_dev / args.steps, "loss": loss_val}))
+        return
     # ---- per-phase timing on the launching stream (roofline of the dominant kernel) ----
     st = T.stream_ptr()
     n_fill = sum(int(t.numel()) for t in y_true)
@@ -266,18 +280,17 @@ def run_b200(args, wl):
     def ph_loss():
         lib.b200_yolo_loss(tp, pp, hw, batch, A, 80, anc_h.ctypes.data_as(ctypes.c_void_p),
                            img_h.ctypes.data_as(ctypes.c_void_p), 0.5, 2, 0, float(global_batch), parts_t.data_ptr(),
-                           loss_t.data_ptr(), ws.data_ptr(), ws.numel(), st)
+                           loss_t.data_ptr(), 0, ws.data_ptr(), ws.numel(), st)
 
     ph_fill(); ph_scatter()
     phases = []
     for name, fn, nbytes, launches in (
             ("fill_zero_kernel x3 (dense y_true zero-fill, write)", ph_fill, n_fill * 4, 3),
-            ("yolo_scatter_targets+fix_collisions", ph_scatter, int(boxes_d.shape[0]) * (16 + 4 + 340), 2),
+            ("yolo_scatter_targets (one CTA per image)", ph_scatter, int(boxes_d.shape[0]) * (16 + 4 + 340), 1),
             ("yolo_loss objects+ignore+finalize (dense-equivalent read of y_true+y_pred)", ph_loss, 2 * n_fill * 4, 3)):
         ms = timed(fn, args.steps, 3) / args.steps
         phases.append({"kernel": name, "ms": ms, "algorithmic_bytes": nbytes, "gbps": nbytes / ms / 1e6, "launches": launches})
-        if name.startswith("fill"):
-            ph_scatter()  # restore targets for the loss phase
+        ph_fill(); ph_scatter()  # restore valid targets (repeated scatters collide with themselves)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -320,10 +333,11 @@ def run_b200(args, wl):
             "config": {"workload": wl["what"], "image": image, "per_gpu_batch": batch, "global_batch": global_batch,
                        "classes": 80, "anchors_per_cell": 3, "gt_boxes_per_image": "U{1..100}",
                        "parallelism": "dp%d (images sharded, one 12-float NCCL all-reduce)" % world,
+                       "launch": "launch by launch" if args.no_graph else "CUDA graph replay of the step",
                        "l2": "inputs larger than L2 (y_pred %.0f MB + y_true %.0f MB per step vs 126 MB L2)" % (
                            n_fill * 4 / 1e6, n_fill * 4 / 1e6)},
             "loss": loss_val, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": 8 * args.steps, "clocks": clocks,
+            "gpu_launches": 5 * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -56,6 +56,11 @@ int b200_version(void);
 /* 0 if a CUDA device is usable, else B200_ERR_CUDA (the library has no CPU path). */
 int b200_device_ok(void);
 
+/* Device-wide hint for the DRAM->L2 fetch granularity (32, 64 or 128 bytes; cudaLimitMaxL2FetchGranularity).
+ * Optional: the sector-sparse loss kernels read less DRAM with 32; nothing depends on it for correctness. */
+int b200_set_l2_fetch_granularity(int bytes);
+int b200_get_l2_fetch_granularity(void);
+
 /* detmath self-test hook: out[i] = f(x[i]) evaluated on the device with csrc/detmath.h. */
 enum {
   B200_DM_EXP = 0, B200_DM_SIGMOID = 1, B200_DM_LOG = 2, B200_DM_LOG1P = 3, B200_DM_ATAN = 4,
@@ -108,13 +113,15 @@ int b200_yolo_decode_dense(const float* head, int B, int H, int W, int A, int C,
  * variant 0 = tf_yolo_utils.GetLoss (+1e-8 in the log, raw_xy multiplied by obj), 1 = Yolov4Loss / unit-test copy.
  * batch_divisor: the batch size the sums are divided by (pass the GLOBAL batch when sharding images over ranks;
  * the 12 partial terms are then summed across ranks by one all-reduce).
- * out_parts [3][4] = per level {xy, wh, obj, cls} / batch_divisor (may be NULL); out_loss: scalar. */
+ * out_parts [3][4] = per level {xy, wh, obj, cls} / batch_divisor (may be NULL); out_loss: scalar;
+ * out_ignore [B, anchors_per_image] (may be NULL): the ignore mask float(best_iou < thr) of tyu:94 as bytes,
+ * anchors in level-major / h / w / a order — not returned by the reference, exposed for parity checks. */
 enum { B200_YOLO_LOSS_TF_YOLO_UTILS = 0, B200_YOLO_LOSS_KERAS_YOLO3 = 1 };
 size_t b200_yolo_loss_workspace_bytes(const int32_t hw[6], int B, int A);
 int b200_yolo_loss(const float* const y_true[3], const float* const y_pred[3], const int32_t hw[6], int B, int A,
                    int C, const float* anchors_wh_host, const float* image_wh_host, float iou_thresh, int metric,
-                   int variant, float batch_divisor, float* out_parts, float* out_loss, void* workspace,
-                   size_t workspace_bytes, void* stream);
+                   int variant, float batch_divisor, float* out_parts, float* out_loss, unsigned char* out_ignore,
+                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* DataGenerator.GetTargets (datasets/coco_dataset.py:185-285), batched: boxes [total,4] pixel corners
  * x1,y1,x2,y2, classes [total] int32, offsets [B+1] int32 (all device).  targets[l]: (B,H_l,W_l,A,5+C), zeroed

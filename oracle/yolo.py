@@ -192,7 +192,7 @@ def _sum32(x):
 
 
 def get_loss(y_true, y_pred, image_wh, anchors_wh, iou_thresh=0.5, iou_type="iou", return_parts=False,
-             variant="tf_yolo_utils"):
+             variant="tf_yolo_utils", return_ignore=False):
     """utils/tf_yolo_utils.py:6-127 GetLoss.
 
     variant="unit_test_copy" reproduces the local copy in yolo_v3/unit_test/loss_test.py:18-150
@@ -205,6 +205,7 @@ def get_loss(y_true, y_pred, image_wh, anchors_wh, iou_thresh=0.5, iou_type="iou
     bf = F(bsz)
     loss = F(0.0)
     parts = []
+    ignores = []
     for l in range(3):
         yt = np.asarray(y_true[l], F)
         yp = np.asarray(y_pred[l], F).reshape(yt.shape)
@@ -245,6 +246,7 @@ def get_loss(y_true, y_pred, image_wh, anchors_wh, iou_thresh=0.5, iou_type="iou
                 best = np.max(m, axis=-1)
             with np.errstate(all="ignore"):
                 ignore[b] = (best < F(iou_thresh)).astype(F)
+        ignores.append(ignore.reshape(bsz, -1).astype(np.uint8))
         ignore = ignore[..., None]
         scale = F(2) - t_wh[..., 0:1] * t_wh[..., 1:2]
         xy_bc = dm.bce_logits(raw_xy, p_xy_raw)
@@ -257,6 +259,8 @@ def get_loss(y_true, y_pred, image_wh, anchors_wh, iou_thresh=0.5, iou_type="iou
         s = [_sum32(xy_loss) / bf, _sum32(wh_loss) / bf, _sum32(obj_loss) / bf, _sum32(cls_loss) / bf]
         parts.append([F(v) for v in s])
         loss = F(loss + F(F(F(s[0] + s[1]) + s[2]) + s[3]))
+    if return_ignore:
+        return loss, np.asarray(parts, dtype=F), np.concatenate(ignores, axis=1)
     if return_parts:
         return loss, np.asarray(parts, dtype=F)
     return loss

@@ -16,6 +16,8 @@ SIGNATURES = {
     "b200_last_error": (ctypes.c_char_p, []),
     "b200_version": (c_i, []),
     "b200_device_ok": (c_i, []),
+    "b200_set_l2_fetch_granularity": (c_i, [c_i]),
+    "b200_get_l2_fetch_granularity": (c_i, []),
     "b200_detmath_eval": (c_i, [c_i, c_p, c_p, c_p, c_sz, c_p]),
     "b200_pairwise_iou": (c_i, [c_p, c_i, c_p, c_i, c_i, c_p, c_p]),
     "b200_elementwise_iou": (c_i, [c_p, c_p, c_sz, c_i, c_p, c_p]),
@@ -25,7 +27,7 @@ SIGNATURES = {
                                    c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "b200_yolo_decode_dense": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
     "b200_yolo_loss_workspace_bytes": (c_sz, [c_p, c_i, c_i]),
-    "b200_yolo_loss": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_f, c_i, c_i, c_f, c_p, c_p, c_p, c_sz, c_p]),
+    "b200_yolo_loss": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_f, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "b200_yolo_assign_targets": (c_i, [c_p, c_p, c_p, c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_p]),
     "b200_fill_zero": (c_i, [c_p, c_sz, c_p]),
 }

@@ -123,7 +123,7 @@ def GetNMSBoxes(y1, y2, y3, anchors_wh, image_wh, classes_num,
 
 
 def _loss_call(y_true, y_pred, image_wh, anchors_wh, iou_thresh, iou_type, variant, batch_divisor=None,
-               return_parts=False, workspace=None):
+               return_parts=False, workspace=None, ignore_out=None):
   lib = _lib.load()
   if len(y_true) != 3 or len(y_pred) != 3:
     raise ValueError('y_true and y_pred must each hold 3 levels')
@@ -153,7 +153,8 @@ def _loss_call(y_true, y_pred, image_wh, anchors_wh, iou_thresh, iou_type, varia
   div = float(B if batch_divisor is None else batch_divisor)
   _lib.check(lib.b200_yolo_loss(tp, pp, hw, B, A, RF - 5, anc.ctypes.data_as(ctypes.c_void_p),
                                 img.ctypes.data_as(ctypes.c_void_p), float(iou_thresh), _lib.METRIC_YOLO[iou_type],
-                                variant, div, T.ptr(parts), T.ptr(loss), T.ptr(workspace), ws_bytes, T.stream_ptr()),
+                                variant, div, T.ptr(parts), T.ptr(loss), T.ptr(ignore_out), T.ptr(workspace), ws_bytes,
+                                T.stream_ptr()),
              'GetLoss')
   return (loss, parts) if return_parts else loss
 

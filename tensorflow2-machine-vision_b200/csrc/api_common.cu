@@ -73,3 +73,16 @@ extern "C" int b200_detmath_eval(int op, const float* x, const float* y, float* 
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
+
+// Device-wide hint: DRAM->L2 fetch granularity (32/64/128 bytes).  The loss kernels touch one 32-byte sector per
+// 340-byte record; with the default granularity every touched 128-byte line is fetched whole.
+extern "C" int b200_set_l2_fetch_granularity(int bytes) {
+  B200_REQUIRE(bytes == 32 || bytes == 64 || bytes == 128, B200_ERR_BAD_ARG, "b200_set_l2_fetch_granularity: %d not in {32,64,128}", bytes);
+  B200_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes));
+  return B200_OK;
+}
+extern "C" int b200_get_l2_fetch_granularity(void) {
+  size_t v = 0;
+  if (cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity) != cudaSuccess) return -1;
+  return (int)v;
+}

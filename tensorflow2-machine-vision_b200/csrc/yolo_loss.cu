@@ -16,13 +16,16 @@
 //  K4c yolo_loss_finalize_kernel  fixed-order fp64 reduction of the per-CTA partials -> parts[3][4] / batch,
 //      loss = sum_l ((xy+wh)+obj)+cls in fp32 in the reference's order (tyu:120-125).  Deterministic run to run.
 //
-// ignore = float(best < thr) with best = max_g metric(pred, gt_g) is evaluated as "no g with metric >= thr"
-// (identical unless a metric is NaN, which needs non-finite boxes).
+// ignore = float(best < thr) with best = max_g metric(pred, gt_g) is evaluated as "no g with metric >= thr or
+// metric NaN": tf.reduce_max propagates NaN and NaN < thr is False, so a NaN pair clears the ignore bit.
 #include "boxmath.cuh"
 #include "common.cuh"
 
 #define YL_LEVELS 3
 #define YL_CHUNK 256
+#ifndef YL_ICHUNK
+#define YL_ICHUNK 128  // records (threads) per CTA of the ignore kernel
+#endif
 
 enum { YL_VARIANT_TF_YOLO_UTILS = 0, YL_VARIANT_KERAS_YOLO3 = 1 };
 
@@ -32,6 +35,9 @@ struct YlLevels {
   int h[YL_LEVELS], w[YL_LEVELS], rec_per_img[YL_LEVELS], anchor_base[YL_LEVELS];
   int chunks_per_img[YL_LEVELS];
   int cta_base[YL_LEVELS + 1];
+  int obj_chunks_per_img[YL_LEVELS];   // objects kernel: 4 records per thread
+  int obj_cta_base[YL_LEVELS + 1];
+  uint32_t magic_w[YL_LEVELS];         // floor(2^32/W)+1
   float anc_w[YL_LEVELS][8], anc_h[YL_LEVELS][8];  // pixels
 };
 
@@ -42,9 +48,16 @@ struct YlParams {
   float thr;
   int metric, variant;
   float* obj_compact;   // [B, n_img]
-  BoxT* gt;             // [B, n_img] (level slices at anchor_base)
+  float4* gt_box;       // [B, n_img] GT corners (level slices at anchor_base)
+  float4* gt_aux;       // [B, n_img] area, atan(w/h), log(area), regular flag (1/0)
+  float log_thr;        // log(thr)
+  float logk[YL_LEVELS][8];  // log(anchor_w*anchor_h/(img_w*img_h)) per level/anchor
+  float tmin_w[YL_LEVELS][8], tmin_h[YL_LEVELS][8];  // lowest tw/th for which the decode-free area bound holds
+  uint32_t magic_a;           // floor(2^32/A)+1: n/A == umulhi(n, magic) for n*A < 2^32
+  unsigned char* out_ignore;  // optional [B, n_img]: the ignore mask (1 = ignored/background), for parity tests
   int32_t* gt_count;    // [B, 3]
-  double* partials;     // [n_cta, 4]  xy, wh, obj, cls
+  double* partials;     // [n_cta]      object_loss partial of each ignore-kernel CTA
+  double* partials_obj; // [n_cta_obj,3] xy, wh, cls partials of each objects-kernel CTA
 };
 
 __device__ __forceinline__ void yl_locate(const YlLevels& lv, int cta, int& l, int& img, int& chunk) {
@@ -56,23 +69,46 @@ __device__ __forceinline__ void yl_locate(const YlLevels& lv, int cta, int& l, i
   chunk = r - img * lv.chunks_per_img[l];
 }
 
+// A box is "regular" when the cheap no-overlap reject is exact for it: finite, strictly positive extent and
+// area, aspect term not NaN.  For two regular boxes  min(a2,b2)-max(a0,b0) <= 0  <=>  a2 <= b0 || b2 <= a0.
+__device__ __forceinline__ bool yl_regular(const BoxT& b) {
+  return (b.c2 > b.c0) && (b.c3 > b.c1) && (b.area > 0.0f) && (b.area < 3.0e38f) && (b.at == b.at) &&
+         (dm_fabsf(b.c0) < 3.0e38f) && (dm_fabsf(b.c1) < 3.0e38f) && (dm_fabsf(b.c2) < 3.0e38f) && (dm_fabsf(b.c3) < 3.0e38f);
+}
+
+#define YL_OBJ_PER_THREAD 4
+#define YL_OBJ_CHUNK (YL_CHUNK * YL_OBJ_PER_THREAD)
+
 __global__ void __launch_bounds__(YL_CHUNK) yolo_loss_objects_kernel(YlParams p) {
-  __shared__ int s_list[YL_CHUNK];
+  __shared__ int s_list[YL_OBJ_CHUNK];
   __shared__ int s_n;
   __shared__ double s_acc[YL_CHUNK / 32][3];
-  int l, img, chunk;
-  yl_locate(p.lv, blockIdx.x, l, img, chunk);
+  // same (level, image, chunk) decomposition as the ignore kernel but with 4x larger chunks
+  int l = 0;
+#pragma unroll
+  for (int k = 1; k < YL_LEVELS; ++k) if ((int)blockIdx.x >= p.lv.obj_cta_base[k]) l = k;
+  const int rcta = blockIdx.x - p.lv.obj_cta_base[l];
+  const int img = rcta / p.lv.obj_chunks_per_img[l];
+  const int chunk = rcta - img * p.lv.obj_chunks_per_img[l];
   const int rpi = p.lv.rec_per_img[l];
-  const int rin = chunk * YL_CHUNK + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
   const float* yt = p.lv.y_true[l] + ((size_t)img * rpi) * p.RF;
   const float* yp = p.lv.y_pred[l] + ((size_t)img * rpi) * p.RF;
-  if (rin < rpi) {
-    const float obj = __ldg(yt + (size_t)rin * p.RF + 4);
-    p.obj_compact[(size_t)img * p.n_img + p.lv.anchor_base[l] + rin] = obj;
-    if (obj != 0.0f) s_list[atomicAdd(&s_n, 1)] = rin;
+  float objv[YL_OBJ_PER_THREAD];
+#pragma unroll
+  for (int u = 0; u < YL_OBJ_PER_THREAD; ++u) {  // independent strided sector reads, all in flight together
+    const int rin = chunk * YL_OBJ_CHUNK + u * YL_CHUNK + (int)threadIdx.x;
+    objv[u] = (rin < rpi) ? __ldcg(yt + (size_t)rin * p.RF + 4) : 0.0f;
+  }
+#pragma unroll
+  for (int u = 0; u < YL_OBJ_PER_THREAD; ++u) {
+    const int rin = chunk * YL_OBJ_CHUNK + u * YL_CHUNK + (int)threadIdx.x;
+    if (rin < rpi) {
+      p.obj_compact[(size_t)img * p.n_img + p.lv.anchor_base[l] + rin] = objv[u];
+      if (objv[u] != 0.0f) s_list[atomicAdd(&s_n, 1)] = rin;
+    }
   }
   __syncthreads();
   const int n = s_n;
@@ -115,7 +151,9 @@ __global__ void __launch_bounds__(YL_CHUNK) yolo_loss_objects_kernel(YlParams p)
       const float hx = DM_DIV(tw, 2.0f), hy = DM_DIV(th, 2.0f);
       BoxT g = bm_prep(DM_SUB(tx, hx), DM_SUB(ty, hy), DM_ADD(tx, hx), DM_ADD(ty, hy), p.metric);
       const int slot = atomicAdd(&p.gt_count[img * YL_LEVELS + l], 1);
-      p.gt[(size_t)img * p.n_img + p.lv.anchor_base[l] + slot] = g;
+      const size_t gi = (size_t)img * p.n_img + p.lv.anchor_base[l] + slot;
+      p.gt_box[gi] = make_float4(g.c0, g.c1, g.c2, g.c3);
+      p.gt_aux[gi] = make_float4(g.area, g.at, dm_logf(g.area), yl_regular(g) ? 1.0f : 0.0f);
     }
   }
   if (lane == 0) { s_acc[warp][0] = a_xy; s_acc[warp][1] = a_wh; s_acc[warp][2] = a_cls; }
@@ -123,90 +161,220 @@ __global__ void __launch_bounds__(YL_CHUNK) yolo_loss_objects_kernel(YlParams p)
   if (threadIdx.x == 0) {
     double x = 0, w = 0, c = 0;
     for (int i = 0; i < YL_CHUNK / 32; ++i) { x += s_acc[i][0]; w += s_acc[i][1]; c += s_acc[i][2]; }
-    double* out = p.partials + (size_t)blockIdx.x * 4;
-    out[0] = x; out[1] = w; out[3] = c;
+    double* out = p.partials_obj + (size_t)blockIdx.x * 3;
+    out[0] = x; out[1] = w; out[2] = c;
   }
 }
 
-#define YL_GT_TILE 128
+// Decode-free necessary conditions for metric(P,G) >= thr when thr >= 0.5 (DESIGN.md "ignore-mask filter"):
+//  (a) every metric of the family is <= IoU <= min(area)/max(area)  =>  both areas within a factor thr of each
+//      other; the predicted area is exp(tw+th)*anchor_area/image_area up to ~1 %, so this is a window on the
+//      raw logit sum  s' = tw + th + log(anchor_area/image_area):  log(thr*Ag) - 0.05 <= s' <= log(Ag/thr) + 0.05;
+//  (b) IoU >= 0.5 needs >= half of P's width and height inside G, so P's centre lies inside G; the centre is
+//      (sigmoid(t)+grid)/grid_wh, i.e. inside the anchor's grid cell, so the cell rectangle (grown by 1e-3)
+//      must intersect G.
+// Both use only tw, th and the cell index; a lane decodes its box (2 sigmoid, 2 exp, atan) only when some GT
+// passes both, and then runs the exact test.  Lanes with |t| outside [-6,4] or NaN, irregular GTs and thr < 0.5
+// take the exact path against every GT.
+#define YL_CELL_MARGIN 1e-3f
+#define YL_LOG_MARGIN 0.05f
 
-__global__ void __launch_bounds__(YL_CHUNK) yolo_loss_ignore_kernel(YlParams p) {
-  __shared__ BoxT s_gt[YL_GT_TILE];
-  __shared__ double s_acc[YL_CHUNK / 32];
+// BCE-with-logits for the (continuous) loss value only: MUFU-based exp/log, relative error ~1e-6 per term,
+// far inside the 1e-4 loss tolerance; decisions never use it.
+__device__ __forceinline__ float yl_fast_bce(float z, float x) {
+  const float e = __expf(-fabsf(x));
+  return fmaxf(x, 0.0f) - x * z + __logf(1.0f + e);
+}
+
+__device__ __forceinline__ int yl_fastdiv(int n, uint32_t magic) {
+  return magic == 0u ? n : (int)__umulhi((uint32_t)n, magic);  // magic 0 encodes divisor 1
+}
+
+// Three phases per CTA of 256 records:
+//  1. (all lanes, decode-free) each record tests the GTs that can touch its warp's strip of grid cells with the
+//     cell / logit-sum windows and pushes surviving (record, gt) pairs to a shared-memory queue;
+//  2. (dense) the queue is drained with one pair per thread: exact decode of the record (2 sigmoid, 2 exp, atan),
+//     exact overlap / area tests and the exact metric — the expensive arithmetic runs at full lane utilisation
+//     and only for pairs that need it;
+//  3. object_loss = obj*bce + (1-obj)*bce*ignore for every record.
+// The GT list is read straight from global memory (packed float4 pairs, L1-resident).
+#define YL_QCAP 1024
+
+__device__ __forceinline__ bool yl_pair_hits(const YlParams& p, int l, int rin, float tx, float ty, float tw, float th,
+                                             const float4 c, const float4 x) {
+  const int W = p.lv.w[l], H = p.lv.h[l];
+  const int cell = yl_fastdiv(rin, p.magic_a);
+  const int a = min(rin - cell * p.A, 7);
+  const int gy = yl_fastdiv(cell, p.lv.magic_w[l]);
+  const int gx = cell - gy * W;
+  // tyu:57,61: xy = (sigmoid(t)+grid)/grid_wh ; wh = exp(t)*anchor/image_wh (no inf guard here, Q7)
+  const float x_ = DM_DIV(DM_ADD(dm_sigmoidf(tx), (float)gx), (float)W);
+  const float y_ = DM_DIV(DM_ADD(dm_sigmoidf(ty), (float)gy), (float)H);
+  const float w_ = DM_DIV(DM_MUL(dm_expf(tw), p.lv.anc_w[l][a]), p.img_w);
+  const float h_ = DM_DIV(DM_MUL(dm_expf(th), p.lv.anc_h[l][a]), p.img_h);
+  const float hx_ = DM_DIV(w_, 2.0f), hy_ = DM_DIV(h_, 2.0f);
+  BoxT pb = bm_prep(DM_SUB(x_, hx_), DM_SUB(y_, hy_), DM_ADD(x_, hx_), DM_ADD(y_, hy_), B200_METRIC_YOLO_IOU);
+  BoxT gb; gb.c0 = c.x; gb.c1 = c.y; gb.c2 = c.z; gb.c3 = c.w; gb.area = x.x; gb.at = x.y;
+  if (x.w != 0.0f && p.thr > 0.0f && yl_regular(pb)) {
+    // exact rejects for regular pairs: no overlap, or areas further apart than thr allows (iou <= min/max)
+    if ((pb.c2 <= c.x) || (c.z <= pb.c0) || (pb.c3 <= c.y) || (c.w <= pb.c1)) return false;
+    if (fminf(pb.area, x.x) < 0.99f * p.thr * fmaxf(pb.area, x.x)) return false;
+  }
+  if (p.metric == B200_METRIC_YOLO_CIOU) pb.at = dm_atanf(DM_DIV(DM_SUB(pb.c2, pb.c0), DM_SUB(pb.c3, pb.c1)));
+  if (bm_surely_below(pb, gb, p.metric, p.thr)) return false;
+  const float mm = bm_metric(pb, gb, p.metric);
+  return (mm >= p.thr) || (mm != mm);  // NaN propagates through tf.reduce_max: best < thr is False
+}
+
+__global__ void __launch_bounds__(YL_ICHUNK, 10) yolo_loss_ignore_kernel(YlParams p) {
+  __shared__ float4 s_t[YL_ICHUNK];
+  __shared__ uint32_t s_q[YL_QCAP];
+  __shared__ uint32_t s_hit[YL_ICHUNK / 32];
+  __shared__ int s_nq;
+  __shared__ double s_acc[YL_ICHUNK / 32];
   int l, img, chunk;
   yl_locate(p.lv, blockIdx.x, l, img, chunk);
   const int rpi = p.lv.rec_per_img[l];
-  const int rin = chunk * YL_CHUNK + threadIdx.x;
+  const int rin = chunk * YL_ICHUNK + (int)threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool active = rin < rpi;
   const int n_gt = p.gt_count[img * YL_LEVELS + l];
-  const BoxT* gt = p.gt + (size_t)img * p.n_img + p.lv.anchor_base[l];
-  float obj = 0.f, pobj = 0.f;
-  BoxT pb;
-  pb.c0 = pb.c1 = pb.c2 = pb.c3 = pb.area = pb.at = 0.f;
+  const float4* gbox = p.gt_box + (size_t)img * p.n_img + p.lv.anchor_base[l];
+  const float4* gaux = p.gt_aux + (size_t)img * p.n_img + p.lv.anchor_base[l];
+  const int W = p.lv.w[l], H = p.lv.h[l];
+  float obj = 0.f, tx = 0.f, ty = 0.f, tw = 0.f, th = 0.f, pobj = 0.f;
   if (active) {
-    const float* q = p.lv.y_pred[l] + ((size_t)img * rpi + rin) * p.RF;
+    const size_t f0 = ((size_t)img * rpi + rin) * p.RF;
     obj = p.obj_compact[(size_t)img * p.n_img + p.lv.anchor_base[l] + rin];
-    pobj = __ldg(q + 4);
-    if (n_gt > 0) {
-      const int W = p.lv.w[l], H = p.lv.h[l];
-      const int cell = rin / p.A, a = rin - cell * p.A;
-      const int gy = cell / W, gx = cell - gy * W;
-      // tyu:57,61: xy = (sigmoid(t)+grid)/grid_wh ; wh = exp(t)*anchor/image_wh (no inf guard here, Q7)
-      const float x = DM_DIV(DM_ADD(dm_sigmoidf(__ldg(q)), (float)gx), (float)W);
-      const float y = DM_DIV(DM_ADD(dm_sigmoidf(__ldg(q + 1)), (float)gy), (float)H);
-      const float w = DM_DIV(DM_MUL(dm_expf(__ldg(q + 2)), p.lv.anc_w[l][a]), p.img_w);
-      const float h = DM_DIV(DM_MUL(dm_expf(__ldg(q + 3)), p.lv.anc_h[l][a]), p.img_h);
-      const float hx = DM_DIV(w, 2.0f), hy = DM_DIV(h, 2.0f);
-      pb = bm_prep(DM_SUB(x, hx), DM_SUB(y, hy), DM_ADD(x, hx), DM_ADD(y, hy), p.metric);
+    if ((reinterpret_cast<uintptr_t>(p.lv.y_pred[l]) & 15) == 0) {
+      // tx,ty,tw,th,conf sit at float offset f0; two aligned 16-byte loads cover them (L1 bypass)
+      const float4 lo = __ldcg(reinterpret_cast<const float4*>(p.lv.y_pred[l]) + (f0 >> 2));
+      const float4 hi = __ldcg(reinterpret_cast<const float4*>(p.lv.y_pred[l]) + (f0 >> 2) + 1);
+      const int sh = (int)(f0 & 3);
+      tx = sh == 0 ? lo.x : sh == 1 ? lo.y : sh == 2 ? lo.z : lo.w;
+      ty = sh == 0 ? lo.y : sh == 1 ? lo.z : sh == 2 ? lo.w : hi.x;
+      tw = sh == 0 ? lo.z : sh == 1 ? lo.w : sh == 2 ? hi.x : hi.y;
+      th = sh == 0 ? lo.w : sh == 1 ? hi.x : sh == 2 ? hi.y : hi.z;
+      pobj = sh == 0 ? hi.x : sh == 1 ? hi.y : sh == 2 ? hi.z : hi.w;
+    } else {
+      const float* q = p.lv.y_pred[l] + f0;
+      tx = __ldcg(q); ty = __ldcg(q + 1); tw = __ldcg(q + 2); th = __ldcg(q + 3); pobj = __ldcg(q + 4);
     }
   }
-  bool hit = false;  // some GT with metric >= thr
-  for (int g0 = 0; g0 < n_gt; g0 += YL_GT_TILE) {
-    const int m = min(YL_GT_TILE, n_gt - g0);
+  bool hit = false;  // some GT with metric >= thr (or NaN)
+  if (n_gt > 0) {    // block-uniform
+    if (threadIdx.x == 0) s_nq = 0;
+    if (threadIdx.x < YL_ICHUNK / 32) s_hit[threadIdx.x] = 0u;
+    s_t[threadIdx.x] = make_float4(tx, ty, tw, th);
     __syncthreads();
-    for (int i = threadIdx.x; i < m * 6; i += YL_CHUNK)
-      reinterpret_cast<float*>(s_gt)[i] = reinterpret_cast<const float*>(gt + g0)[i];
-    __syncthreads();
-    if (active && !hit) {
-      for (int g = 0; g < m; ++g) {
-        const BoxT gb = s_gt[g];
-        if (bm_surely_below(pb, gb, p.metric, p.thr)) continue;
-        if (bm_metric(pb, gb, p.metric) >= p.thr) { hit = true; break; }
+    // ---------------- phase 1 ----------------
+    const int cell = yl_fastdiv(rin, p.magic_a);
+    const int a = min(rin - cell * p.A, 7);
+    const int gy = yl_fastdiv(cell, p.lv.magic_w[l]);
+    const int gx = cell - gy * W;
+    const bool filter_ok = p.thr >= 0.5f;
+    // lanes whose logits are in the range where the decode-free bounds are proven
+    const bool nice = active && filter_ok && (tw >= p.tmin_w[l][a]) && (tw <= 4.0f) && (th >= p.tmin_h[l][a]) &&
+                      (th <= 4.0f) && (tx == tx) && (ty == ty);
+    const float sp = tw + th + p.logk[l][a];
+    const float invW = 1.0f / (float)W, invH = 1.0f / (float)H;
+    // rectangle that certainly contains the decoded centre (grid cell grown by the margin)
+    const float cx0 = (float)gx * invW - YL_CELL_MARGIN, cx1 = (float)(gx + 1) * invW + YL_CELL_MARGIN;
+    const float cy0 = (float)gy * invH - YL_CELL_MARGIN, cy1 = (float)(gy + 1) * invH + YL_CELL_MARGIN;
+    // the warp's 32 consecutive records cover a run of cells: rows gy(first)..gy(last); one row -> x range of
+    // the run, several rows -> full width.  (Superset of the nice lanes' cells: conservative.)
+    const uint32_t act = __ballot_sync(0xffffffffu, active);
+    float ux0 = 0.f, ux1 = 0.f, uy0 = 0.f, uy1 = 0.f;
+    if (act) {
+      const int first = __ffs(act) - 1, last = 31 - __clz(act);
+      const float fx0 = __shfl_sync(0xffffffffu, cx0, first), fy0 = __shfl_sync(0xffffffffu, cy0, first);
+      const float lx1 = __shfl_sync(0xffffffffu, cx1, last), ly1 = __shfl_sync(0xffffffffu, cy1, last);
+      const int gyf = __shfl_sync(0xffffffffu, gy, first), gyl = __shfl_sync(0xffffffffu, gy, last);
+      uy0 = fy0; uy1 = ly1;
+      ux0 = (gyf == gyl) ? fx0 : -1.0f;
+      ux1 = (gyf == gyl) ? lx1 : 2.0f;
+    }
+    const bool any_rough = __any_sync(0xffffffffu, active && !nice);
+    const float lo_k = p.log_thr - YL_LOG_MARGIN, hi_k = -p.log_thr + YL_LOG_MARGIN;
+    for (int j0 = 0; j0 < n_gt; j0 += 32) {
+      const int j = j0 + lane;
+      bool relevant = false;
+      if (j < n_gt) {
+        const float4 c = __ldg(gbox + j);
+        // irregular GTs (aux.w == 0) and warps with rough lanes need every GT
+        relevant = any_rough || (__ldg(gaux + j).w == 0.0f) || !((ux1 < c.x) || (c.z < ux0) || (uy1 < c.y) || (c.w < uy0));
+      }
+      uint32_t mask = __ballot_sync(0xffffffffu, relevant);
+      while (mask) {
+        const int g = j0 + __ffs(mask) - 1;
+        mask &= mask - 1u;
+        if (!active || hit) continue;
+        const float4 c = __ldg(gbox + g);
+        const float4 x = __ldg(gaux + g);  // area, atan term, log(area), regular flag
+        if (nice && x.w != 0.0f) {
+          if ((cx1 < c.x) || (c.z < cx0) || (cy1 < c.y) || (c.w < cy0)) continue;
+          if ((sp < x.z + lo_k) || (sp > x.z + hi_k)) continue;
+        }
+        const int slot = atomicAdd(&s_nq, 1);
+        if (slot < YL_QCAP) s_q[slot] = (threadIdx.x << 24) | (uint32_t)g;            // drained in phase 2
+        else if (yl_pair_hits(p, l, rin, tx, ty, tw, th, c, x)) hit = true;             // queue full: inline
       }
     }
+    if (hit) atomicOr(&s_hit[warp], 1u << lane);
+    __syncthreads();
+    // ---------------- phase 2 ----------------
+    const int nq = min(s_nq, YL_QCAP);
+    for (int q = threadIdx.x; q < nq; q += YL_ICHUNK) {
+      const uint32_t e = s_q[q];
+      const int r = (int)(e >> 24), g = (int)(e & 0xffffffu);
+      if ((s_hit[r >> 5] >> (r & 31)) & 1u) continue;  // already decided (benign race: only skips work)
+      const float4 t = s_t[r];
+      if (yl_pair_hits(p, l, chunk * YL_ICHUNK + r, t.x, t.y, t.z, t.w, __ldg(gbox + g), __ldg(gaux + g)))
+        atomicOr(&s_hit[r >> 5], 1u << (r & 31));
+    }
+    __syncthreads();
+    hit = (s_hit[warp] >> lane) & 1u;
   }
+  // ---------------- phase 3 ----------------
   float e = 0.f;
   if (active) {
-    const float bc = dm_bce_logits(obj, pobj);
+    const float bc = yl_fast_bce(obj, pobj);
     const float ign = hit ? 0.0f : 1.0f;
-    // obj*bc + (1-obj)*bc*ignore, tyu:114
-    e = DM_ADD(DM_MUL(obj, bc), DM_MUL(DM_MUL(DM_SUB(1.0f, obj), bc), ign));
+    if (p.out_ignore) p.out_ignore[(size_t)img * p.n_img + p.lv.anchor_base[l] + rin] = hit ? 0 : 1;
+    e = obj * bc + (1.0f - obj) * bc * ign;  // tyu:114
   }
-  double d = warp_sum_d((double)e);
-  if (lane == 0) s_acc[warp] = d;
+  e = warp_sum(e);  // 32 fp32 terms; the cross-warp and cross-CTA sums are fp64
+  if (lane == 0) s_acc[warp] = (double)e;
   __syncthreads();
   if (threadIdx.x == 0) {
-    double s = 0;
-    for (int i = 0; i < YL_CHUNK / 32; ++i) s += s_acc[i];
-    p.partials[(size_t)blockIdx.x * 4 + 2] = s;
+    double sum = 0;
+    for (int i = 0; i < YL_ICHUNK / 32; ++i) sum += s_acc[i];
+    p.partials[blockIdx.x] = sum;
   }
 }
 
-__global__ void __launch_bounds__(1024) yolo_loss_finalize_kernel(const double* __restrict__ partials, int cta_base0,
-                                                                   int cta_base1, int cta_base2, int cta_base3,
-                                                                   float batch_divisor, float* __restrict__ parts,
-                                                                   float* __restrict__ loss) {
+struct YlFinalize {
+  const double* partials; const double* partials_obj;
+  int cta_base[YL_LEVELS + 1]; int obj_cta_base[YL_LEVELS + 1];
+  float batch_divisor; float* parts; float* loss;
+};
+
+__global__ void __launch_bounds__(1024) yolo_loss_finalize_kernel(YlFinalize f) {
   __shared__ double s_red[32][12];
-  const int base[4] = {cta_base0, cta_base1, cta_base2, cta_base3};
   double acc[12];
 #pragma unroll
   for (int i = 0; i < 12; ++i) acc[i] = 0.0;
-  for (int l = 0; l < 3; ++l)
-    for (int c = base[l] + threadIdx.x; c < base[l + 1]; c += blockDim.x) {
 #pragma unroll
-      for (int t = 0; t < 4; ++t) acc[l * 4 + t] += partials[(size_t)c * 4 + t];
+  for (int l = 0; l < 3; ++l) {
+#pragma unroll 4
+    for (int c = f.cta_base[l] + (int)threadIdx.x; c < f.cta_base[l + 1]; c += 1024) acc[l * 4 + 2] += f.partials[c];
+#pragma unroll 2
+    for (int c = f.obj_cta_base[l] + (int)threadIdx.x; c < f.obj_cta_base[l + 1]; c += 1024) {
+      acc[l * 4 + 0] += f.partials_obj[(size_t)c * 3 + 0];
+      acc[l * 4 + 1] += f.partials_obj[(size_t)c * 3 + 1];
+      acc[l * 4 + 3] += f.partials_obj[(size_t)c * 3 + 2];
     }
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < 12; ++i) {
@@ -214,46 +382,54 @@ __global__ void __launch_bounds__(1024) yolo_loss_finalize_kernel(const double* 
     if (lane == 0) s_red[warp][i] = v;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (warp == 0) {
+    float v = 0.0f;
+    if (lane < 12) {
+      double s = 0.0;
+      for (int w = 0; w < 32; ++w) s += s_red[w][lane];
+      v = DM_DIV((float)s, f.batch_divisor);  // reduce_sum(...) / batch_size_float, tyu:120-123
+      if (f.parts) f.parts[lane] = v;
+    }
     float total = 0.0f;
     for (int l = 0; l < 3; ++l) {
-      float t4[4];
-      for (int t = 0; t < 4; ++t) {
-        double s = 0.0;
-        for (int w = 0; w < 32; ++w) s += s_red[w][l * 4 + t];
-        t4[t] = DM_DIV((float)s, batch_divisor);  // reduce_sum(...) / batch_size_float, tyu:120-123
-        if (parts) parts[l * 4 + t] = t4[t];
-      }
-      total = DM_ADD(total, DM_ADD(DM_ADD(DM_ADD(t4[0], t4[1]), t4[2]), t4[3]));  // tyu:125
+      const float t0 = __shfl_sync(0xffffffffu, v, l * 4 + 0), t1 = __shfl_sync(0xffffffffu, v, l * 4 + 1);
+      const float t2 = __shfl_sync(0xffffffffu, v, l * 4 + 2), t3 = __shfl_sync(0xffffffffu, v, l * 4 + 3);
+      total = DM_ADD(total, DM_ADD(DM_ADD(DM_ADD(t0, t1), t2), t3));  // tyu:125
     }
-    *loss = total;
+    if (lane == 0) *f.loss = total;
   }
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-struct YlWs { size_t obj, gt, cnt, part, total; int n_cta; };
+struct YlWs { size_t obj, gt, gtl, cnt, part, part_obj, total; int n_cta, n_cta_obj; };
 
 static YlWs yl_layout(const int32_t hw[6], int B, int A, int* n_img_out, YlLevels* lv) {
   YlWs w;
-  int n_img = 0, cta = 0;
+  int n_img = 0, cta = 0, octa = 0;
   for (int l = 0; l < YL_LEVELS; ++l) {
     const int rpi = hw[2 * l] * hw[2 * l + 1] * A;
-    const int cpi = (rpi + YL_CHUNK - 1) / YL_CHUNK;
+    const int cpi = (rpi + YL_ICHUNK - 1) / YL_ICHUNK;
+    const int ocpi = (rpi + YL_OBJ_CHUNK - 1) / YL_OBJ_CHUNK;
     if (lv) {
       lv->h[l] = hw[2 * l]; lv->w[l] = hw[2 * l + 1]; lv->rec_per_img[l] = rpi; lv->anchor_base[l] = n_img;
       lv->chunks_per_img[l] = cpi; lv->cta_base[l] = cta;
+      lv->obj_chunks_per_img[l] = ocpi; lv->obj_cta_base[l] = octa;
     }
     n_img += rpi;
     cta += cpi * B;
+    octa += ocpi * B;
   }
-  if (lv) lv->cta_base[YL_LEVELS] = cta;
+  if (lv) { lv->cta_base[YL_LEVELS] = cta; lv->obj_cta_base[YL_LEVELS] = octa; }
   if (n_img_out) *n_img_out = n_img;
   w.n_cta = cta;
+  w.n_cta_obj = octa;
   size_t o = 0;
   w.cnt = o; o = b200_align_up(o + sizeof(int32_t) * (size_t)B * YL_LEVELS, 256);
   w.obj = o; o = b200_align_up(o + sizeof(float) * (size_t)B * n_img, 256);
-  w.gt = o; o = b200_align_up(o + sizeof(BoxT) * (size_t)B * n_img, 256);
-  w.part = o; o = b200_align_up(o + sizeof(double) * 4 * (size_t)cta, 256);
+  w.gt = o; o = b200_align_up(o + sizeof(float4) * (size_t)B * n_img, 256);
+  w.gtl = o; o = b200_align_up(o + sizeof(float4) * (size_t)B * n_img, 256);
+  w.part = o; o = b200_align_up(o + sizeof(double) * (size_t)cta, 256);
+  w.part_obj = o; o = b200_align_up(o + sizeof(double) * 3 * (size_t)octa, 256);
   w.total = o;
   return w;
 }
@@ -265,7 +441,8 @@ extern "C" size_t b200_yolo_loss_workspace_bytes(const int32_t hw[6], int B, int
 extern "C" int b200_yolo_loss(const float* const y_true[3], const float* const y_pred[3], const int32_t hw[6], int B,
                               int A, int C, const float* anchors_wh_host, const float* image_wh_host,
                               float iou_thresh, int metric, int variant, float batch_divisor, float* out_parts,
-                              float* out_loss, void* workspace, size_t workspace_bytes, void* stream_) {
+                              float* out_loss, unsigned char* out_ignore, void* workspace, size_t workspace_bytes,
+                              void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_REQUIRE(y_true && y_pred && hw && anchors_wh_host && image_wh_host && out_loss, B200_ERR_BAD_ARG, "b200_yolo_loss: null argument");
   B200_REQUIRE(B >= 1 && A >= 1 && A <= 8 && C >= 0, B200_ERR_BAD_ARG, "b200_yolo_loss: unsupported shape B=%d A=%d C=%d", B, A, C);
@@ -292,17 +469,35 @@ extern "C" int b200_yolo_loss(const float* const y_true[3], const float* const y
   p.img_w = image_wh_host[0]; p.img_h = image_wh_host[1];
   p.thr = iou_thresh; p.metric = metric; p.variant = variant;
   p.obj_compact = reinterpret_cast<float*>(wsb + ws.obj);
-  p.gt = reinterpret_cast<BoxT*>(wsb + ws.gt);
+  p.gt_box = reinterpret_cast<float4*>(wsb + ws.gt);
+  p.gt_aux = reinterpret_cast<float4*>(wsb + ws.gtl);
+  p.log_thr = iou_thresh > 0.0f ? logf(iou_thresh) : 0.0f;
+  for (int l = 0; l < YL_LEVELS; ++l)
+    for (int a = 0; a < A; ++a)
+    {
+      p.logk[l][a] = (float)log(((double)p.lv.anc_w[l][a] * (double)p.lv.anc_h[l][a]) / ((double)image_wh_host[0] * (double)image_wh_host[1]));
+      // width/height must stay >= 4e-5 (normalised) so that the rounding of x +- w/2 (<= 1.2e-7) is < 0.4 %
+      const double tw = log(4e-5 * (double)image_wh_host[0] / (double)p.lv.anc_w[l][a]);
+      const double th = log(4e-5 * (double)image_wh_host[1] / (double)p.lv.anc_h[l][a]);
+      p.tmin_w[l][a] = (float)(tw > -6.0 ? tw : -6.0);
+      p.tmin_h[l][a] = (float)(th > -6.0 ? th : -6.0);
+    }
+  p.out_ignore = out_ignore;
+  p.magic_a = A == 1 ? 0u : (uint32_t)((1ull << 32) / (unsigned long long)A + 1ull);
+  for (int l = 0; l < YL_LEVELS; ++l) p.lv.magic_w[l] = p.lv.w[l] == 1 ? 0u : (uint32_t)((1ull << 32) / (unsigned long long)p.lv.w[l] + 1ull);
   p.gt_count = reinterpret_cast<int32_t*>(wsb + ws.cnt);
   p.partials = reinterpret_cast<double*>(wsb + ws.part);
+  p.partials_obj = reinterpret_cast<double*>(wsb + ws.part_obj);
   B200_CUDA(cudaMemsetAsync(wsb + ws.cnt, 0, sizeof(int32_t) * (size_t)B * YL_LEVELS, stream));
-  B200_CUDA(cudaMemsetAsync(wsb + ws.part, 0, sizeof(double) * 4 * (size_t)ws.n_cta, stream));
-  yolo_loss_objects_kernel<<<ws.n_cta, YL_CHUNK, 0, stream>>>(p);
+  yolo_loss_objects_kernel<<<ws.n_cta_obj, YL_CHUNK, 0, stream>>>(p);
   B200_LAUNCH_CHECK();
-  yolo_loss_ignore_kernel<<<ws.n_cta, YL_CHUNK, 0, stream>>>(p);
+  yolo_loss_ignore_kernel<<<ws.n_cta, YL_ICHUNK, 0, stream>>>(p);
   B200_LAUNCH_CHECK();
-  yolo_loss_finalize_kernel<<<1, 1024, 0, stream>>>(p.partials, p.lv.cta_base[0], p.lv.cta_base[1], p.lv.cta_base[2],
-                                                    p.lv.cta_base[3], batch_divisor, out_parts, out_loss);
+  YlFinalize f;
+  f.partials = p.partials; f.partials_obj = p.partials_obj;
+  for (int l = 0; l <= YL_LEVELS; ++l) { f.cta_base[l] = p.lv.cta_base[l]; f.obj_cta_base[l] = p.lv.obj_cta_base[l]; }
+  f.batch_divisor = batch_divisor; f.parts = out_parts; f.loss = out_loss;
+  yolo_loss_finalize_kernel<<<1, 1024, 0, stream>>>(f);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

@@ -4,14 +4,15 @@
 //   K5a fill_zero_kernel        dense targets start as zeros (tf.scatter_nd into a zero tensor, cds:265-276):
 //                               128-bit streaming stores, persistent grid — the HBM-write-bound part (7.7 MB/img
 //                               at 608x608).
-//   K5b yolo_scatter_targets    one thread per ground-truth box: floor-div centre (cds:193), normalise (:196-197),
+//   K5b yolo_scatter_targets    one CTA per image, one thread per ground-truth box: floor-div centre (cds:193), normalise (:196-197),
 //                               IoU of the origin-centred box against the 9 origin-centred anchors with GetIOU
 //                               exactly as written — normalised box vs *pixel* anchors (cds:200-219, quirk Q8) —
 //                               first-max argmax (:222), layer = idx // layers_num, anchor = idx % layers_num
 //                               (:237,241), cell = floor(xy[::-1] * layer_hw) (:244).  The obj channel is bumped
 //                               with atomicAdd; the thread that saw 0 writes the record.
-//   K5c yolo_fix_collisions     scatter_nd sums duplicates, then every record with obj > 1 is zeroed (cds:279-284):
-//                               each box re-derives its record and clears it when obj > 1.
+//                               scatter_nd sums duplicates, then every record with obj > 1 is zeroed (cds:279-284):
+//                               collisions can only happen inside an image, so one CTA owns one image and clears
+//                               the collided records after a block barrier (single launch).
 #include "boxmath.cuh"
 #include "common.cuh"
 
@@ -26,6 +27,25 @@ __global__ void fill_zero_kernel(float4* __restrict__ dst, size_t n_vec, float* 
   if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) tail[threadIdx.x] = 0.0f;
 }
 
+struct FillMulti {
+  float4* dst[YT_LEVELS];
+  unsigned long long n_vec[YT_LEVELS];  // cumulative end (in float4) of each buffer in the virtual concatenation
+};
+
+// one launch for the three level tensors (all sizes are multiples of 4 floats when checked by the caller)
+__global__ void fill_zero_multi_kernel(FillMulti f) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  const unsigned long long total = f.n_vec[YT_LEVELS - 1];
+#pragma unroll 4
+  for (; i < total; i += stride) {
+    if (i < f.n_vec[0]) __stcs(f.dst[0] + i, z);
+    else if (i < f.n_vec[1]) __stcs(f.dst[1] + (i - f.n_vec[0]), z);
+    else __stcs(f.dst[2] + (i - f.n_vec[1]), z);
+  }
+}
+
 struct YtParams {
   const float* boxes;       // [total,4] pixel corners x1,y1,x2,y2
   const int32_t* classes;   // [total]
@@ -37,17 +57,11 @@ struct YtParams {
   float anc_w[YT_LEVELS * 8], anc_h[YT_LEVELS * 8];  // flattened (layers*A) in reshape(-1,2) order, pixels
 };
 
-// returns the record pointer for box i (nullptr when the cell falls outside the grid) and the update fields
-__device__ __forceinline__ float* yt_locate(const YtParams& p, int i, float& nx, float& ny, float& nw, float& nh) {
-  // image index: binary search in offsets
-  int lo = 0, hi = p.B;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (p.offsets[mid] <= i) lo = mid; else hi = mid;
-  }
-  const int img = lo;
-  const float x1 = p.boxes[4 * (size_t)i], y1 = p.boxes[4 * (size_t)i + 1];
-  const float x2 = p.boxes[4 * (size_t)i + 2], y2 = p.boxes[4 * (size_t)i + 3];
+// returns the record pointer for box i of image `img` (nullptr when the cell falls outside the grid) and the
+// update fields
+__device__ __forceinline__ float* yt_locate(const YtParams& p, int img, int i, float& nx, float& ny, float& nw, float& nh) {
+  const float4 bx = __ldg(reinterpret_cast<const float4*>(p.boxes) + i);
+  const float x1 = bx.x, y1 = bx.y, x2 = bx.z, y2 = bx.w;
   // (x2y2 + x1y1) // 2 : float floor division
   const float cx = floorf(DM_DIV(DM_ADD(x2, x1), 2.0f)), cy = floorf(DM_DIV(DM_ADD(y2, y1), 2.0f));
   const float bw = DM_SUB(x2, x1), bh = DM_SUB(y2, y1);
@@ -73,31 +87,47 @@ __device__ __forceinline__ float* yt_locate(const YtParams& p, int i, float& nx,
   return p.target[layer] + ((((size_t)img * p.h[layer] + yy) * p.w[layer] + xx) * p.A + anchor) * p.RF;
 }
 
-__global__ void yolo_scatter_targets_kernel(YtParams p) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.total) return;
-  float nx, ny, nw, nh;
-  float* rec = yt_locate(p, i, nx, ny, nw, nh);
-  if (!rec) return;
-  const float old = atomicAdd(rec + 4, 1.0f);
-  if (old == 0.0f) {
-    rec[0] = nx; rec[1] = ny; rec[2] = nw; rec[3] = nh;
-    const int c = p.classes[i];
-    if (c >= 0 && c < p.C) rec[5 + c] = 1.0f;  // tf.one_hot: out of range -> all zeros
+// One CTA per image (collisions can only happen inside an image): scatter, barrier, clear collided records.
+__global__ void __launch_bounds__(128) yolo_scatter_targets_kernel(YtParams p) {
+  const int img = blockIdx.x;
+  const int beg = p.offsets[img], end = p.offsets[img + 1];
+  for (int i0 = beg; i0 < end; i0 += 128 * 4) {
+    float* recs[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 128 + (int)threadIdx.x;
+      recs[u] = nullptr;
+      if (i < end) {
+        float nx, ny, nw, nh;
+        float* rec = yt_locate(p, img, i, nx, ny, nw, nh);
+        recs[u] = rec;
+        if (rec) {
+          const float old = atomicAdd(rec + 4, 1.0f);
+          if (old == 0.0f) {
+            rec[0] = nx; rec[1] = ny; rec[2] = nw; rec[3] = nh;
+            const int c = p.classes[i];
+            if (c >= 0 && c < p.C) rec[5 + c] = 1.0f;  // tf.one_hot: out of range -> all zeros
+          }
+        }
+      }
+    }
+    // up to 512 boxes per image are resolved per round; more than that loops (records stay consistent because
+    // the obj counter keeps accumulating and the clear below re-runs every round)
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float* rec = recs[u];
+      if (rec && rec[4] > 1.0f) {
+        for (int c = 0; c < p.RF; ++c) if (c != 4) rec[c] = 0.0f;
+      }
+    }
+    __syncthreads();
   }
-}
-
-__global__ void yolo_fix_collisions_kernel(YtParams p) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.total) return;
-  float nx, ny, nw, nh;
-  float* rec = yt_locate(p, i, nx, ny, nw, nh);
-  if (!rec) return;
-  // obj is a small integer count here; any writer clearing it concurrently also clears the whole record
-  if (rec[4] > 1.0f) {
-    for (int c = 0; c < p.RF; ++c) if (c != 4) rec[c] = 0.0f;
-    __threadfence();
-    rec[4] = 0.0f;
+  // obj counters of collided records are cleared last so that every colliding thread saw them > 1
+  for (int i = beg + (int)threadIdx.x; i < end; i += 128) {
+    float nx, ny, nw, nh;
+    float* rec = yt_locate(p, img, i, nx, ny, nw, nh);
+    if (rec && rec[4] > 1.0f) rec[4] = 0.0f;
   }
 }
 
@@ -133,17 +163,34 @@ extern "C" int b200_yolo_assign_targets(const float* boxes, const int32_t* class
   }
   for (int k = 0; k < YT_LEVELS * A; ++k) { p.anc_w[k] = anchors_wh_host[2 * k]; p.anc_h[k] = anchors_wh_host[2 * k + 1]; }
   if (zero_fill) {
+    bool vec_ok = true;
+    FillMulti f;
+    unsigned long long cum = 0;
     for (int l = 0; l < YT_LEVELS; ++l) {
-      int st = b200_fill_zero(targets[l], (size_t)B * p.h[l] * p.w[l] * A * p.RF, stream_);
-      if (st != B200_OK) return st;
+      const size_t n = (size_t)B * p.h[l] * p.w[l] * A * p.RF;
+      vec_ok = vec_ok && (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(targets[l]) & 15) == 0);
+      f.dst[l] = reinterpret_cast<float4*>(targets[l]);
+      cum += n / 4;
+      f.n_vec[l] = cum;
+    }
+    if (vec_ok) {
+      unsigned long long blocks = (cum + 255) / 256;
+      const unsigned long long cap = (unsigned long long)b200_sm_count() * 8;
+      if (blocks > cap) blocks = cap;
+      if (blocks < 1) blocks = 1;
+      fill_zero_multi_kernel<<<(int)blocks, 256, 0, stream>>>(f);
+      B200_LAUNCH_CHECK();
+    } else {
+      for (int l = 0; l < YT_LEVELS; ++l) {
+        int st = b200_fill_zero(targets[l], (size_t)B * p.h[l] * p.w[l] * A * p.RF, stream_);
+        if (st != B200_OK) return st;
+      }
     }
   }
   if (total_boxes > 0) {
     B200_REQUIRE(boxes && classes && offsets, B200_ERR_BAD_ARG, "b200_yolo_assign_targets: null box arrays");
-    const int blocks = (total_boxes + 127) / 128;
-    yolo_scatter_targets_kernel<<<blocks, 128, 0, stream>>>(p);
-    B200_LAUNCH_CHECK();
-    yolo_fix_collisions_kernel<<<blocks, 128, 0, stream>>>(p);
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(boxes) & 15) == 0, B200_ERR_BAD_ARG, "b200_yolo_assign_targets: boxes not 16-byte aligned");
+    yolo_scatter_targets_kernel<<<B, 128, 0, stream>>>(p);
     B200_LAUNCH_CHECK();
   }
   return B200_OK;

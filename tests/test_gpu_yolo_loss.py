@@ -67,9 +67,14 @@ def test_get_loss_matches_oracle(lib, cuda, image, batch, iou_type, normalised):
         yp = y_pred[l].reshape(yt.shape)
         m = yt[..., 4] > 0
         yp[m, 2:4] = np.log(np.maximum(yt[m, 2:4] * image, 1e-3) / anc[l][np.nonzero(m)[3]]) + rng.normal(0, 0.1, (int(m.sum()), 2))
-    want, want_parts = oy.get_loss(y_true, y_pred, (image, image), anc, 0.5, iou_type, return_parts=True)
+    import torch
+    want, want_parts, want_ign = oy.get_loss(y_true, y_pred, (image, image), anc, 0.5, iou_type, return_ignore=True)
+    ign = torch.full(want_ign.shape, 7, dtype=torch.uint8, device=cuda)
     got, parts = _loss_call([_t(t, cuda) for t in y_true], [_t(t, cuda) for t in y_pred], (image, image), anc, 0.5, iou_type, 0,
-                            return_parts=True)
+                            return_parts=True, ignore_out=ign)
+    # the ignore mask is a discrete output: bit-exact, and it must contain both values to mean anything
+    assert np.array_equal(ign.cpu().numpy(), want_ign)
+    assert 0 < int(want_ign.sum()) < want_ign.size
     np.testing.assert_allclose(parts.cpu().numpy(), want_parts, rtol=LOSS_RTOL, atol=1e-6)
     assert abs(float(got) - float(want)) <= LOSS_RTOL * abs(float(want))
     got2 = GetLoss([_t(t, cuda) for t in y_true], [_t(t, cuda) for t in y_pred], image_wh=(image, image), anchors_wh=anc,
@@ -96,3 +101,44 @@ def test_reference_unit_test_relation_on_gpu(lib, cuda):
     c = _loss_call([_t(t, cuda) for t in yt], [_t(t, cuda) for t in yp], (64, 64), anc, 0.5, "ciou", 0)
     want_c = oy.get_loss(yt, yp, (64, 64), anc, 0.5, "ciou")
     assert abs(float(c) - float(want_c)) <= LOSS_RTOL * abs(float(want_c))
+
+
+@pytest.mark.parametrize("iou_type,thr,sigma", [("ciou", 0.5, 2.5), ("iou", 0.5, 2.0), ("diou", 0.7, 2.5), ("ciou", 0.3, 2.0),
+                                                ("iou", 0.05, 1.0), ("ciou", 0.5, 6.0)])
+def test_ignore_mask_stress_bit_exact(lib, cuda, iou_type, thr, sigma):
+    """The ignore mask decides on exact metric >= thr comparisons; the kernel's decode-free filters (cell / logit-sum
+    windows, thr >= 0.5) and the exact fall-back paths (thr < 0.5, out-of-range logits) must agree with the oracle
+    bit for bit.  Wide logits make predicted boxes of every size, many of them overlapping ground truth."""
+    import torch
+    from oracle import yolo as oy
+    from tfmv_b200 import synth
+    from tfmv_b200.ai_models.utils.tf_yolo_utils import _loss_call
+    image, batch = 256, 3
+    rng = np.random.default_rng(int(thr * 100) + int(sigma * 10))
+    anc = (synth.yolo_anchors().astype(F) * F(image / 608.0)).astype(F)
+    _, _, _, y_true = _dense_targets(rng, batch, image, anc, max_boxes=60, normalised_anchors=True)
+    y_pred = [h * F(sigma) for h in synth.yolo_heads(rng, batch, image)]
+    # plant predictions that sit right on their targets (IoU near 1) and near-threshold rescaled copies
+    for l in range(3):
+        yt = y_true[l]
+        yp = y_pred[l].reshape(yt.shape)
+        b, yy, xx, aa = np.nonzero(yt[..., 4] > 0)
+        for k in range(len(b)):
+            g = yt.shape[1]
+            t = yt[b[k], yy[k], xx[k], aa[k]]
+            s = [1.0, 1.0, np.sqrt(thr), 1.0 / np.sqrt(max(thr, 1e-3))][k % 4] * (1.0 + rng.normal(0, 0.01))
+            a2 = (aa[k] + k) % 3
+            fx, fy = t[0] * g - xx[k], t[1] * g - yy[k]
+            fx, fy = min(max(fx, 1e-3), 1 - 1e-3), min(max(fy, 1e-3), 1 - 1e-3)
+            yp[b[k], yy[k], xx[k], a2, 0] = np.log(fx / (1 - fx))
+            yp[b[k], yy[k], xx[k], a2, 1] = np.log(fy / (1 - fy))
+            yp[b[k], yy[k], xx[k], a2, 2:4] = np.log(np.maximum(t[2:4] * image * s, 1e-3) / anc[l][a2])
+    want, _, want_ign = oy.get_loss(y_true, y_pred, (image, image), anc, thr, iou_type, return_ignore=True)
+    ign = torch.full(want_ign.shape, 7, dtype=torch.uint8, device=cuda)
+    got = _loss_call([_t(t, cuda) for t in y_true], [_t(t, cuda) for t in y_pred], (image, image), anc, thr, iou_type, 0,
+                     ignore_out=ign)
+    g = ign.cpu().numpy()
+    assert np.array_equal(g, want_ign), "%d ignore bits differ" % int((g != want_ign).sum())
+    assert int((want_ign == 0).sum()) > 20
+    if np.isfinite(want):
+        assert abs(float(got) - float(want)) <= LOSS_RTOL * abs(float(want))
