@@ -131,6 +131,61 @@ int b200_yolo_assign_targets(const float* boxes, const int32_t* classes, const i
                              const int32_t hw[6], float* const targets[3], int zero_fill, void* stream);
 int b200_fill_zero(float* dst, size_t n, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * EfficientDet (efficientnet/utils/anchors.py, iou.py, nms.py; losses/focal_loss.py, box_loss.py;
+ * efficientnet/efficientdet_net_train.py:41-52).  Levels are described by hw = {H0,W0,H1,W1,...} and A anchors
+ * per location; anchors are rebuilt in-kernel from a device table of b200_effdet_table_floats() floats laid out
+ * per level as [yc(H) | xc(W) | hy(A) | hx(A)]: row/column centres tf.range(stride/2, size, stride) and half
+ * extents anchor_scale*stride*2^(octave/num_scales)*aspect/2 (anc:58-71; aspect[1] scales x, aspect[0] scales y),
+ * a = octave*len(aspects)+aspect_index.  The host computes the table. */
+size_t b200_effdet_table_floats(int num_levels, const int32_t* hw, int A);
+/* Anchors._generate_boxes anc:46-84 for one level: out (H,W,A,4) y1,x1,y2,x2 pixels. */
+int b200_effdet_anchors(int num_levels, const int32_t* hw, int A, const float* table_dev, int level, float* out,
+                        void* stream);
+/* convert_outputs_boxes / _boxes_decoder anc:141-158,245-274: rel[l] (B,H,W,A,4) ty,tx,th,tw -> out[l] y1,x1,y2,x2. */
+int b200_effdet_decode(int num_levels, const int32_t* hw, int A, const float* table_dev, int B,
+                       const float* const rel[], float* const out[], void* stream);
+/* convert_outputs_one anc:161-202 for images [first_image, first_image+num_images) of a batch of B:
+ * per anchor argmax/max over the C class logits, background (id 0) dropped, class-agnostic get_nms (enms:5-61)
+ * on the raw max logits with score_thr (reference: max_out 200, iou_thr 0.5, score_thr 1e-4, diou), sigmoid of the
+ * survivors' scores.  boxes[l] (B,H,W,A,4) decoded, classes[l] (B,H,W,A,C) logits.  Outputs padded to max_out rows:
+ * out_boxes [n,max_out,4], out_class_id [n,max_out] int64, out_score [n,max_out], out_sel_idx (position in the
+ * reference's concatenated candidate list, may be NULL), out_sel_anchor (flat anchor index, may be NULL),
+ * out_count [n]. */
+size_t b200_effdet_postprocess_workspace_bytes(int num_levels, const int32_t* hw, int A, int num_images, int max_out);
+int b200_effdet_postprocess(int num_levels, const int32_t* hw, int A, int C, int B, int first_image, int num_images,
+                            const float* const boxes[], const float* const classes[], int max_out, float iou_thr,
+                            float score_thr, int metric, float* out_boxes, long long* out_class_id, float* out_score,
+                            int32_t* out_sel_idx, int32_t* out_sel_anchor, int32_t* out_count, void* workspace,
+                            size_t workspace_bytes, void* stream);
+/* Anchors.generate_targets anc:91-138 + _boxes_encoder anc:219-243, batched: gt_boxes [total,4] y1,x1,y2,x2,
+ * gt_classes [total] int32, gt_offsets [B+1].  Per level: out_boxes (B,H,W,A,4), out_onehot (B,H,W,A,C),
+ * out_mask (B,H,W,A,1) bytes.  Anchor -> best GT (first max IoU), mask = max >= iou_thr; unmatched anchors get
+ * one-hot class 0 and zero box targets.  An image without GT yields all-unmatched (the reference would raise). */
+int b200_effdet_assign_targets(int num_levels, const int32_t* hw, int A, const float* table_dev, int C, int B,
+                               const float* gt_boxes, const int32_t* gt_classes, const int32_t* gt_offsets,
+                               float iou_thr, float* const out_boxes[], float* const out_onehot[],
+                               unsigned char* const out_mask[], void* stream);
+/* FocalLoss.call focal_loss.py:26-52, elementwise: out = alpha_factor*modulating*ce/normalizer. */
+int b200_focal_elementwise(const float* y_true, const float* y_pred, size_t n, float normalizer, float alpha,
+                           float gamma, float label_smoothing, float* out, void* stream);
+/* _get_loss edt:41-52 in two steps so a data-parallel caller can all-reduce in between:
+ * partial_sums -> sums_out[2L+1] (device fp64): [0,L) sum of alpha*mod*ce per level, [L,2L) sum of masked Huber
+ * per level, [2L] number of positive anchors.  anchors_per_level[l] = B*H*W*A of this call; a level may omit its
+ * class half or its box half (NULL pointers) for stand-alone FocalLoss / BoxLoss.
+ * finalize: num_pos = sums[2L]+1; box_l = huber_l/(4 num_pos); focal_l = focal_l/num_pos/numel_l (numel_l = GLOBAL
+ * element count of level l's class tensor, host array); out_parts [L][2] = {box_l, focal_l} (may be NULL);
+ * out_loss = sum_l (50 box_l + focal_l); out_num_positives may be NULL. */
+size_t b200_focal_box_workspace_bytes(int num_levels, const unsigned long long* anchors_per_level, int C);
+int b200_focal_box_partial_sums(int num_levels, const unsigned long long* anchors_per_level, int C,
+                                const float* const true_boxes[], const float* const true_classes[],
+                                const unsigned char* const true_masks[], const float* const pred_boxes[],
+                                const float* const pred_classes[], float alpha, float gamma, float delta,
+                                float label_smoothing, double* sums_out, void* workspace, size_t workspace_bytes,
+                                void* stream);
+int b200_focal_box_finalize(int num_levels, const double* sums, const double* numel_per_level_host, float* out_parts,
+                            float* out_loss, float* out_num_positives, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,17 @@ SIGNATURES = {
     "b200_yolo_loss": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_f, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "b200_yolo_assign_targets": (c_i, [c_p, c_p, c_p, c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_p]),
     "b200_fill_zero": (c_i, [c_p, c_sz, c_p]),
+    "b200_effdet_table_floats": (c_sz, [c_i, c_p, c_i]),
+    "b200_effdet_anchors": (c_i, [c_i, c_p, c_i, c_p, c_i, c_p, c_p]),
+    "b200_effdet_decode": (c_i, [c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p]),
+    "b200_effdet_postprocess_workspace_bytes": (c_sz, [c_i, c_p, c_i, c_i, c_i]),
+    "b200_effdet_postprocess": (c_i, [c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_f, c_f, c_i,
+                                      c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "b200_effdet_assign_targets": (c_i, [c_i, c_p, c_i, c_p, c_i, c_i, c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_p]),
+    "b200_focal_elementwise": (c_i, [c_p, c_p, c_sz, c_f, c_f, c_f, c_f, c_p, c_p]),
+    "b200_focal_box_workspace_bytes": (c_sz, [c_i, c_p, c_i]),
+    "b200_focal_box_partial_sums": (c_i, [c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_f, c_p, c_p, c_sz, c_p]),
+    "b200_focal_box_finalize": (c_i, [c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
 }
 
 METRIC_YOLO = {"iou": 0, "diou": 1, "ciou": 2}

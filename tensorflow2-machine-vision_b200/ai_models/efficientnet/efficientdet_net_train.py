@@ -1,0 +1,46 @@
+"""Drop-in for the loss aggregation of the reference's efficientnet/efficientdet_net_train.py
+(EfficientDetNetTrain._get_loss :41-52).  The L2-regularisation term (:21-28,42) is over model weights and stays
+in the TF graph; add it to the value returned here."""
+import ctypes
+
+import numpy as np
+import torch
+
+from ... import _lib, _tensors as T
+from ..losses.focal_loss import _partial_sums
+
+
+def get_loss(y_true_boxes, y_true_classes, y_true_masks, y_pred_boxes, y_pred_classes, alpha=0.25, gamma=1.5,
+             delta=0.1, global_batch_scale=1, group=None, return_parts=False):
+  '''sum over levels of (50 * box_loss + focal_loss) with num_positives = sum(masks) + 1.
+
+  Data parallel: every rank passes its shard; the 2L+1 fp64 partial sums are all-reduced once (NCCL) before the
+  normalisation.  `global_batch_scale` = world size when the per-level element count of the Keras mean must refer
+  to the global batch.
+  '''
+  lib = _lib.load()
+  sums, numel = _partial_sums(list(y_true_boxes), list(y_true_classes), list(y_true_masks), list(y_pred_boxes),
+                              list(y_pred_classes), alpha, gamma, delta, 0.0)
+  import torch.distributed as dist
+  if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    global_batch_scale = dist.get_world_size(group)
+  L = len(numel)
+  nm = (ctypes.c_double * L)(*[n * global_batch_scale for n in numel])
+  parts = torch.empty((L, 2), dtype=torch.float32, device=sums.device)
+  loss = torch.empty((), dtype=torch.float32, device=sums.device)
+  npos = torch.empty((), dtype=torch.float32, device=sums.device)
+  _lib.check(lib.b200_focal_box_finalize(L, T.ptr(sums), nm, T.ptr(parts), T.ptr(loss), T.ptr(npos), T.stream_ptr()),
+             '_get_loss')
+  return (loss, parts, npos) if return_parts else loss
+
+
+class EfficientDetNetTrain(object):
+  '''Only the head-loss part of the reference class: `_get_loss` with the reference's argument order.'''
+
+  def __init__(self, alpha=0.25, gamma=1.5, **unused):
+    self.alpha = alpha
+    self.gamma = gamma
+
+  def _get_loss(self, y_true_boxes, y_true_classes, y_true_masks, y_pred_boxes, y_pred_classes):
+    return get_loss(y_true_boxes, y_true_classes, y_true_masks, y_pred_boxes, y_pred_classes, self.alpha, self.gamma)

@@ -1,0 +1,209 @@
+"""Drop-in for the reference's efficientnet/utils/anchors.py (Anchors :12-274).
+
+Same constructor and method names / argument order / return arity; tensors are torch CUDA tensors (or anything
+DLPack / array-like).  Anchor boxes are never read from memory by the kernels: they are rebuilt from a small
+per-level table (row/column centres, half extents) computed here with the reference's own Python arithmetic.
+"""
+import ctypes
+import math
+from typing import List, Tuple, Union
+
+import numpy as np
+import torch
+
+from .... import _lib, _tensors as T
+from .get_feat_sizes import get_feat_sizes
+
+EPSILON = 1e-8
+
+
+def _range_f32(start, limit, delta):
+  '''tf.range(start, limit, delta) on float32: ceil((limit-start)/delta) values, accumulated in fp32.'''
+  start, limit, delta = np.float32(start), np.float32(limit), np.float32(delta)
+  n = int(math.ceil(abs((float(limit) - float(start)) / float(delta))))
+  out = np.empty((n,), dtype=np.float32)
+  v = start
+  for i in range(n):
+    out[i] = v
+    v = np.float32(v + delta)
+  return out
+
+
+class Anchors(object):
+  '''Anchor generation, target assignment, decode and per-image post-processing.'''
+
+  def __init__(self, min_level: int, max_level: int, image_size: Tuple[int, int],
+               num_scales: int, aspect_ratios: List[Tuple[float, float]],
+               anchor_scale: Union[float, List[float]]):
+    '''
+    Args:
+      image_size: (H, W)
+      min_level / max_level: feature levels
+      num_scales: octave scales per level
+      aspect_ratios: list of (y, x) ratios — aspect[1] scales x and aspect[0] scales y (reference :66-67)
+      anchor_scale: scalar or one value per level
+    '''
+    self.min_level = min_level
+    self.max_level = max_level
+    self.image_size = image_size
+    self.num_scales = num_scales
+    self.aspect_ratios = aspect_ratios
+    self.anchor_scale = anchor_scale
+    if isinstance(anchor_scale, (list, tuple)):
+      assert len(anchor_scale) == max_level - min_level + 1
+      self.anchor_scales = anchor_scale
+    else:
+      self.anchor_scales = [anchor_scale] * (max_level - min_level + 1)
+    self.feat_sizes = get_feat_sizes(self.image_size, self.max_level)
+    self._num_levels = max_level - min_level + 1
+    self._A = self.get_anchors_per_location()
+    self._level_hw = [self.feat_sizes[l] for l in range(min_level, max_level + 1)]
+    self._hw = (ctypes.c_int32 * (2 * self._num_levels))(*[d for hw in self._level_hw for d in hw])
+    self._table_host = self._build_table()
+    self._table = None   # device copy, created on first use
+    self._boxes = None
+
+  # -- host-side table: exactly the reference's Python float arithmetic, then one fp32 rounding -----------
+  def _build_table(self):
+    fs = self.feat_sizes
+    parts = []
+    for level in range(self.min_level, self.max_level + 1):
+      stride = (fs[0][0] / float(fs[level][0]), fs[0][1] / float(fs[level][1]))
+      # centres of the level must tile the level's feature map exactly
+      yc = _range_f32(stride[0] / 2, self.image_size[0], stride[0])
+      xc = _range_f32(stride[1] / 2, self.image_size[1], stride[1])
+      if len(yc) != fs[level][0] or len(xc) != fs[level][1]:
+        raise ValueError('image_size %r does not tile level %d (%r centres vs feature size %r)' % (
+          self.image_size, level, (len(yc), len(xc)), fs[level]))
+      hy, hx = [], []
+      for scale_octave in range(self.num_scales):
+        for aspect in self.aspect_ratios:
+          octave_scale = scale_octave / float(self.num_scales)
+          a_scale = self.anchor_scales[level - self.min_level]
+          hx.append(a_scale * stride[1] * 2**octave_scale * aspect[1] / 2.0)
+          hy.append(a_scale * stride[0] * 2**octave_scale * aspect[0] / 2.0)
+      parts += [yc, xc, np.asarray(hy, dtype=np.float32), np.asarray(hx, dtype=np.float32)]
+    return np.ascontiguousarray(np.concatenate(parts).astype(np.float32))
+
+  def _dev_table(self):
+    if self._table is None:
+      self._table = T.to_cuda(self._table_host)
+      assert self._table.numel() == _lib.load().b200_effdet_table_floats(self._num_levels, self._hw, self._A)
+    return self._table
+
+  @property
+  def boxes(self):
+    '''List over levels of (H, W, anchors, [y1, x1, y2, x2]) tensors (reference attribute `boxes`).'''
+    if self._boxes is None:
+      lib = _lib.load()
+      tab = self._dev_table()
+      out = []
+      for l, (h, w) in enumerate(self._level_hw):
+        t = torch.empty((h, w, self._A, 4), dtype=torch.float32, device=tab.device)
+        _lib.check(lib.b200_effdet_anchors(self._num_levels, self._hw, self._A, T.ptr(tab), l, T.ptr(t),
+                                           T.stream_ptr()), 'Anchors._generate_boxes')
+        out.append(t)
+      self._boxes = out
+    return self._boxes
+
+  def _generate_boxes(self):
+    return self.boxes
+
+  def get_anchors_per_location(self):
+    return self.num_scales * len(self.aspect_ratios)
+
+  # -- targets ------------------------------------------------------------------------------------------
+  def generate_targets_batch(self, boxes, classes, offsets, classes_num, iou_threshold=0.5):
+    '''Batched generate_targets: boxes [total,4] yxyx, classes [total], offsets [B+1] ->
+    (boxes, classes, masks) tuples over levels of (B,H,W,A,4), (B,H,W,A,classes_num), (B,H,W,A,1) bool.'''
+    lib = _lib.load()
+    tab = self._dev_table()
+    gb = T.to_cuda(boxes).reshape(-1, 4)
+    gc = T.to_cuda(classes, torch.int32).reshape(-1)
+    go = T.to_cuda(offsets, torch.int32).reshape(-1)
+    B = go.numel() - 1
+    C = int(classes_num)
+    dev = tab.device
+    ob = [torch.empty((B, h, w, self._A, 4), dtype=torch.float32, device=dev) for h, w in self._level_hw]
+    oc = [torch.empty((B, h, w, self._A, C), dtype=torch.float32, device=dev) for h, w in self._level_hw]
+    om = [torch.empty((B, h, w, self._A, 1), dtype=torch.bool, device=dev) for h, w in self._level_hw]
+    L = self._num_levels
+    pb = (ctypes.c_void_p * L)(*[t.data_ptr() for t in ob])
+    pc = (ctypes.c_void_p * L)(*[t.data_ptr() for t in oc])
+    pm = (ctypes.c_void_p * L)(*[t.data_ptr() for t in om])
+    _lib.check(lib.b200_effdet_assign_targets(L, self._hw, self._A, T.ptr(tab), C, B, T.ptr(gb), T.ptr(gc), T.ptr(go),
+                                              float(iou_threshold), pb, pc, pm, T.stream_ptr()), 'generate_targets')
+    return tuple(ob), tuple(oc), tuple(om)
+
+  def generate_targets(self, boxes, classes, classes_num, iou_threshold=0.5):
+    '''
+    One image: boxes [n, 4] yxyx, classes [n] ->
+      boxes:   [level, [h, w, anchors, [ty, tx, th, tw]]]
+      classes: [level, [h, w, anchors, classes_num]]   (one-hot, unmatched anchors = class 0)
+      masks:   [level, [h, w, anchors, 1]] bool
+    '''
+    n = T.to_cuda(boxes).reshape(-1, 4).shape[0]
+    ob, oc, om = self.generate_targets_batch(boxes, classes, np.array([0, n], dtype=np.int32), classes_num, iou_threshold)
+    return tuple(t[0] for t in ob), tuple(t[0] for t in oc), tuple(t[0] for t in om)
+
+  # -- decode -------------------------------------------------------------------------------------------
+  def convert_outputs_boxes(self, outputs_boxes):
+    '''[level, [batch, h, w, anchors, [ty, tx, th, tw]]] -> [level, [batch, h, w, anchors, [y1, x1, y2, x2]]]'''
+    lib = _lib.load()
+    tab = self._dev_table()
+    rel = [T.to_cuda(t) for t in outputs_boxes]
+    if len(rel) != self._num_levels:
+      raise ValueError('expected %d levels, got %d' % (self._num_levels, len(rel)))
+    B = rel[0].shape[0]
+    for t, (h, w) in zip(rel, self._level_hw):
+      if tuple(t.shape) != (B, h, w, self._A, 4):
+        raise ValueError('level shape %r != %r' % (tuple(t.shape), (B, h, w, self._A, 4)))
+    out = [torch.empty_like(t) for t in rel]
+    L = self._num_levels
+    pr = (ctypes.c_void_p * L)(*[t.data_ptr() for t in rel])
+    po = (ctypes.c_void_p * L)(*[t.data_ptr() for t in out])
+    _lib.check(lib.b200_effdet_decode(L, self._hw, self._A, T.ptr(tab), B, pr, po, T.stream_ptr()), 'convert_outputs_boxes')
+    return tuple(out)
+
+  # -- post-processing ----------------------------------------------------------------------------------
+  def convert_outputs_batch(self, outputs_boxes, outputs_classes, first_image=0, num_images=None, max_output_size=200,
+                            iou_threshold=0.5, score_threshold=0.0001, iou_type='diou', with_indices=False):
+    '''convert_outputs_one for a range of images in one launch.  Returns a dict of padded tensors
+    [n, max_output_size, ...] (boxes, classes_id int64, scores) and `count` [n].'''
+    assert iou_type in ('iou', 'giou', 'diou', 'ciou')
+    lib = _lib.load()
+    bx = [T.to_cuda(t) for t in outputs_boxes]
+    cl = [T.to_cuda(t) for t in outputs_classes]
+    L = self._num_levels
+    if len(bx) != L or len(cl) != L:
+      raise ValueError('expected %d levels' % L)
+    B = cl[0].shape[0]
+    C = cl[0].shape[-1]
+    n = B - first_image if num_images is None else int(num_images)
+    K = int(max_output_size)
+    dev = cl[0].device
+    out = {
+      'boxes': torch.empty((n, K, 4), dtype=torch.float32, device=dev),
+      'classes_id': torch.empty((n, K), dtype=torch.int64, device=dev),
+      'scores': torch.empty((n, K), dtype=torch.float32, device=dev),
+      'count': torch.zeros((n,), dtype=torch.int32, device=dev),
+    }
+    if with_indices:
+      out['sel_idx'] = torch.empty((n, K), dtype=torch.int32, device=dev)
+      out['sel_anchor'] = torch.empty((n, K), dtype=torch.int32, device=dev)
+    ws_bytes = lib.b200_effdet_postprocess_workspace_bytes(L, self._hw, self._A, n, K)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    pb = (ctypes.c_void_p * L)(*[t.data_ptr() for t in bx])
+    pc = (ctypes.c_void_p * L)(*[t.data_ptr() for t in cl])
+    _lib.check(lib.b200_effdet_postprocess(L, self._hw, self._A, C, B, int(first_image), n, pb, pc, K,
+                                           float(iou_threshold), float(score_threshold), _lib.METRIC_EFF[iou_type],
+                                           T.ptr(out['boxes']), T.ptr(out['classes_id']), T.ptr(out['scores']),
+                                           T.ptr(out.get('sel_idx')), T.ptr(out.get('sel_anchor')), T.ptr(out['count']),
+                                           T.ptr(ws), ws_bytes, T.stream_ptr()), 'convert_outputs_one')
+    return out
+
+  def convert_outputs_one(self, batch_index, outputs_boxes, outputs_classes):
+    '''One image of the batch: (nms_boxes [K,4], nms_classes_id [K] int64, nms_scores [K]); K <= 200.'''
+    r = self.convert_outputs_batch(outputs_boxes, outputs_classes, first_image=int(batch_index), num_images=1)
+    k = int(r['count'][0].item())
+    return r['boxes'][0, :k], r['classes_id'][0, :k], r['scores'][0, :k]

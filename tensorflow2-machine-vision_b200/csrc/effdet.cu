@@ -1,0 +1,548 @@
+// effdet.cu — EfficientDet head utilities: anchors, box decode, per-image post-processing, target assignment.
+//
+// Replaces (paths relative to AIServer/ai_api/ai_models/):
+//   efficientnet/utils/anchors.py:46-84    Anchors._generate_boxes        -> effdet_anchors_kernel
+//   efficientnet/utils/anchors.py:141-158, 245-274  convert_outputs_boxes / _boxes_decoder -> effdet_decode_kernel
+//   efficientnet/utils/anchors.py:161-202  convert_outputs_one            -> effdet_filter_kernel + effdet_nms_finalize_kernel
+//   efficientnet/utils/anchors.py:91-138, 219-243   generate_targets / _boxes_encoder -> effdet_assign_kernel
+//
+// Anchors are never read from HBM: every kernel rebuilds an anchor box from a tiny per-level table
+// (row centres yc[H], column centres xc[W], half extents hy[A], hx[A]; built on the host with the reference's own
+// double-precision Python arithmetic) exactly as the reference does — box = [yc-hy, xc-hx, yc+hy, xc+hx] in fp32,
+// then centre/size re-derived from those corners (anc:204-217) — so results are bit-identical to reading
+// Anchors.boxes while saving 0.8 MB (D0) / 7 MB (D7) of reads per image.
+#include "nms.cuh"
+
+#define EF_MAX_LEVELS 8
+#define EF_STAGES 2
+
+struct EfLevels {
+  int num_levels, A;
+  int h[EF_MAX_LEVELS], w[EF_MAX_LEVELS];
+  int anc_per_img[EF_MAX_LEVELS];   // h*w*A
+  int anchor_base[EF_MAX_LEVELS];   // flat anchor index of the level's first anchor within an image
+  const float* table;               // device
+  int tab_off[EF_MAX_LEVELS];       // float offset of the level's [yc(h) | xc(w) | hy(A) | hx(A)] block
+};
+
+struct AnchorBox { float y1, x1, y2, x2; };
+
+__device__ __forceinline__ AnchorBox ef_anchor(const EfLevels& lv, int l, int y, int x, int a) {
+  const float* t = lv.table + lv.tab_off[l];
+  const float yc = __ldg(t + y), xc = __ldg(t + lv.h[l] + x);
+  const float hy = __ldg(t + lv.h[l] + lv.w[l] + a), hx = __ldg(t + lv.h[l] + lv.w[l] + lv.A + a);
+  AnchorBox b;
+  b.y1 = DM_SUB(yc, hy); b.x1 = DM_SUB(xc, hx); b.y2 = DM_ADD(yc, hy); b.x2 = DM_ADD(xc, hx);  // anc:77-78
+  return b;
+}
+
+__device__ __forceinline__ void ef_split(const EfLevels& lv, int l, int rin, int& y, int& x, int& a) {
+  const int cell = rin / lv.A;
+  a = rin - cell * lv.A;
+  y = cell / lv.w[l];
+  x = cell - y * lv.w[l];
+}
+
+// ---- anchors -------------------------------------------------------------------------------------
+__global__ void effdet_anchors_kernel(EfLevels lv, int l, float4* __restrict__ out) {
+  const int n = lv.anc_per_img[l];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int y, x, a;
+    ef_split(lv, l, i, y, x, a);
+    const AnchorBox b = ef_anchor(lv, l, y, x, a);
+    out[i] = make_float4(b.y1, b.x1, b.y2, b.x2);
+  }
+}
+
+// ---- decode (anc:245-274) ---------------------------------------------------------------------------
+struct EfDecodeParams {
+  EfLevels lv;
+  int B;
+  const float4* rel[EF_MAX_LEVELS];
+  float4* out[EF_MAX_LEVELS];
+  long long elem_base[EF_MAX_LEVELS + 1];  // cumulative B*anc_per_img
+};
+
+__global__ void __launch_bounds__(256) effdet_decode_kernel(EfDecodeParams p) {
+  const long long total = p.elem_base[p.lv.num_levels];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < EF_MAX_LEVELS; ++k) if (k < p.lv.num_levels && i >= p.elem_base[k]) l = k;
+    const long long e = i - p.elem_base[l];
+    const int rin = (int)(e % p.lv.anc_per_img[l]);
+    int y, x, a;
+    ef_split(p.lv, l, rin, y, x, a);
+    const AnchorBox an = ef_anchor(p.lv, l, y, x, a);
+    const float yca = DM_DIV(DM_ADD(an.y2, an.y1), 2.0f), xca = DM_DIV(DM_ADD(an.x2, an.x1), 2.0f);
+    const float ha = DM_SUB(an.y2, an.y1), wa = DM_SUB(an.x2, an.x1);
+    const float4 r = __ldcs(p.rel[l] + e);  // ty, tx, th, tw
+    const float w = DM_MUL(dm_expf(r.w), wa), h = DM_MUL(dm_expf(r.z), ha);
+    const float yc = DM_ADD(DM_MUL(r.x, ha), yca), xc = DM_ADD(DM_MUL(r.y, wa), xca);
+    const float hh = DM_DIV(h, 2.0f), hw = DM_DIV(w, 2.0f);
+    __stcs(p.out[l] + e, make_float4(DM_SUB(yc, hh), DM_SUB(xc, hw), DM_ADD(yc, hh), DM_ADD(xc, hw)));
+  }
+}
+
+// ---- class argmax / background filter (anc:168-189), streaming like yolo_decode_filter_kernel ----------
+struct EfFilterParams {
+  EfLevels lv;
+  int B0, NB, C;                 // images [B0, B0+NB) of a batch of size B
+  int B;
+  int n_img;                     // anchors per image
+  const float* cls[EF_MAX_LEVELS];    // (B,H,W,A,C) logits
+  const float4* boxes[EF_MAX_LEVELS]; // (B,H,W,A,4) decoded
+  long long tile_base[EF_MAX_LEVELS + 1];  // tiles of 32 anchors over the NB images of each level
+  float4* cand_box; float* cand_score; int32_t* cand_cls; uint32_t* cand_aidx;  // [NB, n_img]
+  int32_t* counts;               // [NB]
+  uint32_t* bitmap; int bitmap_words;
+};
+
+__device__ __forceinline__ uint32_t ef_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(256, 1) effdet_filter_kernel(EfFilterParams p) {
+  extern __shared__ __align__(128) unsigned char ef_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const int C = p.C;
+  const uint32_t slab_bytes = 128u * (uint32_t)C;
+  float* slab0 = reinterpret_cast<float*>(ef_smem) + (size_t)(warp * EF_STAGES) * (slab_bytes / 4);
+  uint64_t* bar0 = reinterpret_cast<uint64_t*>(ef_smem + (size_t)wpc * EF_STAGES * slab_bytes) + warp * EF_STAGES;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < EF_STAGES; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ef_smem_u32(bar0 + s)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const long long n_tiles = p.tile_base[p.lv.num_levels];
+  const long long gwarp = (long long)blockIdx.x * wpc + warp, gstride = (long long)gridDim.x * wpc;
+
+  auto locate = [&](long long tile, int& l, long long& rec0, int& nrec) {
+    l = 0;
+#pragma unroll
+    for (int k = 1; k < EF_MAX_LEVELS; ++k) if (k < p.lv.num_levels && tile >= p.tile_base[k]) l = k;
+    rec0 = (tile - p.tile_base[l]) * 32;  // record index within the NB-image slice of level l
+    const long long remain = (long long)p.NB * p.lv.anc_per_img[l] - rec0;
+    nrec = remain < 32 ? (int)remain : 32;
+  };
+  auto issue = [&](long long tile, int s) {
+    int l, nrec; long long rec0;
+    locate(tile, l, rec0, nrec);
+    const float* src = p.cls[l] + ((long long)p.B0 * p.lv.anc_per_img[l] + rec0) * C;
+    const uint32_t bytes = (uint32_t)nrec * (uint32_t)C * 4u;
+    float* dst = slab0 + (size_t)s * (slab_bytes / 4);
+    if ((bytes & 15u) == 0u && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ef_smem_u32(bar0 + s)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ef_smem_u32(dst)),
+                     "l"(src), "r"(bytes), "r"(ef_smem_u32(bar0 + s)) : "memory");
+      }
+    } else {
+      for (int i = lane; i < nrec * C; i += 32) dst[i] = __ldg(src + i);
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ef_smem_u32(bar0 + s)) : "memory");
+    }
+  };
+  long long t_issue = gwarp;
+#pragma unroll
+  for (int s = 0; s < EF_STAGES; ++s) { if (t_issue < n_tiles) issue(t_issue, s); t_issue += gstride; }
+  uint32_t phase = 0;
+  int stage = 0;
+  for (long long tile = gwarp; tile < n_tiles; tile += gstride) {
+    {
+      const uint32_t bar = ef_smem_u32(bar0 + stage);
+      asm volatile("{\n.reg .pred p;\nEF_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra EF_DONE;\nbra EF_WAIT;\nEF_DONE:\n}\n" ::"r"(bar), "r"(phase) : "memory");
+    }
+    int l, nrec; long long rec0;
+    locate(tile, l, rec0, nrec);
+    const float* r = slab0 + (size_t)stage * (slab_bytes / 4) + lane * C;
+    bool pass = false;
+    int img = 0, cls = 0;
+    float score = 0.f;
+    uint32_t aidx = 0;
+    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < nrec) {
+      // tf.math.argmax: first maximal index; reduce_max: the maximum (anc:172-174)
+      float m = r[0];
+      int mi = 0;
+      for (int c = 1; c < C; ++c) { const float v = r[c]; if (v > m) { m = v; mi = c; } }
+      if (mi != 0) {  // classes_mask = classes_id != 0 (anc:179)
+        const long long rec = rec0 + lane;
+        const int api = p.lv.anc_per_img[l];
+        img = (int)(rec / api);
+        const int rin = (int)(rec - (long long)img * api);
+        pass = true; cls = mi; score = m;
+        aidx = (uint32_t)(p.lv.anchor_base[l] + rin);
+        box = __ldg(p.boxes[l] + (long long)(p.B0 + img) * api + rin);
+      }
+    }
+    uint32_t todo = __ballot_sync(0xffffffffu, pass);
+    while (todo) {
+      const int leader = __ffs(todo) - 1;
+      const int limg = __shfl_sync(0xffffffffu, img, leader);
+      const uint32_t grp = __ballot_sync(0xffffffffu, pass && img == limg);
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&p.counts[limg], __popc(grp));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (pass && img == limg) {
+        const size_t slot = (size_t)limg * p.n_img + base + __popc(grp & ((1u << lane) - 1u));
+        p.cand_box[slot] = box; p.cand_score[slot] = score; p.cand_cls[slot] = cls; p.cand_aidx[slot] = aidx;
+        if (p.bitmap) atomicOr(&p.bitmap[(size_t)limg * p.bitmap_words + (aidx >> 5)], 1u << (aidx & 31u));
+      }
+      todo &= ~grp;
+    }
+    __syncwarp();
+    if (t_issue < n_tiles) issue(t_issue, stage);
+    t_issue += gstride;
+    if (++stage == EF_STAGES) { stage = 0; phase ^= 1u; }
+  }
+}
+
+struct EfFinalizeParams {
+  int NB, n_img;
+  NmsConfig cfg;
+  const float4* cand_box; const float* cand_score; const int32_t* cand_cls; const uint32_t* cand_aidx;
+  const int32_t* counts; const uint32_t* bitmap; int bitmap_words;
+  int32_t* nms_pos;
+  float* out_boxes; long long* out_cls; float* out_score; int32_t* out_sel_idx; int32_t* out_sel_anchor; int32_t* out_count;
+};
+
+__global__ void __launch_bounds__(NMS_THREADS, 1) effdet_nms_finalize_kernel(EfFinalizeParams p) {
+  extern __shared__ __align__(16) unsigned char nms_smem[];
+  const int img = blockIdx.x;
+  const size_t cbase = (size_t)img * p.n_img;
+  NmsSegment seg;
+  seg.boxes = reinterpret_cast<const float*>(p.cand_box + cbase);
+  seg.scores = p.cand_score + cbase;
+  seg.classes = nullptr;
+  seg.order_id = p.cand_aidx + cbase;
+  seg.n = p.counts[img];
+  int32_t* pos = p.nms_pos + (size_t)img * p.cfg.max_out;
+  const int kept = nms_run_segment(seg, p.cfg, pos, nms_smem);
+  __syncthreads();
+  if (threadIdx.x == 0) p.out_count[img] = kept;
+  const size_t obase = (size_t)img * p.cfg.max_out;
+  uint32_t* wprefix = reinterpret_cast<uint32_t*>(nms_smem);
+  if (p.out_sel_idx && p.bitmap) {
+    const uint32_t* bm = p.bitmap + (size_t)img * p.bitmap_words;
+    if (threadIdx.x < 32) {
+      uint32_t run = 0;
+      for (int w0 = 0; w0 < p.bitmap_words; w0 += 32) {
+        const int w = w0 + (int)threadIdx.x;
+        const int c = (w < p.bitmap_words) ? __popc(bm[w]) : 0;
+        const int inc = warp_scan_incl(c);
+        if (w < p.bitmap_words) wprefix[w] = run + (uint32_t)(inc - c);
+        run += (uint32_t)__shfl_sync(0xffffffffu, inc, 31);
+      }
+    }
+    __syncthreads();
+  }
+  for (int k = threadIdx.x; k < kept; k += blockDim.x) {
+    const int q = pos[k];
+    reinterpret_cast<float4*>(p.out_boxes)[obase + k] = p.cand_box[cbase + q];
+    p.out_cls[obase + k] = (long long)p.cand_cls[cbase + q];               // tf.argmax -> int64 (anc:172)
+    p.out_score[obase + k] = dm_sigmoidf(p.cand_score[cbase + q]);          // sigmoid only on survivors (anc:200)
+    const uint32_t a = p.cand_aidx[cbase + q];
+    if (p.out_sel_anchor) p.out_sel_anchor[obase + k] = (int32_t)a;
+    if (p.out_sel_idx && p.bitmap) {
+      const uint32_t wv = p.bitmap[(size_t)img * p.bitmap_words + (a >> 5)];
+      p.out_sel_idx[obase + k] = (int32_t)(wprefix[a >> 5] + __popc(wv & ((1u << (a & 31u)) - 1u)));
+    }
+  }
+}
+
+// ---- target assignment (anc:91-138) ------------------------------------------------------------------
+struct EfAssignParams {
+  EfLevels lv;
+  int B, C;
+  float thr;
+  const float* gt_boxes;      // [total,4] yxyx
+  const int32_t* gt_classes;  // [total]
+  const int32_t* gt_offsets;  // [B+1]
+  float4* out_boxes[EF_MAX_LEVELS];        // (B,H,W,A,4)
+  float* out_onehot[EF_MAX_LEVELS];        // (B,H,W,A,C)
+  unsigned char* out_mask[EF_MAX_LEVELS];  // (B,H,W,A,1)
+  int cta_base[EF_MAX_LEVELS + 1];         // CTAs of 256 anchors, per (level, image)
+  int chunks_per_img[EF_MAX_LEVELS];
+};
+
+#define EF_GT_TILE 128
+
+__global__ void __launch_bounds__(256) effdet_assign_kernel(EfAssignParams p) {
+  __shared__ float4 s_gt[EF_GT_TILE];
+  __shared__ float s_ga[EF_GT_TILE];
+  __shared__ int s_cls[256];
+  int l = 0;
+#pragma unroll
+  for (int k = 1; k < EF_MAX_LEVELS; ++k) if (k < p.lv.num_levels && (int)blockIdx.x >= p.cta_base[k]) l = k;
+  const int rc = blockIdx.x - p.cta_base[l];
+  const int img = rc / p.chunks_per_img[l];
+  const int chunk = rc - img * p.chunks_per_img[l];
+  const int api = p.lv.anc_per_img[l];
+  const int rin = chunk * 256 + (int)threadIdx.x;
+  const bool active = rin < api;
+  const int g_beg = p.gt_offsets[img], n_gt = p.gt_offsets[img + 1] - g_beg;
+  BoxT an;
+  an.c0 = an.c1 = an.c2 = an.c3 = an.area = an.at = 0.f;
+  if (active) {
+    int y, x, a;
+    ef_split(p.lv, l, rin, y, x, a);
+    const AnchorBox b = ef_anchor(p.lv, l, y, x, a);
+    an = bm_prep(b.y1, b.x1, b.y2, b.x2, B200_METRIC_EFF_IOU);
+  }
+  float best = -INFINITY;
+  int best_i = 0;
+  for (int g0 = 0; g0 < n_gt; g0 += EF_GT_TILE) {
+    const int m = min(EF_GT_TILE, n_gt - g0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += 256) {
+      const float* q = p.gt_boxes + 4 * (size_t)(g_beg + g0 + i);
+      const BoxT g = bm_prep(q[0], q[1], q[2], q[3], B200_METRIC_EFF_IOU);
+      s_gt[i] = make_float4(g.c0, g.c1, g.c2, g.c3);
+      s_ga[i] = g.area;
+    }
+    __syncthreads();
+    if (active) {
+      for (int g = 0; g < m; ++g) {
+        const float4 c = s_gt[g];
+        // clamped intersection extents (eiou:58-64); zero overlap -> iou = divide_no_nan(0, union) = +0 exactly
+        const float iw = dm_max(0.0f, DM_SUB(dm_min(an.c3, c.w), dm_max(an.c1, c.y)));
+        const float ih = dm_max(0.0f, DM_SUB(dm_min(an.c2, c.z), dm_max(an.c0, c.x)));
+        float v = 0.0f;
+        if (iw > 0.0f && ih > 0.0f) {
+          const float inter = DM_MUL(iw, ih);
+          v = bm_dnn(inter, DM_SUB(DM_ADD(an.area, s_ga[g]), inter));
+        } else if (!(iw == iw) || !(ih == ih)) {
+          BoxT gb; gb.c0 = c.x; gb.c1 = c.y; gb.c2 = c.z; gb.c3 = c.w; gb.area = s_ga[g]; gb.at = 0.f;
+          v = bm_metric(an, gb, B200_METRIC_EFF_IOU);
+        }
+        if (v > best) { best = v; best_i = g0 + g; }  // tf.argmax: first maximal index
+      }
+    }
+  }
+  // encode + outputs
+  const bool matched = active && (n_gt > 0) && (best >= p.thr);  // iou_max >= thr (anc:121)
+  int cls = 0;
+  float4 enc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (matched) {
+    const float* q = p.gt_boxes + 4 * (size_t)(g_beg + best_i);
+    const float by1 = q[0], bx1 = q[1], by2 = q[2], bx2 = q[3];
+    cls = p.gt_classes[g_beg + best_i];
+    // _boxes_encoder, anc:231-243
+    const float yca = DM_DIV(DM_ADD(an.c2, an.c0), 2.0f), xca = DM_DIV(DM_ADD(an.c3, an.c1), 2.0f);
+    const float ha = dm_max(1e-8f, DM_SUB(an.c2, an.c0)), wa = dm_max(1e-8f, DM_SUB(an.c3, an.c1));
+    const float yc = DM_DIV(DM_ADD(by2, by1), 2.0f), xc = DM_DIV(DM_ADD(bx2, bx1), 2.0f);
+    const float h = dm_max(1e-8f, DM_SUB(by2, by1)), w = dm_max(1e-8f, DM_SUB(bx2, bx1));
+    enc.x = DM_DIV(DM_SUB(yc, yca), ha);
+    enc.y = DM_DIV(DM_SUB(xc, xca), wa);
+    enc.z = dm_logf(DM_DIV(h, ha));
+    enc.w = dm_logf(DM_DIV(w, wa));
+  }
+  const size_t abase = (size_t)img * api;
+  if (active) {
+    p.out_boxes[l][abase + rin] = enc;
+    p.out_mask[l][abase + rin] = matched ? 1 : 0;
+  }
+  // one-hot rows (C floats per anchor, class 0 = background for unmatched anchors, anc:131-133): the CTA's
+  // 256 rows are contiguous, so they are written as one coalesced stream
+  s_cls[threadIdx.x] = active ? cls : -1;
+  __syncthreads();
+  const int rows = min(256, api - chunk * 256);
+  float* dst = p.out_onehot[l] + (abase + (size_t)chunk * 256) * p.C;
+  const int total = rows * p.C;
+  for (int i = threadIdx.x; i < total; i += 256) {
+    const int r = i / p.C, c = i - r * p.C;
+    __stcs(dst + i, (s_cls[r] == c) ? 1.0f : 0.0f);  // tf.one_hot: out-of-range class -> all zeros
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+static int ef_fill_levels(EfLevels& lv, int num_levels, const int32_t* hw, int A, const float* table_dev) {
+  if (num_levels < 1 || num_levels > EF_MAX_LEVELS || A < 1) return -1;
+  lv.num_levels = num_levels; lv.A = A; lv.table = table_dev;
+  int base = 0, off = 0;
+  for (int l = 0; l < EF_MAX_LEVELS; ++l) {
+    if (l < num_levels) {
+      lv.h[l] = hw[2 * l]; lv.w[l] = hw[2 * l + 1];
+      if (lv.h[l] <= 0 || lv.w[l] <= 0) return -1;
+      lv.anc_per_img[l] = lv.h[l] * lv.w[l] * A;
+      lv.anchor_base[l] = base; base += lv.anc_per_img[l];
+      lv.tab_off[l] = off; off += lv.h[l] + lv.w[l] + 2 * A;
+    } else {
+      lv.h[l] = lv.w[l] = 1; lv.anc_per_img[l] = 0; lv.anchor_base[l] = base; lv.tab_off[l] = off;
+    }
+  }
+  return base;
+}
+
+extern "C" size_t b200_effdet_table_floats(int num_levels, const int32_t* hw, int A) {
+  size_t n = 0;
+  for (int l = 0; l < num_levels; ++l) n += (size_t)hw[2 * l] + hw[2 * l + 1] + 2 * (size_t)A;
+  return n;
+}
+
+extern "C" int b200_effdet_anchors(int num_levels, const int32_t* hw, int A, const float* table_dev, int level,
+                                   float* out, void* stream) {
+  EfLevels lv;
+  B200_REQUIRE(hw && table_dev && out, B200_ERR_BAD_ARG, "b200_effdet_anchors: null argument");
+  B200_REQUIRE(ef_fill_levels(lv, num_levels, hw, A, table_dev) >= 0, B200_ERR_BAD_ARG, "b200_effdet_anchors: bad level spec");
+  B200_REQUIRE(level >= 0 && level < num_levels, B200_ERR_BAD_ARG, "b200_effdet_anchors: bad level %d", level);
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, B200_ERR_BAD_ARG, "b200_effdet_anchors: out not 16-byte aligned");
+  const int n = lv.anc_per_img[level];
+  effdet_anchors_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(lv, level, reinterpret_cast<float4*>(out));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" int b200_effdet_decode(int num_levels, const int32_t* hw, int A, const float* table_dev, int B,
+                                  const float* const rel[], float* const out[], void* stream) {
+  EfDecodeParams p;
+  B200_REQUIRE(hw && table_dev && rel && out, B200_ERR_BAD_ARG, "b200_effdet_decode: null argument");
+  B200_REQUIRE(ef_fill_levels(p.lv, num_levels, hw, A, table_dev) >= 0, B200_ERR_BAD_ARG, "b200_effdet_decode: bad level spec");
+  B200_REQUIRE(B >= 0, B200_ERR_BAD_ARG, "b200_effdet_decode: negative batch");
+  if (B == 0) return B200_OK;
+  p.B = B;
+  long long cum = 0;
+  for (int l = 0; l < EF_MAX_LEVELS; ++l) {
+    p.elem_base[l] = cum;
+    if (l < num_levels) {
+      B200_REQUIRE(rel[l] && out[l], B200_ERR_BAD_ARG, "b200_effdet_decode: null level %d", l);
+      B200_REQUIRE(((reinterpret_cast<uintptr_t>(rel[l]) | reinterpret_cast<uintptr_t>(out[l])) & 15) == 0, B200_ERR_BAD_ARG,
+                   "b200_effdet_decode: level %d not 16-byte aligned", l);
+      p.rel[l] = reinterpret_cast<const float4*>(rel[l]);
+      p.out[l] = reinterpret_cast<float4*>(out[l]);
+      cum += (long long)B * p.lv.anc_per_img[l];
+    } else { p.rel[l] = nullptr; p.out[l] = nullptr; }
+  }
+  p.elem_base[EF_MAX_LEVELS] = cum;
+  for (int l = num_levels; l <= EF_MAX_LEVELS; ++l) p.elem_base[l] = cum;
+  long long blocks = (cum + 255) / 256;
+  const long long cap = (long long)b200_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  effdet_decode_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+struct EfWs { size_t counts, bitmap, box, score, cls, aidx, pos, total; int bitmap_words; };
+static EfWs ef_ws_layout(int NB, int n_img, int max_out) {
+  EfWs w;
+  size_t o = 0;
+  w.bitmap_words = (n_img + 31) / 32;
+  w.counts = o; o = b200_align_up(o + sizeof(int32_t) * NB, 256);
+  w.bitmap = o; o = b200_align_up(o + sizeof(uint32_t) * (size_t)NB * w.bitmap_words, 256);
+  w.box = o; o = b200_align_up(o + sizeof(float4) * (size_t)NB * n_img, 256);
+  w.score = o; o = b200_align_up(o + sizeof(float) * (size_t)NB * n_img, 256);
+  w.cls = o; o = b200_align_up(o + sizeof(int32_t) * (size_t)NB * n_img, 256);
+  w.aidx = o; o = b200_align_up(o + sizeof(uint32_t) * (size_t)NB * n_img, 256);
+  w.pos = o; o = b200_align_up(o + sizeof(int32_t) * (size_t)NB * max_out, 256);
+  w.total = o;
+  return w;
+}
+
+extern "C" size_t b200_effdet_postprocess_workspace_bytes(int num_levels, const int32_t* hw, int A, int num_images, int max_out) {
+  int n_img = 0;
+  for (int l = 0; l < num_levels; ++l) n_img += hw[2 * l] * hw[2 * l + 1] * A;
+  return ef_ws_layout(num_images, n_img, max_out).total;
+}
+
+extern "C" int b200_effdet_postprocess(int num_levels, const int32_t* hw, int A, int C, int B, int first_image,
+                                       int num_images, const float* const boxes[], const float* const classes[],
+                                       int max_out, float iou_thr, float score_thr, int metric, float* out_boxes,
+                                       long long* out_class_id, float* out_score, int32_t* out_sel_idx,
+                                       int32_t* out_sel_anchor, int32_t* out_count, void* workspace,
+                                       size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EfFilterParams fp;
+  B200_REQUIRE(hw && boxes && classes, B200_ERR_BAD_ARG, "b200_effdet_postprocess: null argument");
+  const int n_img = ef_fill_levels(fp.lv, num_levels, hw, A, nullptr);
+  B200_REQUIRE(n_img >= 0, B200_ERR_BAD_ARG, "b200_effdet_postprocess: bad level spec");
+  B200_REQUIRE(C >= 1 && C <= 400, B200_ERR_UNSUPPORTED, "b200_effdet_postprocess: classes_num %d outside [1,400]", C);
+  B200_REQUIRE(first_image >= 0 && num_images >= 0 && first_image + num_images <= B, B200_ERR_BAD_ARG, "b200_effdet_postprocess: image range outside the batch");
+  B200_REQUIRE(metric >= B200_METRIC_EFF_IOU && metric <= B200_METRIC_EFF_CIOU, B200_ERR_BAD_ARG, "b200_effdet_postprocess: iou_type must be iou/giou/diou/ciou");
+  B200_REQUIRE(max_out >= 1 && max_out <= NMS_MAX_OUT_LIMIT, B200_ERR_UNSUPPORTED, "b200_effdet_postprocess: max_out %d outside [1,%d]", max_out, NMS_MAX_OUT_LIMIT);
+  if (num_images == 0) return B200_OK;
+  B200_REQUIRE(out_boxes && out_class_id && out_score && out_count, B200_ERR_BAD_ARG, "b200_effdet_postprocess: null output");
+  EfWs ws = ef_ws_layout(num_images, n_img, max_out);
+  B200_REQUIRE(workspace && workspace_bytes >= ws.total, B200_ERR_WORKSPACE, "b200_effdet_postprocess: workspace %zu < required %zu", workspace_bytes, ws.total);
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, B200_ERR_BAD_ARG, "b200_effdet_postprocess: workspace not 256-byte aligned");
+  unsigned char* wsb = static_cast<unsigned char*>(workspace);
+  fp.B0 = first_image; fp.NB = num_images; fp.C = C; fp.B = B; fp.n_img = n_img;
+  long long tb = 0;
+  for (int l = 0; l < EF_MAX_LEVELS; ++l) {
+    fp.tile_base[l] = tb;
+    if (l < num_levels) {
+      B200_REQUIRE(boxes[l] && classes[l], B200_ERR_BAD_ARG, "b200_effdet_postprocess: null level %d", l);
+      B200_REQUIRE((reinterpret_cast<uintptr_t>(boxes[l]) & 15) == 0, B200_ERR_BAD_ARG, "b200_effdet_postprocess: boxes level %d not 16-byte aligned", l);
+      fp.cls[l] = classes[l];
+      fp.boxes[l] = reinterpret_cast<const float4*>(boxes[l]);
+      tb += ((long long)num_images * fp.lv.anc_per_img[l] + 31) / 32;
+    } else { fp.cls[l] = nullptr; fp.boxes[l] = nullptr; }
+  }
+  for (int l = num_levels; l <= EF_MAX_LEVELS; ++l) fp.tile_base[l] = tb;
+  fp.cand_box = reinterpret_cast<float4*>(wsb + ws.box);
+  fp.cand_score = reinterpret_cast<float*>(wsb + ws.score);
+  fp.cand_cls = reinterpret_cast<int32_t*>(wsb + ws.cls);
+  fp.cand_aidx = reinterpret_cast<uint32_t*>(wsb + ws.aidx);
+  fp.counts = reinterpret_cast<int32_t*>(wsb + ws.counts);
+  fp.bitmap = out_sel_idx ? reinterpret_cast<uint32_t*>(wsb + ws.bitmap) : nullptr;
+  fp.bitmap_words = ws.bitmap_words;
+  B200_CUDA(cudaMemsetAsync(wsb, 0, out_sel_idx ? ws.box : ws.bitmap, stream));
+  const uint32_t slab = 128u * (uint32_t)C;
+  int warps = 8;
+  while (warps > 1 && (size_t)warps * EF_STAGES * slab + 256 > 200 * 1024) warps >>= 1;
+  const size_t smem1 = (size_t)warps * EF_STAGES * slab + sizeof(uint64_t) * warps * EF_STAGES + 16;
+  B200_CUDA(cudaFuncSetAttribute(effdet_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+  long long want = (tb + warps - 1) / warps;
+  int grid = (int)(want < (long long)b200_sm_count() ? want : (long long)b200_sm_count());
+  if (grid < 1) grid = 1;
+  effdet_filter_kernel<<<grid, warps * 32, smem1, stream>>>(fp);
+  B200_LAUNCH_CHECK();
+
+  EfFinalizeParams np;
+  np.NB = num_images; np.n_img = n_img;
+  np.cfg.metric = metric; np.cfg.mode = B200_NMS_AGNOSTIC; np.cfg.iou_thr = iou_thr; np.cfg.score_thr = score_thr;
+  np.cfg.use_score_thr = 1; np.cfg.max_out = max_out;
+  np.cand_box = fp.cand_box; np.cand_score = fp.cand_score; np.cand_cls = fp.cand_cls; np.cand_aidx = fp.cand_aidx;
+  np.counts = fp.counts; np.bitmap = fp.bitmap; np.bitmap_words = ws.bitmap_words;
+  np.nms_pos = reinterpret_cast<int32_t*>(wsb + ws.pos);
+  np.out_boxes = out_boxes; np.out_cls = out_class_id; np.out_score = out_score; np.out_sel_idx = out_sel_idx;
+  np.out_sel_anchor = out_sel_anchor; np.out_count = out_count;
+  size_t smem2 = nms_smem_bytes(max_out);
+  if (smem2 < (size_t)ws.bitmap_words * 4) smem2 = (size_t)ws.bitmap_words * 4;
+  B200_REQUIRE(smem2 <= 220 * 1024, B200_ERR_UNSUPPORTED, "b200_effdet_postprocess: too many anchors per image for the rank table");
+  B200_CUDA(cudaFuncSetAttribute(effdet_nms_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+  effdet_nms_finalize_kernel<<<num_images, NMS_THREADS, smem2, stream>>>(np);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" int b200_effdet_assign_targets(int num_levels, const int32_t* hw, int A, const float* table_dev, int C, int B,
+                                          const float* gt_boxes, const int32_t* gt_classes, const int32_t* gt_offsets,
+                                          float iou_thr, float* const out_boxes[], float* const out_onehot[],
+                                          unsigned char* const out_mask[], void* stream) {
+  EfAssignParams p;
+  B200_REQUIRE(hw && table_dev && gt_offsets && out_boxes && out_onehot && out_mask, B200_ERR_BAD_ARG, "b200_effdet_assign_targets: null argument");
+  B200_REQUIRE(ef_fill_levels(p.lv, num_levels, hw, A, table_dev) >= 0, B200_ERR_BAD_ARG, "b200_effdet_assign_targets: bad level spec");
+  B200_REQUIRE(B >= 0 && C >= 1, B200_ERR_BAD_ARG, "b200_effdet_assign_targets: bad sizes");
+  if (B == 0) return B200_OK;
+  p.B = B; p.C = C; p.thr = iou_thr;
+  p.gt_boxes = gt_boxes; p.gt_classes = gt_classes; p.gt_offsets = gt_offsets;
+  int cta = 0;
+  for (int l = 0; l < EF_MAX_LEVELS; ++l) {
+    p.cta_base[l] = cta;
+    if (l < num_levels) {
+      B200_REQUIRE(out_boxes[l] && out_onehot[l] && out_mask[l], B200_ERR_BAD_ARG, "b200_effdet_assign_targets: null level %d", l);
+      B200_REQUIRE((reinterpret_cast<uintptr_t>(out_boxes[l]) & 15) == 0, B200_ERR_BAD_ARG, "b200_effdet_assign_targets: out_boxes level %d not 16-byte aligned", l);
+      p.out_boxes[l] = reinterpret_cast<float4*>(out_boxes[l]);
+      p.out_onehot[l] = out_onehot[l];
+      p.out_mask[l] = out_mask[l];
+      p.chunks_per_img[l] = (p.lv.anc_per_img[l] + 255) / 256;
+      cta += p.chunks_per_img[l] * B;
+    } else { p.out_boxes[l] = nullptr; p.out_onehot[l] = nullptr; p.out_mask[l] = nullptr; p.chunks_per_img[l] = 1; }
+  }
+  for (int l = num_levels; l <= EF_MAX_LEVELS; ++l) p.cta_base[l] = cta;
+  effdet_assign_kernel<<<cta, 256, 0, (cudaStream_t)stream>>>(p);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}

@@ -1,0 +1,258 @@
+// effdet_loss.cu — EfficientDet training loss: FocalLoss (losses/focal_loss.py:26-52) + Keras mean reduction,
+// BoxLoss / Huber(delta=0.1) (losses/box_loss.py:17-29) and the aggregation of
+// EfficientDetNetTrain._get_loss (efficientnet/efficientdet_net_train.py:41-52), L2-regularisation excluded
+// (it is over model weights and stays in the TF graph).
+//
+//   K8a focal_box_partials_kernel  one pass over every level: class logits + one-hot targets as 128-bit streaming
+//        loads (the HBM-bound part: 2 x 15.9 MB per D0 image), box outputs/targets/masks per anchor; per-CTA fp64
+//        partial sums of {focal_l, huber_l, positives}.  Element math uses MUFU exp/log/rcp/sqrt: the loss is a
+//        continuous output with a 1e-4 relative budget; nothing discrete depends on it.
+//   K8b focal_box_reduce_kernel    fixed-order reduction of the partials -> sums[2L+1] (fp64, un-normalised) so a
+//        data-parallel caller can all-reduce them before normalising.
+//   K8c focal_box_finalize_kernel  num_pos = sum(mask)+1; box_l = huber_l/(4 num_pos); focal_l = focal_l/num_pos/numel_l
+//        (FocalLoss.call divides per element, Keras SUM_OVER_BATCH_SIZE then takes the mean over the level, Q14);
+//        loss = sum_l (50 box_l + focal_l) in fp32 in the reference's order.
+#include "common.cuh"
+#include "detmath.h"
+
+#define EL_MAX_LEVELS 8
+#define EL_THREADS 256
+
+struct ElParams {
+  int num_levels;
+  const float4* cls_pred[EL_MAX_LEVELS];
+  const float4* cls_true[EL_MAX_LEVELS];
+  unsigned long long cls_vec[EL_MAX_LEVELS];   // float4 count of the class tensors
+  const float* cls_pred_tail[EL_MAX_LEVELS]; const float* cls_true_tail[EL_MAX_LEVELS]; int cls_tail[EL_MAX_LEVELS];
+  const float4* box_pred[EL_MAX_LEVELS];
+  const float4* box_true[EL_MAX_LEVELS];
+  const unsigned char* mask[EL_MAX_LEVELS];
+  unsigned long long anchors[EL_MAX_LEVELS];   // B*H*W*A
+  int cta_base[EL_MAX_LEVELS + 1];
+  float alpha, gamma, delta, label_smoothing;
+  double* partials;  // [n_cta, 3]
+};
+
+__device__ __forceinline__ float el_focal(float y, float x, float alpha, float gamma, float ls) {
+  // focal_loss.py:36-52
+  const float e = __expf(-fabsf(x));
+  const float r = __frcp_rn(1.0f + e);
+  const float p = (x >= 0.0f) ? r : e * r;          // sigmoid(x)
+  const float p_t = y * p + (1.0f - y) * (1.0f - p);
+  const float af = y * alpha + (1.0f - y) * (1.0f - alpha);
+  const float q = 1.0f - p_t;
+  const float mod = (gamma == 1.5f) ? q * sqrtf(q) : __powf(q, gamma);
+  const float ys = y * (1.0f - ls) + 0.5f * ls;
+  const float ce = fmaxf(x, 0.0f) - x * ys - __logf(r);  // log1p(exp(-|x|)) = -log(1/(1+e))
+  return af * mod * ce;
+}
+
+__device__ __forceinline__ float el_huber(float t, float o, float delta) {
+  // keras Huber on the size-1 last axis: |e| <= d ? 0.5 e^2 : d|e| - 0.5 d^2, masked by target != 0 (box_loss.py:24)
+  if (t == 0.0f) return 0.0f;
+  const float e = o - t, a = fabsf(e);
+  return (a <= delta) ? 0.5f * e * e : delta * a - 0.5f * delta * delta;
+}
+
+__global__ void __launch_bounds__(EL_THREADS) focal_box_partials_kernel(ElParams p) {
+  __shared__ double s_red[EL_THREADS / 32][3];
+  int l = 0;
+#pragma unroll
+  for (int k = 1; k < EL_MAX_LEVELS; ++k) if (k < p.num_levels && (int)blockIdx.x >= p.cta_base[k]) l = k;
+  const int ncta = p.cta_base[l + 1] - p.cta_base[l];
+  const int cta = blockIdx.x - p.cta_base[l];
+  const unsigned long long stride = (unsigned long long)ncta * EL_THREADS;
+  float f0 = 0.f, f1 = 0.f;  // two fp32 accumulators per thread, folded into fp64 per thread at the end
+  double focal = 0.0;
+  const float4* __restrict__ cp = p.cls_pred[l];
+  const float4* __restrict__ ct = p.cls_true[l];
+  const unsigned long long nv = p.cls_vec[l];
+  unsigned long long i = (unsigned long long)cta * EL_THREADS + threadIdx.x;
+  int it = 0;
+#pragma unroll 2
+  for (; i < nv; i += stride) {
+    const float4 x = __ldcs(cp + i);
+    const float4 y = __ldcs(ct + i);
+    f0 += el_focal(y.x, x.x, p.alpha, p.gamma, p.label_smoothing) + el_focal(y.y, x.y, p.alpha, p.gamma, p.label_smoothing);
+    f1 += el_focal(y.z, x.z, p.alpha, p.gamma, p.label_smoothing) + el_focal(y.w, x.w, p.alpha, p.gamma, p.label_smoothing);
+    if ((++it & 63) == 0) { focal += (double)f0 + (double)f1; f0 = f1 = 0.f; }
+  }
+  if (cta == 0 && (int)threadIdx.x < p.cls_tail[l])
+    f0 += el_focal(p.cls_true_tail[l][threadIdx.x], p.cls_pred_tail[l][threadIdx.x], p.alpha, p.gamma, p.label_smoothing);
+  focal += (double)f0 + (double)f1;
+  float hub = 0.f;
+  unsigned int pos = 0;
+  const unsigned long long na = p.anchors[l];
+  for (unsigned long long a = (unsigned long long)cta * EL_THREADS + threadIdx.x; a < na; a += stride) {
+    const float4 o = __ldcs(p.box_pred[l] + a);
+    const float4 t = __ldcs(p.box_true[l] + a);
+    hub += el_huber(t.x, o.x, p.delta) + el_huber(t.y, o.y, p.delta) + el_huber(t.z, o.z, p.delta) + el_huber(t.w, o.w, p.delta);
+    pos += p.mask[l][a] ? 1u : 0u;
+  }
+  double v0 = warp_sum_d(focal), v1 = warp_sum_d((double)hub), v2 = warp_sum_d((double)pos);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_red[warp][0] = v0; s_red[warp][1] = v1; s_red[warp][2] = v2; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double s = 0.0;
+    for (int w = 0; w < EL_THREADS / 32; ++w) s += s_red[w][threadIdx.x];
+    p.partials[(size_t)blockIdx.x * 3 + threadIdx.x] = s;
+  }
+}
+
+struct ElReduce { const double* partials; int num_levels; int cta_base[EL_MAX_LEVELS + 1]; double* sums; };
+
+// sums layout: [0..L) focal_l, [L..2L) huber_l, [2L] positives
+__global__ void __launch_bounds__(256) focal_box_reduce_kernel(ElReduce r) {
+  __shared__ double s_red[8][3];
+  const int l = blockIdx.x;
+  double a[3] = {0.0, 0.0, 0.0};
+  for (int c = r.cta_base[l] + threadIdx.x; c < r.cta_base[l + 1]; c += 256) {
+    a[0] += r.partials[(size_t)c * 3 + 0]; a[1] += r.partials[(size_t)c * 3 + 1]; a[2] += r.partials[(size_t)c * 3 + 2];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { const double v = warp_sum_d(a[k]); if (lane == 0) s_red[warp][k] = v; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s[3] = {0.0, 0.0, 0.0};
+    for (int w = 0; w < 8; ++w) for (int k = 0; k < 3; ++k) s[k] += s_red[w][k];
+    r.sums[l] = s[0];
+    r.sums[r.num_levels + l] = s[1];
+    atomicAdd(&r.sums[2 * r.num_levels], s[2]);  // integer-valued: exact and order-independent
+  }
+}
+
+struct ElFinalize { const double* sums; int num_levels; double numel[EL_MAX_LEVELS]; float* parts; float* loss; float* num_pos; };
+
+__global__ void focal_box_finalize_kernel(ElFinalize f) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int L = f.num_levels;
+  const float npos = DM_ADD((float)f.sums[2 * L], 1.0f);         // edt:43-46
+  if (f.num_pos) *f.num_pos = npos;
+  float loss = 0.0f;
+  for (int l = 0; l < L; ++l) {
+    const float box = DM_DIV((float)f.sums[L + l], DM_MUL(npos, 4.0f));            // box_loss.py:23,29
+    const float focal = (float)((f.sums[l] / (double)npos) / f.numel[l]);          // focal_loss.py:52 + Keras mean
+    if (f.parts) { f.parts[2 * l] = box; f.parts[2 * l + 1] = focal; }
+    loss = DM_ADD(loss, DM_ADD(DM_MUL(box, 50.0f), focal));                         // edt:51
+  }
+  *f.loss = loss;
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+static int el_cta_plan(int num_levels, const unsigned long long* cls_elems, int* cta_base) {
+  // CTAs proportional to the class-tensor size of each level, ~8 per SM in total, at least 1 per level
+  unsigned long long tot = 0;
+  for (int l = 0; l < num_levels; ++l) tot += cls_elems[l];
+  const int budget = b200_sm_count() * 8;
+  int c = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    cta_base[l] = c;
+    unsigned long long want = tot ? (cls_elems[l] * (unsigned long long)budget + tot - 1) / tot : 1;
+    const unsigned long long max_useful = (cls_elems[l] / 4 + EL_THREADS - 1) / EL_THREADS;
+    if (want > max_useful) want = max_useful;
+    if (want < 1) want = 1;
+    c += (int)want;
+  }
+  for (int l = num_levels; l <= EL_MAX_LEVELS; ++l) cta_base[l] = c;
+  return c;
+}
+
+// FocalLoss.call (focal_loss.py:26-52): the per-element tensor alpha*mod*ce/normalizer.
+__global__ void focal_elementwise_kernel(const float* __restrict__ y, const float* __restrict__ x, size_t n, float normalizer,
+                                         float alpha, float gamma, float ls, float* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = el_focal(y[i], x[i], alpha, gamma, ls) / normalizer;
+}
+
+extern "C" int b200_focal_elementwise(const float* y_true, const float* y_pred, size_t n, float normalizer, float alpha,
+                                      float gamma, float label_smoothing, float* out, void* stream) {
+  if (n == 0) return B200_OK;
+  B200_REQUIRE(y_true && y_pred && out, B200_ERR_BAD_ARG, "b200_focal_elementwise: null pointer");
+  size_t blocks = (n + 255) / 256;
+  const size_t cap = (size_t)b200_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  focal_elementwise_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(y_true, y_pred, n, normalizer, alpha, gamma, label_smoothing, out);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" size_t b200_focal_box_workspace_bytes(int num_levels, const unsigned long long* anchors_per_level, int C) {
+  unsigned long long elems[EL_MAX_LEVELS];
+  int cta_base[EL_MAX_LEVELS + 1];
+  if (num_levels < 1 || num_levels > EL_MAX_LEVELS) return 0;
+  for (int l = 0; l < num_levels; ++l) elems[l] = anchors_per_level[l] * (unsigned long long)C;
+  const int n = el_cta_plan(num_levels, elems, cta_base);
+  return b200_align_up(sizeof(double) * 3 * (size_t)n, 256);
+}
+
+// anchors_per_level[l] = B*H_l*W_l*A of THIS call (local shard); sums_out: device double[2L+1]
+extern "C" int b200_focal_box_partial_sums(int num_levels, const unsigned long long* anchors_per_level, int C,
+                                           const float* const true_boxes[], const float* const true_classes[],
+                                           const unsigned char* const true_masks[], const float* const pred_boxes[],
+                                           const float* const pred_classes[], float alpha, float gamma, float delta,
+                                           float label_smoothing, double* sums_out, void* workspace,
+                                           size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B200_REQUIRE(num_levels >= 1 && num_levels <= EL_MAX_LEVELS && C >= 1, B200_ERR_BAD_ARG, "b200_focal_box_partial_sums: bad level count / classes");
+  B200_REQUIRE(anchors_per_level && true_boxes && true_classes && true_masks && pred_boxes && pred_classes && sums_out,
+               B200_ERR_BAD_ARG, "b200_focal_box_partial_sums: null argument");
+  ElParams p;
+  unsigned long long elems[EL_MAX_LEVELS];
+  p.num_levels = num_levels;
+  for (int l = 0; l < EL_MAX_LEVELS; ++l) {
+    if (l < num_levels) {
+      // either half of a level may be absent (stand-alone FocalLoss / BoxLoss calls)
+      const bool has_cls = true_classes[l] && pred_classes[l];
+      const bool has_box = true_boxes[l] && pred_boxes[l] && true_masks[l];
+      B200_REQUIRE(has_cls || has_box, B200_ERR_BAD_ARG, "b200_focal_box_partial_sums: null level %d", l);
+      const uintptr_t al = reinterpret_cast<uintptr_t>(true_boxes[l]) | reinterpret_cast<uintptr_t>(true_classes[l]) |
+                           reinterpret_cast<uintptr_t>(pred_boxes[l]) | reinterpret_cast<uintptr_t>(pred_classes[l]);
+      B200_REQUIRE((al & 15) == 0, B200_ERR_BAD_ARG, "b200_focal_box_partial_sums: level %d tensors must be 16-byte aligned", l);
+      elems[l] = has_cls ? anchors_per_level[l] * (unsigned long long)C : 0ull;
+      p.cls_pred[l] = reinterpret_cast<const float4*>(pred_classes[l]);
+      p.cls_true[l] = reinterpret_cast<const float4*>(true_classes[l]);
+      p.cls_vec[l] = elems[l] / 4;
+      p.cls_tail[l] = (int)(elems[l] - p.cls_vec[l] * 4);
+      p.cls_pred_tail[l] = pred_classes[l] + p.cls_vec[l] * 4;
+      p.cls_true_tail[l] = true_classes[l] + p.cls_vec[l] * 4;
+      p.box_pred[l] = reinterpret_cast<const float4*>(pred_boxes[l]);
+      p.box_true[l] = reinterpret_cast<const float4*>(true_boxes[l]);
+      p.mask[l] = true_masks[l];
+      p.anchors[l] = has_box ? anchors_per_level[l] : 0ull;
+    } else {
+      elems[l] = 0; p.cls_pred[l] = p.cls_true[l] = nullptr; p.cls_vec[l] = 0; p.cls_tail[l] = 0;
+      p.cls_pred_tail[l] = p.cls_true_tail[l] = nullptr; p.box_pred[l] = p.box_true[l] = nullptr; p.mask[l] = nullptr; p.anchors[l] = 0;
+    }
+  }
+  unsigned long long plan[EL_MAX_LEVELS];
+  for (int l = 0; l < EL_MAX_LEVELS; ++l) plan[l] = elems[l] > p.anchors[l] * 4ull ? elems[l] : p.anchors[l] * 4ull;
+  const int n_cta = el_cta_plan(num_levels, plan, p.cta_base);
+  const size_t need = b200_align_up(sizeof(double) * 3 * (size_t)n_cta, 256);
+  B200_REQUIRE(workspace && workspace_bytes >= need, B200_ERR_WORKSPACE, "b200_focal_box_partial_sums: workspace %zu < required %zu", workspace_bytes, need);
+  p.alpha = alpha; p.gamma = gamma; p.delta = delta; p.label_smoothing = label_smoothing;
+  p.partials = static_cast<double*>(workspace);
+  B200_CUDA(cudaMemsetAsync(sums_out, 0, sizeof(double) * (2 * num_levels + 1), stream));
+  focal_box_partials_kernel<<<n_cta, EL_THREADS, 0, stream>>>(p);
+  B200_LAUNCH_CHECK();
+  ElReduce r;
+  r.partials = p.partials; r.num_levels = num_levels; r.sums = sums_out;
+  for (int l = 0; l <= EL_MAX_LEVELS; ++l) r.cta_base[l] = p.cta_base[l];
+  focal_box_reduce_kernel<<<num_levels, 256, 0, stream>>>(r);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+// numel_per_level[l] = GLOBAL element count B_global*H*W*A*C of level l (the Keras mean divisor)
+extern "C" int b200_focal_box_finalize(int num_levels, const double* sums, const double* numel_per_level_host,
+                                       float* out_parts, float* out_loss, float* out_num_positives, void* stream) {
+  B200_REQUIRE(num_levels >= 1 && num_levels <= EL_MAX_LEVELS && sums && numel_per_level_host && out_loss, B200_ERR_BAD_ARG,
+               "b200_focal_box_finalize: bad argument");
+  ElFinalize f;
+  f.sums = sums; f.num_levels = num_levels; f.parts = out_parts; f.loss = out_loss; f.num_pos = out_num_positives;
+  for (int l = 0; l < EL_MAX_LEVELS; ++l) f.numel[l] = l < num_levels ? numel_per_level_host[l] : 1.0;
+  focal_box_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}

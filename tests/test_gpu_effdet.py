@@ -1,0 +1,151 @@
+"""GPU parity for the EfficientDet utilities against the oracle."""
+import numpy as np
+import pytest
+
+from test_gpu_core import _t, assert_bits_equal
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+LOSS_RTOL = 1e-4
+CFGS = {
+    "tiny": dict(min_level=0, max_level=0, image_size=(10, 10), num_scales=3, aspect_ratios=[(1.0, 1.0)], anchor_scale=3.0),
+    "small": dict(min_level=3, max_level=7, image_size=(128, 128), num_scales=3,
+                  aspect_ratios=[(1.0, 1.0), (1.4, 0.7), (0.7, 1.4)], anchor_scale=4.0),
+    "rect": dict(min_level=3, max_level=5, image_size=(128, 256), num_scales=2,
+                 aspect_ratios=[(1.0, 1.0), (1.4, 0.7)], anchor_scale=[3.0, 4.0, 5.0]),
+    "d0": dict(min_level=3, max_level=7, image_size=(512, 512), num_scales=3,
+               aspect_ratios=[(1.0, 1.0), (1.4, 0.7), (0.7, 1.4)], anchor_scale=4.0),
+}
+
+
+def _pair(name):
+    from oracle import effdet as oe
+    from tfmv_b200.ai_models.efficientnet.utils.anchors import Anchors
+    c = CFGS[name]
+    args = (c["min_level"], c["max_level"], c["image_size"], c["num_scales"], c["aspect_ratios"], c["anchor_scale"])
+    return Anchors(*args), oe.Anchors(*args)
+
+
+@pytest.mark.parametrize("name", ["tiny", "small", "rect", "d0"])
+def test_anchor_boxes_bit_exact(lib, cuda, name):
+    a, o = _pair(name)
+    assert len(a.boxes) == len(o.boxes) and a.get_anchors_per_location() == o.get_anchors_per_location()
+    for g, w in zip(a.boxes, o.boxes):
+        assert_bits_equal(g.cpu().numpy(), w)
+
+
+@pytest.mark.parametrize("name,batch", [("small", 3), ("rect", 2), ("d0", 2)])
+def test_decode_bit_exact(lib, cuda, name, batch):
+    a, o = _pair(name)
+    rng = np.random.default_rng(3)
+    rel = [(rng.standard_normal((batch,) + b.shape, dtype=F) * F(0.25)) for b in o.boxes]
+    rel[0][0, 0, 0, 0, 2] = 120.0  # exp overflow -> inf box, kept as is (anc:266)
+    want = o.convert_outputs_boxes(rel)
+    got = a.convert_outputs_boxes([_t(r, cuda) for r in rel])
+    for g, w in zip(got, want):
+        assert_bits_equal(g.cpu().numpy(), w)
+
+
+def test_reference_anchor_fixture(lib, cuda):
+    """tests/test_anchors.py:10-34 end to end: generate_targets -> convert_outputs_boxes -> convert_outputs_one."""
+    a, o = _pair("tiny")
+    boxes = np.array([[3, 3, 6, 6], [5, 5, 9, 9]], F)
+    classes = np.array([1, 2])
+    ob, oc, om = a.generate_targets(_t(boxes, cuda), classes, 3, iou_threshold=0.5)
+    wb, wc, wm = o.generate_targets(boxes, classes, 3, iou_threshold=0.5)
+    assert tuple(ob[0].shape) == (10, 10, 3, 4) and tuple(oc[0].shape) == (10, 10, 3, 3) and tuple(om[0].shape) == (10, 10, 3, 1)
+    assert_bits_equal(ob[0].cpu().numpy(), wb[0])
+    assert_bits_equal(oc[0].cpu().numpy(), wc[0])
+    assert np.array_equal(om[0].cpu().numpy(), wm[0])
+    dec = a.convert_outputs_boxes([ob[0][None]])
+    b, c, s = a.convert_outputs_one(0, dec, [oc[0][None]])
+    assert c.cpu().tolist() == [1, 2] and str(c.dtype) == "torch.int64"
+    np.testing.assert_allclose(b.cpu().numpy(), [[3, 3, 6, 6], [5, 5, 9, 9]], atol=2e-5)
+    np.testing.assert_allclose(s.cpu().numpy(), [0.7310586, 0.7310586], rtol=1e-6)
+
+
+@pytest.mark.parametrize("name,batch,nmax", [("small", 3, 40), ("rect", 2, 10), ("d0", 2, 100)])
+def test_generate_targets_bit_exact(lib, cuda, name, batch, nmax):
+    from tfmv_b200 import synth
+    a, o = _pair(name)
+    rng = np.random.default_rng(20261018 + 3 + batch)
+    ih, iw = CFGS[name]["image_size"]
+    boxes, classes, off = synth.gt_batch(rng, batch, (iw, ih), max_boxes=nmax, order="yxyx")
+    classes = (classes % 80 + 1).astype(np.int32)  # class 0 is background
+    classes[0] = 200  # out of range -> all-zero one-hot row (tf.one_hot)
+    C = 81
+    gb, gc, gm = a.generate_targets_batch(_t(boxes, cuda), _t(classes, cuda), _t(off, cuda), C)
+    npos = 0
+    for b in range(batch):
+        wb, wc, wm = o.generate_targets(boxes[off[b]:off[b + 1]], classes[off[b]:off[b + 1]], C)
+        for l in range(len(wb)):
+            assert_bits_equal(gb[l][b].cpu().numpy(), wb[l])
+            assert_bits_equal(gc[l][b].cpu().numpy(), wc[l])
+            assert np.array_equal(gm[l][b].cpu().numpy(), wm[l])
+            npos += int(wm[l].sum())
+    assert npos > 0
+
+
+@pytest.mark.parametrize("name,batch,iou_type", [("small", 3, "diou"), ("rect", 2, "ciou"), ("d0", 2, "diou"), ("small", 2, "giou")])
+def test_convert_outputs_one_matches_oracle(lib, cuda, name, batch, iou_type):
+    a, o = _pair(name)
+    rng = np.random.default_rng(20261018 + 4 + batch)
+    C = 81
+    rel = [(rng.standard_normal((batch,) + b.shape, dtype=F) * F(0.25)) for b in o.boxes]
+    cls = [rng.standard_normal((batch,) + b.shape[:-1] + (C,), dtype=F) for b in o.boxes]
+    cls[0][0, 0, 0, :, :] = 0.5          # ties across classes -> argmax 0 -> background, dropped
+    cls[0][0, 0, 1, :, 7] = 3.0          # exact score ties between anchors -> lower index first
+    dec_w = o.convert_outputs_boxes(rel)
+    dec = a.convert_outputs_boxes([_t(r, cuda) for r in rel])
+    r = a.convert_outputs_batch(dec, [_t(c, cuda) for c in cls], iou_type=iou_type, with_indices=True)
+    r = {k: v.cpu().numpy() for k, v in r.items()}
+    for b in range(batch):
+        w = o.convert_outputs_one_ex(b, dec_w, cls, iou_type=iou_type)
+        k = int(r["count"][b])
+        assert k == w["selected"].shape[0] and k > 0
+        assert r["sel_idx"][b, :k].tolist() == w["selected"].tolist()
+        assert r["sel_anchor"][b, :k].tolist() == w["cand_anchor"][w["selected"]].tolist()
+        assert r["classes_id"][b, :k].tolist() == w["classes_id"].tolist()
+        assert_bits_equal(r["boxes"][b, :k], w["boxes"])
+        assert_bits_equal(r["scores"][b, :k], w["scores"])
+    # reference signature, one image
+    bx, ci, sc = a.convert_outputs_one(1, dec, [_t(c, cuda) for c in cls]) if iou_type == "diou" else (None, None, None)
+    if bx is not None:
+        w = o.convert_outputs_one_ex(1, dec_w, cls)
+        assert ci.cpu().tolist() == w["classes_id"].tolist()
+        assert_bits_equal(bx.cpu().numpy(), w["boxes"])
+
+
+@pytest.mark.parametrize("name,batch", [("small", 4), ("d0", 2)])
+def test_get_loss_matches_oracle(lib, cuda, name, batch):
+    from oracle import effdet as oe
+    from tfmv_b200 import synth
+    from tfmv_b200.ai_models.efficientnet.efficientdet_net_train import get_loss
+    from tfmv_b200.ai_models.losses.box_loss import BoxLoss
+    from tfmv_b200.ai_models.losses.focal_loss import FocalLoss
+    a, o = _pair(name)
+    rng = np.random.default_rng(20261018 + 3)
+    ih, iw = CFGS[name]["image_size"]
+    C = 81
+    boxes, classes, off = synth.gt_batch(rng, batch, (iw, ih), max_boxes=30, order="yxyx")
+    classes = (classes % 80 + 1).astype(np.int32)
+    per = [o.generate_targets(boxes[off[b]:off[b + 1]], classes[off[b]:off[b + 1]], C) for b in range(batch)]
+    L = len(o.boxes)
+    tb = [np.stack([p[0][l] for p in per], 0) for l in range(L)]
+    tc = [np.stack([p[1][l] for p in per], 0) for l in range(L)]
+    tm = [np.stack([p[2][l] for p in per], 0) for l in range(L)]
+    pb = [(rng.standard_normal(t.shape, dtype=F) * F(0.25)) for t in tb]
+    pc = [rng.standard_normal(t.shape, dtype=F) for t in tc]
+    want, wparts, wnpos = oe.get_loss(tb, tc, tm, pb, pc, return_parts=True)
+    d = lambda xs: [_t(x, cuda) for x in xs]
+    got, parts, npos = get_loss(d(tb), d(tc), d(tm), d(pb), d(pc), return_parts=True)
+    assert float(npos) == float(wnpos) > 1
+    np.testing.assert_allclose(parts.cpu().numpy(), wparts, rtol=LOSS_RTOL, atol=1e-9)
+    assert abs(float(got) - float(want)) <= LOSS_RTOL * abs(float(want))
+    # stand-alone Keras-style losses
+    fl = FocalLoss(0.25, 1.5)([float(wnpos), _t(tc[0], cuda)], _t(pc[0], cuda))
+    assert abs(float(fl) - float(oe.focal_loss(wnpos, tc[0], pc[0]))) <= LOSS_RTOL * abs(float(oe.focal_loss(wnpos, tc[0], pc[0])))
+    bl = BoxLoss()([float(wnpos), _t(tb[0], cuda)], _t(pb[0], cuda))
+    assert abs(float(bl) - float(oe.box_loss(wnpos, tb[0], pb[0]))) <= LOSS_RTOL * abs(float(oe.box_loss(wnpos, tb[0], pb[0])))
+    el = FocalLoss(0.25, 1.5).call([3.0, _t(tc[1], cuda)], _t(pc[1], cuda)).cpu().numpy()
+    np.testing.assert_allclose(el, oe.focal_loss_elements(3.0, tc[1], pc[1]), rtol=2e-5, atol=1e-9)
