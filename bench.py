@@ -211,9 +211,7 @@ def run_b200(args, wl):
         loss, parts = tyu._loss_call(y_true, heads, (image, image), anc, 0.5, "ciou", 0, batch_divisor=global_batch,
                                      return_parts=True, workspace=ws)
         if world > 1:
-            dist.all_reduce(parts, op=dist.ReduceOp.SUM)  # the single collective of the path: 12 floats
-            loss = ((parts[:, 0] + parts[:, 1]) + parts[:, 2]) + parts[:, 3]
-            loss = (loss[0] + loss[1]) + loss[2]
+            loss = tyu.combine_loss_parts(parts)  # the single collective of the path: 12 floats over NCCL
         parts_buf["loss"] = loss
         return loss
 

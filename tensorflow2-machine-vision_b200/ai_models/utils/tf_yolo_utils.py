@@ -175,6 +175,24 @@ def GetLoss(y_true, y_pred, image_wh, anchors_wh, iou_thresh=0.5, iou_type='iou'
   return _loss_call(y_true, y_pred, image_wh, anchors_wh, iou_thresh, iou_type, 0)
 
 
+def combine_loss_parts(parts, group=None):
+  '''The multi-GPU exchange step of GetLoss: `parts` (3,4) = per level {xy, wh, obj, cls} already divided by the
+  GLOBAL batch on every rank.  One all-reduce(sum) of the 12 floats, then the reference's order of additions
+  (tyu:125).  Works on any torch.distributed backend (NCCL on the GPUs, gloo in the CPU tests).'''
+  import torch.distributed as dist
+  if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    dist.all_reduce(parts, op=dist.ReduceOp.SUM, group=group)
+  per_level = ((parts[:, 0] + parts[:, 1]) + parts[:, 2]) + parts[:, 3]
+  return (per_level[0] + per_level[1]) + per_level[2]
+
+
+def shard_range(batch, rank, world):
+  '''Contiguous image range [lo, hi) of `rank` when `batch` images are sharded over `world` ranks.'''
+  base, rem = divmod(int(batch), int(world))
+  lo = rank * base + min(rank, rem)
+  return lo, lo + base + (1 if rank < rem else 0)
+
+
 def GetLossSharded(y_true, y_pred, image_wh, anchors_wh, iou_thresh=0.5, iou_type='iou', global_batch=None,
                    group=None):
   '''Data-parallel GetLoss: every rank passes its own images; the 12 per-level terms (already divided by the
@@ -187,7 +205,5 @@ def GetLossSharded(y_true, y_pred, image_wh, anchors_wh, iou_thresh=0.5, iou_typ
   loss, parts = _loss_call(y_true, y_pred, image_wh, anchors_wh, iou_thresh, iou_type, 0,
                            batch_divisor=global_batch, return_parts=True)
   if world > 1:
-    dist.all_reduce(parts, op=dist.ReduceOp.SUM, group=group)
-    loss = ((parts[:, 0] + parts[:, 1]) + parts[:, 2]) + parts[:, 3]
-    loss = (loss[0] + loss[1]) + loss[2]
+    loss = combine_loss_parts(parts, group)
   return loss
