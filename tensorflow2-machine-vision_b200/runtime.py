@@ -19,7 +19,8 @@ class CapturedStep(object):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread_local: other threads of the process (e.g. NCCL's watchdog) may keep calling the CUDA runtime
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.out = fn()
 
     def __call__(self):
