@@ -70,7 +70,9 @@ __global__ void __launch_bounds__(256) effdet_decode_kernel(EfDecodeParams p) {
 #pragma unroll
     for (int k = 1; k < EF_MAX_LEVELS; ++k) if (k < p.lv.num_levels && i >= p.elem_base[k]) l = k;
     const long long e = i - p.elem_base[l];
-    const int rin = (int)(e % p.lv.anc_per_img[l]);
+    const unsigned int api = (unsigned int)p.lv.anc_per_img[l];
+    const unsigned int img = (unsigned int)(e / api);  // e < 2^31*api in practice; 64/32 division only here
+    const int rin = (int)(e - (long long)img * api);
     int y, x, a;
     ef_split(p.lv, l, rin, y, x, a);
     const AnchorBox an = ef_anchor(p.lv, l, y, x, a);
@@ -207,6 +209,7 @@ struct EfFinalizeParams {
   float* out_boxes; long long* out_cls; float* out_score; int32_t* out_sel_idx; int32_t* out_sel_anchor; int32_t* out_count;
 };
 
+template <int METRIC>
 __global__ void __launch_bounds__(NMS_THREADS, 1) effdet_nms_finalize_kernel(EfFinalizeParams p) {
   extern __shared__ __align__(16) unsigned char nms_smem[];
   const int img = blockIdx.x;
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) effdet_nms_finalize_kernel(EfF
   seg.order_id = p.cand_aidx + cbase;
   seg.n = p.counts[img];
   int32_t* pos = p.nms_pos + (size_t)img * p.cfg.max_out;
-  const int kept = nms_run_segment(seg, p.cfg, pos, nms_smem);
+  const int kept = nms_run_segment<METRIC>(seg, p.cfg, pos, nms_smem);
   __syncthreads();
   if (threadIdx.x == 0) p.out_count[img] = kept;
   const size_t obase = (size_t)img * p.cfg.max_out;
@@ -349,10 +352,14 @@ __global__ void __launch_bounds__(256) effdet_assign_kernel(EfAssignParams p) {
   __syncthreads();
   const int rows = min(256, api - chunk * 256);
   float* dst = p.out_onehot[l] + (abase + (size_t)chunk * 256) * p.C;
-  const int total = rows * p.C;
-  for (int i = threadIdx.x; i < total; i += 256) {
-    const int r = i / p.C, c = i - r * p.C;
-    __stcs(dst + i, (s_cls[r] == c) ? 1.0f : 0.0f);  // tf.one_hot: out-of-range class -> all zeros
+  // warp w writes rows w, w+8, ...: a row is C consecutive floats, so the lanes' 4-byte stores coalesce
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < rows; r += 8) {
+      const int rc = s_cls[r];
+      float* row = dst + (size_t)r * p.C;
+      for (int c = lane; c < p.C; c += 32) __stcs(row + c, (rc == c) ? 1.0f : 0.0f);  // tf.one_hot: out of range -> zeros
+    }
   }
 }
 
@@ -511,8 +518,11 @@ extern "C" int b200_effdet_postprocess(int num_levels, const int32_t* hw, int A,
   size_t smem2 = nms_smem_bytes(max_out);
   if (smem2 < (size_t)ws.bitmap_words * 4) smem2 = (size_t)ws.bitmap_words * 4;
   B200_REQUIRE(smem2 <= 220 * 1024, B200_ERR_UNSUPPORTED, "b200_effdet_postprocess: too many anchors per image for the rank table");
-  B200_CUDA(cudaFuncSetAttribute(effdet_nms_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-  effdet_nms_finalize_kernel<<<num_images, NMS_THREADS, smem2, stream>>>(np);
+#define EF_LAUNCH(M)                                                                                                     \
+  B200_CUDA(cudaFuncSetAttribute(effdet_nms_finalize_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
+  effdet_nms_finalize_kernel<M><<<num_images, NMS_THREADS, smem2, stream>>>(np)
+  NMS_DISPATCH_METRIC(metric, EF_LAUNCH)
+#undef EF_LAUNCH
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

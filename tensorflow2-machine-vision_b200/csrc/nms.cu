@@ -13,6 +13,7 @@ struct NmsBatchParams {
   int32_t* out_count;
 };
 
+template <int METRIC>
 __global__ void __launch_bounds__(NMS_THREADS, 1) nms_batch_kernel(NmsBatchParams p) {
   extern __shared__ __align__(16) unsigned char nms_smem[];
   const int s = blockIdx.x;
@@ -23,7 +24,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_batch_kernel(NmsBatchParam
   seg.classes = p.classes ? p.classes + beg : nullptr;
   seg.order_id = p.order_id ? p.order_id + beg : nullptr;
   seg.n = end - beg;
-  int kept = nms_run_segment(seg, p.cfg, p.out_idx + (size_t)s * p.cfg.max_out, nms_smem);
+  int kept = nms_run_segment<METRIC>(seg, p.cfg, p.out_idx + (size_t)s * p.cfg.max_out, nms_smem);
   if (threadIdx.x == 0) p.out_count[s] = kept;
 }
 
@@ -46,8 +47,11 @@ extern "C" int b200_nms(const float* boxes, const float* scores, const int32_t* 
   p.cfg.use_score_thr = use_score_thr; p.cfg.max_out = max_out;
   p.out_idx = out_idx; p.out_count = out_count;
   size_t smem = nms_smem_bytes(max_out);
-  B200_CUDA(cudaFuncSetAttribute(nms_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  nms_batch_kernel<<<num_segments, NMS_THREADS, smem, (cudaStream_t)stream>>>(p);
+#define NMS_LAUNCH(M)                                                                                          \
+  B200_CUDA(cudaFuncSetAttribute(nms_batch_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+  nms_batch_kernel<M><<<num_segments, NMS_THREADS, smem, (cudaStream_t)stream>>>(p)
+  NMS_DISPATCH_METRIC(metric, NMS_LAUNCH)
+#undef NMS_LAUNCH
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

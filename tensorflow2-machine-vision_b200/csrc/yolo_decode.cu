@@ -6,7 +6,7 @@
 // Kernel 1  yolo_decode_filter_kernel  (HBM-read bound: every head byte is read exactly once)
 //   * each level tensor is treated as a flat array of records of RF = 5+C floats; a warp owns tiles of 32
 //     records (32*RF*4 bytes, always a multiple of 16) staged into its own shared-memory ring by 1-D bulk
-//     async copies (cp.async.bulk + mbarrier, SASS UBLKCP), two tiles in flight per warp;
+//     async copies (cp.async.bulk + mbarrier, SASS UBLKCP); 16 warps per SM, each with its own tile in flight;
 //   * lane <-> record; the stride RF between lanes is odd for the 85-float COCO record so the column reads are
 //     bank-conflict free; conf is thresholded first, then the class maximum is found on raw logits and the
 //     sigmoid is evaluated only for logits inside a guard band of the maximum (max / first-argmax are taken
@@ -21,7 +21,7 @@
 #include "nms.cuh"
 
 #define YD_MAX_LEVELS 3
-#define YD_STAGES 2
+#define YD_STAGES 1
 
 struct YoloLevels {
   const float* head[YD_MAX_LEVELS];
@@ -75,28 +75,46 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 // max and first-argmax of sigmoid(x_c), c in [0,C), reading a record with stride 1 from shared memory.
+// One pass keeps the largest logit (first index on ties) and the second largest value.  When the runner-up is
+// outside the guard band of the maximum, its sigmoid is certainly smaller and the answer is (sigmoid(m1), i1):
+// for -80 < m < 8, d ln(sigmoid)/dx >= 3.3e-4, so logits below m - 0.01 are > 3.3e-6 relative below sigmoid(m)
+// while detmath's sigmoid is within 2.4 ulp = 2.9e-7 of exact (oracle/DETMATH_REPORT.md; it is not monotone at
+// ulp level, which is why the band exists).  Otherwise (rare) every logit inside the band is evaluated and max /
+// first-argmax are taken in sigmoid space, exactly as tf.reduce_max / tf.argmax of sigmoid(classes) do.
 __device__ __forceinline__ void class_max_sigmoid(const float* __restrict__ cls, int C, float& best_s, int& best_c) {
-  float m0 = cls[0], m1 = m0, m2 = m0, m3 = m0;
+  // pass 1: the maximum logit, four independent chains (2 instructions per element)
+  float a0 = cls[0], a1 = a0, a2 = a0, a3 = a0;
   int c = 0;
   for (; c + 4 <= C; c += 4) {
-    m0 = fmaxf(m0, cls[c]); m1 = fmaxf(m1, cls[c + 1]); m2 = fmaxf(m2, cls[c + 2]); m3 = fmaxf(m3, cls[c + 3]);
+    a0 = fmaxf(a0, cls[c]); a1 = fmaxf(a1, cls[c + 1]); a2 = fmaxf(a2, cls[c + 2]); a3 = fmaxf(a3, cls[c + 3]);
   }
-  for (; c < C; ++c) m0 = fmaxf(m0, cls[c]);
-  const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-  // guard band: logits below m - 0.01 have a strictly smaller computed sigmoid when -80 < m < 8
-  // (d ln sigmoid/dx >= 3.3e-4 there, so the gap is > 3.3e-6 relative vs <= 2.4 ulp = 2.9e-7 error per value)
-  const float lo = (m < 8.0f && m > -80.0f) ? (m - 0.01f) : -INFINITY;
-  best_s = -1.0f;
+  for (; c < C; ++c) a0 = fmaxf(a0, cls[c]);
+  const float m1 = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));  // fmaxf drops NaNs; a NaN row is caught below
+  // pass 2: first index of the maximum, and how many logits fall inside the guard band
+  const bool banded = (m1 < 8.0f) && (m1 > -80.0f);
+  const float lo = banded ? (m1 - 0.01f) : -INFINITY;
+  int i1 = C, in_band = 0;
+#pragma unroll 4
+  for (c = C - 1; c >= 0; --c) {
+    const float x = cls[c];
+    i1 = (x == m1) ? c : i1;
+    in_band += (x >= lo || x != x) ? 1 : 0;
+  }
+  if (in_band == 1 && i1 < C) {  // the maximum is alone in its band: its sigmoid is the largest, certainly
+    best_s = dm_sigmoidf(m1);
+    best_c = i1;
+    return;
+  }
+  best_s = 0.0f;
   best_c = 0;
   bool any = false;
   for (c = 0; c < C; ++c) {
-    float x = cls[c];
+    const float x = cls[c];
     if (x >= lo || x != x) {
-      float s = dm_sigmoidf(x);
+      const float s = dm_sigmoidf(x);
       if (!any || s > best_s) { best_s = s; best_c = c; any = true; }
     }
   }
-  if (!any) { best_s = dm_sigmoidf(cls[0]); best_c = 0; }  // all-NaN row
 }
 
 struct Decoded { float x1, y1, x2, y2; bool valid; };
@@ -117,7 +135,7 @@ __device__ __forceinline__ Decoded decode_box(float tx, float ty, float tw, floa
   return d;
 }
 
-__global__ void __launch_bounds__(256, 1) yolo_decode_filter_kernel(YoloDecodeParams p) {
+__global__ void __launch_bounds__(512, 1) yolo_decode_filter_kernel(YoloDecodeParams p) {
   extern __shared__ __align__(128) unsigned char yd_smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -245,6 +263,7 @@ struct YoloFinalizeParams {
   int32_t* out_sel_idx; int32_t* out_sel_anchor; int32_t* out_count;
 };
 
+template <int METRIC>
 __global__ void __launch_bounds__(NMS_THREADS, 1) yolo_nms_finalize_kernel(YoloFinalizeParams p) {
   extern __shared__ __align__(16) unsigned char nms_smem[];
   const int img = blockIdx.x;
@@ -256,7 +275,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) yolo_nms_finalize_kernel(YoloF
   seg.order_id = p.cand_aidx + cbase;
   seg.n = p.counts[img];
   int32_t* pos = p.nms_pos + (size_t)img * p.cfg.max_out;
-  const int kept = nms_run_segment(seg, p.cfg, pos, nms_smem);
+  const int kept = nms_run_segment<METRIC>(seg, p.cfg, pos, nms_smem);
   __syncthreads();
   if (threadIdx.x == 0) p.out_count[img] = kept;
   const size_t obase = (size_t)img * p.cfg.max_out;
@@ -291,20 +310,25 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) yolo_nms_finalize_kernel(YoloF
       p.out_sel_idx[obase + k] = (int32_t)(wprefix[a >> 5] + __popc(wv & ((1u << (a & 31u)) - 1u)));
     }
   }
-  // sigmoid(classes) rows of the selected boxes, read back from the head tensors (tyu:140,265)
-  if (p.out_classes) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int k = warp; k < kept; k += nw) {
-      const uint32_t a = p.cand_aidx[cbase + pos[k]];
-      int l = 0;
+}
+
+// sigmoid(classes) rows of the selected boxes, read back from the head tensors (tyu:140,265).  A separate launch
+// so the B*max_out*C sigmoids spread over the whole GPU instead of serialising inside the per-image NMS CTAs.
+__global__ void __launch_bounds__(256) yolo_classes_kernel(YoloFinalizeParams p) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // row = img * max_out + k
+  if (row >= p.B * p.cfg.max_out) return;
+  const int img = row / p.cfg.max_out, k = row - img * p.cfg.max_out;
+  if (k >= p.out_count[img]) return;
+  const size_t cbase = (size_t)img * p.n_img;
+  const uint32_t a = p.cand_aidx[cbase + p.nms_pos[(size_t)img * p.cfg.max_out + k]];
+  int l = 0;
 #pragma unroll
-      for (int j = 1; j < YD_MAX_LEVELS; ++j) if ((int)a >= p.lv.anchor_base[j]) l = j;
-      const long long rec = (long long)img * p.lv.rec_per_img[l] + ((int)a - p.lv.anchor_base[l]);
-      const float* src = p.lv.head[l] + rec * p.RF + 5;
-      float* dst = p.out_classes + (obase + k) * p.C;
-      for (int c = lane; c < p.C; c += 32) dst[c] = dm_sigmoidf(__ldg(src + c));
-    }
-  }
+  for (int j = 1; j < YD_MAX_LEVELS; ++j) if ((int)a >= p.lv.anchor_base[j]) l = j;
+  const long long rec = (long long)img * p.lv.rec_per_img[l] + ((int)a - p.lv.anchor_base[l]);
+  const float* src = p.lv.head[l] + rec * p.RF + 5;
+  float* dst = p.out_classes + (size_t)row * p.C;
+  for (int c = lane; c < p.C; c += 32) dst[c] = dm_sigmoidf(__ldg(src + c));
 }
 
 // ---- dense decode for the stand-alone GetBoxes shim ---------------------------------------------
@@ -425,7 +449,7 @@ extern "C" int b200_yolo_decode_nms(const float* const heads[3], const int32_t h
   B200_CUDA(cudaMemsetAsync(wsb, 0, out_sel_idx ? ws.box : ws.bitmap, stream));
 
   const uint32_t slab = 128u * (uint32_t)dp.RF;
-  int warps = 8;
+  int warps = 16;  // one tile in flight per warp; the warps of an SM overlap each other's loads
   while (warps > 1 && (size_t)warps * YD_STAGES * slab + 256 > 200 * 1024) warps >>= 1;
   B200_REQUIRE((size_t)warps * YD_STAGES * slab + 256 <= 220 * 1024, B200_ERR_UNSUPPORTED, "b200_yolo_decode_nms: record too large (C=%d)", C);
   const size_t smem1 = (size_t)warps * YD_STAGES * slab + sizeof(uint64_t) * warps * YD_STAGES + 16;
@@ -449,9 +473,17 @@ extern "C" int b200_yolo_decode_nms(const float* const heads[3], const int32_t h
   size_t smem2 = nms_smem_bytes(max_out);
   const size_t need_prefix = (size_t)ws.bitmap_words * 4;
   if (smem2 < need_prefix) smem2 = need_prefix;
-  B200_CUDA(cudaFuncSetAttribute(yolo_nms_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-  yolo_nms_finalize_kernel<<<B, NMS_THREADS, smem2, stream>>>(fp);
+#define YD_LAUNCH(M)                                                                                                   \
+  B200_CUDA(cudaFuncSetAttribute(yolo_nms_finalize_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
+  yolo_nms_finalize_kernel<M><<<B, NMS_THREADS, smem2, stream>>>(fp)
+  NMS_DISPATCH_METRIC(metric, YD_LAUNCH)
+#undef YD_LAUNCH
   B200_LAUNCH_CHECK();
+  if (out_classes) {
+    const long long rows = (long long)B * max_out;
+    yolo_classes_kernel<<<(int)((rows + 7) / 8), 256, 0, stream>>>(fp);
+    B200_LAUNCH_CHECK();
+  }
   return B200_OK;
 }
 

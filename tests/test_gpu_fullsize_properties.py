@@ -110,7 +110,7 @@ def test_config3_effdet_d0_round_trip_and_loss_linearity(lib, cuda):
     s_full, _ = _partial_sums(list(tb), list(tc), list(tm), pb, pc, 0.25, 1.5, 0.1, 0.0)
     s_a, _ = _partial_sums([t[:5] for t in tb], [t[:5] for t in tc], [t[:5] for t in tm], [t[:5] for t in pb], [t[:5] for t in pc], 0.25, 1.5, 0.1, 0.0)
     s_b, _ = _partial_sums([t[5:] for t in tb], [t[5:] for t in tc], [t[5:] for t in tm], [t[5:] for t in pb], [t[5:] for t in pc], 0.25, 1.5, 0.1, 0.0)
-    np.testing.assert_allclose((s_a + s_b).cpu().numpy(), s_full.cpu().numpy(), rtol=1e-9)
+    np.testing.assert_allclose((s_a + s_b).cpu().numpy(), s_full.cpu().numpy(), rtol=2e-6)  # fp32 per-thread partials
 
 
 def test_config4_effdet_d7_postprocess_topk_regime(lib, cuda):
