@@ -206,6 +206,8 @@ struct EfFinalizeParams {
   const float4* cand_box; const float* cand_score; const int32_t* cand_cls; const uint32_t* cand_aidx;
   const int32_t* counts; const uint32_t* bitmap; int bitmap_words;
   int32_t* nms_pos;
+  const unsigned long long* pre_keys; const uint32_t* pre_pos; const int* pre_count; const int* pre_elig;
+  const unsigned long long* pre_khi;  // all nullptr when the pre-selection kernel was not run
   float* out_boxes; long long* out_cls; float* out_score; int32_t* out_sel_idx; int32_t* out_sel_anchor; int32_t* out_count;
 };
 
@@ -221,7 +223,12 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) effdet_nms_finalize_kernel(EfF
   seg.order_id = p.cand_aidx + cbase;
   seg.n = p.counts[img];
   int32_t* pos = p.nms_pos + (size_t)img * p.cfg.max_out;
-  const int kept = nms_run_segment<METRIC>(seg, p.cfg, pos, nms_smem);
+  NmsPre pre;
+  if (p.pre_keys) {
+    pre.keys = p.pre_keys + (size_t)img * NMS_WINDOW; pre.pos = p.pre_pos + (size_t)img * NMS_WINDOW;
+    pre.count = p.pre_count + img; pre.eligible = p.pre_elig + img; pre.khi = p.pre_khi + img;
+  }
+  const int kept = nms_run_segment<METRIC>(seg, p.cfg, pos, nms_smem, p.pre_keys ? &pre : nullptr);
   __syncthreads();
   if (threadIdx.x == 0) p.out_count[img] = kept;
   const size_t obase = (size_t)img * p.cfg.max_out;
@@ -431,21 +438,32 @@ extern "C" int b200_effdet_decode(int num_levels, const int32_t* hw, int A, cons
   return B200_OK;
 }
 
-struct EfWs { size_t counts, bitmap, box, score, cls, aidx, pos, total; int bitmap_words; };
+struct EfWs { size_t counts, pre_count, pre_elig, bitmap, box, score, cls, aidx, pos, pre_khi, pre_keys, pre_pos, total; int bitmap_words; };
 static EfWs ef_ws_layout(int NB, int n_img, int max_out) {
   EfWs w;
   size_t o = 0;
   w.bitmap_words = (n_img + 31) / 32;
   w.counts = o; o = b200_align_up(o + sizeof(int32_t) * NB, 256);
+  w.pre_count = o; o = b200_align_up(o + sizeof(int32_t) * NB, 256);   // zeroed together with counts
+  w.pre_elig = o; o = b200_align_up(o + sizeof(int32_t) * NB, 256);
   w.bitmap = o; o = b200_align_up(o + sizeof(uint32_t) * (size_t)NB * w.bitmap_words, 256);
   w.box = o; o = b200_align_up(o + sizeof(float4) * (size_t)NB * n_img, 256);
   w.score = o; o = b200_align_up(o + sizeof(float) * (size_t)NB * n_img, 256);
   w.cls = o; o = b200_align_up(o + sizeof(int32_t) * (size_t)NB * n_img, 256);
   w.aidx = o; o = b200_align_up(o + sizeof(uint32_t) * (size_t)NB * n_img, 256);
   w.pos = o; o = b200_align_up(o + sizeof(int32_t) * (size_t)NB * max_out, 256);
+  w.pre_khi = o; o = b200_align_up(o + sizeof(unsigned long long) * NB, 256);
+  w.pre_keys = o; o = b200_align_up(o + sizeof(unsigned long long) * (size_t)NB * NMS_WINDOW, 256);
+  w.pre_pos = o; o = b200_align_up(o + sizeof(uint32_t) * (size_t)NB * NMS_WINDOW, 256);
   w.total = o;
   return w;
 }
+
+__global__ void __launch_bounds__(NMS_THREADS, 1) effdet_nms_pivot_kernel(NmsPreselectParams p) {
+  extern __shared__ __align__(16) unsigned char pre_smem[];
+  nms_pivot_body(p, pre_smem);
+}
+__global__ void __launch_bounds__(512) effdet_nms_pregather_kernel(NmsPreselectParams p) { nms_pregather_body(p); }
 
 extern "C" size_t b200_effdet_postprocess_workspace_bytes(int num_levels, const int32_t* hw, int A, int num_images, int max_out) {
   int n_img = 0;
@@ -513,6 +531,27 @@ extern "C" int b200_effdet_postprocess(int num_levels, const int32_t* hw, int A,
   np.cand_box = fp.cand_box; np.cand_score = fp.cand_score; np.cand_cls = fp.cand_cls; np.cand_aidx = fp.cand_aidx;
   np.counts = fp.counts; np.bitmap = fp.bitmap; np.bitmap_words = ws.bitmap_words;
   np.nms_pos = reinterpret_cast<int32_t*>(wsb + ws.pos);
+  np.pre_keys = nullptr; np.pre_pos = nullptr; np.pre_count = nullptr; np.pre_elig = nullptr; np.pre_khi = nullptr;
+  if (n_img > 32768) {
+    // large segments: several CTAs per image gather the first NMS window so the single NMS CTA does not have to
+    // scan hundreds of thousands of scores alone
+    NmsPreselectParams pp;
+    int slices = (4 * b200_sm_count() + num_images - 1) / num_images;
+    if (slices < 1) slices = 1;
+    if (slices > 32) slices = 32;
+    pp.scores = fp.cand_score; pp.order_id = fp.cand_aidx; pp.counts = fp.counts; pp.stride = n_img; pp.slices = slices;
+    pp.use_score_thr = 1; pp.score_thr = score_thr;
+    pp.keys = reinterpret_cast<unsigned long long*>(wsb + ws.pre_keys);
+    pp.pos = reinterpret_cast<uint32_t*>(wsb + ws.pre_pos);
+    pp.count = reinterpret_cast<int*>(wsb + ws.pre_count);
+    pp.eligible = reinterpret_cast<int*>(wsb + ws.pre_elig);
+    pp.khi = reinterpret_cast<unsigned long long*>(wsb + ws.pre_khi);
+    effdet_nms_pivot_kernel<<<num_images, NMS_THREADS, (size_t)NMS_PRE_SAMPLES * 8, stream>>>(pp);
+    B200_LAUNCH_CHECK();
+    effdet_nms_pregather_kernel<<<num_images * slices, 512, 0, stream>>>(pp);
+    B200_LAUNCH_CHECK();
+    np.pre_keys = pp.keys; np.pre_pos = pp.pos; np.pre_count = pp.count; np.pre_elig = pp.eligible; np.pre_khi = pp.khi;
+  }
   np.out_boxes = out_boxes; np.out_cls = out_class_id; np.out_score = out_score; np.out_sel_idx = out_sel_idx;
   np.out_sel_anchor = out_sel_anchor; np.out_count = out_count;
   size_t smem2 = nms_smem_bytes(max_out);

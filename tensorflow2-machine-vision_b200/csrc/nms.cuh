@@ -14,13 +14,11 @@
 //      key below the pivot into shared memory (if the count leaves [1024, 4096] the pivot is rescaled from the
 //      samples, then bisected on the key value — rare); a bitonic sort of the gathered window gives the exact
 //      global order of its members.  Segments with <= 4096 candidates are gathered whole;
-//   2. the window is consumed in chunks of 1024 sorted candidates; each chunk is suppressed in tiles of 64:
-//      64x64 ballot bitmask + one-warp sweep (skipped when the tile has no internal conflict), then every later
-//      candidate of the chunk tests itself against the boxes the tile emitted — for per-class NMS only against
-//      emitted boxes in its own class bucket (shared 256-entry table of 64-bit masks).  Work is
-//      O(emitted x chunk), not O(chunk^2), and stops as soon as max_out boxes are out;
-//   3. candidates of later chunks / windows are first tested against all boxes emitted so far (kept list in
-//      shared memory).
+//   2. the sorted window is consumed lazily in tiles of 64 candidates: a tile is first tested against every box
+//      emitted so far (kept list in shared memory; 64 x n_kept pairs spread over the 1024 threads), then resolved
+//      internally with a 64x64 ballot bitmask and a one-warp sweep (skipped when the tile has no internal
+//      conflict).  Only as many tiles as are needed to emit max_out boxes are touched, so the work is
+//      O(emitted^2) and independent of the window size.
 // The metric is a template parameter so each instantiation carries one metric's code (the 7-way runtime switch
 // inlined at three call sites was 150 KB of SASS and did not fit the instruction cache).
 #pragma once
@@ -32,6 +30,7 @@
 #define NMS_WINDOW 4096
 #define NMS_SAMPLES 2048
 #define NMS_TARGET 1536
+#define NMS_MIN_WIN 768   // smallest window worth accepting when more candidates remain
 #define NMS_MAX_OUT_LIMIT 4096
 
 struct NmsSegment {
@@ -40,6 +39,16 @@ struct NmsSegment {
   const int32_t* classes;    // [n] or nullptr (required for BY_CLASS)
   const uint32_t* order_id;  // [n] unique tie-break ids (ascending = earlier) or nullptr -> position
   int n;
+};
+
+// Optional pre-gathered first window of a segment (produced by nms_preselect_kernel with several CTAs per
+// segment, for segments too large for one CTA to scan quickly).  Ignored unless its counters show a valid window.
+struct NmsPre {
+  const unsigned long long* keys;  // [NMS_WINDOW]
+  const uint32_t* pos;             // [NMS_WINDOW]
+  const int* count;                // gathered (may exceed NMS_WINDOW: then invalid)
+  const int* eligible;             // eligible candidates in the whole segment
+  const unsigned long long* khi;   // pivot used
 };
 
 struct NmsConfig {
@@ -53,7 +62,7 @@ struct NmsConfig {
 
 __host__ __device__ inline size_t nms_smem_bytes(int max_out) {
   // window keys 32K + window pos 16K + samples 16K + cand 28K + class buckets 2K + kept 28B*max_out + small
-  return (size_t)NMS_WINDOW * 12 + (size_t)NMS_SAMPLES * 8 + NMS_CHUNK * 28 + 256 * 8 + (size_t)max_out * 28 + 1024;
+  return (size_t)NMS_WINDOW * 12 + (size_t)NMS_SAMPLES * 8 + NMS_CHUNK * 28 + 256 * 8 + (size_t)max_out * 32 + 1024;
 }
 
 __device__ __forceinline__ uint32_t nms_dkey(float s) {
@@ -75,7 +84,9 @@ __device__ __forceinline__ bool nms_suppresses(const BoxT& kept, int kept_cls, c
   return !(bm_metric(kept, cand, METRIC) < thr);
 }
 
-// ascending bitonic sort of sK[0..npad) (npad a power of two) with optional payload sP, whole CTA
+// ascending bitonic sort of sK[0..npad) (npad a power of two) with optional payload sP, whole CTA.
+// (A register/shuffle variant with ~3x fewer block barriers was measured slower: every element then does its own
+// compare, twice the ALU work of the pairwise exchange below, and the barriers were not the bottleneck.)
 __device__ __forceinline__ void nms_bitonic(unsigned long long* sK, uint32_t* sP, int npad) {
   for (int k = 2; k <= npad; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
@@ -99,7 +110,7 @@ __device__ __forceinline__ void nms_bitonic(unsigned long long* sK, uint32_t* sP
 // positions (0..n-1) of emitted candidates in emit order; returns the number emitted (uniform across threads).
 template <int METRIC>
 static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cfg, int32_t* __restrict__ out_pos,
-                                      unsigned char* smem_raw) {
+                                      unsigned char* smem_raw, const NmsPre* pre = nullptr) {
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
@@ -116,20 +127,23 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
   float* cAr = cC3 + NMS_CHUNK;
   float* cAt = cAr + NMS_CHUNK;
   int* cCl = reinterpret_cast<int*>(cAt + NMS_CHUNK);
-  unsigned long long* sBucket = reinterpret_cast<unsigned long long*>(cCl + NMS_CHUNK);  // [256]
-  float* kC0 = reinterpret_cast<float*>(sBucket + 256);
+  int* sHead = reinterpret_cast<int*>(cCl + NMS_CHUNK);  // [256] newest kept index per class bucket (-1 = empty)
+  int* sNextPad = sHead + 256;                            // [256] unused padding (keeps the 2 KB slot)
+  float* kC0 = reinterpret_cast<float*>(sNextPad + 256);
   float* kC1 = kC0 + cfg.max_out;
   float* kC2 = kC1 + cfg.max_out;
   float* kC3 = kC2 + cfg.max_out;
   float* kAr = kC3 + cfg.max_out;
   float* kAt = kAr + cfg.max_out;
   int* kCl = reinterpret_cast<int*>(kAt + cfg.max_out);
-  uintptr_t misc_addr = (reinterpret_cast<uintptr_t>(kCl + cfg.max_out) + 15) & ~uintptr_t(15);
+  int* kNext = kCl + cfg.max_out;  // per-class chain: previous kept index in the same bucket
+  uintptr_t misc_addr = (reinterpret_cast<uintptr_t>(kNext + cfg.max_out) + 15) & ~uintptr_t(15);
   unsigned long long* sMask = reinterpret_cast<unsigned long long*>(misc_addr);  // [64]
   uint32_t* sAlive = reinterpret_cast<uint32_t*>(sMask + 64);                    // [32]
   unsigned long long* sKeptMask = reinterpret_cast<unsigned long long*>(sAlive + 32);
   int* sScalar = reinterpret_cast<int*>(sKeptMask + 1);  // [0]=gathered [1]=eligible [2]=nk
 
+  if (tid < 256) sHead[tid] = -1;
   const int n = seg.n;
   int n_kept = 0;
   unsigned long long klo = 0ull;  // inclusive lower bound of not-yet-consumed keys
@@ -141,7 +155,9 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
     unsigned long long khi = ~0ull;   // exclusive upper bound; ~0 = everything that is left
     unsigned long long rank = 0;
     const int n_samp = (n > 65536) ? NMS_SAMPLES : NMS_SAMPLES / 2;  // rank noise only matters for huge segments
-    if (!take_all) {
+    const bool pre_ok = pre && klo == 0ull && (*pre->eligible > 0) && (*pre->count <= NMS_WINDOW) &&
+                        (*pre->count >= NMS_MIN_WIN || *pre->count >= *pre->eligible);
+    if (!take_all && !pre_ok) {
       for (int t = tid; t < n_samp; t += NMS_THREADS) {
         const int i = (int)(((long long)t * n) / n_samp);
         const float s = seg.scores[i];
@@ -158,7 +174,21 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
     }
     unsigned long long b_lo = klo, b_hi = ~0ull;  // bisection bounds: khi <= b_lo admits too few, khi >= b_hi too many
     int n_win = 0;
-    for (int attempt = 0; attempt < 80; ++attempt) {
+    bool from_pre = false;
+    if (pre && klo == 0ull) {
+      const int c = *pre->count, e = *pre->eligible;
+      if (e > 0 && c <= NMS_WINDOW && (c >= NMS_MIN_WIN || c >= e)) {
+        for (int t = tid; t < c; t += NMS_THREADS) { sK[t] = pre->keys[t]; sPos[t] = pre->pos[t]; }
+        n_win = c;
+        khi = (c >= e) ? ~0ull : *pre->khi;
+        from_pre = true;
+        __syncthreads();
+      } else if (e == 0) {
+        exhausted = true;
+        break;
+      }
+    }
+    for (int attempt = 0; attempt < 80 && !from_pre; ++attempt) {
       if (tid == 0) { sScalar[0] = 0; sScalar[1] = 0; }
       __syncthreads();
       int my_el = 0;
@@ -181,7 +211,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
       __syncthreads();
       if (e == 0) { n_win = 0; break; }
       const bool too_many = c > NMS_WINDOW;
-      const bool too_few = (c < NMS_CHUNK) && (c < e);
+      const bool too_few = (c < NMS_MIN_WIN) && (c < e);
       if (!too_many && !too_few) {
         n_win = c;
         if (c >= e) khi = ~0ull;  // the window holds everything that was left
@@ -213,41 +243,55 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
       nms_bitonic(sK, sPos, npad);
     }
 
-    // ---------------- 2. consume the window in chunks of NMS_CHUNK sorted candidates ----------------
+    // ---------------- 2. consume the window in tiles of 64 sorted candidates, lazily ----------------
+    // Only as many tiles as are needed to emit max_out boxes are ever touched: a tile is first tested against
+    // every box emitted so far (64 x n_kept pairs spread over the 1024 threads), then resolved internally with a
+    // 64x64 ballot bitmask and a one-warp sweep.  Work is O(emitted^2), independent of the window size.
     for (int w0 = 0; w0 < n_win && n_kept < cfg.max_out; w0 += NMS_CHUNK) {
       const int n_chunk = min(NMS_CHUNK, n_win - w0);
-      BoxT mine; int my_cls = 0; bool alive = false;
-      mine.c0 = mine.c1 = mine.c2 = mine.c3 = mine.area = mine.at = 0.0f;
       if (tid < n_chunk) {
         const uint32_t p = sPos[w0 + tid];
         const float4 b = __ldg(reinterpret_cast<const float4*>(seg.boxes) + p);
-        mine = bm_prep(b.x, b.y, b.z, b.w, METRIC);
-        my_cls = seg.classes ? seg.classes[p] : 0;
-        alive = true;
+        const BoxT mine = bm_prep(b.x, b.y, b.z, b.w, METRIC);
         cC0[tid] = mine.c0; cC1[tid] = mine.c1; cC2[tid] = mine.c2; cC3[tid] = mine.c3;
-        cAr[tid] = mine.area; cAt[tid] = mine.at; cCl[tid] = my_cls;
+        cAr[tid] = mine.area; cAt[tid] = mine.at; cCl[tid] = seg.classes ? seg.classes[p] : 0;
       }
-      // against everything emitted by earlier chunks / windows
-      if (alive) {
-        for (int k = 0; k < n_kept; ++k) {
-          if (mode == B200_NMS_BY_CLASS && kCl[k] != my_cls) continue;
-          BoxT kb; kb.c0 = kC0[k]; kb.c1 = kC1[k]; kb.c2 = kC2[k]; kb.c3 = kC3[k]; kb.area = kAr[k]; kb.at = kAt[k];
-          if (nms_suppresses<METRIC>(kb, kCl[k], mine, my_cls, mode, thr)) { alive = false; break; }
-        }
-      }
-      {
-        const uint32_t bal = __ballot_sync(0xffffffffu, alive);
-        if (lane == 0) sAlive[warp] = bal;
-      }
+      if (tid < 2) sAlive[tid] = 0u;
       __syncthreads();
-
       const int n_tiles = (n_chunk + 63) >> 6;
       for (int T = 0; T < n_tiles && n_kept < cfg.max_out; ++T) {
         const int t0 = T << 6;
-        const unsigned long long tile_alive =
-            (unsigned long long)sAlive[2 * T] | ((unsigned long long)sAlive[2 * T + 1] << 32);
-        if (tid < 256) sBucket[tid] = 0ull;
-        // intra-tile mask via ballots: warp w owns rows 2w, 2w+1
+        // phase 1: tile candidates vs the kept list.  warp w: candidates 32*(w&1)..+31, kept indices (w>>1) + 16 j
+        {
+          const int c = ((warp & 1) << 5) + lane;
+          const int gj = t0 + c;
+          bool supp = false;
+          if (gj < n_chunk && n_kept > 0) {
+            BoxT cb; cb.c0 = cC0[gj]; cb.c1 = cC1[gj]; cb.c2 = cC2[gj]; cb.c3 = cC3[gj]; cb.area = cAr[gj]; cb.at = cAt[gj];
+            const int ccls = cCl[gj];
+            if (mode == B200_NMS_BY_CLASS) {
+              // only emitted boxes of the same class can suppress: walk the class bucket's chain (two warps)
+              if (warp < 2) {
+                for (int k = sHead[(uint32_t)ccls & 255u]; k >= 0; k = kNext[k]) {
+                  if (kCl[k] != ccls) continue;
+                  BoxT kb; kb.c0 = kC0[k]; kb.c1 = kC1[k]; kb.c2 = kC2[k]; kb.c3 = kC3[k]; kb.area = kAr[k]; kb.at = kAt[k];
+                  if (nms_suppresses<METRIC>(kb, ccls, cb, ccls, mode, thr)) { supp = true; break; }
+                }
+              }
+            } else {
+              for (int k = warp >> 1; k < n_kept; k += 16) {
+                BoxT kb; kb.c0 = kC0[k]; kb.c1 = kC1[k]; kb.c2 = kC2[k]; kb.c3 = kC3[k]; kb.area = kAr[k]; kb.at = kAt[k];
+                if (nms_suppresses<METRIC>(kb, 0, cb, 0, mode, thr)) { supp = true; break; }
+              }
+            }
+          }
+          const uint32_t bits = __ballot_sync(0xffffffffu, supp);
+          if (lane == 0 && bits) atomicOr(&sAlive[warp & 1], bits);  // sAlive holds the SUPPRESSED bits of the tile
+        }
+        __syncthreads();
+        unsigned long long tile_alive = ~((unsigned long long)sAlive[0] | ((unsigned long long)sAlive[1] << 32));
+        if (n_chunk - t0 < 64) tile_alive &= (1ull << (n_chunk - t0)) - 1ull;
+        // phase 2: intra-tile mask via ballots: warp w owns rows 2w, 2w+1
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
           const int r = 2 * warp + rr;
@@ -303,40 +347,22 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
             }
             *sKeptMask = keptmask;
             sScalar[2] = __popcll(keptmask);
+            sAlive[0] = 0u; sAlive[1] = 0u;  // reset the suppressed bits for the next tile
           }
         }
         __syncthreads();
         const unsigned long long keptmask = *sKeptMask;
         const int nk = sScalar[2];
-        // emit; per-class: publish the emitted boxes by class bucket
-        if (tid >= t0 && tid < t0 + 64) {
-          const int r = tid - t0;
-          if ((keptmask >> r) & 1ull) {
-            const int slot = n_kept + __popcll(keptmask & ((1ull << r) - 1ull));
-            kC0[slot] = mine.c0; kC1[slot] = mine.c1; kC2[slot] = mine.c2; kC3[slot] = mine.c3;
-            kAr[slot] = mine.area; kAt[slot] = mine.at; kCl[slot] = my_cls;
-            out_pos[slot] = (int32_t)sPos[w0 + tid];
-            if (mode == B200_NMS_BY_CLASS) atomicOr(&sBucket[(uint32_t)my_cls & 255u], 1ull << r);
-          }
-          alive = false;  // tile resolved
-        }
-        if (mode == B200_NMS_BY_CLASS) __syncthreads();
-        // later candidates of the chunk against the boxes this tile emitted
-        if (tid >= t0 + 64 && alive) {
-          unsigned long long km = (mode == B200_NMS_BY_CLASS) ? (keptmask & sBucket[(uint32_t)my_cls & 255u]) : keptmask;
-          while (km) {
-            const int i = __ffsll((long long)km) - 1;
-            km &= km - 1ull;
-            const int gi = t0 + i;
-            BoxT kb; kb.c0 = cC0[gi]; kb.c1 = cC1[gi]; kb.c2 = cC2[gi]; kb.c3 = cC3[gi]; kb.area = cAr[gi]; kb.at = cAt[gi];
-            if (nms_suppresses<METRIC>(kb, cCl[gi], mine, my_cls, mode, thr)) { alive = false; break; }
-          }
+        // emit: append to the kept list
+        if (tid < 64 && ((keptmask >> tid) & 1ull)) {
+          const int gi = t0 + tid;
+          const int slot = n_kept + __popcll(keptmask & ((1ull << tid) - 1ull));
+          kC0[slot] = cC0[gi]; kC1[slot] = cC1[gi]; kC2[slot] = cC2[gi]; kC3[slot] = cC3[gi];
+          kAr[slot] = cAr[gi]; kAt[slot] = cAt[gi]; kCl[slot] = cCl[gi];
+          out_pos[slot] = (int32_t)sPos[w0 + gi];
+          if (mode == B200_NMS_BY_CLASS) kNext[slot] = atomicExch(&sHead[(uint32_t)cCl[gi] & 255u], slot);
         }
         n_kept += nk;
-        {
-          const uint32_t bal = __ballot_sync(0xffffffffu, alive);
-          if (lane == 0) sAlive[warp] = bal;
-        }
         __syncthreads();
       }
       __syncthreads();
@@ -346,6 +372,100 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
     __syncthreads();
   }
   return n_kept;
+}
+
+// ---- multi-CTA pre-selection of the first window ---------------------------------------------------------
+struct NmsPreselectParams {
+  const float* scores;          // [num_segments, stride]
+  const uint32_t* order_id;     // [num_segments, stride] or nullptr
+  const int32_t* counts;        // [num_segments] candidates per segment
+  int stride;                   // elements between segments
+  int slices;                   // CTAs per segment
+  int use_score_thr; float score_thr;
+  unsigned long long* keys; uint32_t* pos;  // [num_segments, NMS_WINDOW]
+  int* count; int* eligible; unsigned long long* khi;  // [num_segments] (count/eligible zeroed by the caller)
+};
+
+#define NMS_PRE_SAMPLES 4096
+#define NMS_PRE_TARGET 1536
+
+// One CTA per segment: pivot = the sample whose rank should admit ~NMS_PRE_TARGET candidates (4096 strided samples,
+// so the admitted count has a relative spread of ~1/sqrt(rank) and stays inside [1024, 4096] with high probability).
+static __device__ void nms_pivot_body(const NmsPreselectParams& p, unsigned char* smem_raw) {
+  unsigned long long* sS = reinterpret_cast<unsigned long long*>(smem_raw);  // [NMS_PRE_SAMPLES]
+  const int tid = threadIdx.x;
+  const int seg = blockIdx.x;
+  const int n = p.counts[seg];
+  const float* scores = p.scores + (size_t)seg * p.stride;
+  const uint32_t* oid_base = p.order_id ? p.order_id + (size_t)seg * p.stride : nullptr;
+  unsigned long long khi = ~0ull;
+  if (n > NMS_WINDOW) {
+    // enough samples for a pivot rank of >= ~32 (relative spread of the admitted count <= ~18 %)
+    int ns = 512;
+    while (ns < NMS_PRE_SAMPLES && (long long)ns * NMS_PRE_TARGET < 32ll * n) ns <<= 1;
+    for (int t = tid; t < ns; t += NMS_THREADS) {
+      const int i = (int)(((long long)t * n) / ns);
+      const float s = scores[i];
+      const uint32_t oid = oid_base ? oid_base[i] : (uint32_t)i;
+      const unsigned long long K = ((unsigned long long)nms_dkey(s) << 32) | oid;
+      sS[t] = (p.use_score_thr && (s < p.score_thr)) ? ~0ull : K;
+    }
+    __syncthreads();
+    nms_bitonic(sS, nullptr, ns);
+    unsigned long long rank = ((unsigned long long)NMS_PRE_TARGET * (unsigned long long)ns) / (unsigned long long)n;
+    if (rank < 2ull) rank = 2ull;
+    khi = rank >= (unsigned long long)ns ? ~0ull : sS[rank];
+  }
+  if (tid == 0) p.khi[seg] = khi;
+}
+
+// `slices` CTAs per segment: each scans its slice (4 independent loads in flight per thread) and appends the eligible
+// keys below the pivot to the segment's window in global memory with warp-aggregated atomics.
+static __device__ void nms_pregather_body(const NmsPreselectParams& p) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int seg = blockIdx.x / p.slices, slice = blockIdx.x - seg * p.slices;
+  const int n = p.counts[seg];
+  const float* scores = p.scores + (size_t)seg * p.stride;
+  const uint32_t* oid_base = p.order_id ? p.order_id + (size_t)seg * p.stride : nullptr;
+  const unsigned long long khi = p.khi[seg];
+  const int lo = (int)(((long long)slice * n) / p.slices), hi = (int)(((long long)(slice + 1) * n) / p.slices);
+  int my_el = 0;
+  const int T = blockDim.x;
+  for (int i0 = lo; i0 < hi; i0 += 4 * T) {
+    float sv[4]; uint32_t ov[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * T + tid;
+      sv[u] = (i < hi) ? scores[i] : 0.0f;
+      ov[u] = (i < hi) ? (oid_base ? oid_base[i] : (uint32_t)i) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * T + tid;
+      bool take = false;
+      unsigned long long K = 0ull;
+      if (i < hi && !(p.use_score_thr && (sv[u] < p.score_thr))) {
+        K = ((unsigned long long)nms_dkey(sv[u]) << 32) | ov[u];
+        ++my_el;
+        take = (khi == ~0ull) || (K < khi);
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, take);
+      if (bal) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&p.count[seg], __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (take) {
+          const int slot = base + __popc(bal & ((1u << lane) - 1u));
+          if (slot < NMS_WINDOW) {
+            p.keys[(size_t)seg * NMS_WINDOW + slot] = K;
+            p.pos[(size_t)seg * NMS_WINDOW + slot] = (uint32_t)i;
+          }
+        }
+      }
+    }
+  }
+  my_el = warp_sum_i(my_el);
+  if (lane == 0 && my_el) atomicAdd(&p.eligible[seg], my_el);
 }
 
 // runs CALL(METRIC) with the runtime metric as a compile-time constant
