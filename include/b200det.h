@@ -131,6 +131,19 @@ int b200_yolo_assign_targets(const float* boxes, const int32_t* classes, const i
                              const int32_t hw[6], float* const targets[3], int zero_fill, void* stream);
 int b200_fill_zero(float* dst, size_t n, void* stream);
 
+/* tf.boolean_mask (row-major order preserved): flags[n] bytes -> pos[n] = exclusive prefix of the flags, *total =
+ * number of set flags (device int).  gather_rows copies the flagged rows of src [n,row_floats] to dst[pos[i]].
+ * Used by GetBoxes (tyu:163-166) and GetGroudTruth. */
+size_t b200_row_positions_workspace_bytes(long long n);
+int b200_row_positions(const unsigned char* flags, long long n, int* pos, int* total, void* workspace,
+                       size_t workspace_bytes, void* stream);
+int b200_gather_rows(const float* src, int row_floats, const unsigned char* flags, const int* pos, long long n,
+                     float* dst, void* stream);
+/* GetGroudTruth (yolo_v4/model.py:380-395) before the boolean_mask: for every record of a dense target
+ * y (…,5+C): rows[i] = [x-w/2, y-h/2, x+w/2, y+h/2, argmax(classes)], flags[i] = (conf != 0). */
+int b200_yolo_ground_truth_rows(const float* y, long long n_records, int C, float* rows, unsigned char* flags,
+                                void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * EfficientDet (efficientnet/utils/anchors.py, iou.py, nms.py; losses/focal_loss.py, box_loss.py;
  * efficientnet/efficientdet_net_train.py:41-52).  Levels are described by hw = {H0,W0,H1,W1,...} and A anchors

@@ -39,8 +39,42 @@ def GetBoxes(y, anchors_wh, classes_num):
   valid = torch.empty((n,), dtype=torch.uint8, device=y.device)
   _lib.check(lib.b200_yolo_decode_dense(T.ptr(y), B, H, W, A, C, T.ptr(anc), T.ptr(boxes), T.ptr(conf),
                                         T.ptr(classes), T.ptr(valid), T.stream_ptr()), 'GetBoxes')
-  keep = valid.bool()  # order-preserving row selection (device-side plumbing, like tf.boolean_mask)
-  return boxes[keep], conf[keep], classes[keep]
+  return _compact_rows(valid, [boxes, conf, classes])
+
+
+def _compact_rows(flags, arrays):
+  '''tf.boolean_mask over rows, order preserved: flags (n,) uint8, arrays of shape (n, k_i).'''
+  lib = _lib.load()
+  n = flags.numel()
+  dev = flags.device
+  pos = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
+  total = torch.zeros((1,), dtype=torch.int32, device=dev)
+  ws_bytes = lib.b200_row_positions_workspace_bytes(n)
+  ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+  _lib.check(lib.b200_row_positions(T.ptr(flags), n, T.ptr(pos), T.ptr(total), T.ptr(ws), ws_bytes, T.stream_ptr()),
+             'boolean_mask')
+  k = int(total.item())
+  out = []
+  for a in arrays:
+    rf = a.shape[1]
+    d = torch.empty((k, rf), dtype=torch.float32, device=dev)
+    if k:
+      _lib.check(lib.b200_gather_rows(T.ptr(a), rf, T.ptr(flags), T.ptr(pos), n, T.ptr(d), T.stream_ptr()), 'boolean_mask')
+    out.append(d)
+  return tuple(out)
+
+
+def GetGroudTruth(y, classes_num=None):
+  '''yolo_v4/model.py:380-395: dense target (…, 5+C) -> (n, 5) rows [x1, y1, x2, y2, class] of the records with
+  conf != 0, in row-major order (the mAP input).'''
+  lib = _lib.load()
+  y = T.to_cuda(y)
+  C = y.shape[-1] - 5 if classes_num is None else int(classes_num)
+  n = y.numel() // (5 + C)
+  rows = torch.empty((n, 5), dtype=torch.float32, device=y.device)
+  flags = torch.empty((n,), dtype=torch.uint8, device=y.device)
+  _lib.check(lib.b200_yolo_ground_truth_rows(T.ptr(y), n, C, T.ptr(rows), T.ptr(flags), T.stream_ptr()), 'GetGroudTruth')
+  return _compact_rows(flags, [rows])[0]
 
 
 def _levels(y1, y2, y3, anchors_wh):

@@ -142,3 +142,35 @@ def test_ignore_mask_stress_bit_exact(lib, cuda, iou_type, thr, sigma):
     assert int((want_ign == 0).sum()) > 20
     if np.isfinite(want):
         assert abs(float(got) - float(want)) <= LOSS_RTOL * abs(float(want))
+
+
+def test_get_ground_truth_and_boolean_mask_order(lib, cuda):
+    """yolo_v4/model.py:380-395 GetGroudTruth: rows in row-major order, corners bit-exact, class = first argmax."""
+    from oracle import yolo as oy
+    from tfmv_b200 import synth
+    from tfmv_b200.ai_models.utils.tf_yolo_utils import GetGroudTruth
+    rng = np.random.default_rng(13)
+    anc = (synth.yolo_anchors().astype(F) / F(416)).astype(F)
+    _, _, _, y_true = _dense_targets(rng, 3, 416, synth.yolo_anchors().astype(F), normalised_anchors=True)
+    for l in range(3):
+        want = oy.get_ground_truth(y_true[l])
+        got = GetGroudTruth(_t(y_true[l], cuda)).cpu().numpy()
+        assert got.shape == want.shape
+        assert_bits_equal(got, want)
+    empty = GetGroudTruth(_t(np.zeros((1, 13, 13, 3, 85), F), cuda))
+    assert tuple(empty.shape) == (0, 5)
+
+
+def test_class_focal_loss_variant(lib, cuda):
+    """losses/class_loss.py:25-60 ClassFocalLoss (demo-only variant): per level sum / (sum(mask)/B), divide_no_nan."""
+    from oracle import effdet as oe
+    from tfmv_b200.ai_models.losses.class_loss import ClassFocalLoss
+    rng = np.random.default_rng(17)
+    shapes = [(4, 8, 8, 9, 11), (4, 4, 4, 9, 11), (4, 2, 2, 9, 11)]
+    tc = [(rng.random(s) < 0.05).astype(F) for s in shapes]
+    pc = [rng.standard_normal(s).astype(F) for s in shapes]
+    tm = [(rng.random(s[:-1] + (1,)) < 0.1) for s in shapes]
+    tm[2][:] = False   # normalizer 0 -> divide_no_nan -> that level contributes 0
+    want = oe.class_focal_loss(tc, pc, tm, 0.25, 1.5)
+    got = ClassFocalLoss(0.25, 1.5)([_t(t, cuda) for t in tc], ([_t(p, cuda) for p in pc], [_t(m, cuda) for m in tm]))
+    assert abs(float(got) - float(want)) <= LOSS_RTOL * abs(float(want))
