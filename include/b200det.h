@@ -123,6 +123,16 @@ int b200_yolo_loss(const float* const y_true[3], const float* const y_pred[3], c
                    int variant, float batch_divisor, float* out_parts, float* out_loss, unsigned char* out_ignore,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* GetLoss forward + analytic backward (tf.GradientTape differentiates GetLoss in train_step,
+ * yolo_v4/model.py:318-338): out_grad[l] (B,H_l,W_l,A*(5+C)) = d loss / d y_pred[l] for an upstream gradient of 1
+ * (d/dt_xy = obj*scale*(sigmoid(t)-raw_xy)/B, d/dt_wh = obj*scale*(t-raw_wh)/B, d/dconf = (sigmoid(p)-obj)*
+ * (obj+(1-obj)*ignore)/B, d/dcls = obj*(sigmoid(c)-t_cls)/B; no gradient through targets or the ignore mask).
+ * Same workspace size as b200_yolo_loss. */
+int b200_yolo_loss_grad(const float* const y_true[3], const float* const y_pred[3], const int32_t hw[6], int B, int A,
+                        int C, const float* anchors_wh_host, const float* image_wh_host, float iou_thresh, int metric,
+                        int variant, float batch_divisor, float* out_parts, float* out_loss, float* const out_grad[3],
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* DataGenerator.GetTargets (datasets/coco_dataset.py:185-285), batched: boxes [total,4] pixel corners
  * x1,y1,x2,y2, classes [total] int32, offsets [B+1] int32 (all device).  targets[l]: (B,H_l,W_l,A,5+C), zeroed
  * here when zero_fill != 0.  Boxes whose cell falls outside the grid are skipped (tf.scatter_nd would raise). */

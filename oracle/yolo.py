@@ -375,3 +375,71 @@ def get_ground_truth(y):
     m = conf != 0
     cls = np.argmax(y[..., 5:][m], axis=-1).astype(F)[:, None] if m.any() else np.zeros((0, 1), F)
     return np.concatenate([boxes[m], cls], axis=-1)
+
+
+# --------------------------------------------------------------------------------------------
+def get_loss_grad(y_true, y_pred, image_wh, anchors_wh, iou_thresh=0.5, iou_type="iou"):
+    """d GetLoss / d y_pred — what tf.GradientTape derives from utils/tf_yolo_utils.py:6-127
+    (BCE-with-logits: sigmoid(x) - z; no gradient through the targets or the boolean ignore mask).
+    Returns (loss, [grad_l shaped like y_true[l]]).  Checked against fp64 central differences in
+    tests/test_oracle_pins.py::test_loss_gradient_matches_finite_differences."""
+    image_wh_f = np.asarray(image_wh, F)
+    anchors_wh_f = np.asarray(anchors_wh, F)
+    loss, _, ign = get_loss(y_true, y_pred, image_wh, anchors_wh, iou_thresh, iou_type, return_ignore=True)
+    bsz = np.asarray(y_true[0]).shape[0]
+    bf = F(bsz)
+    grads = []
+    base = 0
+    for l in range(3):
+        yt = np.asarray(y_true[l], F)
+        yp = np.asarray(y_pred[l], F).reshape(yt.shape)
+        h, w = yt.shape[1], yt.shape[2]
+        n_l = h * w * yt.shape[3]
+        ig = ign[:, base:base + n_l].reshape(yt.shape[:4] + (1,)).astype(F)
+        base += n_l
+        grid = grid_meshgrid(h, w)
+        grid_wh = np.array([w, h], dtype=F)
+        obj = yt[..., 4:5]
+        raw_xy = obj * (yt[..., 0:2] * grid_wh - grid)
+        with np.errstate(all="ignore"):
+            raw_wh = dm.log((yt[..., 2:4] * image_wh_f[::-1] + F(1e-8)) / anchors_wh_f[l])
+        raw_wh = np.where(obj.astype(bool), raw_wh, F(0.0))
+        scale = F(2) - yt[..., 2:3] * yt[..., 3:4]
+        sig = dm.sigmoid(yp)
+        g = np.zeros_like(yp)
+        g[..., 0:2] = obj * scale * (sig[..., 0:2] - raw_xy) / bf
+        g[..., 2:4] = obj * scale * (yp[..., 2:4] - raw_wh) / bf
+        g[..., 4:5] = (sig[..., 4:5] - obj) * (obj + (F(1) - obj) * ig) / bf
+        g[..., 5:] = obj * (sig[..., 5:] - yt[..., 5:]) / bf
+        grads.append(g)
+    return loss, grads
+
+
+def loss_fp64_fixed_ignore(y_true, y_pred, image_wh, anchors_wh, ignore):
+    """The same loss in float64 with the ignore mask held fixed — the differentiable function whose finite
+    differences pin get_loss_grad."""
+    image_wh_d = np.asarray(image_wh, np.float64)
+    total = 0.0
+    bsz = np.asarray(y_true[0]).shape[0]
+    base = 0
+    for l in range(3):
+        yt = np.asarray(y_true[l], np.float64)
+        yp = np.asarray(y_pred[l], np.float64).reshape(yt.shape)
+        h, w = yt.shape[1], yt.shape[2]
+        n_l = h * w * yt.shape[3]
+        ig = ignore[:, base:base + n_l].reshape(yt.shape[:4] + (1,)).astype(np.float64)
+        base += n_l
+        grid = grid_meshgrid(h, w).astype(np.float64)
+        obj = yt[..., 4:5]
+        raw_xy = obj * (yt[..., 0:2] * np.array([w, h], np.float64) - grid)
+        with np.errstate(all="ignore"):
+            raw_wh = np.log((yt[..., 2:4] * image_wh_d[::-1] + 1e-8) / np.asarray(anchors_wh, np.float64)[l])
+        raw_wh = np.where(obj != 0, raw_wh, 0.0)
+        scale = 2.0 - yt[..., 2:3] * yt[..., 3:4]
+        bce = lambda z, x: np.maximum(x, 0) - x * z + np.log1p(np.exp(-np.abs(x)))
+        xy = obj * scale * bce(raw_xy, yp[..., 0:2])
+        wh = obj * scale * 0.5 * (raw_wh - yp[..., 2:4]) ** 2
+        ob = obj * bce(obj, yp[..., 4:5]) + (1 - obj) * bce(obj, yp[..., 4:5]) * ig
+        cl = obj * bce(yt[..., 5:], yp[..., 5:])
+        total += (xy.sum() + wh.sum() + ob.sum() + cl.sum()) / bsz
+    return total

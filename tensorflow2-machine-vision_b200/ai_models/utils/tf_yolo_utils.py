@@ -157,7 +157,7 @@ def GetNMSBoxes(y1, y2, y3, anchors_wh, image_wh, classes_num,
 
 
 def _loss_call(y_true, y_pred, image_wh, anchors_wh, iou_thresh, iou_type, variant, batch_divisor=None,
-               return_parts=False, workspace=None, ignore_out=None):
+               return_parts=False, workspace=None, ignore_out=None, with_grad=False):
   lib = _lib.load()
   if len(y_true) != 3 or len(y_pred) != 3:
     raise ValueError('y_true and y_pred must each hold 3 levels')
@@ -185,6 +185,14 @@ def _loss_call(y_true, y_pred, image_wh, anchors_wh, iou_thresh, iou_type, varia
   if workspace is None or workspace.numel() < ws_bytes:
     workspace = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
   div = float(B if batch_divisor is None else batch_divisor)
+  if with_grad:
+    grads = [torch.empty_like(t) for t in yp]
+    gp = (ctypes.c_void_p * 3)(*[t.data_ptr() for t in grads])
+    _lib.check(lib.b200_yolo_loss_grad(tp, pp, hw, B, A, RF - 5, anc.ctypes.data_as(ctypes.c_void_p),
+                                       img.ctypes.data_as(ctypes.c_void_p), float(iou_thresh),
+                                       _lib.METRIC_YOLO[iou_type], variant, div, T.ptr(parts), T.ptr(loss), gp,
+                                       T.ptr(workspace), ws_bytes, T.stream_ptr()), 'GetLoss')
+    return loss, parts, grads
   _lib.check(lib.b200_yolo_loss(tp, pp, hw, B, A, RF - 5, anc.ctypes.data_as(ctypes.c_void_p),
                                 img.ctypes.data_as(ctypes.c_void_p), float(iou_thresh), _lib.METRIC_YOLO[iou_type],
                                 variant, div, T.ptr(parts), T.ptr(loss), T.ptr(ignore_out), T.ptr(workspace), ws_bytes,
@@ -207,6 +215,14 @@ def GetLoss(y_true, y_pred, image_wh, anchors_wh, iou_thresh=0.5, iou_type='iou'
   '''
   assert iou_type in ['iou','diou','ciou']
   return _loss_call(y_true, y_pred, image_wh, anchors_wh, iou_thresh, iou_type, 0)
+
+
+def GetLossAndGrad(y_true, y_pred, image_wh, anchors_wh, iou_thresh=0.5, iou_type='iou'):
+  '''GetLoss plus d loss / d y_pred (list of 3 tensors shaped like y_pred) for an upstream gradient of 1 —
+  what tf.GradientTape derives from the reference's GetLoss.  Wrap with tf.custom_gradient.'''
+  assert iou_type in ['iou','diou','ciou']
+  loss, _, grads = _loss_call(y_true, y_pred, image_wh, anchors_wh, iou_thresh, iou_type, 0, with_grad=True)
+  return loss, grads
 
 
 def combine_loss_parts(parts, group=None):

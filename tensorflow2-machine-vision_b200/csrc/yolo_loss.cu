@@ -54,6 +54,9 @@ struct YlParams {
   float logk[YL_LEVELS][8];  // log(anchor_w*anchor_h/(img_w*img_h)) per level/anchor
   float tmin_w[YL_LEVELS][8], tmin_h[YL_LEVELS][8];  // lowest tw/th for which the decode-free area bound holds
   uint32_t magic_a;           // floor(2^32/A)+1: n/A == umulhi(n, magic) for n*A < 2^32
+  float* conf_grad;           // optional [level-major: B*anchor_base[l] + image*rec_per_img + rin]: d loss / d conf logit
+  int32_t* obj_index;         // optional [B, n_img]: record index of each GT-list slot (backward pass)
+  float inv_div;              // 1 / batch_divisor
   unsigned char* out_ignore;  // optional [B, n_img]: the ignore mask (1 = ignored/background), for parity tests
   int32_t* gt_count;    // [B, 3]
   double* partials;     // [n_cta]      object_loss partial of each ignore-kernel CTA
@@ -154,6 +157,7 @@ __global__ void __launch_bounds__(YL_CHUNK) yolo_loss_objects_kernel(YlParams p)
       const size_t gi = (size_t)img * p.n_img + p.lv.anchor_base[l] + slot;
       p.gt_box[gi] = make_float4(g.c0, g.c1, g.c2, g.c3);
       p.gt_aux[gi] = make_float4(g.area, g.at, dm_logf(g.area), yl_regular(g) ? 1.0f : 0.0f);
+      if (p.obj_index) p.obj_index[gi] = r;
     }
   }
   if (lane == 0) { s_acc[warp][0] = a_xy; s_acc[warp][1] = a_wh; s_acc[warp][2] = a_cls; }
@@ -342,6 +346,13 @@ __global__ void __launch_bounds__(YL_ICHUNK, 10) yolo_loss_ignore_kernel(YlParam
     const float ign = hit ? 0.0f : 1.0f;
     if (p.out_ignore) p.out_ignore[(size_t)img * p.n_img + p.lv.anchor_base[l] + rin] = hit ? 0 : 1;
     e = obj * bc + (1.0f - obj) * bc * ign;  // tyu:114
+    if (p.conf_grad) {
+      // d/dp [obj*bce + (1-obj)*bce*ignore] = (sigmoid(p) - obj) * (obj + (1-obj)*ignore); the mask has no gradient
+      const float ex = __expf(-fabsf(pobj));
+      const float rr = 1.0f / (1.0f + ex);
+      const float sg = pobj >= 0.0f ? rr : ex * rr;
+      p.conf_grad[(size_t)p.B * p.lv.anchor_base[l] + (size_t)img * rpi + rin] = (sg - obj) * (obj + (1.0f - obj) * ign) * p.inv_div;
+    }
   }
   e = warp_sum(e);  // 32 fp32 terms; the cross-warp and cross-CTA sums are fp64
   if (lane == 0) s_acc[warp] = (double)e;
@@ -400,8 +411,89 @@ __global__ void __launch_bounds__(1024) yolo_loss_finalize_kernel(YlFinalize f) 
   }
 }
 
+// ---- backward: d loss / d y_pred ----------------------------------------------------------
+// GetLoss is differentiated by tf.GradientTape in train_step (yolo_v4/model.py:318-338).  With BCE-with-logits
+// d/dx = sigmoid(x) - z, and no gradient through the targets or the (boolean) ignore mask:
+//   d/dt_xy  = obj*scale*(sigmoid(t) - raw_xy)/B      d/dt_wh = obj*scale*(t - raw_wh)/B
+//   d/dconf  = (sigmoid(p) - obj)*(obj + (1-obj)*ignore)/B      d/dcls = obj*(sigmoid(c) - t_cls)/B
+// The gradient tensor is dense like y_pred (7.7 MB/image at 608x608) but only the conf channel of every record and
+// the full record of object cells are non-zero: one streaming write pass (conf values saved by the forward ignore
+// kernel, 4 bytes/record) plus one warp per object record.
+struct YlGradDense {
+  float4* grad[YL_LEVELS];
+  const float* conf_grad[YL_LEVELS];
+  unsigned long long n_vec[YL_LEVELS];  // cumulative float4 counts
+  unsigned long long n_floats[YL_LEVELS];  // floats per level (the last n%4 are written as scalars)
+  int RF;
+};
+
+__global__ void __launch_bounds__(256) yolo_loss_grad_dense_kernel(YlGradDense g) {
+  const unsigned long long total = g.n_vec[YL_LEVELS - 1];
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int l = 0;
+    unsigned long long v = i;
+    if (i >= g.n_vec[1]) { l = 2; v = i - g.n_vec[1]; } else if (i >= g.n_vec[0]) { l = 1; v = i - g.n_vec[0]; }
+    const unsigned long long e0 = v * 4ull;
+    unsigned long long rec = e0 / (unsigned long long)g.RF;
+    int c = (int)(e0 - rec * (unsigned long long)g.RF);
+    float out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      out[k] = (c == 4) ? __ldg(g.conf_grad[l] + rec) : 0.0f;
+      if (++c == g.RF) { c = 0; ++rec; }
+    }
+    __stcs(g.grad[l] + v, make_float4(out[0], out[1], out[2], out[3]));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 4 * YL_LEVELS) {  // scalar tails (element counts that are not multiples of 4)
+    const int l = threadIdx.x >> 2, k = threadIdx.x & 3;
+    const unsigned long long e = (g.n_floats[l] & ~3ull) + (unsigned long long)k;
+    if (e < g.n_floats[l]) {
+      const unsigned long long rec = e / (unsigned long long)g.RF;
+      const int c = (int)(e - rec * (unsigned long long)g.RF);
+      reinterpret_cast<float*>(g.grad[l])[e] = (c == 4) ? g.conf_grad[l][rec] : 0.0f;
+    }
+  }
+}
+
+// one CTA per (image, level): a warp per object record overwrites channels 0-3 and 5.. of that record
+__global__ void __launch_bounds__(256) yolo_loss_grad_objects_kernel(YlParams p, float* g0, float* g1, float* g2) {
+  const int img = blockIdx.x / YL_LEVELS, l = blockIdx.x - img * YL_LEVELS;
+  float* grad = (l == 0 ? g0 : l == 1 ? g1 : g2);
+  const int n = p.gt_count[img * YL_LEVELS + l];
+  const int rpi = p.lv.rec_per_img[l];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int W = p.lv.w[l], H = p.lv.h[l];
+  const float* yt = p.lv.y_true[l] + ((size_t)img * rpi) * p.RF;
+  const float* yp = p.lv.y_pred[l] + ((size_t)img * rpi) * p.RF;
+  float* gr = grad + ((size_t)img * rpi) * p.RF;
+  for (int k = warp; k < n; k += 8) {
+    const int r = p.obj_index[(size_t)img * p.n_img + p.lv.anchor_base[l] + k];
+    const float* t = yt + (size_t)r * p.RF;
+    const float* q = yp + (size_t)r * p.RF;
+    float* o = gr + (size_t)r * p.RF;
+    const float obj = __ldg(t + 4);
+    const float tx = __ldg(t), ty = __ldg(t + 1), tw = __ldg(t + 2), th = __ldg(t + 3);
+    const float os = (obj * (2.0f - tw * th)) * p.inv_div;
+    if (lane < 2) {
+      const int cell = r / p.A;
+      const int gy = cell / W, gx = cell - gy * W;
+      float raw = (lane == 0 ? tx * (float)W - (float)gx : ty * (float)H - (float)gy);
+      if (p.variant == YL_VARIANT_TF_YOLO_UTILS) raw = obj * raw;
+      o[lane] = os * (dm_sigmoidf(__ldg(q + lane)) - raw);
+    } else if (lane < 4) {
+      const int a = r - (r / p.A) * p.A;
+      float num = (lane == 2 ? tw * p.img_w : th * p.img_h);
+      if (p.variant == YL_VARIANT_TF_YOLO_UTILS) num += 1e-8f;
+      const float raw = dm_logf(num / (lane == 2 ? p.lv.anc_w[l][a] : p.lv.anc_h[l][a]));
+      o[lane] = os * (__ldg(q + lane) - raw);
+    }
+    for (int c = 5 + lane; c < p.RF; c += 32) o[c] = (obj * p.inv_div) * (dm_sigmoidf(__ldg(q + c)) - __ldg(t + c));
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------
-struct YlWs { size_t obj, gt, gtl, cnt, part, part_obj, total; int n_cta, n_cta_obj; };
+struct YlWs { size_t obj, gt, gtl, cnt, part, part_obj, cgrad, oidx, total; int n_cta, n_cta_obj; };
 
 static YlWs yl_layout(const int32_t hw[6], int B, int A, int* n_img_out, YlLevels* lv) {
   YlWs w;
@@ -430,6 +522,8 @@ static YlWs yl_layout(const int32_t hw[6], int B, int A, int* n_img_out, YlLevel
   w.gtl = o; o = b200_align_up(o + sizeof(float4) * (size_t)B * n_img, 256);
   w.part = o; o = b200_align_up(o + sizeof(double) * (size_t)cta, 256);
   w.part_obj = o; o = b200_align_up(o + sizeof(double) * 3 * (size_t)octa, 256);
+  w.cgrad = o; o = b200_align_up(o + sizeof(float) * (size_t)B * n_img, 256);
+  w.oidx = o; o = b200_align_up(o + sizeof(int32_t) * (size_t)B * n_img, 256);
   w.total = o;
   return w;
 }
@@ -438,11 +532,11 @@ extern "C" size_t b200_yolo_loss_workspace_bytes(const int32_t hw[6], int B, int
   return yl_layout(hw, B, A, nullptr, nullptr).total;
 }
 
-extern "C" int b200_yolo_loss(const float* const y_true[3], const float* const y_pred[3], const int32_t hw[6], int B,
-                              int A, int C, const float* anchors_wh_host, const float* image_wh_host,
-                              float iou_thresh, int metric, int variant, float batch_divisor, float* out_parts,
-                              float* out_loss, unsigned char* out_ignore, void* workspace, size_t workspace_bytes,
-                              void* stream_) {
+static int yolo_loss_impl(const float* const y_true[3], const float* const y_pred[3], const int32_t hw[6], int B,
+                          int A, int C, const float* anchors_wh_host, const float* image_wh_host,
+                          float iou_thresh, int metric, int variant, float batch_divisor, float* out_parts,
+                          float* out_loss, unsigned char* out_ignore, float* const out_grad[3], void* workspace,
+                          size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_REQUIRE(y_true && y_pred && hw && anchors_wh_host && image_wh_host && out_loss, B200_ERR_BAD_ARG, "b200_yolo_loss: null argument");
   B200_REQUIRE(B >= 1 && A >= 1 && A <= 8 && C >= 0, B200_ERR_BAD_ARG, "b200_yolo_loss: unsupported shape B=%d A=%d C=%d", B, A, C);
@@ -483,6 +577,9 @@ extern "C" int b200_yolo_loss(const float* const y_true[3], const float* const y
       p.tmin_h[l][a] = (float)(th > -6.0 ? th : -6.0);
     }
   p.out_ignore = out_ignore;
+  p.inv_div = 1.0f / batch_divisor;
+  p.conf_grad = out_grad ? reinterpret_cast<float*>(wsb + ws.cgrad) : nullptr;
+  p.obj_index = out_grad ? reinterpret_cast<int32_t*>(wsb + ws.oidx) : nullptr;
   p.magic_a = A == 1 ? 0u : (uint32_t)((1ull << 32) / (unsigned long long)A + 1ull);
   for (int l = 0; l < YL_LEVELS; ++l) p.lv.magic_w[l] = p.lv.w[l] == 1 ? 0u : (uint32_t)((1ull << 32) / (unsigned long long)p.lv.w[l] + 1ull);
   p.gt_count = reinterpret_cast<int32_t*>(wsb + ws.cnt);
@@ -499,5 +596,45 @@ extern "C" int b200_yolo_loss(const float* const y_true[3], const float* const y
   f.batch_divisor = batch_divisor; f.parts = out_parts; f.loss = out_loss;
   yolo_loss_finalize_kernel<<<1, 1024, 0, stream>>>(f);
   B200_LAUNCH_CHECK();
+  if (out_grad) {
+    YlGradDense g;
+    g.RF = p.RF;
+    unsigned long long cum = 0;
+    for (int l = 0; l < YL_LEVELS; ++l) {
+      B200_REQUIRE(out_grad[l] && (reinterpret_cast<uintptr_t>(out_grad[l]) & 15) == 0, B200_ERR_BAD_ARG, "b200_yolo_loss_grad: grad level %d null or not 16-byte aligned", l);
+      const unsigned long long nfl = (unsigned long long)B * p.lv.rec_per_img[l] * p.RF;
+      g.n_floats[l] = nfl;
+      g.grad[l] = reinterpret_cast<float4*>(out_grad[l]);
+      g.conf_grad[l] = p.conf_grad + (size_t)B * p.lv.anchor_base[l];
+      cum += nfl / 4ull;
+      g.n_vec[l] = cum;
+    }
+    unsigned long long blocks = (cum + 255) / 256;
+    const unsigned long long cap = (unsigned long long)b200_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    yolo_loss_grad_dense_kernel<<<(int)blocks, 256, 0, stream>>>(g);
+    B200_LAUNCH_CHECK();
+    yolo_loss_grad_objects_kernel<<<B * YL_LEVELS, 256, 0, stream>>>(p, out_grad[0], out_grad[1], out_grad[2]);
+    B200_LAUNCH_CHECK();
+  }
   return B200_OK;
+}
+
+extern "C" int b200_yolo_loss(const float* const y_true[3], const float* const y_pred[3], const int32_t hw[6], int B,
+                              int A, int C, const float* anchors_wh_host, const float* image_wh_host,
+                              float iou_thresh, int metric, int variant, float batch_divisor, float* out_parts,
+                              float* out_loss, unsigned char* out_ignore, void* workspace, size_t workspace_bytes,
+                              void* stream_) {
+  return yolo_loss_impl(y_true, y_pred, hw, B, A, C, anchors_wh_host, image_wh_host, iou_thresh, metric, variant,
+                        batch_divisor, out_parts, out_loss, out_ignore, nullptr, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int b200_yolo_loss_grad(const float* const y_true[3], const float* const y_pred[3], const int32_t hw[6],
+                                   int B, int A, int C, const float* anchors_wh_host, const float* image_wh_host,
+                                   float iou_thresh, int metric, int variant, float batch_divisor, float* out_parts,
+                                   float* out_loss, float* const out_grad[3], void* workspace, size_t workspace_bytes,
+                                   void* stream_) {
+  B200_REQUIRE(out_grad, B200_ERR_BAD_ARG, "b200_yolo_loss_grad: null out_grad");
+  return yolo_loss_impl(y_true, y_pred, hw, B, A, C, anchors_wh_host, image_wh_host, iou_thresh, metric, variant,
+                        batch_divisor, out_parts, out_loss, nullptr, out_grad, workspace, workspace_bytes, stream_);
 }

@@ -174,3 +174,32 @@ def test_class_focal_loss_variant(lib, cuda):
     want = oe.class_focal_loss(tc, pc, tm, 0.25, 1.5)
     got = ClassFocalLoss(0.25, 1.5)([_t(t, cuda) for t in tc], ([_t(p, cuda) for p in pc], [_t(m, cuda) for m in tm]))
     assert abs(float(got) - float(want)) <= LOSS_RTOL * abs(float(want))
+
+
+@pytest.mark.parametrize("image,batch,iou_type", [(416, 2, "ciou"), (96, 5, "iou"), (608, 2, "ciou")])
+def test_get_loss_gradient_matches_oracle(lib, cuda, image, batch, iou_type):
+    """d GetLoss / d y_pred, dense like y_pred, against the oracle's analytic gradient (itself pinned
+    to fp64 finite differences on the CPU)."""
+    from oracle import yolo as oy
+    from tfmv_b200 import synth
+    from tfmv_b200.ai_models.utils.tf_yolo_utils import GetLossAndGrad
+    rng = np.random.default_rng(29 + batch)
+    anc = synth.yolo_anchors().astype(F)
+    _, _, _, y_true = _dense_targets(rng, batch, image, anc, normalised_anchors=True)
+    y_pred = synth.yolo_heads(rng, batch, image)
+    for l in range(3):   # overlapping predictions so the ignore mask has zeros
+        yt = y_true[l]
+        yp = y_pred[l].reshape(yt.shape)
+        m = yt[..., 4] > 0
+        yp[m, 2:4] = np.log(np.maximum(yt[m, 2:4] * image, 1e-3) / (anc[l] / 1.0)[np.nonzero(m)[3]]) + rng.normal(0, 0.1, (int(m.sum()), 2))
+    a = anc / F(image)
+    want_loss, want = oy.get_loss_grad(y_true, y_pred, (image, image), a * F(image), 0.5, iou_type)
+    got_loss, got = GetLossAndGrad([_t(t, cuda) for t in y_true], [_t(t, cuda) for t in y_pred], (image, image), a * F(image), 0.5, iou_type)
+    assert abs(float(got_loss) - float(want_loss)) <= LOSS_RTOL * abs(float(want_loss))
+    for l in range(3):
+        g = got[l].cpu().numpy().reshape(want[l].shape)
+        assert g.shape == want[l].shape
+        np.testing.assert_allclose(g, want[l], rtol=1e-4, atol=1e-7)
+        # structure: non-object records carry a gradient only in the conf channel
+        nobj = y_true[l][..., 4] == 0
+        assert np.count_nonzero(np.delete(g[nobj], 4, axis=-1)) == 0

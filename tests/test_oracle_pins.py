@@ -155,3 +155,38 @@ def test_detmath_against_numpy():
     z = (rng.random(x.shape) < 0.5).astype(F)
     ref = np.maximum(x, 0) - x * z + np.log1p(np.exp(-np.abs(x.astype(np.float64))))
     np.testing.assert_allclose(dm.bce_logits(z, x), ref, rtol=1e-6, atol=1e-7)
+
+
+def test_loss_gradient_matches_finite_differences():
+    """The analytic backward of GetLoss (oracle.get_loss_grad) against fp64 central differences of the same loss."""
+    from tfmv_b200 import synth
+    rng = np.random.default_rng(23)
+    image, batch = 64, 2
+    anc = (synth.yolo_anchors().astype(F) / F(416)).astype(F)
+    boxes, classes, off = synth.gt_batch(rng, batch, (image, image), max_boxes=6)
+    per = [oy.get_targets(boxes[off[b]:off[b + 1]], classes[off[b]:off[b + 1]], anc, (image, image), 80) for b in range(batch)]
+    y_true = [np.stack([p[l] for p in per], 0) for l in range(3)]
+    y_pred = synth.yolo_heads(rng, batch, image)
+    loss, grads = oy.get_loss_grad(y_true, y_pred, (image, image), anc, 0.5, "ciou")
+    _, _, ign = oy.get_loss(y_true, y_pred, (image, image), anc, 0.5, "ciou", return_ignore=True)
+    f = lambda yp: oy.loss_fp64_fixed_ignore(y_true, yp, (image, image), anc, ign)
+    assert abs(f(y_pred) - float(loss)) < 1e-4 * abs(float(loss))
+    eps = 1e-4
+    checked = 0
+    for l in range(3):
+        g = grads[l].reshape(y_pred[l].shape)
+        flat_idx = list(rng.integers(0, y_pred[l].size, 12))
+        obj_rec = np.argwhere(y_true[l][..., 4] > 0)
+        for r in obj_rec[:2]:   # make sure object records (xy, wh, class channels) are covered
+            for c in (0, 1, 2, 3, 4, 5 + int(np.argmax(y_true[l][tuple(r)][5:])), 9):
+                flat_idx.append(np.ravel_multi_index((r[0], r[1], r[2], r[3] * 85 + c), y_pred[l].shape))
+        for fi in flat_idx:
+            idx = np.unravel_index(int(fi), y_pred[l].shape)
+            yp_p = [a.astype(np.float64) for a in y_pred]
+            yp_m = [a.astype(np.float64) for a in y_pred]
+            yp_p[l][idx] += eps
+            yp_m[l][idx] -= eps
+            fd = (f(yp_p) - f(yp_m)) / (2 * eps)
+            assert abs(fd - float(g[idx])) <= 2e-4 * max(abs(fd), 1e-3), (l, idx, fd, float(g[idx]))
+            checked += 1
+    assert checked > 40
