@@ -208,6 +208,14 @@ int b200_focal_box_partial_sums(int num_levels, const unsigned long long* anchor
                                 void* stream);
 int b200_focal_box_finalize(int num_levels, const double* sums, const double* numel_per_level_host, float* out_parts,
                             float* out_loss, float* out_num_positives, void* stream);
+/* Backward of _get_loss: grad_classes[l] = d loss / d pred_classes[l], grad_boxes[l] = d loss /
+ * d pred_boxes[l] for an upstream gradient of 1 (entries / arrays may be NULL).  `sums` as produced by
+ * b200_focal_box_partial_sums (after the all-reduce when data-parallel); num_positives is a constant of the targets. */
+int b200_focal_box_grad(int num_levels, const unsigned long long* anchors_per_level, int C,
+                        const float* const true_boxes[], const float* const true_classes[],
+                        const float* const pred_boxes[], const float* const pred_classes[], float alpha, float gamma,
+                        float delta, float label_smoothing, const double* sums, const double* numel_per_level_host,
+                        float* const grad_boxes[], float* const grad_classes[], void* stream);
 
 #ifdef __cplusplus
 }

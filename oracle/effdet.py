@@ -314,3 +314,42 @@ def class_focal_loss(class_targets, class_outputs, masks, alpha=0.25, gamma=1.5,
         e = _dnn(e, np.full_like(e, normalizer))
         total = F(total + F(np.sum(e.astype(np.float64))))
     return total
+
+
+def get_loss_grad(y_true_boxes, y_true_classes, y_true_masks, y_pred_boxes, y_pred_classes, alpha=0.25, gamma=1.5, delta=0.1):
+    """d get_loss / d y_pred_boxes, d / d y_pred_classes in float64 (what tf.GradientTape derives; num_positives is
+    a constant of the targets).  Pinned to central differences in tests/test_oracle_pins.py."""
+    npos = 1.0 + sum(float(np.sum(np.asarray(m).astype(np.float64))) for m in y_true_masks)
+    gb, gc = [], []
+    for l in range(len(y_true_boxes)):
+        y = np.asarray(y_true_classes[l], np.float64)
+        x = np.asarray(y_pred_classes[l], np.float64)
+        p = 1.0 / (1.0 + np.exp(-x))
+        p_t = y * p + (1 - y) * (1 - p)
+        af = y * alpha + (1 - y) * (1 - alpha)
+        q = 1 - p_t
+        ce = np.maximum(x, 0) - x * y + np.log1p(np.exp(-np.abs(x)))
+        dq = -(2 * y - 1) * p * (1 - p)
+        g = af * (gamma * np.power(q, gamma - 1) * dq * ce + np.power(q, gamma) * (p - y))
+        gc.append(g / (npos * x.size))
+        t = np.asarray(y_true_boxes[l], np.float64)
+        o = np.asarray(y_pred_boxes[l], np.float64)
+        e = o - t
+        gb.append(np.where(t != 0, np.where(np.abs(e) <= delta, e, delta * np.sign(e)), 0.0) * 50.0 / (4.0 * npos))
+    return gb, gc
+
+
+def loss_fp64(y_true_boxes, y_true_classes, y_true_masks, y_pred_boxes, y_pred_classes, alpha=0.25, gamma=1.5, delta=0.1):
+    npos = 1.0 + sum(float(np.sum(np.asarray(m).astype(np.float64))) for m in y_true_masks)
+    total = 0.0
+    for l in range(len(y_true_boxes)):
+        y = np.asarray(y_true_classes[l], np.float64)
+        x = np.asarray(y_pred_classes[l], np.float64)
+        p = 1.0 / (1.0 + np.exp(-x))
+        p_t = y * p + (1 - y) * (1 - p)
+        f = (y * alpha + (1 - y) * (1 - alpha)) * np.power(1 - p_t, gamma) * (np.maximum(x, 0) - x * y + np.log1p(np.exp(-np.abs(x))))
+        t = np.asarray(y_true_boxes[l], np.float64)
+        e = np.abs(np.asarray(y_pred_boxes[l], np.float64) - t)
+        hub = np.where(e <= delta, 0.5 * e * e, delta * e - 0.5 * delta * delta) * (t != 0)
+        total += 50.0 * hub.sum() / (4.0 * npos) + f.sum() / npos / x.size
+    return total

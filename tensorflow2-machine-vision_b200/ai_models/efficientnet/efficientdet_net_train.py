@@ -11,7 +11,7 @@ from ..losses.focal_loss import _partial_sums
 
 
 def get_loss(y_true_boxes, y_true_classes, y_true_masks, y_pred_boxes, y_pred_classes, alpha=0.25, gamma=1.5,
-             delta=0.1, global_batch_scale=1, group=None, return_parts=False):
+             delta=0.1, global_batch_scale=1, group=None, return_parts=False, with_grad=False):
   '''sum over levels of (50 * box_loss + focal_loss) with num_positives = sum(masks) + 1.
 
   Data parallel: every rank passes its shard; the 2L+1 fp64 partial sums are all-reduced once (NCCL) before the
@@ -32,7 +32,28 @@ def get_loss(y_true_boxes, y_true_classes, y_true_masks, y_pred_boxes, y_pred_cl
   npos = torch.empty((), dtype=torch.float32, device=sums.device)
   _lib.check(lib.b200_focal_box_finalize(L, T.ptr(sums), nm, T.ptr(parts), T.ptr(loss), T.ptr(npos), T.stream_ptr()),
              '_get_loss')
+  if with_grad:
+    tb = [T.to_cuda(t) for t in y_true_boxes]
+    tc = [T.to_cuda(t) for t in y_true_classes]
+    pb = [T.to_cuda(t) for t in y_pred_boxes]
+    pc = [T.to_cuda(t) for t in y_pred_classes]
+    gb = [torch.empty_like(t) for t in pb]
+    gc = [torch.empty_like(t) for t in pc]
+    C = pc[0].shape[-1]
+    anc = (ctypes.c_ulonglong * L)(*[t.numel() // C for t in pc])
+    arr = lambda ts: (ctypes.c_void_p * L)(*[t.data_ptr() for t in ts])
+    _lib.check(lib.b200_focal_box_grad(L, anc, C, arr(tb), arr(tc), arr(pb), arr(pc), float(alpha), float(gamma),
+                                       float(delta), 0.0, T.ptr(sums), nm, arr(gb), arr(gc), T.stream_ptr()),
+               '_get_loss backward')
+    return loss, tuple(gb), tuple(gc)
   return (loss, parts, npos) if return_parts else loss
+
+
+def get_loss_and_grad(y_true_boxes, y_true_classes, y_true_masks, y_pred_boxes, y_pred_classes, alpha=0.25, gamma=1.5,
+                      delta=0.1):
+  '''_get_loss plus (d loss / d y_pred_boxes[l], d loss / d y_pred_classes[l]) for an upstream gradient of 1.'''
+  return get_loss(y_true_boxes, y_true_classes, y_true_masks, y_pred_boxes, y_pred_classes, alpha, gamma, delta,
+                  with_grad=True)
 
 
 class EfficientDetNetTrain(object):

@@ -147,6 +147,87 @@ __global__ void focal_box_finalize_kernel(ElFinalize f) {
   *f.loss = loss;
 }
 
+// ---- backward: d _get_loss / d class logits and d / d box outputs --------------------------
+// focal: f = af*mod*ce, mod = q^gamma, q = 1-p_t, p_t = y p + (1-y)(1-p):
+//   df/dx = af * ( gamma q^(gamma-1) * (-(2y-1) p (1-p)) * ce + mod * (p - y_smoothed) );  scaled by 1/(num_pos*numel_l)
+// box:   d huber/d o = (|e| <= delta ? e : delta sign(e)) for target != 0, scaled by 50/(4 num_pos)
+// num_pos comes from the (all-reduced) partial sums and is a constant of the targets.
+struct ElGradParams {
+  int num_levels;
+  const float4* cls_pred[EL_MAX_LEVELS]; const float4* cls_true[EL_MAX_LEVELS]; float4* cls_grad[EL_MAX_LEVELS];
+  unsigned long long cls_vec[EL_MAX_LEVELS];
+  int cls_tail[EL_MAX_LEVELS];  // floats after the last whole float4
+  const float4* box_pred[EL_MAX_LEVELS]; const float4* box_true[EL_MAX_LEVELS]; float4* box_grad[EL_MAX_LEVELS];
+  unsigned long long anchors[EL_MAX_LEVELS];
+  double numel[EL_MAX_LEVELS];
+  int cta_base[EL_MAX_LEVELS + 1];
+  float alpha, gamma, delta, label_smoothing;
+  const double* sums;  // [2L+1], sums[2L] = positives
+};
+
+__device__ __forceinline__ float el_focal_grad(float y, float x, float alpha, float gamma, float ls) {
+  const float e = el_ex2(-1.4426950408889634f * fabsf(x));
+  const float r = el_rcp(1.0f + e);
+  const float p = (x >= 0.0f) ? r : e * r;
+  const float p_t = y * p + (1.0f - y) * (1.0f - p);
+  const float af = y * alpha + (1.0f - y) * (1.0f - alpha);
+  const float q = fmaxf(1.0f - p_t, 0.0f);
+  const float sq = el_sqrt(q);
+  const float mod = (gamma == 1.5f) ? q * sq : __powf(q, gamma);
+  const float dmod = (gamma == 1.5f) ? 1.5f * sq : (q > 0.0f ? gamma * __powf(q, gamma - 1.0f) : 0.0f);
+  const float ys = y * (1.0f - ls) + 0.5f * ls;
+  const float ce = fmaxf(x, 0.0f) - x * ys - 0.6931471805599453f * el_lg2(r);
+  const float dq = -(2.0f * y - 1.0f) * p * (1.0f - p);
+  return af * (dmod * dq * ce + mod * (p - ys));
+}
+
+__device__ __forceinline__ float el_huber_grad(float t, float o, float delta) {
+  if (t == 0.0f) return 0.0f;
+  const float e = o - t;
+  return fabsf(e) <= delta ? e : copysignf(delta, e);
+}
+
+__global__ void __launch_bounds__(EL_THREADS) focal_box_grad_kernel(ElGradParams p) {
+  int l = 0;
+#pragma unroll
+  for (int k = 1; k < EL_MAX_LEVELS; ++k) if (k < p.num_levels && (int)blockIdx.x >= p.cta_base[k]) l = k;
+  const int ncta = p.cta_base[l + 1] - p.cta_base[l];
+  const int cta = blockIdx.x - p.cta_base[l];
+  const unsigned long long stride = (unsigned long long)ncta * EL_THREADS;
+  const float npos = (float)p.sums[2 * p.num_levels] + 1.0f;
+  const float cs = (float)(1.0 / ((double)npos * p.numel[l]));
+  const float bs = 50.0f / (4.0f * npos);
+  if (p.cls_grad[l]) {
+    const unsigned long long nv = p.cls_vec[l];
+#pragma unroll 2
+    for (unsigned long long i = (unsigned long long)cta * EL_THREADS + threadIdx.x; i < nv; i += stride) {
+      const float4 x = __ldcs(p.cls_pred[l] + i);
+      const float4 y = __ldcs(p.cls_true[l] + i);
+      float4 g;
+      g.x = cs * el_focal_grad(y.x, x.x, p.alpha, p.gamma, p.label_smoothing);
+      g.y = cs * el_focal_grad(y.y, x.y, p.alpha, p.gamma, p.label_smoothing);
+      g.z = cs * el_focal_grad(y.z, x.z, p.alpha, p.gamma, p.label_smoothing);
+      g.w = cs * el_focal_grad(y.w, x.w, p.alpha, p.gamma, p.label_smoothing);
+      __stcs(p.cls_grad[l] + i, g);
+    }
+    if (cta == 0 && (int)threadIdx.x < p.cls_tail[l]) {
+      const unsigned long long e = nv * 4ull + threadIdx.x;
+      reinterpret_cast<float*>(p.cls_grad[l])[e] =
+          cs * el_focal_grad(reinterpret_cast<const float*>(p.cls_true[l])[e], reinterpret_cast<const float*>(p.cls_pred[l])[e],
+                             p.alpha, p.gamma, p.label_smoothing);
+    }
+  }
+  if (p.box_grad[l]) {
+    const unsigned long long na = p.anchors[l];
+    for (unsigned long long a = (unsigned long long)cta * EL_THREADS + threadIdx.x; a < na; a += stride) {
+      const float4 o = __ldcs(p.box_pred[l] + a);
+      const float4 t = __ldcs(p.box_true[l] + a);
+      __stcs(p.box_grad[l] + a, make_float4(bs * el_huber_grad(t.x, o.x, p.delta), bs * el_huber_grad(t.y, o.y, p.delta),
+                                             bs * el_huber_grad(t.z, o.z, p.delta), bs * el_huber_grad(t.w, o.w, p.delta)));
+    }
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 static int el_cta_plan(int num_levels, const unsigned long long* cls_elems, int* cta_base) {
   // CTAs proportional to the class-tensor size of each level, ~8 per SM in total, at least 1 per level
@@ -260,6 +341,55 @@ extern "C" int b200_focal_box_finalize(int num_levels, const double* sums, const
   f.sums = sums; f.num_levels = num_levels; f.parts = out_parts; f.loss = out_loss; f.num_pos = out_num_positives;
   for (int l = 0; l < EL_MAX_LEVELS; ++l) f.numel[l] = l < num_levels ? numel_per_level_host[l] : 1.0;
   focal_box_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+// d loss / d pred_classes[l] and d loss / d pred_boxes[l] (either array entry may be NULL).  `sums` is the device
+// array b200_focal_box_partial_sums produced (after the all-reduce, if any); numel_per_level_host as in finalize.
+extern "C" int b200_focal_box_grad(int num_levels, const unsigned long long* anchors_per_level, int C,
+                                   const float* const true_boxes[], const float* const true_classes[],
+                                   const float* const pred_boxes[], const float* const pred_classes[], float alpha,
+                                   float gamma, float delta, float label_smoothing, const double* sums,
+                                   const double* numel_per_level_host, float* const grad_boxes[],
+                                   float* const grad_classes[], void* stream) {
+  B200_REQUIRE(num_levels >= 1 && num_levels <= EL_MAX_LEVELS && C >= 1 && anchors_per_level && sums && numel_per_level_host,
+               B200_ERR_BAD_ARG, "b200_focal_box_grad: bad argument");
+  ElGradParams p;
+  unsigned long long plan[EL_MAX_LEVELS];
+  p.num_levels = num_levels;
+  for (int l = 0; l < EL_MAX_LEVELS; ++l) {
+    p.cls_pred[l] = p.cls_true[l] = nullptr; p.cls_grad[l] = nullptr; p.box_pred[l] = p.box_true[l] = nullptr; p.box_grad[l] = nullptr;
+    p.cls_vec[l] = 0; p.cls_tail[l] = 0; p.anchors[l] = 0; p.numel[l] = 1.0; plan[l] = 0;
+    if (l >= num_levels) continue;
+    p.numel[l] = numel_per_level_host[l];
+    if (grad_classes && grad_classes[l]) {
+      B200_REQUIRE(true_classes && pred_classes && true_classes[l] && pred_classes[l], B200_ERR_BAD_ARG, "b200_focal_box_grad: null class tensors at level %d", l);
+      const unsigned long long n = anchors_per_level[l] * (unsigned long long)C;
+      const uintptr_t al = reinterpret_cast<uintptr_t>(true_classes[l]) | reinterpret_cast<uintptr_t>(pred_classes[l]) | reinterpret_cast<uintptr_t>(grad_classes[l]);
+      B200_REQUIRE((al & 15) == 0, B200_ERR_BAD_ARG, "b200_focal_box_grad: level %d class tensors must be 16-byte aligned", l);
+      p.cls_pred[l] = reinterpret_cast<const float4*>(pred_classes[l]);
+      p.cls_true[l] = reinterpret_cast<const float4*>(true_classes[l]);
+      p.cls_grad[l] = reinterpret_cast<float4*>(grad_classes[l]);
+      p.cls_vec[l] = n / 4ull;
+      p.cls_tail[l] = (int)(n - p.cls_vec[l] * 4ull);
+      plan[l] = n;
+    }
+    if (grad_boxes && grad_boxes[l]) {
+      B200_REQUIRE(true_boxes && pred_boxes && true_boxes[l] && pred_boxes[l], B200_ERR_BAD_ARG, "b200_focal_box_grad: null box tensors at level %d", l);
+      const uintptr_t al = reinterpret_cast<uintptr_t>(true_boxes[l]) | reinterpret_cast<uintptr_t>(pred_boxes[l]) | reinterpret_cast<uintptr_t>(grad_boxes[l]);
+      B200_REQUIRE((al & 15) == 0, B200_ERR_BAD_ARG, "b200_focal_box_grad: level %d box tensors must be 16-byte aligned", l);
+      p.box_pred[l] = reinterpret_cast<const float4*>(pred_boxes[l]);
+      p.box_true[l] = reinterpret_cast<const float4*>(true_boxes[l]);
+      p.box_grad[l] = reinterpret_cast<float4*>(grad_boxes[l]);
+      p.anchors[l] = anchors_per_level[l];
+      if (plan[l] < anchors_per_level[l] * 4ull) plan[l] = anchors_per_level[l] * 4ull;
+    }
+    if (plan[l] == 0) plan[l] = 4;
+  }
+  const int n_cta = el_cta_plan(num_levels, plan, p.cta_base);
+  p.alpha = alpha; p.gamma = gamma; p.delta = delta; p.label_smoothing = label_smoothing; p.sums = sums;
+  focal_box_grad_kernel<<<n_cta, EL_THREADS, 0, (cudaStream_t)stream>>>(p);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

@@ -149,3 +149,30 @@ def test_get_loss_matches_oracle(lib, cuda, name, batch):
     assert abs(float(bl) - float(oe.box_loss(wnpos, tb[0], pb[0]))) <= LOSS_RTOL * abs(float(oe.box_loss(wnpos, tb[0], pb[0])))
     el = FocalLoss(0.25, 1.5).call([3.0, _t(tc[1], cuda)], _t(pc[1], cuda)).cpu().numpy()
     np.testing.assert_allclose(el, oe.focal_loss_elements(3.0, tc[1], pc[1]), rtol=2e-5, atol=1e-9)
+
+
+def test_get_loss_gradient_matches_oracle(lib, cuda):
+    """SURVEY §8f N1 for EfficientDet: d _get_loss / d class logits and box outputs vs the fp64 analytic oracle."""
+    from oracle import effdet as oe
+    from tfmv_b200 import synth
+    from tfmv_b200.ai_models.efficientnet.efficientdet_net_train import get_loss_and_grad
+    a, o = _pair("small")
+    rng = np.random.default_rng(37)
+    batch, C = 3, 81
+    boxes, classes, off = synth.gt_batch(rng, batch, (128, 128), max_boxes=20, order="yxyx")
+    classes = (classes % 80 + 1).astype(np.int32)
+    per = [o.generate_targets(boxes[off[b]:off[b + 1]], classes[off[b]:off[b + 1]], C) for b in range(batch)]
+    L = len(o.boxes)
+    tb = [np.stack([p[0][l] for p in per], 0) for l in range(L)]
+    tc = [np.stack([p[1][l] for p in per], 0) for l in range(L)]
+    tm = [np.stack([p[2][l] for p in per], 0) for l in range(L)]
+    pb = [(rng.standard_normal(t.shape, dtype=F) * F(0.25)) for t in tb]
+    pc = [rng.standard_normal(t.shape, dtype=F) for t in tc]
+    d = lambda xs: [_t(x, cuda) for x in xs]
+    loss, gb, gc = get_loss_and_grad(d(tb), d(tc), d(tm), d(pb), d(pc))
+    want = oe.get_loss(tb, tc, tm, pb, pc)
+    assert abs(float(loss) - float(want)) <= LOSS_RTOL * abs(float(want))
+    wb, wc = oe.get_loss_grad(tb, tc, tm, pb, pc)
+    for l in range(L):
+        np.testing.assert_allclose(gc[l].cpu().numpy(), wc[l], rtol=2e-4, atol=1e-12)
+        np.testing.assert_allclose(gb[l].cpu().numpy(), wb[l], rtol=2e-4, atol=1e-12)

@@ -190,3 +190,28 @@ def test_loss_gradient_matches_finite_differences():
             assert abs(fd - float(g[idx])) <= 2e-4 * max(abs(fd), 1e-3), (l, idx, fd, float(g[idx]))
             checked += 1
     assert checked > 40
+
+
+def test_effdet_loss_gradient_matches_finite_differences():
+    rng = np.random.default_rng(31)
+    shapes = [(2, 4, 4, 9), (2, 2, 2, 9)]
+    tc = [(rng.random(s + (11,)) < 0.08).astype(F) for s in shapes]
+    pc = [rng.standard_normal(s + (11,)).astype(F) for s in shapes]
+    tb = [(rng.standard_normal(s + (4,)) * (rng.random(s + (4,)) < 0.3)).astype(F) for s in shapes]
+    pb = [(rng.standard_normal(s + (4,)) * 0.2).astype(F) for s in shapes]
+    tm = [rng.random(s + (1,)) < 0.2 for s in shapes]
+    assert abs(oe.loss_fp64(tb, tc, tm, pb, pc) - float(oe.get_loss(tb, tc, tm, pb, pc))) < 1e-5 * abs(float(oe.get_loss(tb, tc, tm, pb, pc)))
+    gb, gc = oe.get_loss_grad(tb, tc, tm, pb, pc)
+    eps = 1e-5
+    for l in range(2):
+        for arr, grad, which in ((pc, gc, "c"), (pb, gb, "b")):
+            for fi in rng.integers(0, arr[l].size, 10):
+                idx = np.unravel_index(int(fi), arr[l].shape)
+                ap = [a.astype(np.float64) for a in arr]
+                am = [a.astype(np.float64) for a in arr]
+                ap[l][idx] += eps
+                am[l][idx] -= eps
+                fp = oe.loss_fp64(tb, tc, tm, ap if which == "b" else pb, ap if which == "c" else pc)
+                fm = oe.loss_fp64(tb, tc, tm, am if which == "b" else pb, am if which == "c" else pc)
+                fd = (fp - fm) / (2 * eps)
+                assert abs(fd - grad[l][idx]) <= 1e-4 * max(abs(fd), 1e-6), (which, l, idx, fd, grad[l][idx])
