@@ -154,6 +154,13 @@ int b200_gather_rows(const float* src, int row_floats, const unsigned char* flag
 int b200_yolo_ground_truth_rows(const float* y, long long n_records, int C, float* rows, unsigned char* flags,
                                 void* stream);
 
+/* Get_mAP_one (utils/mAP.py:114-125), batched: gt [total_gt,5] x1,y1,x2,y2,class; pred [total_pred,6]
+ * x1,y1,x2,y2,class,score (fp32, as test_step concatenates them); offsets [num_images+1] int32; out [num_images] fp64.
+ * max_*_per_image are upper bounds used to size shared memory.  fp64 arithmetic like the NumPy original. */
+int b200_map_per_image(const float* gt, const int32_t* gt_offsets, const float* pred, const int32_t* pred_offsets,
+                       int num_images, int max_gt_per_image, int max_pred_per_image, int class_num, double thresh,
+                       double* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * EfficientDet (efficientnet/utils/anchors.py, iou.py, nms.py; losses/focal_loss.py, box_loss.py;
  * efficientnet/efficientdet_net_train.py:41-52).  Levels are described by hw = {H0,W0,H1,W1,...} and A anchors

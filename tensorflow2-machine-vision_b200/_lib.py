@@ -47,6 +47,7 @@ SIGNATURES = {
     "b200_row_positions": (c_i, [c_p, ctypes.c_longlong, c_p, c_p, c_p, c_sz, c_p]),
     "b200_gather_rows": (c_i, [c_p, c_i, c_p, c_p, ctypes.c_longlong, c_p, c_p]),
     "b200_yolo_ground_truth_rows": (c_i, [c_p, ctypes.c_longlong, c_i, c_p, c_p, c_p]),
+    "b200_map_per_image": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, ctypes.c_double, c_p, c_p]),
 }
 
 METRIC_YOLO = {"iou": 0, "diou": 1, "ciou": 2}
