@@ -30,7 +30,6 @@
 #define NMS_WINDOW 4096
 #define NMS_SAMPLES 2048
 #define NMS_TARGET 1536
-#define NMS_MIN_WIN 768   // smallest window worth accepting when more candidates remain
 #define NMS_MAX_OUT_LIMIT 4096
 
 struct NmsSegment {
@@ -61,8 +60,17 @@ struct NmsConfig {
 };
 
 __host__ __device__ inline size_t nms_smem_bytes(int max_out) {
-  // window keys 32K + window pos 16K + samples 16K + cand 28K + class buckets 2K + kept 28B*max_out + small
-  return (size_t)NMS_WINDOW * 12 + (size_t)NMS_SAMPLES * 8 + NMS_CHUNK * 28 + 256 * 8 + (size_t)max_out * 32 + 1024;
+  // window keys 32K + window pos 16K + samples 16K + cand 28K + class-bucket heads 1K + kept 32B*max_out + small
+  return (size_t)NMS_WINDOW * 12 + (size_t)NMS_SAMPLES * 8 + NMS_CHUNK * 28 + 256 * 4 + (size_t)max_out * 32 + 1024;
+}
+
+// Large segments pay a full gather pass per extra window, so they keep the big window.
+__host__ __device__ inline int nms_window_target(int max_out, int n) {
+  if (n > 32768) return NMS_TARGET;
+  int t = max_out + (max_out >> 1);
+  if (t < 512) t = 512;
+  if (t > NMS_TARGET) t = NMS_TARGET;
+  return t;
 }
 
 __device__ __forceinline__ uint32_t nms_dkey(float s) {
@@ -128,8 +136,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
   float* cAt = cAr + NMS_CHUNK;
   int* cCl = reinterpret_cast<int*>(cAt + NMS_CHUNK);
   int* sHead = reinterpret_cast<int*>(cCl + NMS_CHUNK);  // [256] newest kept index per class bucket (-1 = empty)
-  int* sNextPad = sHead + 256;                            // [256] unused padding (keeps the 2 KB slot)
-  float* kC0 = reinterpret_cast<float*>(sNextPad + 256);
+  float* kC0 = reinterpret_cast<float*>(sHead + 256);
   float* kC1 = kC0 + cfg.max_out;
   float* kC2 = kC1 + cfg.max_out;
   float* kC3 = kC2 + cfg.max_out;
@@ -139,12 +146,16 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
   int* kNext = kCl + cfg.max_out;  // per-class chain: previous kept index in the same bucket
   uintptr_t misc_addr = (reinterpret_cast<uintptr_t>(kNext + cfg.max_out) + 15) & ~uintptr_t(15);
   unsigned long long* sMask = reinterpret_cast<unsigned long long*>(misc_addr);  // [64]
-  uint32_t* sAlive = reinterpret_cast<uint32_t*>(sMask + 64);                    // [32]
-  unsigned long long* sKeptMask = reinterpret_cast<unsigned long long*>(sAlive + 32);
+  uint32_t* sSupp = reinterpret_cast<uint32_t*>(sMask + 64);                    // [32]
+  unsigned long long* sKeptMask = reinterpret_cast<unsigned long long*>(sSupp + 32);
   int* sScalar = reinterpret_cast<int*>(sKeptMask + 1);  // [0]=gathered [1]=eligible [2]=nk
 
   if (tid < 256) sHead[tid] = -1;
   const int n = seg.n;
+  // window size goal: enough candidates to emit max_out boxes when little is suppressed, small enough that the
+  // bitonic sort of the window (the dominant cost of a lightly suppressed image) stays cheap
+  const int target = nms_window_target(cfg.max_out, n);
+  const int min_win = target >> 1;
   int n_kept = 0;
   unsigned long long klo = 0ull;  // inclusive lower bound of not-yet-consumed keys
   bool exhausted = (n <= 0);
@@ -154,9 +165,10 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
     const bool take_all = (n <= NMS_WINDOW);
     unsigned long long khi = ~0ull;   // exclusive upper bound; ~0 = everything that is left
     unsigned long long rank = 0;
-    const int n_samp = (n > 65536) ? NMS_SAMPLES : NMS_SAMPLES / 2;  // rank noise only matters for huge segments
+    int n_samp = 256;  // enough samples for a pivot rank of >= ~48 (relative spread of the admitted count <= ~15 %)
+    while (n_samp < NMS_SAMPLES && (long long)n_samp * target < 48ll * n) n_samp <<= 1;
     const bool pre_ok = pre && klo == 0ull && (*pre->eligible > 0) && (*pre->count <= NMS_WINDOW) &&
-                        (*pre->count >= NMS_MIN_WIN || *pre->count >= *pre->eligible);
+                        (*pre->count >= min_win || *pre->count >= *pre->eligible);
     if (!take_all && !pre_ok) {
       for (int t = tid; t < n_samp; t += NMS_THREADS) {
         const int i = (int)(((long long)t * n) / n_samp);
@@ -168,7 +180,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
       }
       __syncthreads();
       nms_bitonic(sS, nullptr, n_samp);
-      rank = ((unsigned long long)NMS_TARGET * (unsigned long long)n_samp) / (unsigned long long)n;
+      rank = ((unsigned long long)target * (unsigned long long)n_samp) / (unsigned long long)n;
       if (rank < 2ull) rank = 2ull;
       khi = rank >= (unsigned long long)n_samp ? ~0ull : sS[rank];
     }
@@ -177,7 +189,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
     bool from_pre = false;
     if (pre && klo == 0ull) {
       const int c = *pre->count, e = *pre->eligible;
-      if (e > 0 && c <= NMS_WINDOW && (c >= NMS_MIN_WIN || c >= e)) {
+      if (e > 0 && c <= NMS_WINDOW && (c >= min_win || c >= e)) {
         for (int t = tid; t < c; t += NMS_THREADS) { sK[t] = pre->keys[t]; sPos[t] = pre->pos[t]; }
         n_win = c;
         khi = (c >= e) ? ~0ull : *pre->khi;
@@ -211,7 +223,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
       __syncthreads();
       if (e == 0) { n_win = 0; break; }
       const bool too_many = c > NMS_WINDOW;
-      const bool too_few = (c < NMS_MIN_WIN) && (c < e);
+      const bool too_few = (c < min_win) && (c < e);
       if (!too_many && !too_few) {
         n_win = c;
         if (c >= e) khi = ~0ull;  // the window holds everything that was left
@@ -222,7 +234,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
       unsigned long long next = 0ull;
       bool have = false;
       if (attempt < 3 && !take_all) {
-        unsigned long long r2 = c > 0 ? (rank * (unsigned long long)NMS_TARGET) / (unsigned long long)c : rank * 8ull;
+        unsigned long long r2 = c > 0 ? (rank * (unsigned long long)target) / (unsigned long long)c : rank * 8ull;
         if (too_few && r2 <= rank) r2 = rank + 1ull;
         if (too_many && r2 >= rank) r2 = rank > 0ull ? rank - 1ull : 0ull;
         rank = r2;
@@ -256,7 +268,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
         cC0[tid] = mine.c0; cC1[tid] = mine.c1; cC2[tid] = mine.c2; cC3[tid] = mine.c3;
         cAr[tid] = mine.area; cAt[tid] = mine.at; cCl[tid] = seg.classes ? seg.classes[p] : 0;
       }
-      if (tid < 2) sAlive[tid] = 0u;
+      if (tid < 2) sSupp[tid] = 0u;
       __syncthreads();
       const int n_tiles = (n_chunk + 63) >> 6;
       for (int T = 0; T < n_tiles && n_kept < cfg.max_out; ++T) {
@@ -286,10 +298,10 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
             }
           }
           const uint32_t bits = __ballot_sync(0xffffffffu, supp);
-          if (lane == 0 && bits) atomicOr(&sAlive[warp & 1], bits);  // sAlive holds the SUPPRESSED bits of the tile
+          if (lane == 0 && bits) atomicOr(&sSupp[warp & 1], bits);  // sSupp: bits of tile candidates suppressed by the kept list
         }
         __syncthreads();
-        unsigned long long tile_alive = ~((unsigned long long)sAlive[0] | ((unsigned long long)sAlive[1] << 32));
+        unsigned long long tile_alive = ~((unsigned long long)sSupp[0] | ((unsigned long long)sSupp[1] << 32));
         if (n_chunk - t0 < 64) tile_alive &= (1ull << (n_chunk - t0)) - 1ull;
         // phase 2: intra-tile mask via ballots: warp w owns rows 2w, 2w+1
 #pragma unroll
@@ -347,7 +359,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
             }
             *sKeptMask = keptmask;
             sScalar[2] = __popcll(keptmask);
-            sAlive[0] = 0u; sAlive[1] = 0u;  // reset the suppressed bits for the next tile
+            sSupp[0] = 0u; sSupp[1] = 0u;  // reset the suppressed bits for the next tile
           }
         }
         __syncthreads();
@@ -387,9 +399,8 @@ struct NmsPreselectParams {
 };
 
 #define NMS_PRE_SAMPLES 4096
-#define NMS_PRE_TARGET 1536
 
-// One CTA per segment: pivot = the sample whose rank should admit ~NMS_PRE_TARGET candidates (4096 strided samples,
+// One CTA per segment: pivot = the sample whose rank should admit ~NMS_TARGET candidates (up to 4096 strided samples,
 // so the admitted count has a relative spread of ~1/sqrt(rank) and stays inside [1024, 4096] with high probability).
 static __device__ void nms_pivot_body(const NmsPreselectParams& p, unsigned char* smem_raw) {
   unsigned long long* sS = reinterpret_cast<unsigned long long*>(smem_raw);  // [NMS_PRE_SAMPLES]
@@ -402,7 +413,7 @@ static __device__ void nms_pivot_body(const NmsPreselectParams& p, unsigned char
   if (n > NMS_WINDOW) {
     // enough samples for a pivot rank of >= ~32 (relative spread of the admitted count <= ~18 %)
     int ns = 512;
-    while (ns < NMS_PRE_SAMPLES && (long long)ns * NMS_PRE_TARGET < 32ll * n) ns <<= 1;
+    while (ns < NMS_PRE_SAMPLES && (long long)ns * NMS_TARGET < 32ll * n) ns <<= 1;
     for (int t = tid; t < ns; t += NMS_THREADS) {
       const int i = (int)(((long long)t * n) / ns);
       const float s = scores[i];
@@ -412,7 +423,7 @@ static __device__ void nms_pivot_body(const NmsPreselectParams& p, unsigned char
     }
     __syncthreads();
     nms_bitonic(sS, nullptr, ns);
-    unsigned long long rank = ((unsigned long long)NMS_PRE_TARGET * (unsigned long long)ns) / (unsigned long long)n;
+    unsigned long long rank = ((unsigned long long)NMS_TARGET * (unsigned long long)ns) / (unsigned long long)n;
     if (rank < 2ull) rank = 2ull;
     khi = rank >= (unsigned long long)ns ? ~0ull : sS[rank];
   }

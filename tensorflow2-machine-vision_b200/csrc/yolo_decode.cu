@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(256) yolo_classes_kernel(YoloFinalizeParams p)
 // ---- dense decode for the stand-alone GetBoxes shim ---------------------------------------------
 // One warp per record: boxes/conf/sigmoid(classes)/valid for every anchor of one level, no filtering.
 __global__ void yolo_decode_dense_kernel(const float* __restrict__ head, long long total_rec, int H, int W, int A,
-                                         int C, float4 anc01, float4 anc23 /* up to 4 anchors unused */,
+                                         int C,
                                          const float* __restrict__ anc_wh, float* __restrict__ boxes,
                                          float* __restrict__ conf, float* __restrict__ classes,
                                          unsigned char* __restrict__ valid) {
@@ -497,9 +497,8 @@ extern "C" int b200_yolo_decode_dense(const float* head, int B, int H, int W, in
   long long blocks = (total + 7) / 8;
   long long cap = (long long)b200_sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  yolo_decode_dense_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(head, total, H, W, A, C, make_float4(0, 0, 0, 0),
-                                                                         make_float4(0, 0, 0, 0), anchors_wh_norm_dev, boxes,
-                                                                         conf, classes, valid);
+  yolo_decode_dense_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(head, total, H, W, A, C, anchors_wh_norm_dev, boxes, conf,
+                                                                         classes, valid);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
