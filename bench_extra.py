@@ -109,10 +109,10 @@ def main():
         if with_loss:
             rng = np.random.default_rng(20261018 + 3)
             boxes, classes, off = synth.gt_batch(rng, batch, (c["image_size"][1], c["image_size"][0]), max_boxes=100, order="yxyx")
-            tb, tc, tm = a.generate_targets_batch(torch.from_numpy(boxes).to(dev), torch.from_numpy((classes + 1).astype(np.int32)).to(dev),
-                                                  torch.from_numpy(off).to(dev), 81)
-            ms_t = timed(wrap(lambda: a.generate_targets_batch(torch.from_numpy(boxes).to(dev), torch.from_numpy((classes + 1).astype(np.int32)).to(dev),
-                                                               torch.from_numpy(off).to(dev), 81)), args.steps, args.warmup) if not args.graph else None
+            d_boxes, d_cls, d_off = (torch.from_numpy(boxes).to(dev), torch.from_numpy((classes + 1).astype(np.int32)).to(dev),
+                                     torch.from_numpy(off).to(dev))
+            tb, tc, tm = a.generate_targets_batch(d_boxes, d_cls, d_off, 81)
+            ms_t = timed(wrap(lambda: a.generate_targets_batch(d_boxes, d_cls, d_off, 81)), args.steps, args.warmup)
 
             def step():
                 loss = get_loss(tb, tc, tm, rel, cls)

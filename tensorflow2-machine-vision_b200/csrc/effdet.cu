@@ -281,7 +281,6 @@ struct EfAssignParams {
 __global__ void __launch_bounds__(256) effdet_assign_kernel(EfAssignParams p) {
   __shared__ float4 s_gt[EF_GT_TILE];
   __shared__ float s_ga[EF_GT_TILE];
-  __shared__ int s_cls[256];
   int l = 0;
 #pragma unroll
   for (int k = 1; k < EF_MAX_LEVELS; ++k) if (k < p.lv.num_levels && (int)blockIdx.x >= p.cta_base[k]) l = k;
@@ -354,20 +353,20 @@ __global__ void __launch_bounds__(256) effdet_assign_kernel(EfAssignParams p) {
     p.out_mask[l][abase + rin] = matched ? 1 : 0;
   }
   // one-hot rows (C floats per anchor, class 0 = background for unmatched anchors, anc:131-133): the CTA's
-  // 256 rows are contiguous, so they are written as one coalesced stream
-  s_cls[threadIdx.x] = active ? cls : -1;
-  __syncthreads();
+  // 256 rows are one contiguous span of rows*C floats.  It is cleared with aligned 16-byte stores (full sectors),
+  // then, after a barrier, each thread drops the single 1.0 of its own row (tf.one_hot: out of range -> zeros).
   const int rows = min(256, api - chunk * 256);
   float* dst = p.out_onehot[l] + (abase + (size_t)chunk * 256) * p.C;
-  // warp w writes rows w, w+8, ...: a row is C consecutive floats, so the lanes' 4-byte stores coalesce
-  {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int r = warp; r < rows; r += 8) {
-      const int rc = s_cls[r];
-      float* row = dst + (size_t)r * p.C;
-      for (int c = lane; c < p.C; c += 32) __stcs(row + c, (rc == c) ? 1.0f : 0.0f);  // tf.one_hot: out of range -> zeros
-    }
-  }
+  const int n_el = rows * p.C;
+  const int head = min(n_el, (int)(((16u - ((unsigned)(uintptr_t)dst & 15u)) & 15u) >> 2));
+  const int n_vec = (n_el - head) >> 2;
+  float4* dst4 = reinterpret_cast<float4*>(dst + head);
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = threadIdx.x; i < n_vec; i += 256) __stcs(dst4 + i, z4);
+  if ((int)threadIdx.x < head) dst[threadIdx.x] = 0.0f;
+  for (int i = head + (n_vec << 2) + threadIdx.x; i < n_el; i += 256) dst[i] = 0.0f;
+  __syncthreads();
+  if (active && cls >= 0 && cls < p.C) dst[(size_t)threadIdx.x * p.C + cls] = 1.0f;
 }
 
 // ---- host side ------------------------------------------------------------------------------------
