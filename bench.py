@@ -371,6 +371,24 @@ def run_b200(args, wl):
                             "the dense-equivalent figure can exceed the physical peak; achieved_dram_gbps/frac_dram use the "
                             "ncu-measured DRAM bytes of the same launch (profiles/traffic.json)")
     log("phase timing done")
+    # ---- same step with persistent target buffers (sparse reset instead of the dense zero-fill); reported beside
+    # the headline, which keeps the reference's fresh-zeros-every-call behaviour ----
+    persistent = None
+    if world == 1:
+        from tfmv_b200.ai_models.datasets.coco_dataset import TargetBuffers
+        tbuf = TargetBuffers()
+
+        def pstep():
+            yt = gen.GetTargetsBatch(classes_d, boxes_d, off_d, buffers=tbuf)
+            return tyu._loss_call(yt, heads_d, (image, image), anc, 0.5, "ciou", 0, batch_divisor=global_batch,
+                                  return_parts=True, workspace=ws)
+        pstep()  # first call: dense fill
+        pfn = pstep if args.no_graph else runtime.capture(pstep)
+        ms_p = timed(pfn, args.steps, 3)
+        ploss = float(pfn()[0].item())
+        persistent = {"what": "GetTargetsBatch(buffers=TargetBuffers) + GetLoss: y_true reused across steps, only the previous "
+                              "step's records are re-zeroed", "value": global_batch * args.steps / (ms_p / 1e3),
+                      "unit": "images/s", "ms_per_step": ms_p / args.steps, "loss": ploss, "loss_equal": ploss == loss_val}
     # ---- end-to-end through the public API with host buffers ----
     e2e_steps = max(3, min(args.steps, 10))
     ms_e2e = timed(lambda: float(step(heads_p, boxes_p, classes_p, off_p).item()), e2e_steps, 2)
@@ -399,7 +417,7 @@ def run_b200(args, wl):
                        "launch": "launch by launch" if args.no_graph else "CUDA graph replay of the step",
                        "l2": "inputs larger than L2 (y_pred %.0f MB + y_true %.0f MB per step vs 126 MB L2)" % (
                            n_fill * 4 / 1e6, n_fill * 4 / 1e6)},
-            "loss": loss_val, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "loss": loss_val, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "persistent_targets": persistent,
             "gpu_launches": 5 * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -140,6 +140,12 @@ int b200_yolo_assign_targets(const float* boxes, const int32_t* classes, const i
                              int total_boxes, const float* anchors_wh_host, int A, const float* image_wh_host, int C,
                              const int32_t hw[6], float* const targets[3], int zero_fill, void* stream);
 int b200_fill_zero(float* dst, size_t n, void* stream);
+/* Sparse reset for a target buffer that is reused step after step (the reference allocates fresh tf.zeros per image,
+ * cds:265-276): zeroes exactly the records b200_yolo_assign_targets touched for the previous ground-truth set
+ * (prev_boxes / prev_offsets, same layout), leaving an all-zero buffer without the dense re-fill. */
+int b200_yolo_reset_targets(const float* prev_boxes, const int32_t* prev_offsets, int B, int total_boxes,
+                            const float* anchors_wh_host, int A, const float* image_wh_host, int C,
+                            const int32_t hw[6], float* const targets[3], void* stream);
 
 /* tf.boolean_mask (row-major order preserved): flags[n] bytes -> pos[n] = exclusive prefix of the flags, *total =
  * number of set flags (device int).  gather_rows copies the flagged rows of src [n,row_floats] to dst[pos[i]].

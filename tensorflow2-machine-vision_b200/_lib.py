@@ -31,6 +31,7 @@ SIGNATURES = {
     "b200_yolo_loss_grad": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_f, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "b200_yolo_assign_targets": (c_i, [c_p, c_p, c_p, c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_p]),
     "b200_fill_zero": (c_i, [c_p, c_sz, c_p]),
+    "b200_yolo_reset_targets": (c_i, [c_p, c_p, c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p]),
     "b200_effdet_table_floats": (c_sz, [c_i, c_p, c_i]),
     "b200_effdet_anchors": (c_i, [c_i, c_p, c_i, c_p, c_i, c_p, c_p]),
     "b200_effdet_decode": (c_i, [c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p]),

@@ -131,6 +131,25 @@ __global__ void __launch_bounds__(128) yolo_scatter_targets_kernel(YtParams p) {
   }
 }
 
+// Sparse reset of a target buffer that is reused step after step: zero exactly the records the scatter kernel
+// touched for the *previous* ground-truth set (same yt_locate), a warp per box.  Replaces the dense re-fill.
+__global__ void __launch_bounds__(128) yolo_reset_targets_kernel(YtParams p) {
+  const int img = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int beg = p.offsets[img], end = p.offsets[img + 1];
+  for (int i0 = beg + warp * 32; i0 < end; i0 += 128) {
+    float* mine = nullptr;
+    if (i0 + lane < end) {
+      float nx, ny, nw, nh;
+      mine = yt_locate(p, img, i0 + lane, nx, ny, nw, nh);
+    }
+    const int n = min(32, end - i0);
+    for (int k = 0; k < n; ++k) {
+      float* rec = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(mine), k));
+      if (rec) for (int c = lane; c < p.RF; c += 32) rec[c] = 0.0f;
+    }
+  }
+}
+
 extern "C" int b200_fill_zero(float* dst, size_t n, void* stream) {
   if (n == 0) return B200_OK;
   B200_REQUIRE(dst, B200_ERR_BAD_ARG, "b200_fill_zero: null pointer");
@@ -146,22 +165,46 @@ extern "C" int b200_fill_zero(float* dst, size_t n, void* stream) {
   return B200_OK;
 }
 
-extern "C" int b200_yolo_assign_targets(const float* boxes, const int32_t* classes, const int32_t* offsets, int B,
-                                        int total_boxes, const float* anchors_wh_host, int A, const float* image_wh_host,
-                                        int C, const int32_t hw[6], float* const targets[3], int zero_fill, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  B200_REQUIRE(B >= 0 && total_boxes >= 0 && A >= 1 && A <= 8 && C >= 0, B200_ERR_BAD_ARG, "b200_yolo_assign_targets: bad sizes");
-  B200_REQUIRE(anchors_wh_host && image_wh_host && hw && targets, B200_ERR_BAD_ARG, "b200_yolo_assign_targets: null argument");
-  if (B == 0) return B200_OK;
-  YtParams p;
+static int yt_fill_params(YtParams& p, const float* boxes, const int32_t* classes, const int32_t* offsets, int B, int total_boxes,
+                          const float* anchors_wh_host, int A, const float* image_wh_host, int C, const int32_t hw[6],
+                          float* const targets[3], const char* who) {
+  B200_REQUIRE(B >= 0 && total_boxes >= 0 && A >= 1 && A <= 8 && C >= 0, B200_ERR_BAD_ARG, "%s: bad sizes", who);
+  B200_REQUIRE(anchors_wh_host && image_wh_host && hw && targets, B200_ERR_BAD_ARG, "%s: null argument", who);
   p.boxes = boxes; p.classes = classes; p.offsets = offsets; p.B = B; p.total = total_boxes; p.A = A; p.C = C; p.RF = 5 + C;
   p.layers_num = YT_LEVELS;  // tf.shape(anchors_wh)[0], cds:191
   p.img_w = image_wh_host[0]; p.img_h = image_wh_host[1];
   for (int l = 0; l < YT_LEVELS; ++l) {
-    B200_REQUIRE(targets[l] && hw[2 * l] > 0 && hw[2 * l + 1] > 0, B200_ERR_BAD_ARG, "b200_yolo_assign_targets: bad level %d", l);
+    B200_REQUIRE(targets[l] && hw[2 * l] > 0 && hw[2 * l + 1] > 0, B200_ERR_BAD_ARG, "%s: bad level %d", who, l);
     p.target[l] = targets[l]; p.h[l] = hw[2 * l]; p.w[l] = hw[2 * l + 1];
   }
   for (int k = 0; k < YT_LEVELS * A; ++k) { p.anc_w[k] = anchors_wh_host[2 * k]; p.anc_h[k] = anchors_wh_host[2 * k + 1]; }
+  return B200_OK;
+}
+
+extern "C" int b200_yolo_reset_targets(const float* prev_boxes, const int32_t* prev_offsets, int B, int total_boxes,
+                                       const float* anchors_wh_host, int A, const float* image_wh_host, int C,
+                                       const int32_t hw[6], float* const targets[3], void* stream_) {
+  YtParams p;
+  const int st = yt_fill_params(p, prev_boxes, nullptr, prev_offsets, B, total_boxes, anchors_wh_host, A, image_wh_host, C, hw,
+                                targets, "b200_yolo_reset_targets");
+  if (st != B200_OK) return st;
+  if (B == 0 || total_boxes == 0) return B200_OK;
+  B200_REQUIRE(prev_boxes && prev_offsets, B200_ERR_BAD_ARG, "b200_yolo_reset_targets: null box arrays");
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(prev_boxes) & 15) == 0, B200_ERR_BAD_ARG, "b200_yolo_reset_targets: boxes not 16-byte aligned");
+  yolo_reset_targets_kernel<<<B, 128, 0, (cudaStream_t)stream_>>>(p);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" int b200_yolo_assign_targets(const float* boxes, const int32_t* classes, const int32_t* offsets, int B,
+                                        int total_boxes, const float* anchors_wh_host, int A, const float* image_wh_host,
+                                        int C, const int32_t hw[6], float* const targets[3], int zero_fill, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  YtParams p;
+  const int st0 = yt_fill_params(p, boxes, classes, offsets, B, total_boxes, anchors_wh_host, A, image_wh_host, C, hw, targets,
+                                 "b200_yolo_assign_targets");
+  if (st0 != B200_OK) return st0;
+  if (B == 0) return B200_OK;
   if (zero_fill) {
     bool vec_ok = true;
     FillMulti f;

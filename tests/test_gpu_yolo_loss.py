@@ -48,6 +48,42 @@ def test_get_targets_bit_exact(lib, cuda, image, batch, normalised):
     assert all(float(x.abs().sum()) == 0.0 for x in te)
 
 
+@pytest.mark.parametrize("image,batch", [(416, 3), (96, 6)])
+def test_get_targets_persistent_buffers(lib, cuda, image, batch):
+    """TargetBuffers: dense fill once, then sparse reset of the previous step's records — every step's tensors must
+    equal a fresh assignment bit for bit (different GT sets, collisions, an empty step, a shrinking/growing total)."""
+    from tfmv_b200 import synth
+    from tfmv_b200.ai_models.datasets.coco_dataset import DataGenerator, TargetBuffers
+    anc = synth.yolo_anchors().astype(F)
+    gen = DataGenerator(80, anc, (image, image))
+    buf = TargetBuffers()
+    ptrs = None
+    for step, max_boxes in enumerate([40, 100, 0, 7, 100]):
+        rng = np.random.default_rng(20261018 + 50 + step)
+        if max_boxes == 0:
+            boxes, classes, off = np.zeros((0, 4), F), np.zeros((0,), np.int32), np.zeros(batch + 1, np.int32)
+            want = [np.zeros((batch, image // s, image // s, 3, 85), F) for s in (32, 16, 8)]
+        else:
+            boxes, classes, off, want = _dense_targets(rng, batch, image, anc, max_boxes=max_boxes)
+            n0 = off[1]
+            if n0 >= 2:  # collision inside image 0
+                boxes[1] = boxes[0]
+                from oracle import yolo as oy
+                p0 = oy.get_targets(boxes[:n0], classes[:n0], anc, (image, image), 80)
+                for l in range(3):
+                    want[l][0] = p0[l]
+        got = gen.GetTargetsBatch(_t(classes, cuda), _t(boxes, cuda), _t(off, cuda), buffers=buf)
+        if ptrs is None:
+            ptrs = [t.data_ptr() for t in got]
+        assert [t.data_ptr() for t in got] == ptrs  # same tensors every step
+        for l in range(3):
+            assert_bits_equal(got[l].cpu().numpy(), want[l])
+    buf.invalidate()
+    got[0].fill_(3.0)
+    got = gen.GetTargetsBatch(_t(classes, cuda), _t(boxes, cuda), _t(off, cuda), buffers=buf)
+    assert_bits_equal(got[0].cpu().numpy(), want[0])
+
+
 @pytest.mark.parametrize("image,batch,iou_type,normalised", [
     (416, 2, "iou", False), (416, 2, "ciou", True), (608, 2, "ciou", False), (416, 3, "diou", True), (96, 5, "ciou", True)])
 def test_get_loss_matches_oracle(lib, cuda, image, batch, iou_type, normalised):
