@@ -2,17 +2,17 @@
 // Yolov4Loss.call (losses/yolo_loss.py:85-159).
 //
 // The reference materialises ~20 (H,W,A,n_gt) broadcast temporaries per image inside a tf.while_loop; here
-// the loss is three launches over the dense NHWC tensors, touching only the sectors the arithmetic needs:
+// the loss is four launches over the dense NHWC tensors, touching only the sectors the arithmetic needs:
 //
-//  K4a yolo_loss_objects_kernel   one CTA per 256 consecutive anchor records of one (level, image):
-//      reads the obj channel of y_true (one 32-byte sector per 340-byte record), stores it to a compact
-//      per-anchor array, and for records with obj != 0 (the ground-truth list, tyu:82) a warp per record reads
-//      the full y_true / y_pred records and produces the xy, wh and class terms (tyu:107-118) and the
-//      prepared GT box (corners, area, atan(w/h)) appended to the (image, level) GT list.
-//  K4b yolo_loss_ignore_kernel    same grid: reads the 5 box/conf logits of every y_pred record, decodes the
-//      predicted box (tyu:57-75), tests it against the GT list held in shared memory with the cheap
-//      "no overlap => metric <= 0 < thr" reject before any exact metric (iou / diou / ciou, tiu:5-65), and
-//      accumulates object_loss = obj*bce + (1-obj)*bce*ignore (tyu:111-114).
+//  K4a yolo_loss_scan_kernel     one CTA per 1024 consecutive anchor records of one (level, image): reads the obj
+//      channel of y_true (one 32-byte sector per 340-byte record), stores it to a compact per-anchor array and appends
+//      the records with obj != 0 (the ground-truth list, tyu:82) to the (image, level) object list.
+//  K4a' yolo_loss_terms_kernel    a warp per object: reads the full y_true / y_pred records and produces the xy, wh
+//      and class terms (tyu:107-118) and the prepared GT box (corners, area, atan(w/h), log area) of the ignore mask.
+//  K4b yolo_loss_ignore_kernel    one CTA per 128 records: reads the 5 box/conf logits of every y_pred record, runs
+//      the decode-free and approximate-IoU rejects against the GT list, queues the surviving (record, GT) pairs for
+//      the exact decode (tyu:57-75) and exact metric (iou / diou / ciou, tiu:5-65), and accumulates
+//      object_loss = obj*bce + (1-obj)*bce*ignore (tyu:111-114).
 //  K4c yolo_loss_finalize_kernel  fixed-order fp64 reduction of the per-CTA partials -> parts[3][4] / batch,
 //      loss = sum_l ((xy+wh)+obj)+cls in fp32 in the reference's order (tyu:120-125).  Deterministic run to run.
 //
@@ -35,7 +35,7 @@ struct YlLevels {
   int h[YL_LEVELS], w[YL_LEVELS], rec_per_img[YL_LEVELS], anchor_base[YL_LEVELS];
   int chunks_per_img[YL_LEVELS];
   int cta_base[YL_LEVELS + 1];
-  int obj_chunks_per_img[YL_LEVELS];   // objects kernel: 4 records per thread
+  int obj_chunks_per_img[YL_LEVELS];   // scan kernel: 4 records per thread
   int obj_cta_base[YL_LEVELS + 1];
   uint32_t magic_w[YL_LEVELS];         // floor(2^32/W)+1
   float anc_w[YL_LEVELS][8], anc_h[YL_LEVELS][8];  // pixels
@@ -55,12 +55,12 @@ struct YlParams {
   float tmin_w[YL_LEVELS][8], tmin_h[YL_LEVELS][8];  // lowest tw/th for which the decode-free area bound holds
   uint32_t magic_a;           // floor(2^32/A)+1: n/A == umulhi(n, magic) for n*A < 2^32
   float* conf_grad;           // optional [level-major: B*anchor_base[l] + image*rec_per_img + rin]: d loss / d conf logit
-  int32_t* obj_index;         // optional [B, n_img]: record index of each GT-list slot (backward pass)
+  int32_t* obj_index;         // [B, n_img]: record index of each object-list / GT-list slot
   float inv_div;              // 1 / batch_divisor
   unsigned char* out_ignore;  // optional [B, n_img]: the ignore mask (1 = ignored/background), for parity tests
   int32_t* gt_count;    // [B, 3]
   double* partials;     // [n_cta]      object_loss partial of each ignore-kernel CTA
-  double* partials_obj; // [n_cta_obj,3] xy, wh, cls partials of each objects-kernel CTA
+  double* partials_obj; // [3*B*YL_TERM_SPLIT,3] xy, wh, cls partials of each terms-kernel CTA (level-major)
 };
 
 __device__ __forceinline__ void yl_locate(const YlLevels& lv, int cta, int& l, int& img, int& chunk) {
@@ -79,14 +79,18 @@ __device__ __forceinline__ bool yl_regular(const BoxT& b) {
          (dm_fabsf(b.c0) < 3.0e38f) && (dm_fabsf(b.c1) < 3.0e38f) && (dm_fabsf(b.c2) < 3.0e38f) && (dm_fabsf(b.c3) < 3.0e38f);
 }
 
+#ifndef YL_OBJ_PER_THREAD
 #define YL_OBJ_PER_THREAD 4
+#endif
 #define YL_OBJ_CHUNK (YL_CHUNK * YL_OBJ_PER_THREAD)
 
-__global__ void __launch_bounds__(YL_CHUNK) yolo_loss_objects_kernel(YlParams p) {
+// K4a: pure stream over the obj channel.  Objects (obj != 0) are appended to the (image, level) object list in
+// obj_index; their terms are computed by the next kernel, when the memory system is no longer saturated by the scan
+// (doing it here cost a second DRAM round trip per CTA behind everyone else's scan loads: 42 us vs 30 + 4).
+__global__ void __launch_bounds__(YL_CHUNK) yolo_loss_scan_kernel(YlParams p) {
   __shared__ int s_list[YL_OBJ_CHUNK];
-  __shared__ int s_n;
-  __shared__ double s_acc[YL_CHUNK / 32][3];
-  // same (level, image, chunk) decomposition as the ignore kernel but with 4x larger chunks
+  __shared__ int s_n, s_base;
+  // same (level, image, chunk) decomposition as the ignore kernel but with larger chunks
   int l = 0;
 #pragma unroll
   for (int k = 1; k < YL_LEVELS; ++k) if ((int)blockIdx.x >= p.lv.obj_cta_base[k]) l = k;
@@ -94,11 +98,9 @@ __global__ void __launch_bounds__(YL_CHUNK) yolo_loss_objects_kernel(YlParams p)
   const int img = rcta / p.lv.obj_chunks_per_img[l];
   const int chunk = rcta - img * p.lv.obj_chunks_per_img[l];
   const int rpi = p.lv.rec_per_img[l];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
   const float* yt = p.lv.y_true[l] + ((size_t)img * rpi) * p.RF;
-  const float* yp = p.lv.y_pred[l] + ((size_t)img * rpi) * p.RF;
   float objv[YL_OBJ_PER_THREAD];
 #pragma unroll
   for (int u = 0; u < YL_OBJ_PER_THREAD; ++u) {  // independent strided sector reads, all in flight together
@@ -115,10 +117,32 @@ __global__ void __launch_bounds__(YL_CHUNK) yolo_loss_objects_kernel(YlParams p)
   }
   __syncthreads();
   const int n = s_n;
+  if (n == 0) return;
+  if (threadIdx.x == 0) s_base = atomicAdd(&p.gt_count[img * YL_LEVELS + l], n);
+  __syncthreads();
+  int32_t* dst = p.obj_index + (size_t)img * p.n_img + p.lv.anchor_base[l] + s_base;
+  for (int i = threadIdx.x; i < n; i += YL_CHUNK) dst[i] = s_list[i];
+}
+
+// K4a': a warp per object record: xy / wh / class terms (tyu:107-118) and the prepared GT box of the ignore mask.
+// Grid = 3 * B * YL_TERM_SPLIT CTAs; CTA (l, img, s) takes objects k = s*8 + warp, stepping by 8*YL_TERM_SPLIT.
+#define YL_TERM_SPLIT 8
+
+__global__ void __launch_bounds__(YL_CHUNK) yolo_loss_terms_kernel(YlParams p) {
+  __shared__ double s_acc[YL_CHUNK / 32][3];
+  const int l = blockIdx.x / (p.B * YL_TERM_SPLIT);
+  const int rem = blockIdx.x - l * (p.B * YL_TERM_SPLIT);
+  const int img = rem / YL_TERM_SPLIT, split = rem - img * YL_TERM_SPLIT;
+  const int rpi = p.lv.rec_per_img[l];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* yt = p.lv.y_true[l] + ((size_t)img * rpi) * p.RF;
+  const float* yp = p.lv.y_pred[l] + ((size_t)img * rpi) * p.RF;
+  const int n = p.gt_count[img * YL_LEVELS + l];
+  const size_t gbase = (size_t)img * p.n_img + p.lv.anchor_base[l];
   double a_xy = 0.0, a_wh = 0.0, a_cls = 0.0;
   const int W = p.lv.w[l], H = p.lv.h[l];
-  for (int k = warp; k < n; k += YL_CHUNK / 32) {
-    const int r = s_list[k];
+  for (int k = split * (YL_CHUNK / 32) + warp; k < n; k += YL_TERM_SPLIT * (YL_CHUNK / 32)) {
+    const int r = p.obj_index[gbase + k];
     const float* t = yt + (size_t)r * p.RF;
     const float* q = yp + (size_t)r * p.RF;
     const float obj = __ldg(t + 4);
@@ -153,11 +177,8 @@ __global__ void __launch_bounds__(YL_CHUNK) yolo_loss_objects_kernel(YlParams p)
       // ground-truth box for the ignore mask: corners of (t_xy, t_wh), tyu:68-71
       const float hx = DM_DIV(tw, 2.0f), hy = DM_DIV(th, 2.0f);
       BoxT g = bm_prep(DM_SUB(tx, hx), DM_SUB(ty, hy), DM_ADD(tx, hx), DM_ADD(ty, hy), p.metric);
-      const int slot = atomicAdd(&p.gt_count[img * YL_LEVELS + l], 1);
-      const size_t gi = (size_t)img * p.n_img + p.lv.anchor_base[l] + slot;
-      p.gt_box[gi] = make_float4(g.c0, g.c1, g.c2, g.c3);
-      p.gt_aux[gi] = make_float4(g.area, g.at, dm_logf(g.area), yl_regular(g) ? 1.0f : 0.0f);
-      if (p.obj_index) p.obj_index[gi] = r;
+      p.gt_box[gbase + k] = make_float4(g.c0, g.c1, g.c2, g.c3);
+      p.gt_aux[gbase + k] = make_float4(g.area, g.at, dm_logf(g.area), yl_regular(g) ? 1.0f : 0.0f);
     }
   }
   if (lane == 0) { s_acc[warp][0] = a_xy; s_acc[warp][1] = a_wh; s_acc[warp][2] = a_cls; }
@@ -180,6 +201,8 @@ __global__ void __launch_bounds__(YL_CHUNK) yolo_loss_objects_kernel(YlParams p)
 // Both use only tw, th and the cell index; a lane decodes its box (2 sigmoid, 2 exp, atan) only when some GT
 // passes both, and then runs the exact test.  Lanes with |t| outside [-6,4] or NaN, irregular GTs and thr < 0.5
 // take the exact path against every GT.
+#define YL_IOU_EPS 5e-3f
+#define YL_IOU_FLOOR 1e-2f
 #define YL_CELL_MARGIN 1e-3f
 #define YL_LOG_MARGIN 0.05f
 
@@ -203,6 +226,9 @@ __device__ __forceinline__ int yl_fastdiv(int n, uint32_t magic) {
 //  3. object_loss = obj*bce + (1-obj)*bce*ignore for every record.
 // The GT list is read straight from global memory (packed float4 pairs, L1-resident).
 #define YL_QCAP 1024
+#ifndef YL_IMINB
+#define YL_IMINB 8   // 64 registers: no spills; 10 (48 registers) spills and is 5 us slower
+#endif
 
 __device__ __forceinline__ bool yl_pair_hits(const YlParams& p, int l, int rin, float tx, float ty, float tw, float th,
                                              const float4 c, const float4 x) {
@@ -230,7 +256,7 @@ __device__ __forceinline__ bool yl_pair_hits(const YlParams& p, int l, int rin, 
   return (mm >= p.thr) || (mm != mm);  // NaN propagates through tf.reduce_max: best < thr is False
 }
 
-__global__ void __launch_bounds__(YL_ICHUNK, 10) yolo_loss_ignore_kernel(YlParams p) {
+__global__ void __launch_bounds__(YL_ICHUNK, YL_IMINB) yolo_loss_ignore_kernel(YlParams p) {
   __shared__ float4 s_t[YL_ICHUNK];
   __shared__ uint32_t s_q[YL_QCAP];
   __shared__ uint32_t s_hit[YL_ICHUNK / 32];
@@ -254,12 +280,12 @@ __global__ void __launch_bounds__(YL_ICHUNK, 10) yolo_loss_ignore_kernel(YlParam
       // tx,ty,tw,th,conf sit at float offset f0; two aligned 16-byte loads cover them (L1 bypass)
       const float4 lo = __ldcg(reinterpret_cast<const float4*>(p.lv.y_pred[l]) + (f0 >> 2));
       const float4 hi = __ldcg(reinterpret_cast<const float4*>(p.lv.y_pred[l]) + (f0 >> 2) + 1);
+      // the record starts 0..3 floats into lo: rotate the 8 loaded floats left by sh with two select stages
       const int sh = (int)(f0 & 3);
-      tx = sh == 0 ? lo.x : sh == 1 ? lo.y : sh == 2 ? lo.z : lo.w;
-      ty = sh == 0 ? lo.y : sh == 1 ? lo.z : sh == 2 ? lo.w : hi.x;
-      tw = sh == 0 ? lo.z : sh == 1 ? lo.w : sh == 2 ? hi.x : hi.y;
-      th = sh == 0 ? lo.w : sh == 1 ? hi.x : sh == 2 ? hi.y : hi.z;
-      pobj = sh == 0 ? hi.x : sh == 1 ? hi.y : sh == 2 ? hi.z : hi.w;
+      const bool s1 = sh & 1, s2 = sh & 2;
+      const float a0 = s1 ? lo.y : lo.x, a1 = s1 ? lo.z : lo.y, a2 = s1 ? lo.w : lo.z, a3 = s1 ? hi.x : lo.w;
+      const float a4 = s1 ? hi.y : hi.x, a5 = s1 ? hi.z : hi.y, a6 = s1 ? hi.w : hi.z;
+      tx = s2 ? a2 : a0; ty = s2 ? a3 : a1; tw = s2 ? a4 : a2; th = s2 ? a5 : a3; pobj = s2 ? a6 : a4;
     } else {
       const float* q = p.lv.y_pred[l] + f0;
       tx = __ldcg(q); ty = __ldcg(q + 1); tw = __ldcg(q + 2); th = __ldcg(q + 3); pobj = __ldcg(q + 4);
@@ -282,6 +308,22 @@ __global__ void __launch_bounds__(YL_ICHUNK, 10) yolo_loss_ignore_kernel(YlParam
                       (th <= 4.0f) && (tx == tx) && (ty == ty);
     const float sp = tw + th + p.logk[l][a];
     const float invW = 1.0f / (float)W, invH = 1.0f / (float)H;
+    // (c) approximate decode (MUFU exp / reciprocal; corner error < 2e-6 for boxes up to 2 image widths) for an
+    // IoU *upper-bound* reject: every metric of the family is <= IoU, so IoU_fast < thr - YL_IOU_EPS with both
+    // overlap extents >= YL_IOU_FLOOR (relative IoU error then < 3.2e-3) proves metric < thr.  Accepts
+    // are never decided here: pairs that survive go to the exact test.
+    float fx0 = 0.f, fy0 = 0.f, fx1 = 0.f, fy1 = 0.f, farea = 0.f;
+    bool fast_ok = false;
+    if (nice) {
+      const float ex = __expf(-fabsf(tx)), ey = __expf(-fabsf(ty));
+      const float rx = __fdividef(1.0f, 1.0f + ex), ry = __fdividef(1.0f, 1.0f + ey);
+      const float fx = ((tx >= 0.0f ? rx : ex * rx) + (float)gx) * invW, fy = ((ty >= 0.0f ? ry : ey * ry) + (float)gy) * invH;
+      const float fw = __expf(tw) * __fdividef(p.lv.anc_w[l][a], p.img_w), fh = __expf(th) * __fdividef(p.lv.anc_h[l][a], p.img_h);
+      fx0 = fx - 0.5f * fw; fx1 = fx + 0.5f * fw; fy0 = fy - 0.5f * fh; fy1 = fy + 0.5f * fh;
+      farea = fw * fh;
+      fast_ok = (fw <= 2.0f) && (fh <= 2.0f);
+    }
+    const float thr_lo = p.thr - YL_IOU_EPS;
     // rectangle that certainly contains the decoded centre (grid cell grown by the margin)
     const float cx0 = (float)gx * invW - YL_CELL_MARGIN, cx1 = (float)(gx + 1) * invW + YL_CELL_MARGIN;
     const float cy0 = (float)gy * invH - YL_CELL_MARGIN, cy1 = (float)(gy + 1) * invH + YL_CELL_MARGIN;
@@ -318,10 +360,21 @@ __global__ void __launch_bounds__(YL_ICHUNK, 10) yolo_loss_ignore_kernel(YlParam
         if (nice && x.w != 0.0f) {
           if ((cx1 < c.x) || (c.z < cx0) || (cy1 < c.y) || (c.w < cy0)) continue;
           if ((sp < x.z + lo_k) || (sp > x.z + hi_k)) continue;
+          const float iw = fminf(fx1, c.z) - fmaxf(fx0, c.x), ih = fminf(fy1, c.w) - fmaxf(fy0, c.y);
+          if ((iw < -1e-5f) || (ih < -1e-5f)) continue;  // disjoint by far more than the decode error
+          if (fast_ok && (iw >= YL_IOU_FLOOR) && (ih >= YL_IOU_FLOOR)) {
+            const float inter = iw * ih;
+            if (inter < thr_lo * (farea + x.x - inter)) continue;
+          }
         }
         const int slot = atomicAdd(&s_nq, 1);
         if (slot < YL_QCAP) s_q[slot] = (threadIdx.x << 24) | (uint32_t)g;            // drained in phase 2
-        else if (yl_pair_hits(p, l, rin, tx, ty, tw, th, c, x)) hit = true;             // queue full: inline
+        else {  // queue full: exact test now.  The logits pass through an opaque asm so that the compiler cannot
+                // hoist the record decode in front of the filter loop (it did: ~200 instructions per warp, always).
+          float otx = tx, oty = ty, otw = tw, oth = th;
+          asm volatile("" : "+f"(otx), "+f"(oty), "+f"(otw), "+f"(oth));
+          if (yl_pair_hits(p, l, rin, otx, oty, otw, oth, c, x)) hit = true;
+        }
       }
     }
     if (hit) atomicOr(&s_hit[warp], 1u << lane);
@@ -521,7 +574,7 @@ static YlWs yl_layout(const int32_t hw[6], int B, int A, int* n_img_out, YlLevel
   w.gt = o; o = b200_align_up(o + sizeof(float4) * (size_t)B * n_img, 256);
   w.gtl = o; o = b200_align_up(o + sizeof(float4) * (size_t)B * n_img, 256);
   w.part = o; o = b200_align_up(o + sizeof(double) * (size_t)cta, 256);
-  w.part_obj = o; o = b200_align_up(o + sizeof(double) * 3 * (size_t)octa, 256);
+  w.part_obj = o; o = b200_align_up(o + sizeof(double) * 3 * (size_t)YL_LEVELS * B * YL_TERM_SPLIT, 256);
   w.cgrad = o; o = b200_align_up(o + sizeof(float) * (size_t)B * n_img, 256);
   w.oidx = o; o = b200_align_up(o + sizeof(int32_t) * (size_t)B * n_img, 256);
   w.total = o;
@@ -579,20 +632,22 @@ static int yolo_loss_impl(const float* const y_true[3], const float* const y_pre
   p.out_ignore = out_ignore;
   p.inv_div = 1.0f / batch_divisor;
   p.conf_grad = out_grad ? reinterpret_cast<float*>(wsb + ws.cgrad) : nullptr;
-  p.obj_index = out_grad ? reinterpret_cast<int32_t*>(wsb + ws.oidx) : nullptr;
+  p.obj_index = reinterpret_cast<int32_t*>(wsb + ws.oidx);
   p.magic_a = A == 1 ? 0u : (uint32_t)((1ull << 32) / (unsigned long long)A + 1ull);
   for (int l = 0; l < YL_LEVELS; ++l) p.lv.magic_w[l] = p.lv.w[l] == 1 ? 0u : (uint32_t)((1ull << 32) / (unsigned long long)p.lv.w[l] + 1ull);
   p.gt_count = reinterpret_cast<int32_t*>(wsb + ws.cnt);
   p.partials = reinterpret_cast<double*>(wsb + ws.part);
   p.partials_obj = reinterpret_cast<double*>(wsb + ws.part_obj);
   B200_CUDA(cudaMemsetAsync(wsb + ws.cnt, 0, sizeof(int32_t) * (size_t)B * YL_LEVELS, stream));
-  yolo_loss_objects_kernel<<<ws.n_cta_obj, YL_CHUNK, 0, stream>>>(p);
+  yolo_loss_scan_kernel<<<ws.n_cta_obj, YL_CHUNK, 0, stream>>>(p);
+  B200_LAUNCH_CHECK();
+  yolo_loss_terms_kernel<<<YL_LEVELS * B * YL_TERM_SPLIT, YL_CHUNK, 0, stream>>>(p);
   B200_LAUNCH_CHECK();
   yolo_loss_ignore_kernel<<<ws.n_cta, YL_ICHUNK, 0, stream>>>(p);
   B200_LAUNCH_CHECK();
   YlFinalize f;
   f.partials = p.partials; f.partials_obj = p.partials_obj;
-  for (int l = 0; l <= YL_LEVELS; ++l) { f.cta_base[l] = p.lv.cta_base[l]; f.obj_cta_base[l] = p.lv.obj_cta_base[l]; }
+  for (int l = 0; l <= YL_LEVELS; ++l) { f.cta_base[l] = p.lv.cta_base[l]; f.obj_cta_base[l] = l * B * YL_TERM_SPLIT; }
   f.batch_divisor = batch_divisor; f.parts = out_parts; f.loss = out_loss;
   yolo_loss_finalize_kernel<<<1, 1024, 0, stream>>>(f);
   B200_LAUNCH_CHECK();
