@@ -339,7 +339,7 @@ def run_b200(args, wl):
     for name, fn, nbytes, launches in (
             ("fill_zero x3 buffers (dense y_true zero-fill, write)", ph_fill, n_fill * 4, 3),
             ("yolo_scatter_targets_kernel (one CTA per image)", ph_scatter, int(boxes_d.shape[0]) * (16 + 4 + 340), 1),
-            ("yolo_loss objects+ignore+finalize kernels (dense-equivalent read of y_true+y_pred)", ph_loss, 2 * n_fill * 4, 3)):
+            ("yolo_loss scan+gtprep+ignore+finalize kernels (dense-equivalent read of y_true+y_pred)", ph_loss, 2 * n_fill * 4, 4)):
         ms = timed(fn, args.steps, 3) / args.steps
         phases.append({"kernel": name, "ms": ms, "algorithmic_bytes": nbytes, "gbps": nbytes / ms / 1e6, "launches": launches})
         ph_fill(); ph_scatter()  # restore valid targets (repeated scatters collide with themselves)
@@ -418,7 +418,7 @@ def run_b200(args, wl):
                        "l2": "inputs larger than L2 (y_pred %.0f MB + y_true %.0f MB per step vs 126 MB L2)" % (
                            n_fill * 4 / 1e6, n_fill * 4 / 1e6)},
             "loss": loss_val, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "persistent_targets": persistent,
-            "gpu_launches": 5 * args.steps, "clocks": clocks,
+            "gpu_launches": 6 * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -7,12 +7,13 @@
 //  K4a yolo_loss_scan_kernel     one CTA per 1024 consecutive anchor records of one (level, image): reads the obj
 //      channel of y_true (one 32-byte sector per 340-byte record), stores it to a compact per-anchor array and appends
 //      the records with obj != 0 (the ground-truth list, tyu:82) to the (image, level) object list.
-//  K4a' yolo_loss_terms_kernel    a warp per object: reads the full y_true / y_pred records and produces the xy, wh
-//      and class terms (tyu:107-118) and the prepared GT box (corners, area, atan(w/h), log area) of the ignore mask.
+//  K4a' yolo_loss_gtprep_kernel   a thread per object: the prepared GT box (corners, area, atan(w/h), log area) of the
+//      ignore mask.
 //  K4b yolo_loss_ignore_kernel    one CTA per 128 records: reads the 5 box/conf logits of every y_pred record, runs
 //      the decode-free and approximate-IoU rejects against the GT list, queues the surviving (record, GT) pairs for
 //      the exact decode (tyu:57-75) and exact metric (iou / diou / ciou, tiu:5-65), and accumulates
-//      object_loss = obj*bce + (1-obj)*bce*ignore (tyu:111-114).
+//      object_loss = obj*bce + (1-obj)*bce*ignore (tyu:111-114).  The trailing CTAs of its grid instead take a warp per
+//      object and produce the xy, wh and class terms (tyu:107-118) from the full y_true / y_pred records.
 //  K4c yolo_loss_finalize_kernel  fixed-order fp64 reduction of the per-CTA partials -> parts[3][4] / batch,
 //      loss = sum_l ((xy+wh)+obj)+cls in fp32 in the reference's order (tyu:120-125).  Deterministic run to run.
 //
@@ -124,14 +125,35 @@ __global__ void __launch_bounds__(YL_CHUNK) yolo_loss_scan_kernel(YlParams p) {
   for (int i = threadIdx.x; i < n; i += YL_CHUNK) dst[i] = s_list[i];
 }
 
-// K4a': a warp per object record: xy / wh / class terms (tyu:107-118) and the prepared GT box of the ignore mask.
-// Grid = 3 * B * YL_TERM_SPLIT CTAs; CTA (l, img, s) takes objects k = s*8 + warp, stepping by 8*YL_TERM_SPLIT.
-#define YL_TERM_SPLIT 8
+// K4a': one thread per object: the prepared GT box of the ignore mask (corners of (t_xy, t_wh), tyu:68-71; area,
+// atan(w/h), log area, "regular" flag).  One CTA per (level, image).
+__global__ void __launch_bounds__(128) yolo_loss_gtprep_kernel(YlParams p) {
+  const int l = blockIdx.x / p.B, img = blockIdx.x - l * p.B;
+  const int rpi = p.lv.rec_per_img[l];
+  const float* yt = p.lv.y_true[l] + ((size_t)img * rpi) * p.RF;
+  const int n = p.gt_count[img * YL_LEVELS + l];
+  const size_t gbase = (size_t)img * p.n_img + p.lv.anchor_base[l];
+  for (int k = threadIdx.x; k < n; k += 128) {
+    const float* t = yt + (size_t)p.obj_index[gbase + k] * p.RF;
+    const float tx = __ldg(t), ty = __ldg(t + 1), tw = __ldg(t + 2), th = __ldg(t + 3);
+    const float hx = DM_DIV(tw, 2.0f), hy = DM_DIV(th, 2.0f);
+    BoxT g = bm_prep(DM_SUB(tx, hx), DM_SUB(ty, hy), DM_ADD(tx, hx), DM_ADD(ty, hy), p.metric);
+    p.gt_box[gbase + k] = make_float4(g.c0, g.c1, g.c2, g.c3);
+    p.gt_aux[gbase + k] = make_float4(g.area, g.at, dm_logf(g.area), yl_regular(g) ? 1.0f : 0.0f);
+  }
+}
 
-__global__ void __launch_bounds__(YL_CHUNK) yolo_loss_terms_kernel(YlParams p) {
-  __shared__ double s_acc[YL_CHUNK / 32][3];
-  const int l = blockIdx.x / (p.B * YL_TERM_SPLIT);
-  const int rem = blockIdx.x - l * (p.B * YL_TERM_SPLIT);
+// A warp per object record: xy / wh / class terms (tyu:107-118).  Runs as the trailing 3*B*YL_TERM_SPLIT CTAs of the
+// ignore kernel's grid (two dependent DRAM round trips and ~600 serial instructions per object: hidden under the
+// ignore pass instead of sitting on the critical path).  CTA (l, img, s) takes objects k = s*4 + warp, stepping by
+// 4*YL_TERM_SPLIT.
+#ifndef YL_TERM_SPLIT
+#define YL_TERM_SPLIT 16
+#endif
+
+__device__ __forceinline__ void yl_terms_body(const YlParams& p, int cta, double (*s_acc)[3]) {
+  const int l = cta / (p.B * YL_TERM_SPLIT);
+  const int rem = cta - l * (p.B * YL_TERM_SPLIT);
   const int img = rem / YL_TERM_SPLIT, split = rem - img * YL_TERM_SPLIT;
   const int rpi = p.lv.rec_per_img[l];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -141,7 +163,7 @@ __global__ void __launch_bounds__(YL_CHUNK) yolo_loss_terms_kernel(YlParams p) {
   const size_t gbase = (size_t)img * p.n_img + p.lv.anchor_base[l];
   double a_xy = 0.0, a_wh = 0.0, a_cls = 0.0;
   const int W = p.lv.w[l], H = p.lv.h[l];
-  for (int k = split * (YL_CHUNK / 32) + warp; k < n; k += YL_TERM_SPLIT * (YL_CHUNK / 32)) {
+  for (int k = split * (YL_ICHUNK / 32) + warp; k < n; k += YL_TERM_SPLIT * (YL_ICHUNK / 32)) {
     const int r = p.obj_index[gbase + k];
     const float* t = yt + (size_t)r * p.RF;
     const float* q = yp + (size_t)r * p.RF;
@@ -172,21 +194,14 @@ __global__ void __launch_bounds__(YL_CHUNK) yolo_loss_terms_kernel(YlParams p) {
     }
     for (int c = 5 + lane; c < p.RF; c += 32) e_cls += DM_MUL(obj, dm_bce_logits(__ldg(t + c), __ldg(q + c)));
     e_xy = warp_sum(e_xy); e_wh = warp_sum(e_wh); e_cls = warp_sum(e_cls);
-    if (lane == 0) {
-      a_xy += (double)e_xy; a_wh += (double)e_wh; a_cls += (double)e_cls;
-      // ground-truth box for the ignore mask: corners of (t_xy, t_wh), tyu:68-71
-      const float hx = DM_DIV(tw, 2.0f), hy = DM_DIV(th, 2.0f);
-      BoxT g = bm_prep(DM_SUB(tx, hx), DM_SUB(ty, hy), DM_ADD(tx, hx), DM_ADD(ty, hy), p.metric);
-      p.gt_box[gbase + k] = make_float4(g.c0, g.c1, g.c2, g.c3);
-      p.gt_aux[gbase + k] = make_float4(g.area, g.at, dm_logf(g.area), yl_regular(g) ? 1.0f : 0.0f);
-    }
+    if (lane == 0) { a_xy += (double)e_xy; a_wh += (double)e_wh; a_cls += (double)e_cls; }
   }
   if (lane == 0) { s_acc[warp][0] = a_xy; s_acc[warp][1] = a_wh; s_acc[warp][2] = a_cls; }
   __syncthreads();
   if (threadIdx.x == 0) {
     double x = 0, w = 0, c = 0;
-    for (int i = 0; i < YL_CHUNK / 32; ++i) { x += s_acc[i][0]; w += s_acc[i][1]; c += s_acc[i][2]; }
-    double* out = p.partials_obj + (size_t)blockIdx.x * 3;
+    for (int i = 0; i < YL_ICHUNK / 32; ++i) { x += s_acc[i][0]; w += s_acc[i][1]; c += s_acc[i][2]; }
+    double* out = p.partials_obj + (size_t)cta * 3;
     out[0] = x; out[1] = w; out[2] = c;
   }
 }
@@ -262,8 +277,16 @@ __global__ void __launch_bounds__(YL_ICHUNK, YL_IMINB) yolo_loss_ignore_kernel(Y
   __shared__ uint32_t s_hit[YL_ICHUNK / 32];
   __shared__ int s_nq;
   __shared__ double s_acc[YL_ICHUNK / 32];
+  const int n_term_cta = YL_LEVELS * p.B * YL_TERM_SPLIT;
+  const int n_icta = (int)gridDim.x - n_term_cta;
+  if ((int)blockIdx.x >= n_icta) {  // block-uniform
+    __shared__ double s_tacc[YL_ICHUNK / 32][3];
+    yl_terms_body(p, blockIdx.x - n_icta, s_tacc);
+    return;
+  }
+  const int icta = blockIdx.x;
   int l, img, chunk;
-  yl_locate(p.lv, blockIdx.x, l, img, chunk);
+  yl_locate(p.lv, icta, l, img, chunk);
   const int rpi = p.lv.rec_per_img[l];
   const int rin = chunk * YL_ICHUNK + (int)threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -413,27 +436,36 @@ __global__ void __launch_bounds__(YL_ICHUNK, YL_IMINB) yolo_loss_ignore_kernel(Y
   if (threadIdx.x == 0) {
     double sum = 0;
     for (int i = 0; i < YL_ICHUNK / 32; ++i) sum += s_acc[i];
-    p.partials[blockIdx.x] = sum;
+    p.partials[icta] = sum;
   }
 }
+
+// K4c: YL_FIN_CTAS CTAs each reduce an interleaved share of the per-CTA partials in fp64 (fixed assignment, fixed
+// order); the CTA that takes the last ticket adds the YL_FIN_CTAS slices in index order and writes parts / loss.
+// Deterministic run to run, and ~3x shorter than one CTA walking all 46 k partials.
+#define YL_FIN_CTAS 32
+#define YL_FIN_THREADS 256
 
 struct YlFinalize {
   const double* partials; const double* partials_obj;
   int cta_base[YL_LEVELS + 1]; int obj_cta_base[YL_LEVELS + 1];
   float batch_divisor; float* parts; float* loss;
+  double* slices;          // [YL_FIN_CTAS][12]
+  unsigned int* ticket;    // zero on entry; reset by the last CTA
 };
 
-__global__ void __launch_bounds__(1024) yolo_loss_finalize_kernel(YlFinalize f) {
-  __shared__ double s_red[32][12];
+__global__ void __launch_bounds__(YL_FIN_THREADS) yolo_loss_finalize_kernel(YlFinalize f) {
+  __shared__ double s_red[YL_FIN_THREADS / 32][12];
+  __shared__ bool s_last;
   double acc[12];
 #pragma unroll
   for (int i = 0; i < 12; ++i) acc[i] = 0.0;
+  const int t0 = blockIdx.x * YL_FIN_THREADS + (int)threadIdx.x, stride = YL_FIN_CTAS * YL_FIN_THREADS;
 #pragma unroll
   for (int l = 0; l < 3; ++l) {
 #pragma unroll 4
-    for (int c = f.cta_base[l] + (int)threadIdx.x; c < f.cta_base[l + 1]; c += 1024) acc[l * 4 + 2] += f.partials[c];
-#pragma unroll 2
-    for (int c = f.obj_cta_base[l] + (int)threadIdx.x; c < f.obj_cta_base[l + 1]; c += 1024) {
+    for (int c = f.cta_base[l] + t0; c < f.cta_base[l + 1]; c += stride) acc[l * 4 + 2] += f.partials[c];
+    for (int c = f.obj_cta_base[l] + t0; c < f.obj_cta_base[l + 1]; c += stride) {
       acc[l * 4 + 0] += f.partials_obj[(size_t)c * 3 + 0];
       acc[l * 4 + 1] += f.partials_obj[(size_t)c * 3 + 1];
       acc[l * 4 + 3] += f.partials_obj[(size_t)c * 3 + 2];
@@ -446,21 +478,32 @@ __global__ void __launch_bounds__(1024) yolo_loss_finalize_kernel(YlFinalize f) 
     if (lane == 0) s_red[warp][i] = v;
   }
   __syncthreads();
+  if (threadIdx.x < 12) {
+    double s = 0.0;
+    for (int w = 0; w < YL_FIN_THREADS / 32; ++w) s += s_red[w][threadIdx.x];
+    f.slices[blockIdx.x * 12 + threadIdx.x] = s;
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(f.ticket, 1u) == YL_FIN_CTAS - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
   if (warp == 0) {
     float v = 0.0f;
     if (lane < 12) {
       double s = 0.0;
-      for (int w = 0; w < 32; ++w) s += s_red[w][lane];
+      for (int g = 0; g < YL_FIN_CTAS; ++g) s += __ldcg(f.slices + g * 12 + lane);
       v = DM_DIV((float)s, f.batch_divisor);  // reduce_sum(...) / batch_size_float, tyu:120-123
       if (f.parts) f.parts[lane] = v;
     }
     float total = 0.0f;
     for (int l = 0; l < 3; ++l) {
-      const float t0 = __shfl_sync(0xffffffffu, v, l * 4 + 0), t1 = __shfl_sync(0xffffffffu, v, l * 4 + 1);
+      const float t0_ = __shfl_sync(0xffffffffu, v, l * 4 + 0), t1 = __shfl_sync(0xffffffffu, v, l * 4 + 1);
       const float t2 = __shfl_sync(0xffffffffu, v, l * 4 + 2), t3 = __shfl_sync(0xffffffffu, v, l * 4 + 3);
-      total = DM_ADD(total, DM_ADD(DM_ADD(DM_ADD(t0, t1), t2), t3));  // tyu:125
+      total = DM_ADD(total, DM_ADD(DM_ADD(DM_ADD(t0_, t1), t2), t3));  // tyu:125
     }
-    if (lane == 0) *f.loss = total;
+    if (lane == 0) { *f.loss = total; *f.ticket = 0u; }
   }
 }
 
@@ -546,7 +589,7 @@ __global__ void __launch_bounds__(256) yolo_loss_grad_objects_kernel(YlParams p,
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-struct YlWs { size_t obj, gt, gtl, cnt, part, part_obj, cgrad, oidx, total; int n_cta, n_cta_obj; };
+struct YlWs { size_t obj, gt, gtl, cnt, part, part_obj, cgrad, oidx, fin, total; int n_cta, n_cta_obj; };
 
 static YlWs yl_layout(const int32_t hw[6], int B, int A, int* n_img_out, YlLevels* lv) {
   YlWs w;
@@ -569,7 +612,7 @@ static YlWs yl_layout(const int32_t hw[6], int B, int A, int* n_img_out, YlLevel
   w.n_cta = cta;
   w.n_cta_obj = octa;
   size_t o = 0;
-  w.cnt = o; o = b200_align_up(o + sizeof(int32_t) * (size_t)B * YL_LEVELS, 256);
+  w.cnt = o; o = b200_align_up(o + sizeof(int32_t) * ((size_t)B * YL_LEVELS + 1), 256);  // + the finalize ticket
   w.obj = o; o = b200_align_up(o + sizeof(float) * (size_t)B * n_img, 256);
   w.gt = o; o = b200_align_up(o + sizeof(float4) * (size_t)B * n_img, 256);
   w.gtl = o; o = b200_align_up(o + sizeof(float4) * (size_t)B * n_img, 256);
@@ -577,6 +620,7 @@ static YlWs yl_layout(const int32_t hw[6], int B, int A, int* n_img_out, YlLevel
   w.part_obj = o; o = b200_align_up(o + sizeof(double) * 3 * (size_t)YL_LEVELS * B * YL_TERM_SPLIT, 256);
   w.cgrad = o; o = b200_align_up(o + sizeof(float) * (size_t)B * n_img, 256);
   w.oidx = o; o = b200_align_up(o + sizeof(int32_t) * (size_t)B * n_img, 256);
+  w.fin = o; o = b200_align_up(o + sizeof(double) * 12 * YL_FIN_CTAS, 256);
   w.total = o;
   return w;
 }
@@ -638,18 +682,20 @@ static int yolo_loss_impl(const float* const y_true[3], const float* const y_pre
   p.gt_count = reinterpret_cast<int32_t*>(wsb + ws.cnt);
   p.partials = reinterpret_cast<double*>(wsb + ws.part);
   p.partials_obj = reinterpret_cast<double*>(wsb + ws.part_obj);
-  B200_CUDA(cudaMemsetAsync(wsb + ws.cnt, 0, sizeof(int32_t) * (size_t)B * YL_LEVELS, stream));
+  B200_CUDA(cudaMemsetAsync(wsb + ws.cnt, 0, sizeof(int32_t) * ((size_t)B * YL_LEVELS + 1), stream));
   yolo_loss_scan_kernel<<<ws.n_cta_obj, YL_CHUNK, 0, stream>>>(p);
   B200_LAUNCH_CHECK();
-  yolo_loss_terms_kernel<<<YL_LEVELS * B * YL_TERM_SPLIT, YL_CHUNK, 0, stream>>>(p);
+  yolo_loss_gtprep_kernel<<<YL_LEVELS * B, 128, 0, stream>>>(p);
   B200_LAUNCH_CHECK();
-  yolo_loss_ignore_kernel<<<ws.n_cta, YL_ICHUNK, 0, stream>>>(p);
+  yolo_loss_ignore_kernel<<<YL_LEVELS * B * YL_TERM_SPLIT + ws.n_cta, YL_ICHUNK, 0, stream>>>(p);
   B200_LAUNCH_CHECK();
   YlFinalize f;
   f.partials = p.partials; f.partials_obj = p.partials_obj;
   for (int l = 0; l <= YL_LEVELS; ++l) { f.cta_base[l] = p.lv.cta_base[l]; f.obj_cta_base[l] = l * B * YL_TERM_SPLIT; }
   f.batch_divisor = batch_divisor; f.parts = out_parts; f.loss = out_loss;
-  yolo_loss_finalize_kernel<<<1, 1024, 0, stream>>>(f);
+  f.slices = reinterpret_cast<double*>(wsb + ws.fin);
+  f.ticket = reinterpret_cast<unsigned int*>(wsb + ws.cnt) + (size_t)B * YL_LEVELS;
+  yolo_loss_finalize_kernel<<<YL_FIN_CTAS, YL_FIN_THREADS, 0, stream>>>(f);
   B200_LAUNCH_CHECK();
   if (out_grad) {
     YlGradDense g;
