@@ -405,6 +405,21 @@ def run_b200(args, wl):
         cpu = {"value": n / dt, "unit": "images/s", "cores": 1, "kind": "port",
                "sample": "%d images of the same workload (NumPy oracle GetTargets+GetLoss, single process), %.1f s" % (n, dt)}
 
+    # ---- sparse-target fusion: the same step without materialising y_true ----
+    fused = None
+    if world == 1:
+        ws_f = torch.empty((lib.b200_yolo_loss_from_boxes_workspace_bytes(hw, batch, A, int(boxes_d.shape[0])),), dtype=torch.uint8, device=dev)
+
+        def fstep():
+            return tyu.GetLossFromBoxes(classes_d, boxes_d, off_d, heads_d, (image, image), anc, 80, 0.5, "ciou",
+                                        batch_divisor=global_batch, return_parts=True, workspace=ws_f)
+        ffn = fstep if args.no_graph else runtime.capture(fstep)
+        ms_f = timed(ffn, args.steps, 3)
+        floss = float(ffn()[0].item())
+        fused = {"what": "GetLossFromBoxes: target assignment + loss from the box lists, no dense y_true (API extension, SURVEY 8f N3)",
+                 "value": global_batch * args.steps / (ms_f / 1e3), "unit": "images/s", "ms_per_step": ms_f / args.steps,
+                 "loss": floss, "loss_rel_diff": abs(floss - loss_val) / abs(loss_val)}
+
     if rank == 0:
         line = {
             "metric": "images/sec", "value": global_batch * args.steps / (ms_dev / 1e3), "unit": "images/s",
@@ -417,7 +432,7 @@ def run_b200(args, wl):
                        "launch": "launch by launch" if args.no_graph else "CUDA graph replay of the step",
                        "l2": "inputs larger than L2 (y_pred %.0f MB + y_true %.0f MB per step vs 126 MB L2)" % (
                            n_fill * 4 / 1e6, n_fill * 4 / 1e6)},
-            "loss": loss_val, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "persistent_targets": persistent,
+            "loss": loss_val, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "persistent_targets": persistent, "sparse_target_fusion": fused,
             "gpu_launches": 6 * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -133,6 +133,20 @@ int b200_yolo_loss_grad(const float* const y_true[3], const float* const y_pred[
                         int variant, float batch_divisor, float* out_parts, float* out_loss, float* const out_grad[3],
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* Sparse-target fusion (an API extension, no reference signature): DataGenerator.GetTargets
+ * (datasets/coco_dataset.py:185-285) followed by GetLoss (utils/tf_yolo_utils.py:6-127) without materialising the
+ * dense y_true.  boxes [total,4] pixel corners x1,y1,x2,y2 / classes [total] / offsets [B+1] as for
+ * b200_yolo_assign_targets; assign_anchors_wh_host = the anchors GetTargets compares against (cds:209-217),
+ * anchors_wh_host = the anchors of the loss.  Same result as assign + b200_yolo_loss up to fp64 summation order;
+ * out_ignore as in b200_yolo_loss.  Forward only. */
+size_t b200_yolo_loss_from_boxes_workspace_bytes(const int32_t hw[6], int B, int A, int total_boxes);
+int b200_yolo_loss_from_boxes(const float* boxes, const int32_t* classes, const int32_t* offsets, int total_boxes,
+                              const float* assign_anchors_wh_host, const float* const y_pred[3], const int32_t hw[6],
+                              int B, int A, int C, const float* anchors_wh_host, const float* image_wh_host,
+                              float iou_thresh, int metric, int variant, float batch_divisor, float* out_parts,
+                              float* out_loss, unsigned char* out_ignore, void* workspace, size_t workspace_bytes,
+                              void* stream);
+
 /* DataGenerator.GetTargets (datasets/coco_dataset.py:185-285), batched: boxes [total,4] pixel corners
  * x1,y1,x2,y2, classes [total] int32, offsets [B+1] int32 (all device).  targets[l]: (B,H_l,W_l,A,5+C), zeroed
  * here when zero_fill != 0.  Boxes whose cell falls outside the grid are skipped (tf.scatter_nd would raise). */

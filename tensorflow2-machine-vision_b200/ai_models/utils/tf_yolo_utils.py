@@ -217,6 +217,58 @@ def GetLoss(y_true, y_pred, image_wh, anchors_wh, iou_thresh=0.5, iou_type='iou'
   return _loss_call(y_true, y_pred, image_wh, anchors_wh, iou_thresh, iou_type, 0)
 
 
+def GetLossFromBoxes(classes, boxes, offsets, y_pred, image_wh, anchors_wh, classes_num, iou_thresh=0.5, iou_type='iou',
+                     target_anchors=None, batch_divisor=None, return_parts=False, workspace=None, ignore_out=None):
+  '''
+  Sparse-target fusion (an API extension, not a reference signature): DataGenerator.GetTargets
+  followed by GetLoss without materialising the dense y_true.  Same value as
+  GetLoss(GetTargetsBatch(classes, boxes, offsets), y_pred, ...) up to fp64 summation order.
+
+  Args:
+    classes [total] int, boxes [total,4] pixel corners x1,y1,x2,y2, offsets [B+1] (image b owns boxes offsets[b]:offsets[b+1])
+    y_pred: three levels (B, H, W, 3*(5+classes_num)) or already split per anchor
+    anchors_wh: (3, anchors_num, 2) pixels, as GetLoss takes them
+    target_anchors: the anchors DataGenerator was constructed with (default: anchors_wh)
+  '''
+  assert iou_type in ['iou','diou','ciou']
+  lib = _lib.load()
+  yp = [T.to_cuda(t) for t in y_pred]
+  if len(yp) != 3:
+    raise ValueError('y_pred must hold 3 levels')
+  boxes = T.to_cuda(boxes).reshape(-1, 4)
+  classes = T.to_cuda(classes, torch.int32).reshape(-1)
+  offsets = T.to_cuda(offsets, torch.int32).reshape(-1)
+  anc = T.host_floats(anchors_wh)
+  if anc.size % 6 != 0:
+    raise ValueError('anchors_wh must be (3, anchors_num, 2)')
+  tanc = anc if target_anchors is None else T.host_floats(target_anchors)
+  if tanc.size != anc.size:
+    raise ValueError('target_anchors must have the shape of anchors_wh')
+  A = anc.size // 6
+  B = offsets.numel() - 1
+  RF = 5 + int(classes_num)
+  for l in range(3):
+    if yp[l].dim() < 3 or yp[l].shape[0] != B or yp[l].numel() != B * yp[l].shape[1] * yp[l].shape[2] * A * RF:
+      raise ValueError('y_pred[%d] must be (B,H,W,%d*(5+C)) with B = len(offsets)-1' % (l, A))
+  img = T.host_floats(image_wh, 2)
+  dev = yp[0].device
+  hw = (ctypes.c_int32 * 6)(*[d for t in yp for d in (t.shape[1], t.shape[2])])
+  pp = (ctypes.c_void_p * 3)(*[t.data_ptr() for t in yp])
+  parts = torch.empty((3, 4), dtype=torch.float32, device=dev)
+  loss = torch.empty((), dtype=torch.float32, device=dev)
+  total = int(boxes.shape[0])
+  ws_bytes = lib.b200_yolo_loss_from_boxes_workspace_bytes(hw, B, A, total)
+  if workspace is None or workspace.numel() < ws_bytes:
+    workspace = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+  div = float(B if batch_divisor is None else batch_divisor)
+  _lib.check(lib.b200_yolo_loss_from_boxes(T.ptr(boxes), T.ptr(classes), T.ptr(offsets), total,
+                                           tanc.ctypes.data_as(ctypes.c_void_p), pp, hw, B, A, RF - 5,
+                                           anc.ctypes.data_as(ctypes.c_void_p), img.ctypes.data_as(ctypes.c_void_p),
+                                           float(iou_thresh), _lib.METRIC_YOLO[iou_type], 0, div, T.ptr(parts), T.ptr(loss),
+                                           T.ptr(ignore_out), T.ptr(workspace), workspace.numel(), T.stream_ptr()), 'GetLossFromBoxes')
+  return (loss, parts) if return_parts else loss
+
+
 def GetLossAndGrad(y_true, y_pred, image_wh, anchors_wh, iou_thresh=0.5, iou_type='iou'):
   '''GetLoss plus d loss / d y_pred (list of 3 tensors shaped like y_pred) for an upstream gradient of 1 —
   what tf.GradientTape derives from the reference's GetLoss.  Wrap with tf.custom_gradient.'''

@@ -19,8 +19,7 @@
 //
 // ignore = float(best < thr) with best = max_g metric(pred, gt_g) is evaluated as "no g with metric >= thr or
 // metric NaN": tf.reduce_max propagates NaN and NaN < thr is False, so a NaN pair clears the ignore bit.
-#include "boxmath.cuh"
-#include "common.cuh"
+#include "yolo_targets.cuh"
 
 #define YL_LEVELS 3
 #define YL_CHUNK 256
@@ -59,6 +58,12 @@ struct YlParams {
   int32_t* obj_index;         // [B, n_img]: record index of each object-list / GT-list slot
   float inv_div;              // 1 / batch_divisor
   unsigned char* out_ignore;  // optional [B, n_img]: the ignore mask (1 = ignored/background), for parity tests
+  // sparse-target mode (b200_yolo_loss_from_boxes: no dense y_true): per object slot the record's (x, y, w, h) and
+  // class, and one obj bit per record
+  const float4* sp_t;         // [B, n_img]
+  const int32_t* sp_cls;      // [B, n_img]
+  const uint32_t* obj_bits;   // [B, bits_words]
+  int bits_words;
   int32_t* gt_count;    // [B, 3]
   double* partials;     // [n_cta]      object_loss partial of each ignore-kernel CTA
   double* partials_obj; // [3*B*YL_TERM_SPLIT,3] xy, wh, cls partials of each terms-kernel CTA (level-major)
@@ -130,12 +135,18 @@ __global__ void __launch_bounds__(YL_CHUNK) yolo_loss_scan_kernel(YlParams p) {
 __global__ void __launch_bounds__(128) yolo_loss_gtprep_kernel(YlParams p) {
   const int l = blockIdx.x / p.B, img = blockIdx.x - l * p.B;
   const int rpi = p.lv.rec_per_img[l];
-  const float* yt = p.lv.y_true[l] + ((size_t)img * rpi) * p.RF;
+  const float* yt = p.sp_t ? nullptr : p.lv.y_true[l] + ((size_t)img * rpi) * p.RF;
   const int n = p.gt_count[img * YL_LEVELS + l];
   const size_t gbase = (size_t)img * p.n_img + p.lv.anchor_base[l];
   for (int k = threadIdx.x; k < n; k += 128) {
-    const float* t = yt + (size_t)p.obj_index[gbase + k] * p.RF;
-    const float tx = __ldg(t), ty = __ldg(t + 1), tw = __ldg(t + 2), th = __ldg(t + 3);
+    float tx, ty, tw, th;
+    if (p.sp_t) {
+      const float4 v = p.sp_t[gbase + k];
+      tx = v.x; ty = v.y; tw = v.z; th = v.w;
+    } else {
+      const float* t = yt + (size_t)p.obj_index[gbase + k] * p.RF;
+      tx = __ldg(t); ty = __ldg(t + 1); tw = __ldg(t + 2); th = __ldg(t + 3);
+    }
     const float hx = DM_DIV(tw, 2.0f), hy = DM_DIV(th, 2.0f);
     BoxT g = bm_prep(DM_SUB(tx, hx), DM_SUB(ty, hy), DM_ADD(tx, hx), DM_ADD(ty, hy), p.metric);
     p.gt_box[gbase + k] = make_float4(g.c0, g.c1, g.c2, g.c3);
@@ -157,7 +168,7 @@ __device__ __forceinline__ void yl_terms_body(const YlParams& p, int cta, double
   const int img = rem / YL_TERM_SPLIT, split = rem - img * YL_TERM_SPLIT;
   const int rpi = p.lv.rec_per_img[l];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float* yt = p.lv.y_true[l] + ((size_t)img * rpi) * p.RF;
+  const float* yt = p.sp_t ? nullptr : p.lv.y_true[l] + ((size_t)img * rpi) * p.RF;
   const float* yp = p.lv.y_pred[l] + ((size_t)img * rpi) * p.RF;
   const int n = p.gt_count[img * YL_LEVELS + l];
   const size_t gbase = (size_t)img * p.n_img + p.lv.anchor_base[l];
@@ -167,8 +178,16 @@ __device__ __forceinline__ void yl_terms_body(const YlParams& p, int cta, double
     const int r = p.obj_index[gbase + k];
     const float* t = yt + (size_t)r * p.RF;
     const float* q = yp + (size_t)r * p.RF;
-    const float obj = __ldg(t + 4);
-    const float tx = __ldg(t), ty = __ldg(t + 1), tw = __ldg(t + 2), th = __ldg(t + 3);
+    float obj, tx, ty, tw, th;
+    int sp_class = -1;
+    if (p.sp_t) {  // the record the dense scatter would have written: obj = 1, one-hot class (cds:246-262)
+      const float4 v = p.sp_t[gbase + k];
+      obj = 1.0f; tx = v.x; ty = v.y; tw = v.z; th = v.w;
+      sp_class = p.sp_cls[gbase + k];
+    } else {
+      obj = __ldg(t + 4);
+      tx = __ldg(t); ty = __ldg(t + 1); tw = __ldg(t + 2); th = __ldg(t + 3);
+    }
     const float scale = DM_SUB(2.0f, DM_MUL(tw, th));
     const float os = DM_MUL(obj, scale);  // (obj * scale) * term, evaluation order of tyu:109-110
     float e_xy = 0.f, e_wh = 0.f, e_cls = 0.f;
@@ -192,7 +211,11 @@ __device__ __forceinline__ void yl_terms_body(const YlParams& p, int cta, double
       const float d = DM_SUB(raw, __ldg(q + lane));
       e_wh = DM_MUL(DM_MUL(os, 0.5f), DM_MUL(d, d));
     }
-    for (int c = 5 + lane; c < p.RF; c += 32) e_cls += DM_MUL(obj, dm_bce_logits(__ldg(t + c), __ldg(q + c)));
+    if (p.sp_t) {
+      for (int c = 5 + lane; c < p.RF; c += 32) e_cls += DM_MUL(obj, dm_bce_logits((c - 5 == sp_class) ? 1.0f : 0.0f, __ldg(q + c)));
+    } else {
+      for (int c = 5 + lane; c < p.RF; c += 32) e_cls += DM_MUL(obj, dm_bce_logits(__ldg(t + c), __ldg(q + c)));
+    }
     e_xy = warp_sum(e_xy); e_wh = warp_sum(e_wh); e_cls = warp_sum(e_cls);
     if (lane == 0) { a_xy += (double)e_xy; a_wh += (double)e_wh; a_cls += (double)e_cls; }
   }
@@ -298,7 +321,12 @@ __global__ void __launch_bounds__(YL_ICHUNK, YL_IMINB) yolo_loss_ignore_kernel(Y
   float obj = 0.f, tx = 0.f, ty = 0.f, tw = 0.f, th = 0.f, pobj = 0.f;
   if (active) {
     const size_t f0 = ((size_t)img * rpi + rin) * p.RF;
-    obj = p.obj_compact[(size_t)img * p.n_img + p.lv.anchor_base[l] + rin];
+    if (p.obj_bits) {
+      const int bit = p.lv.anchor_base[l] + rin;
+      obj = ((__ldg(p.obj_bits + (size_t)img * p.bits_words + (bit >> 5)) >> (bit & 31)) & 1u) ? 1.0f : 0.0f;
+    } else {
+      obj = p.obj_compact[(size_t)img * p.n_img + p.lv.anchor_base[l] + rin];
+    }
     if ((reinterpret_cast<uintptr_t>(p.lv.y_pred[l]) & 15) == 0) {
       // tx,ty,tw,th,conf sit at float offset f0; two aligned 16-byte loads cover them (L1 bypass)
       const float4 lo = __ldcg(reinterpret_cast<const float4*>(p.lv.y_pred[l]) + (f0 >> 2));
@@ -588,6 +616,43 @@ __global__ void __launch_bounds__(256) yolo_loss_grad_objects_kernel(YlParams p,
   }
 }
 
+// ---- sparse-target mode -------------------------------------------------------------
+// GetTargets + GetLoss without the dense y_true: one CTA per image assigns every box (same arithmetic as the dense
+// scatter, yolo_targets.cuh), drops the boxes that collide on a record (scatter_nd would sum them and the whole
+// record is then zeroed, cds:279-284) and writes the object list the dense path's scan kernel would have found.
+__global__ void __launch_bounds__(128) yolo_loss_assign_sparse_kernel(YtParams t, YlParams p, int* __restrict__ keys,
+                                                                      float4* __restrict__ sp_t, int32_t* __restrict__ sp_cls,
+                                                                      uint32_t* __restrict__ obj_bits) {
+  __shared__ int s_cnt[YL_LEVELS];
+  const int img = blockIdx.x;
+  const int beg = t.offsets[img], end = t.offsets[img + 1];
+  if (threadIdx.x < YL_LEVELS) s_cnt[threadIdx.x] = 0;
+  for (int i = beg + (int)threadIdx.x; i < end; i += 128) {
+    int layer, rin;
+    float nx, ny, nw, nh;
+    keys[i] = yt_assign(t, i, layer, rin, nx, ny, nw, nh) ? p.lv.anchor_base[layer] + rin : -1;
+  }
+  __syncthreads();
+  for (int i = beg + (int)threadIdx.x; i < end; i += 128) {
+    const int key = keys[i];
+    if (key < 0) continue;
+    bool dup = false;
+    for (int j = beg; j < end; ++j) dup |= (j != i) && (keys[j] == key);
+    if (dup) continue;
+    int layer, rin;
+    float nx, ny, nw, nh;
+    yt_assign(t, i, layer, rin, nx, ny, nw, nh);
+    const int slot = atomicAdd(&s_cnt[layer], 1);
+    const size_t gi = (size_t)img * p.n_img + p.lv.anchor_base[layer] + slot;
+    p.obj_index[gi] = rin;
+    sp_t[gi] = make_float4(nx, ny, nw, nh);
+    sp_cls[gi] = t.classes[i];
+    atomicOr(obj_bits + (size_t)img * p.bits_words + (key >> 5), 1u << (key & 31));
+  }
+  __syncthreads();
+  if (threadIdx.x < YL_LEVELS) p.gt_count[img * YL_LEVELS + threadIdx.x] = s_cnt[threadIdx.x];
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 struct YlWs { size_t obj, gt, gtl, cnt, part, part_obj, cgrad, oidx, fin, total; int n_cta, n_cta_obj; };
 
@@ -629,13 +694,32 @@ extern "C" size_t b200_yolo_loss_workspace_bytes(const int32_t hw[6], int B, int
   return yl_layout(hw, B, A, nullptr, nullptr).total;
 }
 
+struct YlSparseIn {  // ground truth as boxes instead of dense y_true (sparse-target mode)
+  const float* boxes; const int32_t* classes; const int32_t* offsets; int total_boxes;
+  const float* assign_anchors_wh_host;  // anchors as DataGenerator.GetTargets receives them (may differ in units from the loss's)
+};
+
+struct YlSparseWs { size_t sp_t, sp_cls, bits, keys, total; int bits_words; };
+
+static YlSparseWs yl_sparse_layout(size_t dense_total, int B, int n_img, int total_boxes) {
+  YlSparseWs w;
+  w.bits_words = (n_img + 31) / 32;
+  size_t o = b200_align_up(dense_total, 256);
+  w.sp_t = o; o = b200_align_up(o + sizeof(float4) * (size_t)B * n_img, 256);
+  w.sp_cls = o; o = b200_align_up(o + sizeof(int32_t) * (size_t)B * n_img, 256);
+  w.bits = o; o = b200_align_up(o + sizeof(uint32_t) * (size_t)B * w.bits_words, 256);
+  w.keys = o; o = b200_align_up(o + sizeof(int32_t) * (size_t)(total_boxes > 0 ? total_boxes : 1), 256);
+  w.total = o;
+  return w;
+}
+
 static int yolo_loss_impl(const float* const y_true[3], const float* const y_pred[3], const int32_t hw[6], int B,
                           int A, int C, const float* anchors_wh_host, const float* image_wh_host,
                           float iou_thresh, int metric, int variant, float batch_divisor, float* out_parts,
                           float* out_loss, unsigned char* out_ignore, float* const out_grad[3], void* workspace,
-                          size_t workspace_bytes, void* stream_) {
+                          size_t workspace_bytes, void* stream_, const YlSparseIn* sparse = nullptr) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  B200_REQUIRE(y_true && y_pred && hw && anchors_wh_host && image_wh_host && out_loss, B200_ERR_BAD_ARG, "b200_yolo_loss: null argument");
+  B200_REQUIRE((y_true || sparse) && y_pred && hw && anchors_wh_host && image_wh_host && out_loss, B200_ERR_BAD_ARG, "b200_yolo_loss: null argument");
   B200_REQUIRE(B >= 1 && A >= 1 && A <= 8 && C >= 0, B200_ERR_BAD_ARG, "b200_yolo_loss: unsupported shape B=%d A=%d C=%d", B, A, C);
   B200_REQUIRE(metric >= B200_METRIC_YOLO_IOU && metric <= B200_METRIC_YOLO_CIOU, B200_ERR_BAD_ARG,
                "b200_yolo_loss: iou_type must be iou/diou/ciou (metric %d)", metric);
@@ -644,11 +728,14 @@ static int yolo_loss_impl(const float* const y_true[3], const float* const y_pre
   YlParams p;
   int n_img = 0;
   YlWs ws = yl_layout(hw, B, A, &n_img, &p.lv);
-  B200_REQUIRE(workspace && workspace_bytes >= ws.total, B200_ERR_WORKSPACE, "b200_yolo_loss: workspace %zu < required %zu", workspace_bytes, ws.total);
+  YlSparseWs sws;
+  sws.total = ws.total;
+  if (sparse) sws = yl_sparse_layout(ws.total, B, n_img, sparse->total_boxes);
+  B200_REQUIRE(workspace && workspace_bytes >= sws.total, B200_ERR_WORKSPACE, "b200_yolo_loss: workspace %zu < required %zu", workspace_bytes, sws.total);
   B200_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, B200_ERR_BAD_ARG, "b200_yolo_loss: workspace not 256-byte aligned");
   for (int l = 0; l < YL_LEVELS; ++l) {
-    B200_REQUIRE(y_true[l] && y_pred[l] && hw[2 * l] > 0 && hw[2 * l + 1] > 0, B200_ERR_BAD_ARG, "b200_yolo_loss: bad level %d", l);
-    p.lv.y_true[l] = y_true[l];
+    B200_REQUIRE((sparse || y_true[l]) && y_pred[l] && hw[2 * l] > 0 && hw[2 * l + 1] > 0, B200_ERR_BAD_ARG, "b200_yolo_loss: bad level %d", l);
+    p.lv.y_true[l] = sparse ? nullptr : y_true[l];
     p.lv.y_pred[l] = y_pred[l];
     for (int a = 0; a < A; ++a) {
       p.lv.anc_w[l][a] = anchors_wh_host[(l * A + a) * 2 + 0];
@@ -683,8 +770,26 @@ static int yolo_loss_impl(const float* const y_true[3], const float* const y_pre
   p.partials = reinterpret_cast<double*>(wsb + ws.part);
   p.partials_obj = reinterpret_cast<double*>(wsb + ws.part_obj);
   B200_CUDA(cudaMemsetAsync(wsb + ws.cnt, 0, sizeof(int32_t) * ((size_t)B * YL_LEVELS + 1), stream));
-  yolo_loss_scan_kernel<<<ws.n_cta_obj, YL_CHUNK, 0, stream>>>(p);
-  B200_LAUNCH_CHECK();
+  p.sp_t = nullptr; p.sp_cls = nullptr; p.obj_bits = nullptr; p.bits_words = 0;
+  if (sparse) {
+    B200_REQUIRE(sparse->total_boxes >= 0 && sparse->offsets && sparse->assign_anchors_wh_host, B200_ERR_BAD_ARG, "b200_yolo_loss_from_boxes: null box arrays");
+    B200_REQUIRE(sparse->total_boxes == 0 || (sparse->boxes && sparse->classes), B200_ERR_BAD_ARG, "b200_yolo_loss_from_boxes: null box arrays");
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(sparse->boxes) & 15) == 0, B200_ERR_BAD_ARG, "b200_yolo_loss_from_boxes: boxes not 16-byte aligned");
+    YtParams t;
+    B200_REQUIRE(yt_fill_geometry(t, A, C, sparse->assign_anchors_wh_host, image_wh_host, hw) == 0, B200_ERR_BAD_ARG, "b200_yolo_loss_from_boxes: bad geometry");
+    t.boxes = sparse->boxes; t.classes = sparse->classes; t.offsets = sparse->offsets; t.B = B; t.total = sparse->total_boxes;
+    p.bits_words = sws.bits_words;
+    float4* sp_t = reinterpret_cast<float4*>(wsb + sws.sp_t);
+    int32_t* sp_cls = reinterpret_cast<int32_t*>(wsb + sws.sp_cls);
+    uint32_t* bits = reinterpret_cast<uint32_t*>(wsb + sws.bits);
+    B200_CUDA(cudaMemsetAsync(bits, 0, sizeof(uint32_t) * (size_t)B * sws.bits_words, stream));
+    yolo_loss_assign_sparse_kernel<<<B, 128, 0, stream>>>(t, p, reinterpret_cast<int*>(wsb + sws.keys), sp_t, sp_cls, bits);
+    B200_LAUNCH_CHECK();
+    p.sp_t = sp_t; p.sp_cls = sp_cls; p.obj_bits = bits;
+  } else {
+    yolo_loss_scan_kernel<<<ws.n_cta_obj, YL_CHUNK, 0, stream>>>(p);
+    B200_LAUNCH_CHECK();
+  }
   yolo_loss_gtprep_kernel<<<YL_LEVELS * B, 128, 0, stream>>>(p);
   B200_LAUNCH_CHECK();
   yolo_loss_ignore_kernel<<<YL_LEVELS * B * YL_TERM_SPLIT + ws.n_cta, YL_ICHUNK, 0, stream>>>(p);
@@ -728,6 +833,25 @@ extern "C" int b200_yolo_loss(const float* const y_true[3], const float* const y
                               void* stream_) {
   return yolo_loss_impl(y_true, y_pred, hw, B, A, C, anchors_wh_host, image_wh_host, iou_thresh, metric, variant,
                         batch_divisor, out_parts, out_loss, out_ignore, nullptr, workspace, workspace_bytes, stream_);
+}
+
+extern "C" size_t b200_yolo_loss_from_boxes_workspace_bytes(const int32_t hw[6], int B, int A, int total_boxes) {
+  int n_img = 0;
+  const YlWs w = yl_layout(hw, B, A, &n_img, nullptr);
+  return yl_sparse_layout(w.total, B, n_img, total_boxes).total;
+}
+
+extern "C" int b200_yolo_loss_from_boxes(const float* boxes, const int32_t* classes, const int32_t* offsets, int total_boxes,
+                                         const float* assign_anchors_wh_host, const float* const y_pred[3], const int32_t hw[6],
+                                         int B, int A, int C, const float* anchors_wh_host, const float* image_wh_host,
+                                         float iou_thresh, int metric, int variant, float batch_divisor, float* out_parts,
+                                         float* out_loss, unsigned char* out_ignore, void* workspace, size_t workspace_bytes,
+                                         void* stream_) {
+  YlSparseIn sp;
+  sp.boxes = boxes; sp.classes = classes; sp.offsets = offsets; sp.total_boxes = total_boxes;
+  sp.assign_anchors_wh_host = assign_anchors_wh_host;
+  return yolo_loss_impl(nullptr, y_pred, hw, B, A, C, anchors_wh_host, image_wh_host, iou_thresh, metric, variant,
+                        batch_divisor, out_parts, out_loss, out_ignore, nullptr, workspace, workspace_bytes, stream_, &sp);
 }
 
 extern "C" int b200_yolo_loss_grad(const float* const y_true[3], const float* const y_pred[3], const int32_t hw[6],

@@ -13,10 +13,7 @@
 //                               scatter_nd sums duplicates, then every record with obj > 1 is zeroed (cds:279-284):
 //                               collisions can only happen inside an image, so one CTA owns one image and clears
 //                               the collided records after a block barrier (single launch).
-#include "boxmath.cuh"
-#include "common.cuh"
-
-#define YT_LEVELS 3
+#include "yolo_targets.cuh"
 
 __global__ void fill_zero_kernel(float4* __restrict__ dst, size_t n_vec, float* __restrict__ tail, int n_tail) {
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -44,47 +41,6 @@ __global__ void fill_zero_multi_kernel(FillMulti f) {
     else if (i < f.n_vec[1]) __stcs(f.dst[1] + (i - f.n_vec[0]), z);
     else __stcs(f.dst[2] + (i - f.n_vec[1]), z);
   }
-}
-
-struct YtParams {
-  const float* boxes;       // [total,4] pixel corners x1,y1,x2,y2
-  const int32_t* classes;   // [total]
-  const int32_t* offsets;   // [B+1]
-  int B, total, A, C, RF, layers_num;
-  float img_w, img_h;
-  float* target[YT_LEVELS];
-  int h[YT_LEVELS], w[YT_LEVELS];
-  float anc_w[YT_LEVELS * 8], anc_h[YT_LEVELS * 8];  // flattened (layers*A) in reshape(-1,2) order, pixels
-};
-
-// returns the record pointer for box i of image `img` (nullptr when the cell falls outside the grid) and the
-// update fields
-__device__ __forceinline__ float* yt_locate(const YtParams& p, int img, int i, float& nx, float& ny, float& nw, float& nh) {
-  const float4 bx = __ldg(reinterpret_cast<const float4*>(p.boxes) + i);
-  const float x1 = bx.x, y1 = bx.y, x2 = bx.z, y2 = bx.w;
-  // (x2y2 + x1y1) // 2 : float floor division
-  const float cx = floorf(DM_DIV(DM_ADD(x2, x1), 2.0f)), cy = floorf(DM_DIV(DM_ADD(y2, y1), 2.0f));
-  const float bw = DM_SUB(x2, x1), bh = DM_SUB(y2, y1);
-  nx = DM_DIV(cx, p.img_w); ny = DM_DIV(cy, p.img_h);
-  nw = DM_DIV(bw, p.img_w); nh = DM_DIV(bh, p.img_h);
-  const float mx = DM_DIV(nw, 2.0f), my = DM_DIV(nh, 2.0f);
-  const BoxT b = bm_prep(-mx, -my, mx, my, B200_METRIC_YOLO_IOU);
-  int best = 0;
-  float best_v = 0.f;
-  const int n_anchor = YT_LEVELS * p.A;
-  for (int k = 0; k < n_anchor; ++k) {
-    const float ax = DM_DIV(p.anc_w[k], 2.0f), ay = DM_DIV(p.anc_h[k], 2.0f);
-    const BoxT a = bm_prep(-ax, -ay, ax, ay, B200_METRIC_YOLO_IOU);
-    const float v = bm_metric(b, a, B200_METRIC_YOLO_IOU);
-    if (k == 0 || v > best_v) { best = k; best_v = v; }  // tf.argmax: first maximal index
-  }
-  const int layer = best / p.layers_num;
-  const int anchor = best % p.layers_num;
-  if (layer >= YT_LEVELS || anchor >= p.A) return nullptr;
-  const int yy = (int)floorf(DM_MUL(ny, (float)p.h[layer]));
-  const int xx = (int)floorf(DM_MUL(nx, (float)p.w[layer]));
-  if (yy < 0 || yy >= p.h[layer] || xx < 0 || xx >= p.w[layer]) return nullptr;
-  return p.target[layer] + ((((size_t)img * p.h[layer] + yy) * p.w[layer] + xx) * p.A + anchor) * p.RF;
 }
 
 // One CTA per image (collisions can only happen inside an image): scatter, barrier, clear collided records.

@@ -118,6 +118,57 @@ def test_get_loss_matches_oracle(lib, cuda, image, batch, iou_type, normalised):
     assert float(got2) == float(got)  # deterministic reduction: bit-identical run to run
 
 
+@pytest.mark.parametrize("image,batch,iou_type,normalised", [(416, 3, "ciou", False), (608, 2, "iou", False), (416, 4, "diou", True),
+                                                             (96, 6, "ciou", True)])
+def test_loss_from_boxes_matches_dense_path_and_oracle(lib, cuda, image, batch, iou_type, normalised):
+    """GetTargets + GetLoss fused without the dense y_true == the oracle's get_targets -> get_loss
+    (loss within 1e-4, ignore mask bit-exact), including colliding boxes, an image without boxes and out-of-range
+    classes; and == the dense GPU path."""
+    import torch
+    from oracle import yolo as oy
+    from tfmv_b200 import synth
+    from tfmv_b200.ai_models.datasets.coco_dataset import DataGenerator
+    from tfmv_b200.ai_models.utils.tf_yolo_utils import GetLossFromBoxes, _loss_call
+    rng = np.random.default_rng(20261018 + 70 + batch)
+    anc = synth.yolo_anchors().astype(F)
+    tanc = anc / F(image) if normalised else anc
+    boxes, classes, off = synth.gt_batch(rng, batch, (image, image), max_boxes=60)
+    n0 = off[1]
+    if n0 >= 3:
+        boxes[1] = boxes[0]; boxes[2] = boxes[0]           # triple collision in image 0: all three dropped
+    classes[-1] = 200                                       # out of range -> all-zero class row
+    if batch > 2:                                           # image 1 without ground truth
+        keep = np.ones(len(boxes), bool); keep[off[1]:off[2]] = False
+        cnt = np.diff(off); cnt[1] = 0
+        boxes, classes, off = boxes[keep], classes[keep], np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+    per = [oy.get_targets(boxes[off[b]:off[b + 1]], classes[off[b]:off[b + 1]], tanc, (image, image), 80) for b in range(batch)]
+    y_true = [np.stack([p[l] for p in per], 0) for l in range(3)]
+    y_pred = synth.yolo_heads(rng, batch, image)
+    for l in range(3):  # some predictions overlap their targets so the ignore mask has zeros
+        yt = y_true[l]
+        yp = y_pred[l].reshape(yt.shape)
+        m = yt[..., 4] > 0
+        yp[m, 2:4] = np.log(np.maximum(yt[m, 2:4] * image, 1e-3) / anc[l][np.nonzero(m)[3]]) + rng.normal(0, 0.1, (int(m.sum()), 2))
+    want, want_parts, want_ign = oy.get_loss(y_true, y_pred, (image, image), anc, 0.5, iou_type, return_ignore=True)
+    ign = torch.full(want_ign.shape, 7, dtype=torch.uint8, device=cuda)
+    dp = [_t(t, cuda) for t in y_pred]
+    got, parts = GetLossFromBoxes(_t(classes, cuda), _t(boxes, cuda), _t(off, cuda), dp, (image, image), anc, 80, 0.5, iou_type,
+                                  target_anchors=tanc, return_parts=True, ignore_out=ign)
+    assert np.array_equal(ign.cpu().numpy(), want_ign)
+    assert sum(float(t[..., 4].sum()) for t in y_true) > 0 and 0 < int(want_ign.sum()) < want_ign.size
+    np.testing.assert_allclose(parts.cpu().numpy(), want_parts, rtol=LOSS_RTOL, atol=1e-6)
+    assert abs(float(got) - float(want)) <= LOSS_RTOL * abs(float(want))
+    gen = DataGenerator(80, tanc, (image, image))
+    dense = gen.GetTargetsBatch(_t(classes, cuda), _t(boxes, cuda), _t(off, cuda))
+    got_d, parts_d = _loss_call(dense, dp, (image, image), anc, 0.5, iou_type, 0, return_parts=True)
+    np.testing.assert_allclose(parts.cpu().numpy(), parts_d.cpu().numpy(), rtol=1e-6, atol=1e-9)
+    # no boxes at all
+    e = GetLossFromBoxes(np.zeros((0,), np.int32), np.zeros((0, 4), F), np.zeros(batch + 1, np.int32), dp, (image, image), anc, 80,
+                         0.5, iou_type)
+    want_e = oy.get_loss([np.zeros_like(t) for t in y_true], y_pred, (image, image), anc, 0.5, iou_type)
+    assert abs(float(e) - float(want_e)) <= LOSS_RTOL * abs(float(want_e))
+
+
 def test_reference_unit_test_relation_on_gpu(lib, cuda):
     """yolo_v3/unit_test/loss_test.py:152-172 on the GPU: GetLoss-copy == Yolov4Loss on uniform-random tensors."""
     from oracle import yolo as oy
