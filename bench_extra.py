@@ -121,11 +121,18 @@ def main():
             ms = timed(wrap(step), args.steps, args.warmup)
             bpi = n_anchor * (81 * 4 * 2 + 16 * 2 + 1 + 16)
             ms_loss = timed(wrap(lambda: get_loss(tb, tc, tm, rel, cls)), args.steps, args.warmup)
+            # sparse-target mode: class ids instead of one-hot rows
+            ib, ic, im = a.generate_targets_batch(d_boxes, d_cls, d_off, 81, class_index=True)
+            ms_t_idx = timed(wrap(lambda: a.generate_targets_batch(d_boxes, d_cls, d_off, 81, class_index=True)), args.steps, args.warmup)
+            ms_loss_idx = timed(wrap(lambda: get_loss(ib, ic, im, rel, cls)), args.steps, args.warmup)
+            loss_rel = abs(float(get_loss(ib, ic, im, rel, cls)) - float(get_loss(tb, tc, tm, rel, cls))) / abs(float(get_loss(tb, tc, tm, rel, cls)))
             ms_dec = timed(wrap(lambda: a.convert_outputs_boxes(rel)), args.steps, args.warmup)
             dec = a.convert_outputs_boxes(rel)
             ms_post = timed(wrap(lambda: a.convert_outputs_batch(dec, cls)), args.steps, args.warmup)
             report(name, "EfficientDet-D0 512 B=128: focal+box loss + decode + post-process (NMS diou, cap 200)", batch, ms, bpi,
                    {"phase_ms": {"loss": ms_loss, "decode": ms_dec, "postprocess": ms_post, "generate_targets": ms_t},
+                    "sparse_target_mode": {"generate_targets_ms": ms_t_idx, "loss_ms": ms_loss_idx, "loss_rel_diff": loss_rel,
+                                           "loss_gbps": n_anchor * (81 * 4 + 37) * batch / ms_loss_idx / 1e6},
                     "loss_gbps": n_anchor * (81 * 8 + 33) * batch / ms_loss / 1e6,
                     "postprocess_gbps": n_anchor * (81 * 4) * batch / ms_post / 1e6})
         else:

@@ -216,6 +216,12 @@ int b200_effdet_assign_targets(int num_levels, const int32_t* hw, int A, const f
                                const float* gt_boxes, const int32_t* gt_classes, const int32_t* gt_offsets,
                                float iou_thr, float* const out_boxes[], float* const out_onehot[],
                                unsigned char* const out_mask[], void* stream);
+/* Sparse-target mode (an API extension): out_class (B,H,W,A) int32 holds the class id whose one-hot row
+ * b200_effdet_assign_targets would write (0 = background for unmatched anchors); everything else is identical. */
+int b200_effdet_assign_targets_indexed(int num_levels, const int32_t* hw, int A, const float* table_dev, int C, int B,
+                                       const float* gt_boxes, const int32_t* gt_classes, const int32_t* gt_offsets,
+                                       float iou_thr, float* const out_boxes[], int32_t* const out_class[],
+                                       unsigned char* const out_mask[], void* stream);
 /* FocalLoss.call focal_loss.py:26-52, elementwise: out = alpha_factor*modulating*ce/normalizer. */
 int b200_focal_elementwise(const float* y_true, const float* y_pred, size_t n, float normalizer, float alpha,
                            float gamma, float label_smoothing, float* out, void* stream);
@@ -233,6 +239,14 @@ int b200_focal_box_partial_sums(int num_levels, const unsigned long long* anchor
                                 const float* const pred_classes[], float alpha, float gamma, float delta,
                                 float label_smoothing, double* sums_out, void* workspace, size_t workspace_bytes,
                                 void* stream);
+/* Same sums with the class targets given as class ids (b200_effdet_assign_targets_indexed): the one-hot rows are
+ * rebuilt on the fly, so the class half reads the logits only (ids outside [0,C) = all-zero row, as tf.one_hot). */
+int b200_focal_box_partial_sums_indexed(int num_levels, const unsigned long long* anchors_per_level, int C,
+                                        const float* const true_boxes[], const int32_t* const true_class_index[],
+                                        const unsigned char* const true_masks[], const float* const pred_boxes[],
+                                        const float* const pred_classes[], float alpha, float gamma, float delta,
+                                        float label_smoothing, double* sums_out, void* workspace, size_t workspace_bytes,
+                                        void* stream);
 int b200_focal_box_finalize(int num_levels, const double* sums, const double* numel_per_level_host, float* out_parts,
                             float* out_loss, float* out_num_positives, void* stream);
 /* Backward of _get_loss: grad_classes[l] = d loss / d pred_classes[l], grad_boxes[l] = d loss /

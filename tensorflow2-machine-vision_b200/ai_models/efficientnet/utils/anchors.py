@@ -113,9 +113,11 @@ class Anchors(object):
     return self.num_scales * len(self.aspect_ratios)
 
   # -- targets ------------------------------------------------------------------------------------------
-  def generate_targets_batch(self, boxes, classes, offsets, classes_num, iou_threshold=0.5):
+  def generate_targets_batch(self, boxes, classes, offsets, classes_num, iou_threshold=0.5, class_index=False):
     '''Batched generate_targets: boxes [total,4] yxyx, classes [total], offsets [B+1] ->
-    (boxes, classes, masks) tuples over levels of (B,H,W,A,4), (B,H,W,A,classes_num), (B,H,W,A,1) bool.'''
+    (boxes, classes, masks) tuples over levels of (B,H,W,A,4), (B,H,W,A,classes_num), (B,H,W,A,1) bool.
+    class_index=True (sparse-target mode): classes are (B,H,W,A) int32 class ids instead of the
+    one-hot rows (0 for unmatched anchors); efficientdet_net_train.get_loss accepts them directly.'''
     lib = _lib.load()
     tab = self._dev_table()
     gb = T.to_cuda(boxes).reshape(-1, 4)
@@ -125,13 +127,17 @@ class Anchors(object):
     C = int(classes_num)
     dev = tab.device
     ob = [torch.empty((B, h, w, self._A, 4), dtype=torch.float32, device=dev) for h, w in self._level_hw]
-    oc = [torch.empty((B, h, w, self._A, C), dtype=torch.float32, device=dev) for h, w in self._level_hw]
+    if class_index:
+      oc = [torch.empty((B, h, w, self._A), dtype=torch.int32, device=dev) for h, w in self._level_hw]
+    else:
+      oc = [torch.empty((B, h, w, self._A, C), dtype=torch.float32, device=dev) for h, w in self._level_hw]
     om = [torch.empty((B, h, w, self._A, 1), dtype=torch.bool, device=dev) for h, w in self._level_hw]
     L = self._num_levels
     pb = (ctypes.c_void_p * L)(*[t.data_ptr() for t in ob])
     pc = (ctypes.c_void_p * L)(*[t.data_ptr() for t in oc])
     pm = (ctypes.c_void_p * L)(*[t.data_ptr() for t in om])
-    _lib.check(lib.b200_effdet_assign_targets(L, self._hw, self._A, T.ptr(tab), C, B, T.ptr(gb), T.ptr(gc), T.ptr(go),
+    assign = lib.b200_effdet_assign_targets_indexed if class_index else lib.b200_effdet_assign_targets
+    _lib.check(assign(L, self._hw, self._A, T.ptr(tab), C, B, T.ptr(gb), T.ptr(gc), T.ptr(go),
                                               float(iou_threshold), pb, pc, pm, T.stream_ptr()), 'generate_targets')
     return tuple(ob), tuple(oc), tuple(om)
 

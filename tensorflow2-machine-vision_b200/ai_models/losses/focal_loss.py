@@ -12,7 +12,10 @@ def _partial_sums(true_boxes, true_classes, true_masks, pred_boxes, pred_classes
   L = len(pred_classes) if pred_classes is not None else len(pred_boxes)
   none = [None] * L
   tb = [T.to_cuda(t) if t is not None else None for t in (true_boxes or none)]
-  tc = [T.to_cuda(t) if t is not None else None for t in (true_classes or none)]
+  # class targets: one-hot float tensors shaped like the logits, or (sparse-target mode) integer class ids with one
+  # entry per anchor
+  indexed = true_classes is not None and any(t is not None and not torch.is_floating_point(torch.as_tensor(t)) for t in true_classes)
+  tc = [(T.to_cuda(t, torch.int32) if indexed else T.to_cuda(t)) if t is not None else None for t in (true_classes or none)]
   tm = [T.to_cuda(t, torch.bool) if t is not None else None for t in (true_masks or none)]
   pb = [T.to_cuda(t) if t is not None else None for t in (pred_boxes or none)]
   pc = [T.to_cuda(t) if t is not None else None for t in (pred_classes or none)]
@@ -20,7 +23,10 @@ def _partial_sums(true_boxes, true_classes, true_masks, pred_boxes, pred_classes
   anchors, numel = [], []
   for l in range(L):
     if pc[l] is not None:
-      if tc[l].shape != pc[l].shape:
+      if indexed:
+        if tc[l].numel() * C != pc[l].numel():
+          raise ValueError('class id / output shapes differ at level %d' % l)
+      elif tc[l].shape != pc[l].shape:
         raise ValueError('class target / output shapes differ at level %d' % l)
       anchors.append(pc[l].numel() // C)
       numel.append(float(pc[l].numel()))
@@ -35,7 +41,8 @@ def _partial_sums(true_boxes, true_classes, true_masks, pred_boxes, pred_classes
   sums = torch.empty((2 * L + 1,), dtype=torch.float64, device=dev)
   ws_bytes = max(int(lib.b200_focal_box_workspace_bytes(L, anc, max(C, 4))), 256)
   ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-  _lib.check(lib.b200_focal_box_partial_sums(L, anc, C, arr(tb), arr(tc), arr(tm), arr(pb), arr(pc), float(alpha),
+  fn = lib.b200_focal_box_partial_sums_indexed if indexed else lib.b200_focal_box_partial_sums
+  _lib.check(fn(L, anc, C, arr(tb), arr(tc), arr(tm), arr(pb), arr(pc), float(alpha),
                                              float(gamma), float(delta), float(label_smoothing), T.ptr(sums), T.ptr(ws),
                                              ws_bytes, T.stream_ptr()), 'focal/box loss')
   return sums, numel

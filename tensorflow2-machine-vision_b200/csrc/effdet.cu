@@ -270,7 +270,8 @@ struct EfAssignParams {
   const int32_t* gt_classes;  // [total]
   const int32_t* gt_offsets;  // [B+1]
   float4* out_boxes[EF_MAX_LEVELS];        // (B,H,W,A,4)
-  float* out_onehot[EF_MAX_LEVELS];        // (B,H,W,A,C)
+  float* out_onehot[EF_MAX_LEVELS];        // (B,H,W,A,C), or null when out_class is used
+  int32_t* out_class[EF_MAX_LEVELS];       // (B,H,W,A): class id instead of the one-hot row (sparse-target mode)
   unsigned char* out_mask[EF_MAX_LEVELS];  // (B,H,W,A,1)
   int cta_base[EF_MAX_LEVELS + 1];         // CTAs of 256 anchors, per (level, image)
   int chunks_per_img[EF_MAX_LEVELS];
@@ -351,6 +352,10 @@ __global__ void __launch_bounds__(256) effdet_assign_kernel(EfAssignParams p) {
   if (active) {
     p.out_boxes[l][abase + rin] = enc;
     p.out_mask[l][abase + rin] = matched ? 1 : 0;
+  }
+  if (p.out_class[l]) {  // sparse-target mode: the class id stands for the one-hot row (block-uniform branch)
+    if (active) p.out_class[l][abase + rin] = cls;
+    return;
   }
   // one-hot rows (C floats per anchor, class 0 = background for unmatched anchors, anc:131-133): the CTA's
   // 256 rows are one contiguous span of rows*C floats.  It is cleared with aligned 16-byte stores (full sectors),
@@ -565,12 +570,12 @@ extern "C" int b200_effdet_postprocess(int num_levels, const int32_t* hw, int A,
   return B200_OK;
 }
 
-extern "C" int b200_effdet_assign_targets(int num_levels, const int32_t* hw, int A, const float* table_dev, int C, int B,
-                                          const float* gt_boxes, const int32_t* gt_classes, const int32_t* gt_offsets,
-                                          float iou_thr, float* const out_boxes[], float* const out_onehot[],
-                                          unsigned char* const out_mask[], void* stream) {
+static int ef_assign_impl(int num_levels, const int32_t* hw, int A, const float* table_dev, int C, int B,
+                          const float* gt_boxes, const int32_t* gt_classes, const int32_t* gt_offsets, float iou_thr,
+                          float* const out_boxes[], float* const out_onehot[], int32_t* const out_class[],
+                          unsigned char* const out_mask[], void* stream) {
   EfAssignParams p;
-  B200_REQUIRE(hw && table_dev && gt_offsets && out_boxes && out_onehot && out_mask, B200_ERR_BAD_ARG, "b200_effdet_assign_targets: null argument");
+  B200_REQUIRE(hw && table_dev && gt_offsets && out_boxes && (out_onehot || out_class) && out_mask, B200_ERR_BAD_ARG, "b200_effdet_assign_targets: null argument");
   B200_REQUIRE(ef_fill_levels(p.lv, num_levels, hw, A, table_dev) >= 0, B200_ERR_BAD_ARG, "b200_effdet_assign_targets: bad level spec");
   B200_REQUIRE(B >= 0 && C >= 1, B200_ERR_BAD_ARG, "b200_effdet_assign_targets: bad sizes");
   if (B == 0) return B200_OK;
@@ -580,17 +585,37 @@ extern "C" int b200_effdet_assign_targets(int num_levels, const int32_t* hw, int
   for (int l = 0; l < EF_MAX_LEVELS; ++l) {
     p.cta_base[l] = cta;
     if (l < num_levels) {
-      B200_REQUIRE(out_boxes[l] && out_onehot[l] && out_mask[l], B200_ERR_BAD_ARG, "b200_effdet_assign_targets: null level %d", l);
+      B200_REQUIRE(out_boxes[l] && (out_onehot ? out_onehot[l] != nullptr : out_class[l] != nullptr) && out_mask[l], B200_ERR_BAD_ARG,
+                   "b200_effdet_assign_targets: null level %d", l);
       B200_REQUIRE((reinterpret_cast<uintptr_t>(out_boxes[l]) & 15) == 0, B200_ERR_BAD_ARG, "b200_effdet_assign_targets: out_boxes level %d not 16-byte aligned", l);
       p.out_boxes[l] = reinterpret_cast<float4*>(out_boxes[l]);
-      p.out_onehot[l] = out_onehot[l];
+      p.out_onehot[l] = out_onehot ? out_onehot[l] : nullptr;
+      p.out_class[l] = out_onehot ? nullptr : out_class[l];
       p.out_mask[l] = out_mask[l];
       p.chunks_per_img[l] = (p.lv.anc_per_img[l] + 255) / 256;
       cta += p.chunks_per_img[l] * B;
-    } else { p.out_boxes[l] = nullptr; p.out_onehot[l] = nullptr; p.out_mask[l] = nullptr; p.chunks_per_img[l] = 1; }
+    } else { p.out_boxes[l] = nullptr; p.out_onehot[l] = nullptr; p.out_class[l] = nullptr; p.out_mask[l] = nullptr; p.chunks_per_img[l] = 1; }
   }
   for (int l = num_levels; l <= EF_MAX_LEVELS; ++l) p.cta_base[l] = cta;
   effdet_assign_kernel<<<cta, 256, 0, (cudaStream_t)stream>>>(p);
   B200_LAUNCH_CHECK();
   return B200_OK;
+}
+
+extern "C" int b200_effdet_assign_targets(int num_levels, const int32_t* hw, int A, const float* table_dev, int C, int B,
+                                          const float* gt_boxes, const int32_t* gt_classes, const int32_t* gt_offsets,
+                                          float iou_thr, float* const out_boxes[], float* const out_onehot[],
+                                          unsigned char* const out_mask[], void* stream) {
+  B200_REQUIRE(out_onehot, B200_ERR_BAD_ARG, "b200_effdet_assign_targets: null argument");
+  return ef_assign_impl(num_levels, hw, A, table_dev, C, B, gt_boxes, gt_classes, gt_offsets, iou_thr, out_boxes, out_onehot,
+                        nullptr, out_mask, stream);
+}
+
+extern "C" int b200_effdet_assign_targets_indexed(int num_levels, const int32_t* hw, int A, const float* table_dev, int C, int B,
+                                                  const float* gt_boxes, const int32_t* gt_classes, const int32_t* gt_offsets,
+                                                  float iou_thr, float* const out_boxes[], int32_t* const out_class[],
+                                                  unsigned char* const out_mask[], void* stream) {
+  B200_REQUIRE(out_class, B200_ERR_BAD_ARG, "b200_effdet_assign_targets_indexed: null argument");
+  return ef_assign_impl(num_levels, hw, A, table_dev, C, B, gt_boxes, gt_classes, gt_offsets, iou_thr, out_boxes, nullptr,
+                        out_class, out_mask, stream);
 }

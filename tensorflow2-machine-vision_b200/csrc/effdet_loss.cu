@@ -22,6 +22,8 @@ struct ElParams {
   int num_levels;
   const float4* cls_pred[EL_MAX_LEVELS];
   const float4* cls_true[EL_MAX_LEVELS];
+  const int32_t* cls_index[EL_MAX_LEVELS];     // sparse-target mode: class id per anchor instead of the one-hot tensor
+  int C;
   unsigned long long cls_vec[EL_MAX_LEVELS];   // float4 count of the class tensors
   const float* cls_pred_tail[EL_MAX_LEVELS]; const float* cls_true_tail[EL_MAX_LEVELS]; int cls_tail[EL_MAX_LEVELS];
   const float4* box_pred[EL_MAX_LEVELS];
@@ -40,6 +42,7 @@ __device__ __forceinline__ float el_lg2(float x) { float y; asm("lg2.approx.ftz.
 __device__ __forceinline__ float el_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float el_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+template <bool G15 = false>
 __device__ __forceinline__ float el_focal(float y, float x, float alpha, float gamma, float ls) {
   // focal_loss.py:36-52
   const float e = el_ex2(-1.4426950408889634f * fabsf(x));   // exp(-|x|)
@@ -48,10 +51,35 @@ __device__ __forceinline__ float el_focal(float y, float x, float alpha, float g
   const float p_t = y * p + (1.0f - y) * (1.0f - p);
   const float af = y * alpha + (1.0f - y) * (1.0f - alpha);
   const float q = fmaxf(1.0f - p_t, 0.0f);
-  const float mod = (gamma == 1.5f) ? q * el_sqrt(q) : __powf(q, gamma);
+  const float mod = (G15 || gamma == 1.5f) ? q * el_sqrt(q) : __powf(q, gamma);
   const float ys = y * (1.0f - ls) + 0.5f * ls;
   const float ce = fmaxf(x, 0.0f) - x * ys - 0.6931471805599453f * el_lg2(r);  // log1p(exp(-|x|)) = -log(1/(1+e))
   return af * mod * ce;
+}
+
+// y == 0 specialisation for the sparse-target mode (every element is background except one per anchor):
+// p_t = 1 - p, alpha factor = 1 - alpha, modulating factor = p^gamma, and log1p(exp(-|x|)) as e*P(e) with a degree-6
+// polynomial on e in (0,1] (max relative error 1.5e-6) so that only 3 of the 4 MUFU operations remain — the focal
+// pass is bound by the SFU pipe (4 lanes per scheduler), not by FP32 issue.
+__device__ __forceinline__ float el_log1p_poly(float e) {
+  float p = 0.014202825725078583f;
+  p = __fmaf_rn(p, e, -0.06658805161714554f);
+  p = __fmaf_rn(p, e, 0.14943458139896393f);
+  p = __fmaf_rn(p, e, -0.23514863848686218f);
+  p = __fmaf_rn(p, e, 0.3311205208301544f);
+  p = __fmaf_rn(p, e, -0.4998719096183777f);
+  p = __fmaf_rn(p, e, 0.9999987483024597f);
+  return p * e;
+}
+
+template <bool G15>
+__device__ __forceinline__ float el_focal_bg(float x, float one_minus_alpha, float gamma, float half_ls) {
+  const float e = el_ex2(-1.4426950408889634f * fabsf(x));   // exp(-|x|)
+  const float r = el_rcp(1.0f + e);
+  const float p = (x >= 0.0f) ? r : e * r;                   // sigmoid(x) = 1 - p_t
+  const float mod = G15 ? p * el_sqrt(p) : __powf(p, gamma);
+  const float ce = __fmaf_rn(-x, half_ls, fmaxf(x, 0.0f)) + el_log1p_poly(e);
+  return one_minus_alpha * mod * ce;
 }
 
 __device__ __forceinline__ float el_huber(float t, float o, float delta) {
@@ -61,6 +89,8 @@ __device__ __forceinline__ float el_huber(float t, float o, float delta) {
   return (a <= delta) ? 0.5f * e * e : delta * a - 0.5f * delta * delta;
 }
 
+// G15: gamma == 1.5 (the reference's value, global_params.py:186) — q^1.5 = q*sqrt(q) without a per-element branch
+template <bool G15>
 __global__ void __launch_bounds__(EL_THREADS) focal_box_partials_kernel(ElParams p) {
   __shared__ double s_red[EL_THREADS / 32][3];
   int l = 0;
@@ -76,16 +106,40 @@ __global__ void __launch_bounds__(EL_THREADS) focal_box_partials_kernel(ElParams
   const unsigned long long nv = p.cls_vec[l];
   unsigned long long i = (unsigned long long)cta * EL_THREADS + threadIdx.x;
   int it = 0;
+  const int32_t* __restrict__ ci = p.cls_index[l];
+  if (ci) {
+    // sparse-target mode: sum over every logit of the background term, then per anchor swap the term of its class
+    // for the y = 1 one
+    const float oma = 1.0f - p.alpha, hls = 0.5f * p.label_smoothing;
 #pragma unroll 2
-  for (; i < nv; i += stride) {
-    const float4 x = __ldcs(cp + i);
-    const float4 y = __ldcs(ct + i);
-    f0 += el_focal(y.x, x.x, p.alpha, p.gamma, p.label_smoothing) + el_focal(y.y, x.y, p.alpha, p.gamma, p.label_smoothing);
-    f1 += el_focal(y.z, x.z, p.alpha, p.gamma, p.label_smoothing) + el_focal(y.w, x.w, p.alpha, p.gamma, p.label_smoothing);
-    if ((++it & 63) == 0) { focal += (double)f0 + (double)f1; f0 = f1 = 0.f; }
+    for (; i < nv; i += stride) {
+      const float4 x = __ldcs(cp + i);
+      f0 += el_focal_bg<G15>(x.x, oma, p.gamma, hls) + el_focal_bg<G15>(x.y, oma, p.gamma, hls);
+      f1 += el_focal_bg<G15>(x.z, oma, p.gamma, hls) + el_focal_bg<G15>(x.w, oma, p.gamma, hls);
+      if ((++it & 63) == 0) { focal += (double)f0 + (double)f1; f0 = f1 = 0.f; }
+    }
+    if (cta == 0 && (int)threadIdx.x < p.cls_tail[l]) f0 += el_focal_bg<G15>(p.cls_pred_tail[l][threadIdx.x], oma, p.gamma, hls);
+    const float* __restrict__ logits = reinterpret_cast<const float*>(cp);
+    const unsigned long long n_anchor = (nv * 4ull + (unsigned long long)p.cls_tail[l]) / (unsigned long long)p.C;
+    for (unsigned long long a = (unsigned long long)cta * EL_THREADS + threadIdx.x; a < n_anchor; a += stride) {
+      const int cls = __ldg(ci + a);
+      if (cls >= 0 && cls < p.C) {  // tf.one_hot: ids outside [0, C) give an all-zero row
+        const float x = __ldg(logits + a * (unsigned long long)p.C + cls);
+        f0 += el_focal<G15>(1.0f, x, p.alpha, p.gamma, p.label_smoothing) - el_focal_bg<G15>(x, oma, p.gamma, hls);
+      }
+    }
+  } else {
+#pragma unroll 2
+    for (; i < nv; i += stride) {
+      const float4 x = __ldcs(cp + i);
+      const float4 y = __ldcs(ct + i);
+      f0 += el_focal<G15>(y.x, x.x, p.alpha, p.gamma, p.label_smoothing) + el_focal<G15>(y.y, x.y, p.alpha, p.gamma, p.label_smoothing);
+      f1 += el_focal<G15>(y.z, x.z, p.alpha, p.gamma, p.label_smoothing) + el_focal<G15>(y.w, x.w, p.alpha, p.gamma, p.label_smoothing);
+      if ((++it & 63) == 0) { focal += (double)f0 + (double)f1; f0 = f1 = 0.f; }
+    }
+    if (cta == 0 && (int)threadIdx.x < p.cls_tail[l])
+      f0 += el_focal<G15>(p.cls_true_tail[l][threadIdx.x], p.cls_pred_tail[l][threadIdx.x], p.alpha, p.gamma, p.label_smoothing);
   }
-  if (cta == 0 && (int)threadIdx.x < p.cls_tail[l])
-    f0 += el_focal(p.cls_true_tail[l][threadIdx.x], p.cls_pred_tail[l][threadIdx.x], p.alpha, p.gamma, p.label_smoothing);
   focal += (double)f0 + (double)f1;
   float hub = 0.f;
   unsigned int pos = 0;
@@ -230,10 +284,12 @@ __global__ void __launch_bounds__(EL_THREADS) focal_box_grad_kernel(ElGradParams
 
 // ---- host side ------------------------------------------------------------------------------------
 static int el_cta_plan(int num_levels, const unsigned long long* cls_elems, int* cta_base) {
-  // CTAs proportional to the class-tensor size of each level, ~8 per SM in total, at least 1 per level
+  // CTAs proportional to the class-tensor size of each level, ~64 per SM in total, at least 1 per level.  Measured on
+  // D0 B=128: 8 per SM 0.80 ms, 16 0.75, 32 0.71, 64 0.69 (92 % of the copy bandwidth), 96 0.69 — many short CTAs
+  // keep the tail of every level busy.
   unsigned long long tot = 0;
   for (int l = 0; l < num_levels; ++l) tot += cls_elems[l];
-  const int budget = b200_sm_count() * 8;
+  const int budget = b200_sm_count() * 64;
   int c = 0;
   for (int l = 0; l < num_levels; ++l) {
     cta_base[l] = c;
@@ -276,17 +332,22 @@ extern "C" size_t b200_focal_box_workspace_bytes(int num_levels, const unsigned 
 }
 
 // anchors_per_level[l] = B*H_l*W_l*A of THIS call (local shard); sums_out: device double[2L+1]
-extern "C" int b200_focal_box_partial_sums(int num_levels, const unsigned long long* anchors_per_level, int C,
-                                           const float* const true_boxes[], const float* const true_classes[],
-                                           const unsigned char* const true_masks[], const float* const pred_boxes[],
-                                           const float* const pred_classes[], float alpha, float gamma, float delta,
-                                           float label_smoothing, double* sums_out, void* workspace,
-                                           size_t workspace_bytes, void* stream_) {
+static int el_partial_sums_impl(int num_levels, const unsigned long long* anchors_per_level, int C,
+                                const float* const true_boxes[], const float* const true_classes_dense[],
+                                const int32_t* const true_class_index[], const unsigned char* const true_masks[],
+                                const float* const pred_boxes[], const float* const pred_classes[], float alpha, float gamma,
+                                float delta, float label_smoothing, double* sums_out, void* workspace, size_t workspace_bytes,
+                                void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_REQUIRE(num_levels >= 1 && num_levels <= EL_MAX_LEVELS && C >= 1, B200_ERR_BAD_ARG, "b200_focal_box_partial_sums: bad level count / classes");
-  B200_REQUIRE(anchors_per_level && true_boxes && true_classes && true_masks && pred_boxes && pred_classes && sums_out,
+  B200_REQUIRE(anchors_per_level && true_boxes && (true_classes_dense || true_class_index) && true_masks && pred_boxes && pred_classes && sums_out,
                B200_ERR_BAD_ARG, "b200_focal_box_partial_sums: null argument");
+  // the class targets of a level: the one-hot tensor, or (sparse-target mode) one class id per anchor
+  const void* true_classes[EL_MAX_LEVELS];
+  for (int l = 0; l < EL_MAX_LEVELS; ++l)
+    true_classes[l] = l < num_levels ? (true_classes_dense ? (const void*)true_classes_dense[l] : (const void*)true_class_index[l]) : nullptr;
   ElParams p;
+  p.C = C;
   unsigned long long elems[EL_MAX_LEVELS];
   p.num_levels = num_levels;
   for (int l = 0; l < EL_MAX_LEVELS; ++l) {
@@ -300,17 +361,18 @@ extern "C" int b200_focal_box_partial_sums(int num_levels, const unsigned long l
       B200_REQUIRE((al & 15) == 0, B200_ERR_BAD_ARG, "b200_focal_box_partial_sums: level %d tensors must be 16-byte aligned", l);
       elems[l] = has_cls ? anchors_per_level[l] * (unsigned long long)C : 0ull;
       p.cls_pred[l] = reinterpret_cast<const float4*>(pred_classes[l]);
-      p.cls_true[l] = reinterpret_cast<const float4*>(true_classes[l]);
+      p.cls_true[l] = true_classes_dense ? reinterpret_cast<const float4*>(true_classes[l]) : nullptr;
+      p.cls_index[l] = true_classes_dense ? nullptr : reinterpret_cast<const int32_t*>(true_classes[l]);
       p.cls_vec[l] = elems[l] / 4;
       p.cls_tail[l] = (int)(elems[l] - p.cls_vec[l] * 4);
       p.cls_pred_tail[l] = pred_classes[l] + p.cls_vec[l] * 4;
-      p.cls_true_tail[l] = true_classes[l] + p.cls_vec[l] * 4;
+      p.cls_true_tail[l] = true_classes_dense ? true_classes_dense[l] + p.cls_vec[l] * 4 : nullptr;
       p.box_pred[l] = reinterpret_cast<const float4*>(pred_boxes[l]);
       p.box_true[l] = reinterpret_cast<const float4*>(true_boxes[l]);
       p.mask[l] = true_masks[l];
       p.anchors[l] = has_box ? anchors_per_level[l] : 0ull;
     } else {
-      elems[l] = 0; p.cls_pred[l] = p.cls_true[l] = nullptr; p.cls_vec[l] = 0; p.cls_tail[l] = 0;
+      elems[l] = 0; p.cls_pred[l] = p.cls_true[l] = nullptr; p.cls_index[l] = nullptr; p.cls_vec[l] = 0; p.cls_tail[l] = 0;
       p.cls_pred_tail[l] = p.cls_true_tail[l] = nullptr; p.box_pred[l] = p.box_true[l] = nullptr; p.mask[l] = nullptr; p.anchors[l] = 0;
     }
   }
@@ -322,7 +384,8 @@ extern "C" int b200_focal_box_partial_sums(int num_levels, const unsigned long l
   p.alpha = alpha; p.gamma = gamma; p.delta = delta; p.label_smoothing = label_smoothing;
   p.partials = static_cast<double*>(workspace);
   B200_CUDA(cudaMemsetAsync(sums_out, 0, sizeof(double) * (2 * num_levels + 1), stream));
-  focal_box_partials_kernel<<<n_cta, EL_THREADS, 0, stream>>>(p);
+  if (gamma == 1.5f) focal_box_partials_kernel<true><<<n_cta, EL_THREADS, 0, stream>>>(p);
+  else focal_box_partials_kernel<false><<<n_cta, EL_THREADS, 0, stream>>>(p);
   B200_LAUNCH_CHECK();
   ElReduce r;
   r.partials = p.partials; r.num_levels = num_levels; r.sums = sums_out;
@@ -330,6 +393,30 @@ extern "C" int b200_focal_box_partial_sums(int num_levels, const unsigned long l
   focal_box_reduce_kernel<<<num_levels, 256, 0, stream>>>(r);
   B200_LAUNCH_CHECK();
   return B200_OK;
+}
+
+extern "C" int b200_focal_box_partial_sums(int num_levels, const unsigned long long* anchors_per_level, int C,
+                                           const float* const true_boxes[], const float* const true_classes[],
+                                           const unsigned char* const true_masks[], const float* const pred_boxes[],
+                                           const float* const pred_classes[], float alpha, float gamma, float delta,
+                                           float label_smoothing, double* sums_out, void* workspace,
+                                           size_t workspace_bytes, void* stream_) {
+  B200_REQUIRE(true_classes, B200_ERR_BAD_ARG, "b200_focal_box_partial_sums: null argument");
+  return el_partial_sums_impl(num_levels, anchors_per_level, C, true_boxes, true_classes, nullptr, true_masks, pred_boxes,
+                              pred_classes, alpha, gamma, delta, label_smoothing, sums_out, workspace, workspace_bytes, stream_);
+}
+
+// Sparse-target mode: true_class_index[l] (B,H,W,A) int32 = the class id whose one-hot row
+// generate_targets would have written (0 for unmatched anchors; out-of-range ids = all-zero row).
+extern "C" int b200_focal_box_partial_sums_indexed(int num_levels, const unsigned long long* anchors_per_level, int C,
+                                                   const float* const true_boxes[], const int32_t* const true_class_index[],
+                                                   const unsigned char* const true_masks[], const float* const pred_boxes[],
+                                                   const float* const pred_classes[], float alpha, float gamma, float delta,
+                                                   float label_smoothing, double* sums_out, void* workspace,
+                                                   size_t workspace_bytes, void* stream_) {
+  B200_REQUIRE(true_class_index, B200_ERR_BAD_ARG, "b200_focal_box_partial_sums_indexed: null argument");
+  return el_partial_sums_impl(num_levels, anchors_per_level, C, true_boxes, nullptr, true_class_index, true_masks, pred_boxes,
+                              pred_classes, alpha, gamma, delta, label_smoothing, sums_out, workspace, workspace_bytes, stream_);
 }
 
 // numel_per_level[l] = GLOBAL element count B_global*H*W*A*C of level l (the Keras mean divisor)

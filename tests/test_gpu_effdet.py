@@ -151,6 +151,49 @@ def test_get_loss_matches_oracle(lib, cuda, name, batch):
     np.testing.assert_allclose(el, oe.focal_loss_elements(3.0, tc[1], pc[1]), rtol=2e-5, atol=1e-9)
 
 
+@pytest.mark.parametrize("name,batch", [("small", 3), ("d0", 2), ("tiny", 2)])
+def test_class_index_targets_match_one_hot_path(lib, cuda, name, batch):
+    """SURVEY §8f N3 for EfficientDet: generate_targets with class ids instead of one-hot rows, and the focal loss
+    rebuilt from them, equal the dense path (ids == argmax/zero-row of the one-hot, loss within 1e-4 of the oracle)."""
+    import torch
+    from oracle import effdet as oe
+    from tfmv_b200 import synth
+    from tfmv_b200.ai_models.efficientnet.efficientdet_net_train import get_loss
+    a, o = _pair(name)
+    rng = np.random.default_rng(20261018 + 90 + batch)
+    ih, iw = CFGS[name]["image_size"]
+    C = 81 if name != "tiny" else 3
+    if name == "tiny":
+        boxes = np.array([[3, 3, 6, 6], [5, 5, 9, 9], [2, 2, 5, 5]], F); classes = np.array([1, 2, 1], np.int32); off = np.array([0, 2, 3], np.int32)
+    else:
+        boxes, classes, off = synth.gt_batch(rng, batch, (iw, ih), max_boxes=40, order="yxyx")
+        classes = (classes % 80 + 1).astype(np.int32)
+        classes[0] = 200  # out of range -> all-zero one-hot row
+    db, dc, do = _t(boxes, cuda), _t(classes, cuda), _t(off, cuda)
+    gb, gc, gm = a.generate_targets_batch(db, dc, do, C)
+    ib, ic, im = a.generate_targets_batch(db, dc, do, C, class_index=True)
+    npos = 0
+    for l in range(len(gb)):
+        assert ic[l].dtype == torch.int32 and tuple(ic[l].shape) == tuple(gc[l].shape[:-1])
+        assert torch.equal(ib[l], gb[l]) and torch.equal(im[l], gm[l])
+        ids = ic[l].long()
+        onehot = torch.zeros_like(gc[l])
+        ok = (ids >= 0) & (ids < C)
+        onehot[ok] = torch.nn.functional.one_hot(ids[ok], C).float()
+        assert torch.equal(onehot, gc[l])
+        npos += int(gm[l].sum())
+    assert npos > 0
+    pb = [torch.randn(t.shape, device=cuda, generator=torch.Generator(cuda).manual_seed(5 + l)) * 0.25 for l, t in enumerate(gb)]
+    pc = [torch.randn(t.shape, device=cuda, generator=torch.Generator(cuda).manual_seed(50 + l)) for l, t in enumerate(gc)]
+    dense, dparts, dn = get_loss(gb, gc, gm, pb, pc, return_parts=True)
+    sparse, sparts, sn = get_loss(ib, ic, im, pb, pc, return_parts=True)
+    assert float(dn) == float(sn)
+    np.testing.assert_allclose(sparts.cpu().numpy(), dparts.cpu().numpy(), rtol=1e-6, atol=1e-12)
+    want = oe.get_loss([t.cpu().numpy() for t in gb], [t.cpu().numpy() for t in gc], [t.cpu().numpy() for t in gm],
+                       [t.cpu().numpy() for t in pb], [t.cpu().numpy() for t in pc])
+    assert abs(float(sparse) - float(want)) <= LOSS_RTOL * abs(float(want))
+
+
 def test_get_loss_gradient_matches_oracle(lib, cuda):
     """SURVEY §8f N1 for EfficientDet: d _get_loss / d class logits and box outputs vs the fp64 analytic oracle."""
     from oracle import effdet as oe
