@@ -435,7 +435,7 @@ extern "C" int b200_effdet_decode(int num_levels, const int32_t* hw, int A, cons
   p.elem_base[EF_MAX_LEVELS] = cum;
   for (int l = num_levels; l <= EF_MAX_LEVELS; ++l) p.elem_base[l] = cum;
   long long blocks = (cum + 255) / 256;
-  const long long cap = (long long)b200_sm_count() * 8;
+  const long long cap = (long long)b200_sm_count() * 64;  // many short CTAs: see el_cta_plan
   if (blocks > cap) blocks = cap;
   effdet_decode_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p);
   B200_LAUNCH_CHECK();

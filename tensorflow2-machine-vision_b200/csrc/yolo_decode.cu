@@ -495,7 +495,7 @@ extern "C" int b200_yolo_decode_dense(const float* head, int B, int H, int W, in
   B200_REQUIRE(head && anchors_wh_norm_dev && boxes && conf && classes && valid, B200_ERR_BAD_ARG, "b200_yolo_decode_dense: null pointer");
   const long long total = (long long)B * H * W * A;
   long long blocks = (total + 7) / 8;
-  long long cap = (long long)b200_sm_count() * 8;
+  long long cap = (long long)b200_sm_count() * 64;
   if (blocks > cap) blocks = cap;
   yolo_decode_dense_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(head, total, H, W, A, C, anchors_wh_norm_dev, boxes, conf,
                                                                          classes, valid);

@@ -816,7 +816,7 @@ static int yolo_loss_impl(const float* const y_true[3], const float* const y_pre
       g.n_vec[l] = cum;
     }
     unsigned long long blocks = (cum + 255) / 256;
-    const unsigned long long cap = (unsigned long long)b200_sm_count() * 8;
+    const unsigned long long cap = (unsigned long long)b200_sm_count() * 64;
     if (blocks > cap) blocks = cap;
     yolo_loss_grad_dense_kernel<<<(int)blocks, 256, 0, stream>>>(g);
     B200_LAUNCH_CHECK();

@@ -113,7 +113,7 @@ extern "C" int b200_fill_zero(float* dst, size_t n, void* stream) {
   const size_t n_vec = n / 4;
   const int n_tail = (int)(n - n_vec * 4);
   size_t blocks = (n_vec + 255) / 256;
-  const size_t cap = (size_t)b200_sm_count() * 8;
+  const size_t cap = (size_t)b200_sm_count() * 128;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   fill_zero_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(dst), n_vec, dst + n_vec * 4, n_tail);
@@ -174,7 +174,8 @@ extern "C" int b200_yolo_assign_targets(const float* boxes, const int32_t* class
     }
     if (vec_ok) {
       unsigned long long blocks = (cum + 255) / 256;
-      const unsigned long long cap = (unsigned long long)b200_sm_count() * 8;
+      // measured (608x608 B=64, 495 MB): 8 CTAs/SM 86 us, 32 78 us, 128 74 us, more: flat
+      const unsigned long long cap = (unsigned long long)b200_sm_count() * 128;
       if (blocks > cap) blocks = cap;
       if (blocks < 1) blocks = 1;
       fill_zero_multi_kernel<<<(int)blocks, 256, 0, stream>>>(f);
