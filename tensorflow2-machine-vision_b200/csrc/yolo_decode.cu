@@ -74,45 +74,98 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
-// max and first-argmax of sigmoid(x_c), c in [0,C), reading a record with stride 1 from shared memory.
-// One pass keeps the largest logit (first index on ties) and the second largest value.  When the runner-up is
-// outside the guard band of the maximum, its sigmoid is certainly smaller and the answer is (sigmoid(m1), i1):
-// for -80 < m < 8, d ln(sigmoid)/dx >= 3.3e-4, so logits below m - 0.01 are > 3.3e-6 relative below sigmoid(m)
-// while detmath's sigmoid is within 2.4 ulp = 2.9e-7 of exact (oracle/DETMATH_REPORT.md; it is not monotone at
-// ulp level, which is why the band exists).  Otherwise (rare) every logit inside the band is evaluated and max /
-// first-argmax are taken in sigmoid space, exactly as tf.reduce_max / tf.argmax of sigmoid(classes) do.
-__device__ __forceinline__ void class_max_sigmoid(const float* __restrict__ cls, int C, float& best_s, int& best_c) {
-  // pass 1: the maximum logit, four independent chains (2 instructions per element)
-  float a0 = cls[0], a1 = a0, a2 = a0, a3 = a0;
-  int c = 0;
-  for (; c + 4 <= C; c += 4) {
-    a0 = fmaxf(a0, cls[c]); a1 = fmaxf(a1, cls[c + 1]); a2 = fmaxf(a2, cls[c + 2]); a3 = fmaxf(a3, cls[c + 3]);
-  }
-  for (; c < C; ++c) a0 = fmaxf(a0, cls[c]);
-  const float m1 = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));  // fmaxf drops NaNs; a NaN row is caught below
-  // pass 2: first index of the maximum, and how many logits fall inside the guard band
-  const bool banded = (m1 < 8.0f) && (m1 > -80.0f);
-  const float lo = banded ? (m1 - 0.01f) : -INFINITY;
-  int i1 = C, in_band = 0;
-#pragma unroll 4
-  for (c = C - 1; c >= 0; --c) {
-    const float x = cls[c];
-    i1 = (x == m1) ? c : i1;
-    in_band += (x >= lo || x != x) ? 1 : 0;
-  }
-  if (in_band == 1 && i1 < C) {  // the maximum is alone in its band: its sigmoid is the largest, certainly
-    best_s = dm_sigmoidf(m1);
+// max and first-argmax of sigmoid(x_c), c in [0,C), for the warp's 32 records (lane <-> record, stride RF in shared
+// memory, conflict-free).  One pass per lane keeps the largest logit with its first index and the second largest
+// value (four independent chains).  When the runner-up is outside the guard band of the maximum its sigmoid is
+// certainly smaller and the answer is (sigmoid(m1), i1): for -80 < m < 8, d ln(sigmoid)/dx >= 3.3e-4, so logits
+// below m - 0.01 are > 3.3e-6 relative below sigmoid(m) while detmath's sigmoid is within 2.4 ulp = 2.9e-7 of exact
+// (oracle/DETMATH_REPORT.md; it is not monotone at ulp level, which is why the band exists).  Otherwise (a few per
+// cent of the records) the whole warp evaluates that record's in-band logits and takes max / first-argmax in sigmoid
+// space, exactly as tf.reduce_max / tf.argmax of sigmoid(classes) do.
+__device__ __forceinline__ void class_max_sigmoid_warp(const float* __restrict__ slab, int RF, int C, bool want, int lane,
+                                                       float& best_s, int& best_c) {
+  const float* __restrict__ cls = slab + lane * RF + 5;
+  bool slow = false;
+  float lo = -INFINITY;
+  if (want) {
+    float a[4], m2[4], nan_acc = 0.0f;
+    int ix[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { a[k] = -INFINITY; m2[k] = -INFINITY; ix[k] = C; }
+    int c = 0;
+    for (; c + 4 <= C; c += 4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float x = cls[c + k];
+        nan_acc = __fmaf_rn(x, 0.0f, nan_acc);            // NaN once any logit is NaN or +-inf
+        m2[k] = fmaxf(m2[k], fminf(a[k], x));
+        const bool g = x > a[k];                            // strict: the first index of a chain's maximum stays
+        a[k] = g ? x : a[k];
+        ix[k] = g ? c + k : ix[k];
+      }
+    }
+    for (; c < C; ++c) {
+      const float x = cls[c];
+      nan_acc = __fmaf_rn(x, 0.0f, nan_acc);
+      m2[0] = fmaxf(m2[0], fminf(a[0], x));
+      const bool g = x > a[0];
+      a[0] = g ? x : a[0];
+      ix[0] = g ? c : ix[0];
+    }
+    // merge the chains: largest value, lowest index on ties; runner-up = largest of the chains' runner-ups and of
+    // the chain maxima that lost
+    float m1 = a[0], r2 = m2[0];
+    int i1 = ix[0];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      const bool g = (a[k] > m1) || (a[k] == m1 && ix[k] < i1);
+      r2 = fmaxf(r2, fmaxf(m2[k], g ? m1 : a[k]));
+      m1 = g ? a[k] : m1;
+      i1 = g ? ix[k] : i1;
+    }
+    const bool banded = (m1 < 8.0f) && (m1 > -80.0f);
+    lo = banded ? (m1 - 0.01f) : -INFINITY;
+    slow = !(nan_acc == 0.0f) || !(r2 < lo) || i1 >= C;
+    best_s = m1;  // sigmoid applied below
     best_c = i1;
-    return;
   }
-  best_s = 0.0f;
-  best_c = 0;
-  bool any = false;
-  for (c = 0; c < C; ++c) {
-    const float x = cls[c];
-    if (x >= lo || x != x) {
-      const float s = dm_sigmoidf(x);
-      if (!any || s > best_s) { best_s = s; best_c = c; any = true; }
+  if (want && !slow) best_s = dm_sigmoidf(best_s);
+  // cooperative exact path, one record at a time
+  uint32_t todo = __ballot_sync(0xffffffffu, want && slow);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1u;
+    const float lo_s = __shfl_sync(0xffffffffu, lo, src);
+    const float* __restrict__ rc = slab + src * RF + 5;
+    // serial semantics being reproduced: walk c upwards over the in-band logits (x >= lo or NaN); the first one
+    // initialises (s, c) even when its sigmoid is NaN; later ones replace it only when s > best
+    float ls = 0.0f;
+    int lc = 0x7fffffff, lfirst = 0x7fffffff;
+    bool lfirst_nan = false;
+    for (int c = lane; c < C; c += 32) {
+      const float x = rc[c];
+      if (x >= lo_s || x != x) {
+        const float sg = dm_sigmoidf(x);
+        if (lfirst == 0x7fffffff) { lfirst = c; lfirst_nan = sg != sg; }
+        if (sg == sg && (lc == 0x7fffffff || sg > ls)) { ls = sg; lc = c; }
+      }
+    }
+    int first = lfirst;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    const bool first_is_nan = __any_sync(0xffffffffu, lfirst == first && first != 0x7fffffff && lfirst_nan);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, ls, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, lc, o);
+      const bool take = (oc != 0x7fffffff) && (lc == 0x7fffffff || os > ls || (os == ls && oc < lc));
+      ls = take ? os : ls;
+      lc = take ? oc : lc;
+    }
+    if (lane == src) {
+      if (first == 0x7fffffff) { best_s = 0.0f; best_c = 0; }               // no in-band logit at all (cannot happen for C >= 1)
+      else if (first_is_nan || lc == 0x7fffffff) { best_s = __int_as_float(0x7fc00000); best_c = first; }
+      else { best_s = ls; best_c = lc; }
     }
   }
 }
@@ -204,24 +257,24 @@ __global__ void __launch_bounds__(512, 1) yolo_decode_filter_kernel(YoloDecodePa
     float score = 0.f, conf = 0.f;
     int cls = 0;
     uint32_t aidx = 0;
+    bool want = false;
     if (in_range) {
       conf = dm_sigmoidf(r[4]);
-      if (conf > p.conf_thr) {
-        class_max_sigmoid(r + 5, p.C, score, cls);
-        if (score > p.score_thr) {
-          const int rpi = p.lv.rec_per_img[l];
-          img = (int)(rec / rpi);
-          const int rin = (int)(rec - (long long)img * rpi);
-          const int cell = rin / p.A, a = rin - cell * p.A;
-          const int W = p.lv.w[l], H = p.lv.h[l];
-          const int gy = cell / W, gx = cell - gy * W;
-          Decoded d = decode_box(r[0], r[1], r[2], r[3], gx, gy, W, H, p.lv.anc_w[l][a], p.lv.anc_h[l][a]);
-          if (d.valid) {
-            pass = true;
-            box = make_float4(d.x1, d.y1, d.x2, d.y2);
-            aidx = (uint32_t)(p.lv.anchor_base[l] + rin);
-          }
-        }
+      want = conf > p.conf_thr;
+    }
+    class_max_sigmoid_warp(my_slab(stage), RF, p.C, want, lane, score, cls);
+    if (want && score > p.score_thr) {
+      const int rpi = p.lv.rec_per_img[l];
+      img = (int)(rec / rpi);
+      const int rin = (int)(rec - (long long)img * rpi);
+      const int cell = rin / p.A, a = rin - cell * p.A;
+      const int W = p.lv.w[l], H = p.lv.h[l];
+      const int gy = cell / W, gx = cell - gy * W;
+      Decoded d = decode_box(r[0], r[1], r[2], r[3], gx, gy, W, H, p.lv.anc_w[l][a], p.lv.anc_h[l][a]);
+      if (d.valid) {
+        pass = true;
+        box = make_float4(d.x1, d.y1, d.x2, d.y2);
+        aidx = (uint32_t)(p.lv.anchor_base[l] + rin);
       }
     }
     // warp-aggregated append, one atomic per (warp, image)
