@@ -381,7 +381,13 @@ __global__ void __launch_bounds__(256) yolo_classes_kernel(YoloFinalizeParams p)
   const long long rec = (long long)img * p.lv.rec_per_img[l] + ((int)a - p.lv.anchor_base[l]);
   const float* src = p.lv.head[l] + rec * p.RF + 5;
   float* dst = p.out_classes + (size_t)row * p.C;
-  for (int c = lane; c < p.C; c += 32) dst[c] = dm_sigmoidf(__ldg(src + c));
+  // the (cold) logits of up to 128 classes are fetched before the first sigmoid starts
+  float x[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) x[j] = (lane + 32 * j < p.C) ? __ldg(src + lane + 32 * j) : 0.0f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) if (lane + 32 * j < p.C) dst[lane + 32 * j] = dm_sigmoidf(x[j]);
+  for (int c = lane + 128; c < p.C; c += 32) dst[c] = dm_sigmoidf(__ldg(src + c));
 }
 
 // ---- dense decode for the stand-alone GetBoxes shim ---------------------------------------------
