@@ -116,9 +116,17 @@ __device__ __forceinline__ void nms_bitonic(unsigned long long* sK, uint32_t* sP
 
 // Runs NMS for one segment with the whole CTA (blockDim.x == NMS_THREADS).  out_pos receives the local
 // positions (0..n-1) of emitted candidates in emit order; returns the number emitted (uniform across threads).
-template <int METRIC>
+// How a candidate's box is obtained when it enters the window: by default a read of seg.boxes; a caller may decode
+// it on demand instead (YOLO: only the few hundred candidates NMS actually looks at are ever decoded).
+struct NmsLoadDirect {
+  __device__ __forceinline__ float4 operator()(const NmsSegment& seg, uint32_t pos) const {
+    return __ldg(reinterpret_cast<const float4*>(seg.boxes) + pos);
+  }
+};
+
+template <int METRIC, class BoxLoad = NmsLoadDirect>
 static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cfg, int32_t* __restrict__ out_pos,
-                                      unsigned char* smem_raw, const NmsPre* pre = nullptr) {
+                                      unsigned char* smem_raw, const NmsPre* pre = nullptr, BoxLoad load_box = BoxLoad()) {
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
@@ -263,7 +271,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
       const int n_chunk = min(NMS_CHUNK, n_win - w0);
       if (tid < n_chunk) {
         const uint32_t p = sPos[w0 + tid];
-        const float4 b = __ldg(reinterpret_cast<const float4*>(seg.boxes) + p);
+        const float4 b = load_box(seg, p);
         const BoxT mine = bm_prep(b.x, b.y, b.z, b.w, METRIC);
         cC0[tid] = mine.c0; cC1[tid] = mine.c1; cC2[tid] = mine.c2; cC3[tid] = mine.c3;
         cAr[tid] = mine.area; cAt[tid] = mine.at; cCl[tid] = seg.classes ? seg.classes[p] : 0;

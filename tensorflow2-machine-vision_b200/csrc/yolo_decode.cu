@@ -18,6 +18,7 @@
 //     NMS tie-break id and as the rank source for `sel_idx`.
 // Kernel 2  yolo_nms_finalize_kernel  (one CTA per image): nms.cuh greedy NMS + gather of the five outputs,
 //   recomputing sigmoid(classes) for the <= max_out selected rows straight from the head tensors.
+#include <cmath>
 #include "nms.cuh"
 
 #define YD_MAX_LEVELS 3
@@ -31,6 +32,9 @@ struct YoloLevels {
   long long total_rec[YD_MAX_LEVELS];  // B*h*w*A
   long long tile_base[YD_MAX_LEVELS + 1];  // first global tile index of each level
   float anc_w[YD_MAX_LEVELS][8], anc_h[YD_MAX_LEVELS][8];  // anchors_wh / image_wh (fp32 division, tyu:185)
+  // lowest tw / th for which the decoded box is certainly valid (w >= 4e-7 so that x + w/2 > x - w/2 in fp32 for any
+  // centre in [0,1]); together with t <= 80 (no overflow) and non-NaN tx, ty the filter can skip the decode
+  float tmin_w[YD_MAX_LEVELS][8], tmin_h[YD_MAX_LEVELS][8];
 };
 
 struct YoloDecodeParams {
@@ -38,6 +42,7 @@ struct YoloDecodeParams {
   int B, A, C, RF;
   int n_img;  // anchors per image over all levels
   float conf_thr, score_thr;
+  float conf_lo, conf_hi;  // logits below / above which sigmoid(conf) > conf_thr is decided without the sigmoid
   // candidate store, stride n_img per image
   float4* cand_box; float* cand_score; int32_t* cand_cls; float* cand_conf; uint32_t* cand_aidx;
   int32_t* counts;     // [B]
@@ -253,14 +258,15 @@ __global__ void __launch_bounds__(512, 1) yolo_decode_filter_kernel(YoloDecodePa
     const float* r = my_slab(stage) + lane * RF;
     bool pass = false;
     int img = 0;
-    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
     float score = 0.f, conf = 0.f;
     int cls = 0;
     uint32_t aidx = 0;
     bool want = false;
     if (in_range) {
-      conf = dm_sigmoidf(r[4]);
-      want = conf > p.conf_thr;
+      // sigmoid(conf) > conf_thr (tyu:191), decided in logit space outside a narrow band around logit(conf_thr)
+      conf = r[4];
+      if (conf > p.conf_hi) want = true;
+      else if (conf >= p.conf_lo) want = dm_sigmoidf(conf) > p.conf_thr;  // NaN fails both comparisons: not wanted
     }
     class_max_sigmoid_warp(my_slab(stage), RF, p.C, want, lane, score, cls);
     if (want && score > p.score_thr) {
@@ -268,12 +274,17 @@ __global__ void __launch_bounds__(512, 1) yolo_decode_filter_kernel(YoloDecodePa
       img = (int)(rec / rpi);
       const int rin = (int)(rec - (long long)img * rpi);
       const int cell = rin / p.A, a = rin - cell * p.A;
-      const int W = p.lv.w[l], H = p.lv.h[l];
-      const int gy = cell / W, gx = cell - gy * W;
-      Decoded d = decode_box(r[0], r[1], r[2], r[3], gx, gy, W, H, p.lv.anc_w[l][a], p.lv.anc_h[l][a]);
-      if (d.valid) {
+      // the box itself is decoded by the NMS pass, and only for the candidates it looks at; here only its validity
+      // (x2 > x1 and y2 > y1, tyu:163) is needed: certain inside the safe logit range, exact decode otherwise
+      const float tx = r[0], ty = r[1], tw = r[2], th = r[3];
+      bool valid = (tw >= p.lv.tmin_w[l][a]) && (tw <= 80.0f) && (th >= p.lv.tmin_h[l][a]) && (th <= 80.0f) && (tx == tx) && (ty == ty);
+      if (!valid) {
+        const int W = p.lv.w[l], H = p.lv.h[l];
+        const int gy = cell / W, gx = cell - gy * W;
+        valid = decode_box(tx, ty, tw, th, gx, gy, W, H, p.lv.anc_w[l][a], p.lv.anc_h[l][a]).valid;
+      }
+      if (valid) {
         pass = true;
-        box = make_float4(d.x1, d.y1, d.x2, d.y2);
         aidx = (uint32_t)(p.lv.anchor_base[l] + rin);
       }
     }
@@ -288,10 +299,9 @@ __global__ void __launch_bounds__(512, 1) yolo_decode_filter_kernel(YoloDecodePa
       base = __shfl_sync(0xffffffffu, base, leader);
       if (pass && img == limg) {
         const size_t slot = (size_t)limg * p.n_img + base + __popc(grp & ((1u << lane) - 1u));
-        p.cand_box[slot] = box;
         p.cand_score[slot] = score;
         p.cand_cls[slot] = cls;
-        p.cand_conf[slot] = conf;
+        p.cand_conf[slot] = conf;  // the logit; the sigmoid is applied to the emitted rows only
         p.cand_aidx[slot] = aidx;
         if (p.bitmap) atomicOr(&p.bitmap[(size_t)limg * p.bitmap_words + (aidx >> 5)], 1u << (aidx & 31u));
       }
@@ -308,12 +318,36 @@ struct YoloFinalizeParams {
   YoloLevels lv;
   int B, A, C, RF, n_img;
   NmsConfig cfg;
-  const float4* cand_box; const float* cand_score; const int32_t* cand_cls; const float* cand_conf;
+  float4* cand_box;  // written by the NMS pass (decode on demand)
+  const float* cand_score; const int32_t* cand_cls; const float* cand_conf;
   const uint32_t* cand_aidx; const int32_t* counts; const uint32_t* bitmap; int bitmap_words;
   int32_t* nms_pos;  // [B, max_out] scratch
   // outputs, all [B, max_out, ...]
   float* out_boxes; int32_t* out_cls; float* out_score; float* out_classes; float* out_conf;
   int32_t* out_sel_idx; int32_t* out_sel_anchor; int32_t* out_count;
+};
+
+// Decode-on-demand for NMS: candidate `pos` of the image -> its record in the head tensor -> decode_box; the result is
+// written back to the candidate store so that the emitted rows can be copied out afterwards.
+struct YoloLazyBox {
+  const YoloLevels* lv;
+  int img, A, RF;
+  float4* cand_box;  // this image's slice
+  __device__ __forceinline__ float4 operator()(const NmsSegment& seg, uint32_t pos) const {
+    const int a_flat = (int)seg.order_id[pos];
+    int l = 0;
+#pragma unroll
+    for (int j = 1; j < YD_MAX_LEVELS; ++j) if (a_flat >= lv->anchor_base[j]) l = j;
+    const int rin = a_flat - lv->anchor_base[l];
+    const float* r = lv->head[l] + ((long long)img * lv->rec_per_img[l] + rin) * RF;
+    const int cell = rin / A, a = rin - cell * A;
+    const int W = lv->w[l], H = lv->h[l];
+    const int gy = cell / W, gx = cell - gy * W;
+    const Decoded d = decode_box(__ldg(r), __ldg(r + 1), __ldg(r + 2), __ldg(r + 3), gx, gy, W, H, lv->anc_w[l][a], lv->anc_h[l][a]);
+    const float4 b = make_float4(d.x1, d.y1, d.x2, d.y2);
+    cand_box[pos] = b;
+    return b;
+  }
 };
 
 template <int METRIC>
@@ -328,7 +362,9 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) yolo_nms_finalize_kernel(YoloF
   seg.order_id = p.cand_aidx + cbase;
   seg.n = p.counts[img];
   int32_t* pos = p.nms_pos + (size_t)img * p.cfg.max_out;
-  const int kept = nms_run_segment<METRIC>(seg, p.cfg, pos, nms_smem);
+  YoloLazyBox lazy;
+  lazy.lv = &p.lv; lazy.img = img; lazy.A = p.A; lazy.RF = p.RF; lazy.cand_box = p.cand_box + cbase;
+  const int kept = nms_run_segment<METRIC, YoloLazyBox>(seg, p.cfg, pos, nms_smem, nullptr, lazy);
   __syncthreads();
   if (threadIdx.x == 0) p.out_count[img] = kept;
   const size_t obase = (size_t)img * p.cfg.max_out;
@@ -355,7 +391,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) yolo_nms_finalize_kernel(YoloF
     reinterpret_cast<float4*>(p.out_boxes)[obase + k] = b;
     p.out_cls[obase + k] = p.cand_cls[cbase + q];
     p.out_score[obase + k] = p.cand_score[cbase + q];
-    p.out_conf[obase + k] = p.cand_conf[cbase + q];
+    p.out_conf[obase + k] = dm_sigmoidf(p.cand_conf[cbase + q]);
     const uint32_t a = p.cand_aidx[cbase + q];
     if (p.out_sel_anchor) p.out_sel_anchor[obase + k] = (int32_t)a;
     if (p.out_sel_idx && p.bitmap) {
@@ -435,6 +471,11 @@ static int fill_levels(YoloLevels& lv, const float* const heads[3], const int32_
     for (int a = 0; a < A; ++a) {
       lv.anc_w[l][a] = anchors_wh_host[(l * A + a) * 2 + 0] / image_wh_host[0];
       lv.anc_h[l][a] = anchors_wh_host[(l * A + a) * 2 + 1] / image_wh_host[1];
+      // w = exp(tw) * anchor >= 4e-7 (twice the 2e-7 that guarantees x + w/2 > x - w/2 for x in [0,1]); anchors that
+      // are not positive and finite never qualify
+      const double aw = lv.anc_w[l][a], ah = lv.anc_h[l][a];
+      lv.tmin_w[l][a] = (aw > 0.0 && aw < 1e30) ? (float)(log(4e-7 / aw) + 1e-3) : INFINITY;
+      lv.tmin_h[l][a] = (ah > 0.0 && ah < 1e30) ? (float)(log(4e-7 / ah) + 1e-3) : INFINITY;
     }
   }
   lv.tile_base[YD_MAX_LEVELS] = tb;
@@ -496,6 +537,15 @@ extern "C" int b200_yolo_decode_nms(const float* const heads[3], const int32_t h
   unsigned char* wsb = static_cast<unsigned char*>(workspace);
   dp.B = B; dp.A = A; dp.C = C; dp.RF = 5 + C; dp.n_img = n_img;
   dp.conf_thr = conf_thr; dp.score_thr = score_thr;
+  // sigmoid(x) > conf_thr is certain for x > logit(thr) + d and certainly false for x < logit(thr) - d, with d ten times
+  // the 2.4-ulp error of the deterministic sigmoid divided by the slope thr(1-thr); thresholds near 0 or 1 (or outside
+  // (0,1)) always take the exact comparison
+  dp.conf_lo = -INFINITY; dp.conf_hi = INFINITY;
+  if (conf_thr >= 1e-3f && conf_thr <= 1.0f - 1e-3f) {
+    const double t = log((double)conf_thr / (1.0 - (double)conf_thr));
+    const double d = 3e-6 / ((double)conf_thr * (1.0 - (double)conf_thr)) + 1e-6 * fabs(t);
+    dp.conf_lo = (float)(t - d); dp.conf_hi = (float)(t + d);
+  }
   dp.cand_box = reinterpret_cast<float4*>(wsb + ws.box);
   dp.cand_score = reinterpret_cast<float*>(wsb + ws.score);
   dp.cand_cls = reinterpret_cast<int32_t*>(wsb + ws.cls);
