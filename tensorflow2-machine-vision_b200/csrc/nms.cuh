@@ -95,10 +95,11 @@ __device__ __forceinline__ bool nms_suppresses(const BoxT& kept, int kept_cls, c
 // ascending bitonic sort of sK[0..npad) (npad a power of two) with optional payload sP, whole CTA.
 // (A register/shuffle variant with ~3x fewer block barriers was measured slower: every element then does its own
 // compare, twice the ALU work of the pairwise exchange below, and the barriers were not the bottleneck.)
+template <int THREADS = NMS_THREADS>
 __device__ __forceinline__ void nms_bitonic(unsigned long long* sK, uint32_t* sP, int npad) {
   for (int k = 2; k <= npad; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < npad; t += NMS_THREADS) {
+      for (int t = threadIdx.x; t < npad; t += THREADS) {
         const int ixj = t ^ j;
         if (ixj > t) {
           const unsigned long long a = sK[t], b = sK[ixj];
@@ -114,7 +115,7 @@ __device__ __forceinline__ void nms_bitonic(unsigned long long* sK, uint32_t* sP
   }
 }
 
-// Runs NMS for one segment with the whole CTA (blockDim.x == NMS_THREADS).  out_pos receives the local
+// Runs NMS for one segment with the whole CTA (blockDim.x == THREADS).  out_pos receives the local
 // positions (0..n-1) of emitted candidates in emit order; returns the number emitted (uniform across threads).
 // How a candidate's box is obtained when it enters the window: by default a read of seg.boxes; a caller may decode
 // it on demand instead (YOLO: only the few hundred candidates NMS actually looks at are ever decoded).
@@ -124,7 +125,9 @@ struct NmsLoadDirect {
   }
 };
 
-template <int METRIC, class BoxLoad = NmsLoadDirect>
+// THREADS = CTA size (a multiple of 64, <= NMS_THREADS): 1024 for the lowest per-image latency; 512 lets two CTAs
+// share an SM (64 registers/thread), which is faster for batches that do not fit one CTA per SM.
+template <int METRIC, class BoxLoad = NmsLoadDirect, int THREADS = NMS_THREADS>
 static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cfg, int32_t* __restrict__ out_pos,
                                       unsigned char* smem_raw, const NmsPre* pre = nullptr, BoxLoad load_box = BoxLoad()) {
   const int tid = threadIdx.x;
@@ -178,7 +181,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
     const bool pre_ok = pre && klo == 0ull && (*pre->eligible > 0) && (*pre->count <= NMS_WINDOW) &&
                         (*pre->count >= min_win || *pre->count >= *pre->eligible);
     if (!take_all && !pre_ok) {
-      for (int t = tid; t < n_samp; t += NMS_THREADS) {
+      for (int t = tid; t < n_samp; t += THREADS) {
         const int i = (int)(((long long)t * n) / n_samp);
         const float s = seg.scores[i];
         const uint32_t oid = seg.order_id ? seg.order_id[i] : (uint32_t)i;
@@ -187,7 +190,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
         sS[t] = el ? K : ~0ull;
       }
       __syncthreads();
-      nms_bitonic(sS, nullptr, n_samp);
+      nms_bitonic<THREADS>(sS, nullptr, n_samp);
       rank = ((unsigned long long)target * (unsigned long long)n_samp) / (unsigned long long)n;
       if (rank < 2ull) rank = 2ull;
       khi = rank >= (unsigned long long)n_samp ? ~0ull : sS[rank];
@@ -198,7 +201,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
     if (pre && klo == 0ull) {
       const int c = *pre->count, e = *pre->eligible;
       if (e > 0 && c <= NMS_WINDOW && (c >= min_win || c >= e)) {
-        for (int t = tid; t < c; t += NMS_THREADS) { sK[t] = pre->keys[t]; sPos[t] = pre->pos[t]; }
+        for (int t = tid; t < c; t += THREADS) { sK[t] = pre->keys[t]; sPos[t] = pre->pos[t]; }
         n_win = c;
         khi = (c >= e) ? ~0ull : *pre->khi;
         from_pre = true;
@@ -212,7 +215,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
       if (tid == 0) { sScalar[0] = 0; sScalar[1] = 0; }
       __syncthreads();
       int my_el = 0;
-      for (int i = tid; i < n; i += NMS_THREADS) {
+      for (int i = tid; i < n; i += THREADS) {
         const float s = seg.scores[i];
         if (cfg.use_score_thr && (s < cfg.score_thr)) continue;
         const uint32_t oid = seg.order_id ? seg.order_id[i] : (uint32_t)i;
@@ -257,10 +260,10 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
     {
       int npad = 64;
       while (npad < n_win) npad <<= 1;
-      for (int t = tid; t < npad; t += NMS_THREADS)
+      for (int t = tid; t < npad; t += THREADS)
         if (t >= n_win) { sK[t] = ~0ull; sPos[t] = 0xffffffffu; }
       __syncthreads();
-      nms_bitonic(sK, sPos, npad);
+      nms_bitonic<THREADS>(sK, sPos, npad);
     }
 
     // ---------------- 2. consume the window in tiles of 64 sorted candidates, lazily ----------------
@@ -269,19 +272,19 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
     // 64x64 ballot bitmask and a one-warp sweep.  Work is O(emitted^2), independent of the window size.
     for (int w0 = 0; w0 < n_win && n_kept < cfg.max_out; w0 += NMS_CHUNK) {
       const int n_chunk = min(NMS_CHUNK, n_win - w0);
-      if (tid < n_chunk) {
-        const uint32_t p = sPos[w0 + tid];
+      for (int ct = tid; ct < n_chunk; ct += THREADS) {
+        const uint32_t p = sPos[w0 + ct];
         const float4 b = load_box(seg, p);
         const BoxT mine = bm_prep(b.x, b.y, b.z, b.w, METRIC);
-        cC0[tid] = mine.c0; cC1[tid] = mine.c1; cC2[tid] = mine.c2; cC3[tid] = mine.c3;
-        cAr[tid] = mine.area; cAt[tid] = mine.at; cCl[tid] = seg.classes ? seg.classes[p] : 0;
+        cC0[ct] = mine.c0; cC1[ct] = mine.c1; cC2[ct] = mine.c2; cC3[ct] = mine.c3;
+        cAr[ct] = mine.area; cAt[ct] = mine.at; cCl[ct] = seg.classes ? seg.classes[p] : 0;
       }
       if (tid < 2) sSupp[tid] = 0u;
       __syncthreads();
       const int n_tiles = (n_chunk + 63) >> 6;
       for (int T = 0; T < n_tiles && n_kept < cfg.max_out; ++T) {
         const int t0 = T << 6;
-        // phase 1: tile candidates vs the kept list.  warp w: candidates 32*(w&1)..+31, kept indices (w>>1) + 16 j
+        // phase 1: tile candidates vs the kept list.  warp w: candidates 32*(w&1)..+31, kept indices (w>>1) + (THREADS/64) j
         {
           const int c = ((warp & 1) << 5) + lane;
           const int gj = t0 + c;
@@ -299,7 +302,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
                 }
               }
             } else {
-              for (int k = warp >> 1; k < n_kept; k += 16) {
+              for (int k = warp >> 1; k < n_kept; k += THREADS / 64) {
                 BoxT kb; kb.c0 = kC0[k]; kb.c1 = kC1[k]; kb.c2 = kC2[k]; kb.c3 = kC3[k]; kb.area = kAr[k]; kb.at = kAt[k];
                 if (nms_suppresses<METRIC>(kb, 0, cb, 0, mode, thr)) { supp = true; break; }
               }
@@ -311,10 +314,10 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
         __syncthreads();
         unsigned long long tile_alive = ~((unsigned long long)sSupp[0] | ((unsigned long long)sSupp[1] << 32));
         if (n_chunk - t0 < 64) tile_alive &= (1ull << (n_chunk - t0)) - 1ull;
-        // phase 2: intra-tile mask via ballots: warp w owns rows 2w, 2w+1
+        // phase 2: intra-tile mask via ballots: warp w owns rows (2048/THREADS) w ... (2 rows at 1024 threads)
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-          const int r = 2 * warp + rr;
+        for (int rr = 0; rr < 2048 / THREADS; ++rr) {
+          const int r = (2048 / THREADS) * warp + rr;
           const int gi = t0 + r;
           const bool row_on = (gi < n_chunk) && ((tile_alive >> r) & 1ull);
           BoxT rb; int rcls = 0;

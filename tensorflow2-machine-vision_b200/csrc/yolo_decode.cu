@@ -350,8 +350,8 @@ struct YoloLazyBox {
   }
 };
 
-template <int METRIC>
-__global__ void __launch_bounds__(NMS_THREADS, 1) yolo_nms_finalize_kernel(YoloFinalizeParams p) {
+template <int METRIC, int THREADS>
+__global__ void __launch_bounds__(THREADS, NMS_THREADS / THREADS) yolo_nms_finalize_kernel(YoloFinalizeParams p) {
   extern __shared__ __align__(16) unsigned char nms_smem[];
   const int img = blockIdx.x;
   const size_t cbase = (size_t)img * p.n_img;
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) yolo_nms_finalize_kernel(YoloF
   int32_t* pos = p.nms_pos + (size_t)img * p.cfg.max_out;
   YoloLazyBox lazy;
   lazy.lv = &p.lv; lazy.img = img; lazy.A = p.A; lazy.RF = p.RF; lazy.cand_box = p.cand_box + cbase;
-  const int kept = nms_run_segment<METRIC, YoloLazyBox>(seg, p.cfg, pos, nms_smem, nullptr, lazy);
+  const int kept = nms_run_segment<METRIC, YoloLazyBox, THREADS>(seg, p.cfg, pos, nms_smem, nullptr, lazy);
   __syncthreads();
   if (threadIdx.x == 0) p.out_count[img] = kept;
   const size_t obase = (size_t)img * p.cfg.max_out;
@@ -579,12 +579,20 @@ extern "C" int b200_yolo_decode_nms(const float* const heads[3], const int32_t h
   fp.nms_pos = reinterpret_cast<int32_t*>(wsb + ws.pos);
   fp.out_boxes = out_boxes; fp.out_cls = out_class_id; fp.out_score = out_score; fp.out_classes = out_classes;
   fp.out_conf = out_conf; fp.out_sel_idx = out_sel_idx; fp.out_sel_anchor = out_sel_anchor; fp.out_count = out_count;
+  // one 1024-thread CTA per SM gives the lowest latency; batches that need more than one wave use 512-thread CTAs,
+  // two per SM (the shared-memory footprint allows it up to max_out ~ 500)
   size_t smem2 = nms_smem_bytes(max_out);
   const size_t need_prefix = (size_t)ws.bitmap_words * 4;
   if (smem2 < need_prefix) smem2 = need_prefix;
+  const bool half_ctas = (B > b200_sm_count()) && (2 * (smem2 + 1024) <= 227 * 1024);
 #define YD_LAUNCH(M)                                                                                                   \
-  B200_CUDA(cudaFuncSetAttribute(yolo_nms_finalize_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
-  yolo_nms_finalize_kernel<M><<<B, NMS_THREADS, smem2, stream>>>(fp)
+  if (half_ctas) {                                                                                                          \
+    B200_CUDA(cudaFuncSetAttribute(yolo_nms_finalize_kernel<M, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
+    yolo_nms_finalize_kernel<M, 512><<<B, 512, smem2, stream>>>(fp);                                                         \
+  } else {                                                                                                                  \
+    B200_CUDA(cudaFuncSetAttribute(yolo_nms_finalize_kernel<M, NMS_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
+    yolo_nms_finalize_kernel<M, NMS_THREADS><<<B, NMS_THREADS, smem2, stream>>>(fp);                                         \
+  }
   NMS_DISPATCH_METRIC(metric, YD_LAUNCH)
 #undef YD_LAUNCH
   B200_LAUNCH_CHECK();

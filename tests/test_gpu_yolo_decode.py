@@ -41,6 +41,31 @@ def test_get_nms_boxes_random_init(lib, cuda, image, batch, iou_type, thr):
         _check_image(r, b, want, 80)
 
 
+@pytest.mark.parametrize("iou_type", ["iou", "ciou"])
+def test_get_nms_boxes_more_images_than_sms(lib, cuda, iou_type):
+    """Batches that need more than one NMS CTA per SM run 512-thread CTAs (two per SM): same results, image by image.
+    Heads mix random-init records with planted duplicates so that suppression really happens."""
+    import torch
+    from oracle import yolo as oy
+    from tfmv_b200 import synth
+    from tfmv_b200.ai_models.utils.tf_yolo_utils import GetNMSBoxesBatch
+    batch = torch.cuda.get_device_properties(0).multi_processor_count + 12
+    image = 96
+    rng = np.random.default_rng(20261018 + 11)
+    heads = synth.yolo_heads_trained_like(rng, batch, image, objects=12, dups=4)
+    for h in heads:
+        h[::2] = rng.standard_normal(h[::2].shape, dtype=F)  # every other image: pure random-init
+    anc = synth.yolo_anchors()
+    r = GetNMSBoxesBatch(*[_t(h, cuda) for h in heads], anc, (image, image), 80, 0.5, 0.3, 0.5, iou_type, with_indices=True)
+    r = {k: v.cpu().numpy() for k, v in r.items()}
+    supp = 0
+    for b in range(batch):
+        want = oy.get_nms_boxes_ex(*[h[b:b + 1] for h in heads], anc, (image, image), 80, 0.5, 0.3, 0.5, iou_type)
+        supp += want["cand_boxes"].shape[0] - want["selected"].shape[0]
+        _check_image(r, b, want, 80)
+    assert supp > 50
+
+
 def test_get_nms_boxes_trained_like_and_dropin_signature(lib, cuda):
     from oracle import yolo as oy
     from tfmv_b200 import synth
