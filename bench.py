@@ -320,29 +320,40 @@ def run_b200(args, wl):
     parts_t = torch.empty((3, 4), dtype=torch.float32, device=dev)
     loss_t = torch.empty((), dtype=torch.float32, device=dev)
 
-    def ph_fill():
-        for t in y_true:
-            lib.b200_fill_zero(t.data_ptr(), t.numel(), st)
+    def ph_fill():  # the step's zero-fill: one fill_zero_multi_kernel launch (no boxes -> no scatter launch)
+        lib.b200_yolo_assign_targets(boxes_d.data_ptr(), classes_d.data_ptr(), off_d.data_ptr(), batch, 0,
+                                     anc_h.ctypes.data_as(ctypes.c_void_p), A, img_h.ctypes.data_as(ctypes.c_void_p), 80,
+                                     hw, tp, 1, st)
 
     def ph_scatter():
         lib.b200_yolo_assign_targets(boxes_d.data_ptr(), classes_d.data_ptr(), off_d.data_ptr(), batch, boxes_d.shape[0],
                                      anc_h.ctypes.data_as(ctypes.c_void_p), A, img_h.ctypes.data_as(ctypes.c_void_p), 80,
                                      hw, tp, 0, st)
 
-    def ph_loss():
-        lib.b200_yolo_loss(tp, pp, hw, batch, A, 80, anc_h.ctypes.data_as(ctypes.c_void_p),
-                           img_h.ctypes.data_as(ctypes.c_void_p), 0.5, 2, 0, float(global_batch), parts_t.data_ptr(),
-                           loss_t.data_ptr(), 0, ws.data_ptr(), ws.numel(), st)
+    def ph_loss_stage(mask):
+        def run():
+            lib.b200_yolo_loss_stages(tp, pp, hw, batch, A, 80, anc_h.ctypes.data_as(ctypes.c_void_p),
+                                      img_h.ctypes.data_as(ctypes.c_void_p), 0.5, 2, 0, float(global_batch), parts_t.data_ptr(),
+                                      loss_t.data_ptr(), ws.data_ptr(), ws.numel(), mask, st)
+        return run
 
+    n_rec = n_fill // RF
     ph_fill(); ph_scatter()
     phases = []
+    # one entry per kernel of the step, each timed alone with CUDA events over `steps` back-to-back launches (the loss
+    # kernels through the stage hook of the C ABI; their state lives in the workspace, so the order below matters)
     for name, fn, nbytes, launches in (
-            ("fill_zero x3 buffers (dense y_true zero-fill, write)", ph_fill, n_fill * 4, 3),
+            ("fill_zero_multi_kernel (dense y_true zero-fill, write)", ph_fill, n_fill * 4, 1),
             ("yolo_scatter_targets_kernel (one CTA per image)", ph_scatter, int(boxes_d.shape[0]) * (16 + 4 + 340), 1),
-            ("yolo_loss scan+gtprep+ignore+finalize kernels (dense-equivalent read of y_true+y_pred)", ph_loss, 2 * n_fill * 4, 4)):
+            ("yolo_loss_scan_kernel (obj channel of y_true; dense-equivalent read of y_true)", ph_loss_stage(1), n_fill * 4, 1),
+            ("yolo_loss_gtprep_kernel (a thread per object)", ph_loss_stage(2), int(boxes_d.shape[0]) * (16 + 32), 1),
+            ("yolo_loss_ignore_kernel (box/conf logits of y_pred + object records; dense-equivalent read of y_pred)",
+             ph_loss_stage(4), n_fill * 4, 1),
+            ("yolo_loss_finalize_kernel (fp64 partial sums)", ph_loss_stage(8), n_rec // 128 * 8, 1)):
         ms = timed(fn, args.steps, 3) / args.steps
         phases.append({"kernel": name, "ms": ms, "algorithmic_bytes": nbytes, "gbps": nbytes / ms / 1e6, "launches": launches})
-        ph_fill(); ph_scatter()  # restore valid targets (repeated scatters collide with themselves)
+        if fn in (ph_fill, ph_scatter):
+            ph_fill(); ph_scatter()  # restore valid targets (repeated scatters collide with themselves)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -365,6 +376,9 @@ def run_b200(args, wl):
     if traffic:
         roofline["achieved_dram_gbps"] = traffic / dom["ms"] / 1e6
         roofline["frac_dram"] = traffic / dom["ms"] / 1e6 / peak
+    roofline["phases_note"] = ("each kernel timed alone, launched back to back from Python: entries below ~15 us are bounded by "
+                               "the launch interval, their device durations are in profiles/r01_launches_step_v12.csv")
+    roofline["loss_kernels_dense_equivalent_gbps"] = 2 * n_fill * 4 / sum(p["ms"] for p in phases[2:]) / 1e6
     if dom["kernel"].startswith("yolo_loss"):
         roofline["note"] = ("achieved/frac use SURVEY 8(d)'s dense algorithmic bytes (y_true + y_pred read once); the loss "
                             "kernels are sector-sparse (obj*(...) makes the class channels of non-object cells dead data), so "

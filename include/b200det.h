@@ -123,6 +123,13 @@ int b200_yolo_loss(const float* const y_true[3], const float* const y_pred[3], c
                    int variant, float batch_divisor, float* out_parts, float* out_loss, unsigned char* out_ignore,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Measurement hook: b200_yolo_loss restricted to a subset of its four launches (bit 0 object scan, 1 GT preparation,
+ * 2 ignore mask + object terms, 3 finalize); the workspace carries the state, stages must be issued in order. */
+int b200_yolo_loss_stages(const float* const y_true[3], const float* const y_pred[3], const int32_t hw[6], int B, int A,
+                          int C, const float* anchors_wh_host, const float* image_wh_host, float iou_thresh, int metric,
+                          int variant, float batch_divisor, float* out_parts, float* out_loss, void* workspace,
+                          size_t workspace_bytes, int stages, void* stream);
+
 /* GetLoss forward + analytic backward (tf.GradientTape differentiates GetLoss in train_step,
  * yolo_v4/model.py:318-338): out_grad[l] (B,H_l,W_l,A*(5+C)) = d loss / d y_pred[l] for an upstream gradient of 1
  * (d/dt_xy = obj*scale*(sigmoid(t)-raw_xy)/B, d/dt_wh = obj*scale*(t-raw_wh)/B, d/dconf = (sigmoid(p)-obj)*
