@@ -97,6 +97,17 @@ def main():
             return loss, r
         ms = timed(wrap(step), args.steps, args.warmup)
         report("c5_b64", "YOLOv4 608 B=64 per GPU: GetLoss(ciou) + decode + per-class NMS(diou)", batch, ms, 15639240)
+    if want("c2_backward"):  # SURVEY 8f N1 on config 2: GetLoss forward + d loss / d y_pred (dense gradient written)
+        batch, image = 64, 608
+        heads = yolo_heads(batch, image)
+        rng = np.random.default_rng(20261018 + 2)
+        boxes, classes, off = synth.gt_batch(rng, batch, (image, image), max_boxes=100)
+        gen = DataGenerator(80, anc, (image, image))
+        y_true = gen.GetTargetsBatch(torch.from_numpy(classes).to(dev), torch.from_numpy(boxes).to(dev), torch.from_numpy(off).to(dev))
+        ms_f = timed(wrap(lambda: tyu.GetLoss(y_true, heads, (image, image), anc, 0.5, "ciou")), args.steps, args.warmup)
+        ms = timed(wrap(lambda: tyu.GetLossAndGrad(y_true, heads, (image, image), anc, 0.5, "ciou")), args.steps, args.warmup)
+        report("c2_backward", "YOLOv4 608 B=64: GetLossAndGrad(ciou) = forward + dense d loss/d y_pred (y_true given)", batch, ms,
+               3 * 7732620, {"forward_only_ms": ms_f, "note": "bytes: read y_true + read y_pred + write the gradient"})
     for name, cfgname, batch, with_loss in (("c3_d0_b128", "d0", 128, True), ("c4_d7_b16", "d7", 16, False)):
         if not want(name):
             continue
@@ -125,12 +136,15 @@ def main():
             ib, ic, im = a.generate_targets_batch(d_boxes, d_cls, d_off, 81, class_index=True)
             ms_t_idx = timed(wrap(lambda: a.generate_targets_batch(d_boxes, d_cls, d_off, 81, class_index=True)), args.steps, args.warmup)
             ms_loss_idx = timed(wrap(lambda: get_loss(ib, ic, im, rel, cls)), args.steps, args.warmup)
+            from tfmv_b200.ai_models.efficientnet.efficientdet_net_train import get_loss_and_grad
+            ms_bwd = timed(wrap(lambda: get_loss_and_grad(tb, tc, tm, rel, cls)), args.steps, args.warmup)
             loss_rel = abs(float(get_loss(ib, ic, im, rel, cls)) - float(get_loss(tb, tc, tm, rel, cls))) / abs(float(get_loss(tb, tc, tm, rel, cls)))
             ms_dec = timed(wrap(lambda: a.convert_outputs_boxes(rel)), args.steps, args.warmup)
             dec = a.convert_outputs_boxes(rel)
             ms_post = timed(wrap(lambda: a.convert_outputs_batch(dec, cls)), args.steps, args.warmup)
             report(name, "EfficientDet-D0 512 B=128: focal+box loss + decode + post-process (NMS diou, cap 200)", batch, ms, bpi,
-                   {"phase_ms": {"loss": ms_loss, "decode": ms_dec, "postprocess": ms_post, "generate_targets": ms_t},
+                   {"phase_ms": {"loss": ms_loss, "decode": ms_dec, "postprocess": ms_post, "generate_targets": ms_t,
+                                 "loss_and_grad": ms_bwd},
                     "sparse_target_mode": {"generate_targets_ms": ms_t_idx, "loss_ms": ms_loss_idx, "loss_rel_diff": loss_rel,
                                            "loss_gbps": n_anchor * (81 * 4 + 37) * batch / ms_loss_idx / 1e6},
                     "loss_gbps": n_anchor * (81 * 8 + 33) * batch / ms_loss / 1e6,

@@ -544,45 +544,64 @@ __global__ void __launch_bounds__(YL_FIN_THREADS) yolo_loss_finalize_kernel(YlFi
 // the full record of object cells are non-zero: one streaming write pass (conf values saved by the forward ignore
 // kernel, 4 bytes/record) plus one warp per object record.
 struct YlGradDense {
-  float4* grad[YL_LEVELS];
+  float* grad[YL_LEVELS];
   const float* conf_grad[YL_LEVELS];
-  unsigned long long n_vec[YL_LEVELS];  // cumulative float4 counts
-  unsigned long long n_floats[YL_LEVELS];  // floats per level (the last n%4 are written as scalars)
+  unsigned long long quads[YL_LEVELS];     // cumulative number of 4-record groups per level
+  unsigned long long records[YL_LEVELS];   // records per level (the last records % 4 are written by scalar stores)
   int RF;
 };
 
+// Four records = RF float4, always 16-byte aligned: a warp writes one such group per iteration (ceil(RF/32) 16-byte
+// stores per lane), all zeros except the four conf channels, whose values are fetched by lanes 0-3 beforehand.  No
+// index division, no load -> store dependency on the streaming path.
 __global__ void __launch_bounds__(256) yolo_loss_grad_dense_kernel(YlGradDense g) {
-  const unsigned long long total = g.n_vec[YL_LEVELS - 1];
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    int l = 0;
-    unsigned long long v = i;
-    if (i >= g.n_vec[1]) { l = 2; v = i - g.n_vec[1]; } else if (i >= g.n_vec[0]) { l = 1; v = i - g.n_vec[0]; }
-    const unsigned long long e0 = v * 4ull;
-    unsigned long long rec = e0 / (unsigned long long)g.RF;
-    int c = (int)(e0 - rec * (unsigned long long)g.RF);
-    float out[4];
+  const int lane = threadIdx.x & 31;
+  const unsigned long long total = g.quads[YL_LEVELS - 1];
+  const unsigned long long wstride = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+  const int RF = g.RF;
+  for (unsigned long long w = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < total; w += wstride) {
+    // explicit selects: indexing the kernel-parameter arrays with a runtime level would copy them to local memory
+    unsigned long long q = w;
+    const float* cg = g.conf_grad[0];
+    float* gr = g.grad[0];
+    if (w >= g.quads[1]) { q = w - g.quads[1]; cg = g.conf_grad[2]; gr = g.grad[2]; }
+    else if (w >= g.quads[0]) { q = w - g.quads[0]; cg = g.conf_grad[1]; gr = g.grad[1]; }
+    const float mine = (lane < 4) ? __ldg(cg + q * 4ull + lane) : 0.0f;
+    const float c0 = __shfl_sync(0xffffffffu, mine, 0), c1 = __shfl_sync(0xffffffffu, mine, 1);
+    const float c2 = __shfl_sync(0xffffffffu, mine, 2), c3 = __shfl_sync(0xffffffffu, mine, 3);
+    float4* dst = reinterpret_cast<float4*>(gr) + q * (unsigned long long)RF;
+    for (int j = lane; j < RF; j += 32) {
+      // float4 j of the group holds elements 4j..4j+3; record r's conf channel is element r*RF + 4
+      const int e = 4 * j;
+      float v[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      out[k] = (c == 4) ? __ldg(g.conf_grad[l] + rec) : 0.0f;
-      if (++c == g.RF) { c = 0; ++rec; }
+      for (int k = 0; k < 4; ++k) {
+        const int x = e + k - 4;  // == r*RF for the conf channel of record r
+        v[k] = (x == 0) ? c0 : (x == RF) ? c1 : (x == 2 * RF) ? c2 : (x == 3 * RF) ? c3 : 0.0f;
+      }
+      __stcs(dst + j, make_float4(v[0], v[1], v[2], v[3]));
     }
-    __stcs(g.grad[l] + v, make_float4(out[0], out[1], out[2], out[3]));
   }
-  if (blockIdx.x == 0 && threadIdx.x < 4 * YL_LEVELS) {  // scalar tails (element counts that are not multiples of 4)
-    const int l = threadIdx.x >> 2, k = threadIdx.x & 3;
-    const unsigned long long e = (g.n_floats[l] & ~3ull) + (unsigned long long)k;
-    if (e < g.n_floats[l]) {
-      const unsigned long long rec = e / (unsigned long long)g.RF;
-      const int c = (int)(e - rec * (unsigned long long)g.RF);
-      reinterpret_cast<float*>(g.grad[l])[e] = (c == 4) ? g.conf_grad[l][rec] : 0.0f;
+  // records beyond the last whole group of each level: scalar stores
+  if (blockIdx.x == 0) {
+#pragma unroll
+    for (int l = 0; l < YL_LEVELS; ++l) {
+      const unsigned long long r0 = g.records[l] & ~3ull, n_tail = (g.records[l] - r0) * (unsigned long long)RF;
+      for (unsigned long long t = threadIdx.x; t < n_tail; t += blockDim.x) {
+        const unsigned long long rec = r0 + t / (unsigned long long)RF;
+        const int c = (int)(t % (unsigned long long)RF);
+        g.grad[l][r0 * (unsigned long long)RF + t] = (c == 4) ? g.conf_grad[l][rec] : 0.0f;
+      }
     }
   }
 }
 
-// one CTA per (image, level): a warp per object record overwrites channels 0-3 and 5.. of that record
+// YL_GRAD_SPLIT CTAs per (image, level): a warp per object record overwrites channels 0-3 and 5.. of that record
+// (each object is two dependent DRAM round trips and ~85 sigmoids: spread wide instead of looping in one CTA)
+#define YL_GRAD_SPLIT 8
 __global__ void __launch_bounds__(256) yolo_loss_grad_objects_kernel(YlParams p, float* g0, float* g1, float* g2) {
-  const int img = blockIdx.x / YL_LEVELS, l = blockIdx.x - img * YL_LEVELS;
+  const int pair = blockIdx.x / YL_GRAD_SPLIT, split = blockIdx.x - pair * YL_GRAD_SPLIT;
+  const int img = pair / YL_LEVELS, l = pair - img * YL_LEVELS;
   float* grad = (l == 0 ? g0 : l == 1 ? g1 : g2);
   const int n = p.gt_count[img * YL_LEVELS + l];
   const int rpi = p.lv.rec_per_img[l];
@@ -591,7 +610,7 @@ __global__ void __launch_bounds__(256) yolo_loss_grad_objects_kernel(YlParams p,
   const float* yt = p.lv.y_true[l] + ((size_t)img * rpi) * p.RF;
   const float* yp = p.lv.y_pred[l] + ((size_t)img * rpi) * p.RF;
   float* gr = grad + ((size_t)img * rpi) * p.RF;
-  for (int k = warp; k < n; k += 8) {
+  for (int k = split * 8 + warp; k < n; k += 8 * YL_GRAD_SPLIT) {
     const int r = p.obj_index[(size_t)img * p.n_img + p.lv.anchor_base[l] + k];
     const float* t = yt + (size_t)r * p.RF;
     const float* q = yp + (size_t)r * p.RF;
@@ -815,19 +834,19 @@ static int yolo_loss_impl(const float* const y_true[3], const float* const y_pre
     unsigned long long cum = 0;
     for (int l = 0; l < YL_LEVELS; ++l) {
       B200_REQUIRE(out_grad[l] && (reinterpret_cast<uintptr_t>(out_grad[l]) & 15) == 0, B200_ERR_BAD_ARG, "b200_yolo_loss_grad: grad level %d null or not 16-byte aligned", l);
-      const unsigned long long nfl = (unsigned long long)B * p.lv.rec_per_img[l] * p.RF;
-      g.n_floats[l] = nfl;
-      g.grad[l] = reinterpret_cast<float4*>(out_grad[l]);
+      g.records[l] = (unsigned long long)B * p.lv.rec_per_img[l];
+      g.grad[l] = out_grad[l];
       g.conf_grad[l] = p.conf_grad + (size_t)B * p.lv.anchor_base[l];
-      cum += nfl / 4ull;
-      g.n_vec[l] = cum;
+      cum += g.records[l] / 4ull;
+      g.quads[l] = cum;
     }
-    unsigned long long blocks = (cum + 255) / 256;
+    unsigned long long blocks = (cum + 7) / 8;  // a warp per group of four records
     const unsigned long long cap = (unsigned long long)b200_sm_count() * 64;
     if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
     yolo_loss_grad_dense_kernel<<<(int)blocks, 256, 0, stream>>>(g);
     B200_LAUNCH_CHECK();
-    yolo_loss_grad_objects_kernel<<<B * YL_LEVELS, 256, 0, stream>>>(p, out_grad[0], out_grad[1], out_grad[2]);
+    yolo_loss_grad_objects_kernel<<<B * YL_LEVELS * YL_GRAD_SPLIT, 256, 0, stream>>>(p, out_grad[0], out_grad[1], out_grad[2]);
     B200_LAUNCH_CHECK();
   }
   return B200_OK;
