@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) effdet_nms_finalize_kernel(EfF
 struct EfAssignParams {
   EfLevels lv;
   int B, C;
+  uint32_t magic_c;           // floor(2^32/C)+1 (exact quotient for dividends below 2^16 * C)
   float thr;
   const float* gt_boxes;      // [total,4] yxyx
   const int32_t* gt_classes;  // [total]
@@ -279,7 +280,7 @@ struct EfAssignParams {
 
 #define EF_GT_TILE 128
 
-__global__ void __launch_bounds__(256) effdet_assign_kernel(EfAssignParams p) {
+__global__ void __launch_bounds__(256, 8) effdet_assign_kernel(EfAssignParams p) {
   __shared__ float4 s_gt[EF_GT_TILE];
   __shared__ float s_ga[EF_GT_TILE];
   int l = 0;
@@ -300,33 +301,69 @@ __global__ void __launch_bounds__(256) effdet_assign_kernel(EfAssignParams p) {
     const AnchorBox b = ef_anchor(p.lv, l, y, x, a);
     an = bm_prep(b.y1, b.x1, b.y2, b.x2, B200_METRIC_EFF_IOU);
   }
+  // Bounding box of the CTA's 256 anchors (a run of cells of one row): a GT that does not overlap it has IoU exactly 0
+  // with every anchor here and, for thr > 0, can neither match nor change the outcome (an all-zero row stays
+  // unmatched whatever its argmax), so each GT tile is culled once per CTA and the anchors walk only the survivors —
+  // in ascending GT order, which keeps tf.argmax's first-maximal-index rule.
+  __shared__ float s_bb[8][4];
+  __shared__ uint32_t s_mask[EF_GT_TILE / 32];
+  {
+    float y1 = active ? an.c0 : INFINITY, x1 = active ? an.c1 : INFINITY;
+    float y2 = active ? an.c2 : -INFINITY, x2 = active ? an.c3 : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      y1 = fminf(y1, __shfl_xor_sync(0xffffffffu, y1, o)); x1 = fminf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+      y2 = fmaxf(y2, __shfl_xor_sync(0xffffffffu, y2, o)); x2 = fmaxf(x2, __shfl_xor_sync(0xffffffffu, x2, o));
+    }
+    if ((threadIdx.x & 31) == 0) { float* d = s_bb[threadIdx.x >> 5]; d[0] = y1; d[1] = x1; d[2] = y2; d[3] = x2; }
+  }
+  __syncthreads();
+  float by1 = s_bb[0][0], bx1 = s_bb[0][1], by2 = s_bb[0][2], bx2 = s_bb[0][3];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) {
+    by1 = fminf(by1, s_bb[w][0]); bx1 = fminf(bx1, s_bb[w][1]); by2 = fmaxf(by2, s_bb[w][2]); bx2 = fmaxf(bx2, s_bb[w][3]);
+  }
+  const bool cull = p.thr > 0.0f;
   float best = -INFINITY;
   int best_i = 0;
   for (int g0 = 0; g0 < n_gt; g0 += EF_GT_TILE) {
     const int m = min(EF_GT_TILE, n_gt - g0);
     __syncthreads();
-    for (int i = threadIdx.x; i < m; i += 256) {
-      const float* q = p.gt_boxes + 4 * (size_t)(g_beg + g0 + i);
-      const BoxT g = bm_prep(q[0], q[1], q[2], q[3], B200_METRIC_EFF_IOU);
-      s_gt[i] = make_float4(g.c0, g.c1, g.c2, g.c3);
-      s_ga[i] = g.area;
+    if (threadIdx.x < EF_GT_TILE) {
+      bool relevant = false;
+      if ((int)threadIdx.x < m) {
+        const float* q = p.gt_boxes + 4 * (size_t)(g_beg + g0 + threadIdx.x);
+        const BoxT g = bm_prep(q[0], q[1], q[2], q[3], B200_METRIC_EFF_IOU);
+        s_gt[threadIdx.x] = make_float4(g.c0, g.c1, g.c2, g.c3);
+        s_ga[threadIdx.x] = g.area;
+        // positive overlap with the bounding box in both axes (false for NaN coordinates, which can never be chosen)
+        relevant = !cull || ((DM_SUB(dm_min(by2, g.c2), dm_max(by1, g.c0)) > 0.0f) && (DM_SUB(dm_min(bx2, g.c3), dm_max(bx1, g.c1)) > 0.0f));
+      }
+      const uint32_t bits = __ballot_sync(0xffffffffu, relevant);
+      if ((threadIdx.x & 31) == 0) s_mask[threadIdx.x >> 5] = bits;
     }
     __syncthreads();
     if (active) {
-      for (int g = 0; g < m; ++g) {
-        const float4 c = s_gt[g];
-        // clamped intersection extents (eiou:58-64); zero overlap -> iou = divide_no_nan(0, union) = +0 exactly
-        const float iw = dm_max(0.0f, DM_SUB(dm_min(an.c3, c.w), dm_max(an.c1, c.y)));
-        const float ih = dm_max(0.0f, DM_SUB(dm_min(an.c2, c.z), dm_max(an.c0, c.x)));
-        float v = 0.0f;
-        if (iw > 0.0f && ih > 0.0f) {
-          const float inter = DM_MUL(iw, ih);
-          v = bm_dnn(inter, DM_SUB(DM_ADD(an.area, s_ga[g]), inter));
-        } else if (!(iw == iw) || !(ih == ih)) {
-          BoxT gb; gb.c0 = c.x; gb.c1 = c.y; gb.c2 = c.z; gb.c3 = c.w; gb.area = s_ga[g]; gb.at = 0.f;
-          v = bm_metric(an, gb, B200_METRIC_EFF_IOU);
+#pragma unroll
+      for (int w = 0; w < EF_GT_TILE / 32; ++w) {
+        uint32_t bits = s_mask[w];
+        while (bits) {
+          const int g = (w << 5) + __ffs(bits) - 1;
+          bits &= bits - 1u;
+          const float4 c = s_gt[g];
+          // clamped intersection extents (eiou:58-64); zero overlap -> iou = divide_no_nan(0, union) = +0 exactly
+          const float iw = dm_max(0.0f, DM_SUB(dm_min(an.c3, c.w), dm_max(an.c1, c.y)));
+          const float ih = dm_max(0.0f, DM_SUB(dm_min(an.c2, c.z), dm_max(an.c0, c.x)));
+          float v = 0.0f;
+          if (iw > 0.0f && ih > 0.0f) {
+            const float inter = DM_MUL(iw, ih);
+            v = bm_dnn(inter, DM_SUB(DM_ADD(an.area, s_ga[g]), inter));
+          } else if (!(iw == iw) || !(ih == ih)) {
+            BoxT gb; gb.c0 = c.x; gb.c1 = c.y; gb.c2 = c.z; gb.c3 = c.w; gb.area = s_ga[g]; gb.at = 0.f;
+            v = bm_metric(an, gb, B200_METRIC_EFF_IOU);
+          }
+          if (v > best) { best = v; best_i = g0 + g; }  // tf.argmax: first maximal index
         }
-        if (v > best) { best = v; best_i = g0 + g; }  // tf.argmax: first maximal index
       }
     }
   }
@@ -357,21 +394,35 @@ __global__ void __launch_bounds__(256) effdet_assign_kernel(EfAssignParams p) {
     if (active) p.out_class[l][abase + rin] = cls;
     return;
   }
-  // one-hot rows (C floats per anchor, class 0 = background for unmatched anchors, anc:131-133): the CTA's
-  // 256 rows are one contiguous span of rows*C floats.  It is cleared with aligned 16-byte stores (full sectors),
-  // then, after a barrier, each thread drops the single 1.0 of its own row (tf.one_hot: out of range -> zeros).
+  // one-hot rows (C floats per anchor, class 0 = background for unmatched anchors, anc:131-133; tf.one_hot: out of
+  // range -> zeros): the CTA's 256 rows are one contiguous span of rows*C floats, written once with aligned 16-byte
+  // streaming stores; the 1.0 of row r sits at flat element r*C + cls[r] of the span.
+  __shared__ int s_hot[256];
+  s_hot[threadIdx.x] = (active && cls >= 0 && cls < p.C) ? (int)threadIdx.x * p.C + cls : -1;
+  __syncthreads();
   const int rows = min(256, api - chunk * 256);
   float* dst = p.out_onehot[l] + (abase + (size_t)chunk * 256) * p.C;
   const int n_el = rows * p.C;
   const int head = min(n_el, (int)(((16u - ((unsigned)(uintptr_t)dst & 15u)) & 15u) >> 2));
-  const int n_vec = (n_el - head) >> 2;
+  const int n_vec = p.C >= 3 ? (n_el - head) >> 2 : 0;  // rows narrower than 3 take the scalar path below
   float4* dst4 = reinterpret_cast<float4*>(dst + head);
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int i = threadIdx.x; i < n_vec; i += 256) __stcs(dst4 + i, z4);
-  if ((int)threadIdx.x < head) dst[threadIdx.x] = 0.0f;
-  for (int i = head + (n_vec << 2) + threadIdx.x; i < n_el; i += 256) dst[i] = 0.0f;
-  __syncthreads();
-  if (active && cls >= 0 && cls < p.C) dst[(size_t)threadIdx.x * p.C + cls] = 1.0f;
+  for (int i = threadIdx.x; i < n_vec; i += 256) {
+    const int e = head + 4 * i;                                   // first flat element of this float4
+    const int r = (int)__umulhi((uint32_t)e, p.magic_c);          // e / C (magic_c = floor(2^32/C)+1, e < 2^16 * C)
+    const int h0 = s_hot[r], h1 = (r + 1 < rows) ? s_hot[r + 1] : -1;  // a float4 touches at most rows r and r+1 when C >= 3
+    float4 v;
+    v.x = (e == h0 || e == h1) ? 1.0f : 0.0f;
+    v.y = (e + 1 == h0 || e + 1 == h1) ? 1.0f : 0.0f;
+    v.z = (e + 2 == h0 || e + 2 == h1) ? 1.0f : 0.0f;
+    v.w = (e + 3 == h0 || e + 3 == h1) ? 1.0f : 0.0f;
+    __stcs(dst4 + i, v);
+  }
+  // unaligned head / tail elements (and every element of rows narrower than 3): scalar stores
+  for (int e = threadIdx.x; e < n_el; e += 256) {
+    if (e >= head && e < head + (n_vec << 2)) continue;
+    const int r = e / p.C;
+    dst[e] = (s_hot[r] == e) ? 1.0f : 0.0f;
+  }
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -580,6 +631,7 @@ static int ef_assign_impl(int num_levels, const int32_t* hw, int A, const float*
   B200_REQUIRE(B >= 0 && C >= 1, B200_ERR_BAD_ARG, "b200_effdet_assign_targets: bad sizes");
   if (B == 0) return B200_OK;
   p.B = B; p.C = C; p.thr = iou_thr;
+  p.magic_c = C == 1 ? 0u : (uint32_t)((1ull << 32) / (unsigned long long)C + 1ull);
   p.gt_boxes = gt_boxes; p.gt_classes = gt_classes; p.gt_offsets = gt_offsets;
   int cta = 0;
   for (int l = 0; l < EF_MAX_LEVELS; ++l) {

@@ -86,6 +86,24 @@ def test_generate_targets_bit_exact(lib, cuda, name, batch, nmax):
     assert npos > 0
 
 
+@pytest.mark.parametrize("C", [1, 2, 4, 7])
+def test_generate_targets_narrow_class_rows(lib, cuda, C):
+    """One-hot rows narrower than a float4 (and odd widths) take the scalar / unaligned store paths."""
+    from tfmv_b200 import synth
+    a, o = _pair("small")
+    rng = np.random.default_rng(20261018 + 40 + C)
+    ih, iw = CFGS["small"]["image_size"]
+    boxes, classes, off = synth.gt_batch(rng, 2, (iw, ih), max_boxes=20, order="yxyx")
+    classes = (classes % (C + 1)).astype(np.int32)  # includes the out-of-range id C
+    gb, gc, gm = a.generate_targets_batch(_t(boxes, cuda), _t(classes, cuda), _t(off, cuda), C)
+    for b in range(2):
+        wb, wc, wm = o.generate_targets(boxes[off[b]:off[b + 1]], classes[off[b]:off[b + 1]], C)
+        for l in range(len(wb)):
+            assert_bits_equal(gb[l][b].cpu().numpy(), wb[l])
+            assert_bits_equal(gc[l][b].cpu().numpy(), wc[l])
+            assert np.array_equal(gm[l][b].cpu().numpy(), wm[l])
+
+
 @pytest.mark.parametrize("name,batch,iou_type", [("small", 3, "diou"), ("rect", 2, "ciou"), ("d0", 2, "diou"), ("small", 2, "giou")])
 def test_convert_outputs_one_matches_oracle(lib, cuda, name, batch, iou_type):
     a, o = _pair(name)
