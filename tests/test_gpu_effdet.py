@@ -86,6 +86,24 @@ def test_generate_targets_bit_exact(lib, cuda, name, batch, nmax):
     assert npos > 0
 
 
+@pytest.mark.parametrize("thr", [0.0, 0.3, 0.9])
+def test_generate_targets_other_thresholds(lib, cuda, thr):
+    """iou_threshold = 0 matches every anchor (argmax of an all-zero IoU row is GT 0): the GT culling must be off there."""
+    from tfmv_b200 import synth
+    a, o = _pair("small")
+    rng = np.random.default_rng(20261018 + 60)
+    ih, iw = CFGS["small"]["image_size"]
+    boxes, classes, off = synth.gt_batch(rng, 2, (iw, ih), max_boxes=12, order="yxyx")
+    classes = (classes % 80 + 1).astype(np.int32)
+    gb, gc, gm = a.generate_targets_batch(_t(boxes, cuda), _t(classes, cuda), _t(off, cuda), 81, iou_threshold=thr)
+    for b in range(2):
+        wb, wc, wm = o.generate_targets(boxes[off[b]:off[b + 1]], classes[off[b]:off[b + 1]], 81, iou_threshold=thr)
+        for l in range(len(wb)):
+            assert_bits_equal(gb[l][b].cpu().numpy(), wb[l])
+            assert_bits_equal(gc[l][b].cpu().numpy(), wc[l])
+            assert np.array_equal(gm[l][b].cpu().numpy(), wm[l])
+
+
 @pytest.mark.parametrize("C", [1, 2, 4, 7])
 def test_generate_targets_narrow_class_rows(lib, cuda, C):
     """One-hot rows narrower than a float4 (and odd widths) take the scalar / unaligned store paths."""
