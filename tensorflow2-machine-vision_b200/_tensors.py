@@ -27,6 +27,12 @@ def to_cuda(x, dtype=torch.float32):
     return t.contiguous()
 
 
+def is_pinned_host_f32(x):
+    """A contiguous fp32 torch tensor in page-locked host memory: device kernels can read it in place (UVA)."""
+    return (isinstance(x, torch.Tensor) and not x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+            and x.is_pinned() and torch.cuda.is_available())
+
+
 def ptr(t):
     return 0 if t is None else t.data_ptr()
 

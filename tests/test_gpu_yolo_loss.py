@@ -169,6 +169,26 @@ def test_loss_from_boxes_matches_dense_path_and_oracle(lib, cuda, image, batch, 
     assert abs(float(e) - float(want_e)) <= LOSS_RTOL * abs(float(want_e))
 
 
+def test_get_loss_reads_pinned_host_predictions_in_place(lib, cuda):
+    """y_pred handed over as pinned host tensors is consumed in place (no staging copy): same bits as device tensors."""
+    import torch
+    from tfmv_b200 import synth
+    from tfmv_b200.ai_models.utils.tf_yolo_utils import GetLoss, GetLossFromBoxes, _loss_call
+    rng = np.random.default_rng(20261018 + 33)
+    image, batch = 416, 3
+    anc = synth.yolo_anchors().astype(F)
+    boxes, classes, off, y_true = _dense_targets(rng, batch, image, anc, normalised_anchors=True)
+    y_pred = synth.yolo_heads(rng, batch, image)
+    dt = [_t(t, cuda) for t in y_true]
+    pinned = [torch.from_numpy(np.ascontiguousarray(h)).pin_memory() for h in y_pred]
+    ign_a = torch.full((batch, 10647), 7, dtype=torch.uint8, device=cuda)
+    ign_b = torch.full((batch, 10647), 9, dtype=torch.uint8, device=cuda)
+    a, pa = _loss_call(dt, [_t(h, cuda) for h in y_pred], (image, image), anc, 0.5, "ciou", 0, return_parts=True, ignore_out=ign_a)
+    b, pb = _loss_call(dt, pinned, (image, image), anc, 0.5, "ciou", 0, return_parts=True, ignore_out=ign_b)
+    assert float(a) == float(b) and torch.equal(pa, pb) and torch.equal(ign_a, ign_b)
+    assert float(GetLoss(dt, pinned, (image, image), anc, 0.5, "ciou")) == float(a)
+
+
 def test_reference_unit_test_relation_on_gpu(lib, cuda):
     """yolo_v3/unit_test/loss_test.py:152-172 on the GPU: GetLoss-copy == Yolov4Loss on uniform-random tensors."""
     from oracle import yolo as oy
