@@ -294,6 +294,9 @@ __device__ __forceinline__ bool yl_pair_hits(const YlParams& p, int l, int rin, 
   return (mm >= p.thr) || (mm != mm);  // NaN propagates through tf.reduce_max: best < thr is False
 }
 
+// PAIRED selects how the five logits of a record are fetched (see the load section): two lanes per record and one
+// request (y_pred in pinned host memory, read over PCIe) or two loads per lane (y_pred in HBM: 4 us faster there).
+template <bool PAIRED>
 __global__ void __launch_bounds__(YL_ICHUNK, YL_IMINB) yolo_loss_ignore_kernel(YlParams p) {
   __shared__ float4 s_t[YL_ICHUNK];
   __shared__ uint32_t s_q[YL_QCAP];
@@ -319,16 +322,19 @@ __global__ void __launch_bounds__(YL_ICHUNK, YL_IMINB) yolo_loss_ignore_kernel(Y
   const float4* gaux = p.gt_aux + (size_t)img * p.n_img + p.lv.anchor_base[l];
   const int W = p.lv.w[l], H = p.lv.h[l];
   float obj = 0.f, tx = 0.f, ty = 0.f, tw = 0.f, th = 0.f, pobj = 0.f;
+  const bool aligned = (reinterpret_cast<uintptr_t>(p.lv.y_pred[l]) & 15) == 0;  // block-uniform
   if (active) {
-    const size_t f0 = ((size_t)img * rpi + rin) * p.RF;
     if (p.obj_bits) {
       const int bit = p.lv.anchor_base[l] + rin;
       obj = ((__ldg(p.obj_bits + (size_t)img * p.bits_words + (bit >> 5)) >> (bit & 31)) & 1u) ? 1.0f : 0.0f;
     } else {
       obj = p.obj_compact[(size_t)img * p.n_img + p.lv.anchor_base[l] + rin];
     }
-    if ((reinterpret_cast<uintptr_t>(p.lv.y_pred[l]) & 15) == 0) {
+  }
+  if (aligned && !PAIRED) {
+    if (active) {
       // tx,ty,tw,th,conf sit at float offset f0; two aligned 16-byte loads cover them (L1 bypass)
+      const size_t f0 = ((size_t)img * rpi + rin) * p.RF;
       const float4 lo = __ldcg(reinterpret_cast<const float4*>(p.lv.y_pred[l]) + (f0 >> 2));
       const float4 hi = __ldcg(reinterpret_cast<const float4*>(p.lv.y_pred[l]) + (f0 >> 2) + 1);
       // the record starts 0..3 floats into lo: rotate the 8 loaded floats left by sh with two select stages
@@ -337,10 +343,50 @@ __global__ void __launch_bounds__(YL_ICHUNK, YL_IMINB) yolo_loss_ignore_kernel(Y
       const float a0 = s1 ? lo.y : lo.x, a1 = s1 ? lo.z : lo.y, a2 = s1 ? lo.w : lo.z, a3 = s1 ? hi.x : lo.w;
       const float a4 = s1 ? hi.y : hi.x, a5 = s1 ? hi.z : hi.y, a6 = s1 ? hi.w : hi.z;
       tx = s2 ? a2 : a0; ty = s2 ? a3 : a1; tw = s2 ? a4 : a2; th = s2 ? a5 : a3; pobj = s2 ? a6 : a4;
-    } else {
-      const float* q = p.lv.y_pred[l] + f0;
-      tx = __ldcg(q); ty = __ldcg(q + 1); tw = __ldcg(q + 2); th = __ldcg(q + 3); pobj = __ldcg(q + 4);
     }
+  } else if (aligned) {
+    // tx,ty,tw,th,conf of a record sit at float offset f0; the two aligned 16-byte chunks that cover them are fetched
+    // by two neighbouring lanes of ONE load instruction (16 records per instruction, two instructions per warp), so a
+    // record costs one memory request (one 128-byte line, 1-2 sectors) instead of two — this halves the request count,
+    // which is what bounds the kernel when y_pred is read in place from pinned host memory over PCIe
+    const float4* base = reinterpret_cast<const float4*>(p.lv.y_pred[l]);
+    const int sub = lane & 1, rsel = lane >> 1;
+    float4 ld[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int rin_t = chunk * YL_ICHUNK + warp * 32 + 16 * t + rsel;
+      ld[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rin_t < rpi) ld[t] = __ldcg(base + ((((size_t)img * rpi + rin_t) * p.RF) >> 2) + sub);
+    }
+    // lane r takes the pair loaded by lanes 2(r mod 16), 2(r mod 16)+1 of instruction r / 16
+    const int src = (lane & 15) << 1;
+    const bool second = lane >= 16;
+    float4 lo, hi;
+    {
+      const float x0 = __shfl_sync(0xffffffffu, ld[0].x, src), x1 = __shfl_sync(0xffffffffu, ld[1].x, src);
+      const float y0 = __shfl_sync(0xffffffffu, ld[0].y, src), y1 = __shfl_sync(0xffffffffu, ld[1].y, src);
+      const float z0 = __shfl_sync(0xffffffffu, ld[0].z, src), z1 = __shfl_sync(0xffffffffu, ld[1].z, src);
+      const float w0 = __shfl_sync(0xffffffffu, ld[0].w, src), w1 = __shfl_sync(0xffffffffu, ld[1].w, src);
+      lo = second ? make_float4(x1, y1, z1, w1) : make_float4(x0, y0, z0, w0);
+    }
+    {
+      const float x0 = __shfl_sync(0xffffffffu, ld[0].x, src + 1), x1 = __shfl_sync(0xffffffffu, ld[1].x, src + 1);
+      const float y0 = __shfl_sync(0xffffffffu, ld[0].y, src + 1), y1 = __shfl_sync(0xffffffffu, ld[1].y, src + 1);
+      const float z0 = __shfl_sync(0xffffffffu, ld[0].z, src + 1), z1 = __shfl_sync(0xffffffffu, ld[1].z, src + 1);
+      const float w0 = __shfl_sync(0xffffffffu, ld[0].w, src + 1), w1 = __shfl_sync(0xffffffffu, ld[1].w, src + 1);
+      hi = second ? make_float4(x1, y1, z1, w1) : make_float4(x0, y0, z0, w0);
+    }
+    if (active) {
+      // the record starts 0..3 floats into lo: rotate the 8 loaded floats left by sh with two select stages
+      const int sh = (int)((((size_t)img * rpi + rin) * p.RF) & 3);
+      const bool s1 = sh & 1, s2 = sh & 2;
+      const float a0 = s1 ? lo.y : lo.x, a1 = s1 ? lo.z : lo.y, a2 = s1 ? lo.w : lo.z, a3 = s1 ? hi.x : lo.w;
+      const float a4 = s1 ? hi.y : hi.x, a5 = s1 ? hi.z : hi.y, a6 = s1 ? hi.w : hi.z;
+      tx = s2 ? a2 : a0; ty = s2 ? a3 : a1; tw = s2 ? a4 : a2; th = s2 ? a5 : a3; pobj = s2 ? a6 : a4;
+    }
+  } else if (active) {
+    const float* q = p.lv.y_pred[l] + ((size_t)img * rpi + rin) * p.RF;
+    tx = __ldcg(q); ty = __ldcg(q + 1); tw = __ldcg(q + 2); th = __ldcg(q + 3); pobj = __ldcg(q + 4);
   }
   bool hit = false;  // some GT with metric >= thr (or NaN)
   if (n_gt > 0) {    // block-uniform
@@ -816,7 +862,14 @@ static int yolo_loss_impl(const float* const y_true[3], const float* const y_pre
     B200_LAUNCH_CHECK();
   }
   if (stages & 4) {
-    yolo_loss_ignore_kernel<<<YL_LEVELS * B * YL_TERM_SPLIT + ws.n_cta, YL_ICHUNK, 0, stream>>>(p);
+    // predictions in pinned host memory are read in place over PCIe: one request per record instead of two
+    cudaPointerAttributes attr;
+    bool host_pred = false;
+    if (cudaPointerGetAttributes(&attr, y_pred[YL_LEVELS - 1]) == cudaSuccess) host_pred = attr.type == cudaMemoryTypeHost;
+    else (void)cudaGetLastError();
+    const int grid = YL_LEVELS * B * YL_TERM_SPLIT + ws.n_cta;
+    if (host_pred) yolo_loss_ignore_kernel<true><<<grid, YL_ICHUNK, 0, stream>>>(p);
+    else yolo_loss_ignore_kernel<false><<<grid, YL_ICHUNK, 0, stream>>>(p);
     B200_LAUNCH_CHECK();
   }
   if (!(stages & 8)) return B200_OK;
