@@ -407,8 +407,8 @@ def run_b200(args, wl):
     e2e_steps = max(3, min(args.steps, 10))
     ms_e2e = timed(lambda: float(step(heads_p, boxes_p, classes_p, off_p).item()), e2e_steps, 2)
     h2d = sum(h.numel() * 4 for h in heads_p) + boxes_p.numel() * 4 + classes_p.numel() * 4 + off_p.numel() * 4
-    e2e = {"value": global_batch * e2e_steps / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
-           "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / e2e_steps}
+    e2e = {"value": global_batch * e2e_steps / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": int(h2d) * world,
+           "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / e2e_steps}  # bytes: all ranks together
 
     # for comparison: the same call after an explicit copy of the whole y_pred to the device
     def copy_step():
@@ -418,8 +418,8 @@ def run_b200(args, wl):
     e2e["y_pred_transfer"] = ("pinned host y_pred is read in place by the loss kernels (they need ~6 % of it: 32-byte sectors "
                               "fetched over PCIe); boxes / classes / offsets are copied")
     n_rec_all = sum(int(h.numel()) for h in heads_p) // RF
-    e2e["h2d_bytes_fetched_estimate"] = int(n_rec_all * 48 + boxes_p.shape[0] * 352 + boxes_p.numel() * 4 + classes_p.numel() * 4
-                                            + off_p.numel() * 4)  # ~1.5 32-byte sectors per record + the object records
+    e2e["h2d_bytes_fetched_estimate"] = world * int(n_rec_all * 48 + boxes_p.shape[0] * 352 + boxes_p.numel() * 4 + classes_p.numel() * 4
+                                                    + off_p.numel() * 4)  # ~1.5 32-byte sectors per record + the object records
     e2e["h2d_bytes_per_step_note"] = "size of the host tensors handed to the call; the kernels fetch only the sectors they use"
     e2e["explicit_copy"] = {"value": global_batch * e2e_steps / (ms_cp / 1e3), "unit": "images/s", "ms_per_step": ms_cp / e2e_steps,
                             "what": "whole y_pred copied host->device first (495 MB per step, PCIe-bound)"}
