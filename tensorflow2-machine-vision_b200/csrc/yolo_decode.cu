@@ -43,6 +43,7 @@ struct YoloDecodeParams {
   int n_img;  // anchors per image over all levels
   float conf_thr, score_thr;
   float conf_lo, conf_hi;  // logits below / above which sigmoid(conf) > conf_thr is decided without the sigmoid
+  uint32_t magic_a;        // floor(2^32/A)+1 (0 for A == 1): rin / A == umulhi(rin, magic_a) for rin * A < 2^32
   // candidate store, stride n_img per image
   float4* cand_box; float* cand_score; int32_t* cand_cls; float* cand_conf; uint32_t* cand_aidx;
   int32_t* counts;     // [B]
@@ -271,9 +272,10 @@ __global__ void __launch_bounds__(512, 1) yolo_decode_filter_kernel(YoloDecodePa
     class_max_sigmoid_warp(my_slab(stage), RF, p.C, want, lane, score, cls);
     if (want && score > p.score_thr) {
       const int rpi = p.lv.rec_per_img[l];
-      img = (int)(rec / rpi);
+      // 32-bit division when the level has fewer than 2^31 records (always, short of ~100k-image batches)
+      img = (p.lv.total_rec[l] < 0x7fffffffLL) ? (int)((uint32_t)rec / (uint32_t)rpi) : (int)(rec / rpi);
       const int rin = (int)(rec - (long long)img * rpi);
-      const int cell = rin / p.A, a = rin - cell * p.A;
+      const int cell = p.magic_a ? (int)__umulhi((uint32_t)rin, p.magic_a) : rin, a = rin - cell * p.A;  // rin / A
       // the box itself is decoded by the NMS pass, and only for the candidates it looks at; here only its validity
       // (x2 > x1 and y2 > y1, tyu:163) is needed: certain inside the safe logit range, exact decode otherwise
       const float tx = r[0], ty = r[1], tw = r[2], th = r[3];
@@ -537,6 +539,7 @@ extern "C" int b200_yolo_decode_nms(const float* const heads[3], const int32_t h
   unsigned char* wsb = static_cast<unsigned char*>(workspace);
   dp.B = B; dp.A = A; dp.C = C; dp.RF = 5 + C; dp.n_img = n_img;
   dp.conf_thr = conf_thr; dp.score_thr = score_thr;
+  dp.magic_a = A == 1 ? 0u : (uint32_t)((1ull << 32) / (unsigned long long)A + 1ull);
   // sigmoid(x) > conf_thr is certain for x > logit(thr) + d and certainly false for x < logit(thr) - d, with d ten times
   // the 2.4-ulp error of the deterministic sigmoid divided by the slope thr(1-thr); thresholds near 0 or 1 (or outside
   // (0,1)) always take the exact comparison
