@@ -265,6 +265,16 @@ int b200_focal_box_grad(int num_levels, const unsigned long long* anchors_per_le
                         float delta, float label_smoothing, const double* sums, const double* numel_per_level_host,
                         float* const grad_boxes[], float* const grad_classes[], void* stream);
 
+/* Serving-path box post-processing (views/object_detection.py:70-85): boxes [B,max_rows,4] normalised
+ * x1,y1,x2,y2 on the letterboxed image (image_size = (w,h) of the network input, padding = (top,bottom,left,right) of
+ * opencvProportionalResize, image_size_old = (w,h) of the original image; host int32) -> pixel boxes on the original
+ * image, clipped, rows with width or height <= 2 dropped, truncated to int32.  counts [B] (device, may be NULL = all
+ * rows).  out_boxes [B,max_rows,4] kept rows first, out_index [B,max_rows] their source rows, out_count [B].
+ * fp32 step by step (NumPy 1.x casting of the reference's era). */
+int b200_unletterbox_boxes(const float* boxes, const int32_t* counts, int B, int max_rows, const int32_t image_size[2],
+                           const int32_t padding[4], const int32_t image_size_old[2], int32_t* out_boxes,
+                           int32_t* out_index, int32_t* out_count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
