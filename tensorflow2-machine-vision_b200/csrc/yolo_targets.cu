@@ -47,6 +47,7 @@ __global__ void fill_zero_multi_kernel(FillMulti f) {
 __global__ void __launch_bounds__(128) yolo_scatter_targets_kernel(YtParams p) {
   const int img = blockIdx.x;
   const int beg = p.offsets[img], end = p.offsets[img + 1];
+  const bool single = (end - beg) <= 128 * 4;  // block-uniform
   for (int i0 = beg; i0 < end; i0 += 128 * 4) {
     float* recs[4];
 #pragma unroll
@@ -70,16 +71,24 @@ __global__ void __launch_bounds__(128) yolo_scatter_targets_kernel(YtParams p) {
     // up to 512 boxes per image are resolved per round; more than that loops (records stay consistent because
     // the obj counter keeps accumulating and the clear below re-runs every round)
     __syncthreads();
+    float cnt[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       float* rec = recs[u];
-      if (rec && rec[4] > 1.0f) {
+      cnt[u] = rec ? __ldcg(rec + 4) : 0.0f;  // final for this round: every atomicAdd of the round is done (read at L2)
+      if (cnt[u] > 1.0f) {
         for (int c = 0; c < p.RF; ++c) if (c != 4) rec[c] = 0.0f;
       }
     }
     __syncthreads();
+    if (single) {  // the only round: the obj counters of collided records can be cleared right away
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (cnt[u] > 1.0f) recs[u][4] = 0.0f;
+    }
   }
-  // obj counters of collided records are cleared last so that every colliding thread saw them > 1
+  if (single) return;
+  // several rounds: obj counters of collided records are cleared last so that every colliding thread, of whatever
+  // round, saw them > 1
   for (int i = beg + (int)threadIdx.x; i < end; i += 128) {
     float nx, ny, nw, nh;
     float* rec = yt_locate(p, img, i, nx, ny, nw, nh);
