@@ -235,7 +235,7 @@ def GetLossFromBoxes(classes, boxes, offsets, y_pred, image_wh, anchors_wh, clas
   '''
   assert iou_type in ['iou','diou','ciou']
   lib = _lib.load()
-  yp = [T.to_cuda(t) for t in y_pred]
+  yp = [t if T.is_pinned_host_f32(t) else T.to_cuda(t) for t in y_pred]  # pinned host predictions are read in place
   if len(yp) != 3:
     raise ValueError('y_pred must hold 3 levels')
   boxes = T.to_cuda(boxes).reshape(-1, 4)
@@ -254,7 +254,7 @@ def GetLossFromBoxes(classes, boxes, offsets, y_pred, image_wh, anchors_wh, clas
     if yp[l].dim() < 3 or yp[l].shape[0] != B or yp[l].numel() != B * yp[l].shape[1] * yp[l].shape[2] * A * RF:
       raise ValueError('y_pred[%d] must be (B,H,W,%d*(5+C)) with B = len(offsets)-1' % (l, A))
   img = T.host_floats(image_wh, 2)
-  dev = yp[0].device
+  dev = boxes.device
   hw = (ctypes.c_int32 * 6)(*[d for t in yp for d in (t.shape[1], t.shape[2])])
   pp = (ctypes.c_void_p * 3)(*[t.data_ptr() for t in yp])
   parts = torch.empty((3, 4), dtype=torch.float32, device=dev)

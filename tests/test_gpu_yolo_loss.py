@@ -187,6 +187,12 @@ def test_get_loss_reads_pinned_host_predictions_in_place(lib, cuda):
     b, pb = _loss_call(dt, pinned, (image, image), anc, 0.5, "ciou", 0, return_parts=True, ignore_out=ign_b)
     assert float(a) == float(b) and torch.equal(pa, pb) and torch.equal(ign_a, ign_b)
     assert float(GetLoss(dt, pinned, (image, image), anc, 0.5, "ciou")) == float(a)
+    tanc = anc / F(image)
+    s_dev = GetLossFromBoxes(_t(classes, cuda), _t(boxes, cuda), _t(off, cuda), [_t(h, cuda) for h in y_pred], (image, image), anc, 80,
+                             0.5, "ciou", target_anchors=tanc)
+    s_pin = GetLossFromBoxes(_t(classes, cuda), _t(boxes, cuda), _t(off, cuda), pinned, (image, image), anc, 80, 0.5, "ciou",
+                             target_anchors=tanc)
+    assert float(s_dev) == float(s_pin) and abs(float(s_dev) - float(a)) <= 1e-6 * abs(float(a))
 
 
 def test_reference_unit_test_relation_on_gpu(lib, cuda):
