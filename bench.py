@@ -376,6 +376,8 @@ def run_b200(args, wl):
     if traffic:
         roofline["achieved_dram_gbps"] = traffic / dom["ms"] / 1e6
         roofline["frac_dram"] = traffic / dom["ms"] / 1e6 / peak
+    roofline["peak_note"] = ("peak is the measured COPY bandwidth (read + write); the write-only zero-fill runs above it, and the "
+                             "dense-equivalent figures of the sector-sparse loss kernels are not physical traffic")
     roofline["phases_note"] = ("each kernel timed alone, launched back to back from Python: entries below ~15 us are bounded by "
                                "the launch interval, their device durations are in profiles/r01_launches_step_v12.csv")
     roofline["loss_kernels_dense_equivalent_gbps"] = 2 * n_fill * 4 / sum(p["ms"] for p in phases[2:]) / 1e6
