@@ -13,7 +13,8 @@ and its only two unit tests (yolo_v3/unit_test/grid_test.py, loss_test.py) asser
 equality; GetLoss-copy == Yolov4Loss), not values.  What IS pinned:
   * the reference's OWN source files for this path (tf_iou_utils.py, tf_yolo_utils.py GetLoss / GetBoxes /
     GetNMSBoxes, datasets/coco_dataset.py GetTargets, efficientnet/utils/{iou,nms,anchors}.py,
-    losses/{focal_loss,box_loss,yolo_loss}.py), imported UNMODIFIED from /root/reference and executed under a
+    losses/{focal_loss,box_loss,class_loss,yolo_loss}.py, efficientdet_net_train.py _get_loss, yolo_v4/model.py
+    GetGroudTruth), imported UNMODIFIED from /root/reference and executed under a
     NumPy stand-in for the ~60 TensorFlow ops they use (tests/golden/fake_tf, tests/golden/make_golden_emulated.py
     -> tests/golden/ref_emulated.npz): tests/test_reference_emulated.py holds this oracle to those outputs —
     NMS indices, class ids, masks, one-hot rows, anchors and dense targets identical, floating-point results to a few

@@ -164,6 +164,33 @@ def main():
         out["gt_%s_boxes" % tag], out["gt_%s_classes" % tag], out["gt_%s_anchors" % tag] = gtb, gtc, anc
         for l in range(3):
             out["gt_%s_t%d" % (tag, l)] = np.asarray(tg[l])
+    # ---- efficientdet_net_train._get_loss (edt:41-52), ClassFocalLoss, yolo_v4/model.py GetGroudTruth ------------
+    for m in ["matplotlib.pyplot", "tensorflow_addons"]:
+        if m not in sys.modules:
+            try:
+                __import__(m)
+            except Exception:
+                mod = types.ModuleType(m)
+                mod.__getattr__ = lambda name: None
+                sys.modules[m] = mod
+    from ai_api.ai_models.efficientnet import efficientdet_net_train as redt
+    from ai_api.ai_models.losses.class_loss import ClassFocalLoss as RClassFocal
+    from ai_api.ai_models.yolo_v4 import model as rm4
+    shapes = [(2, 8, 8, 6), (2, 4, 4, 6), (2, 2, 2, 6)]
+    glb = [(rng.standard_normal(sh + (4,)) * (rng.random(sh + (1,)) < 0.15)).astype(F) for sh in shapes]
+    glm = [(np.abs(t).sum(-1, keepdims=True) > 0) for t in glb]
+    glc = [np.eye(5, dtype=F)[np.where(m[..., 0], rng.integers(1, 5, m.shape[:-1]), 0)] for m in glm]
+    gpb = [(rng.standard_normal(sh + (4,)) * 0.3).astype(F) for sh in shapes]
+    gpc = [rng.standard_normal(sh + (5,)).astype(F) for sh in shapes]
+    stub = types.SimpleNamespace(box_loss=RBox(), focal_loss=RFocal(0.25, 1.5, label_smoothing=0.0), _reg_l2_loss=lambda wd: F(0.0))
+    out["gl_loss"] = np.asarray(redt.EfficientDetNetTrain._get_loss(stub, glb, glc, glm, gpb, gpc), dtype=F)
+    for l in range(3):
+        out["gl_tb%d" % l], out["gl_tc%d" % l], out["gl_tm%d" % l], out["gl_pb%d" % l], out["gl_pc%d" % l] = glb[l], glc[l], glm[l], gpb[l], gpc[l]
+    glm2 = [m.copy() for m in glm]; glm2[2][:] = False           # a level without positives: divide_no_nan -> 0
+    out["cfl_loss"] = np.asarray(RClassFocal(0.25, 1.5).call(glc, (gpc, glm2)), dtype=F)
+    gstub = types.SimpleNamespace(classes_num=6)
+    for l in range(3):
+        out["ggt%d" % l] = np.asarray(rm4.YoloV4Model.GetGroudTruth(gstub, y_true[l]))
     path = os.path.join(HERE, "ref_emulated.npz")
     np.savez_compressed(path, **out)
     print("wrote %s: %d arrays" % (path, len(out)))

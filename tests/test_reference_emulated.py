@@ -106,3 +106,16 @@ def test_get_targets_identical():
             used += int(want[..., 4].sum() > 0)
         assert G["gt_%s_t2" % tag][..., 4].sum() < 30                                     # the triple collision was zeroed
     assert used >= 4   # pixel anchors put everything on one layer (quirk Q8); normalised anchors use all three
+
+
+def test_effdet_get_loss_class_focal_loss_and_ground_truth_rows():
+    tb = [G["gl_tb%d" % l] for l in range(3)]; tc = [G["gl_tc%d" % l] for l in range(3)]; tm = [G["gl_tm%d" % l] for l in range(3)]
+    pb = [G["gl_pb%d" % l] for l in range(3)]; pc = [G["gl_pc%d" % l] for l in range(3)]
+    want = float(G["gl_loss"])                                   # EfficientDetNetTrain._get_loss with the L2 term at 0
+    assert abs(float(oe.get_loss(tb, tc, tm, pb, pc)) - want) <= 1e-5 * abs(want) and want > 0
+    tm2 = [m.copy() for m in tm]; tm2[2][:] = False
+    want = float(G["cfl_loss"])
+    assert abs(float(oe.class_focal_loss(tc, pc, tm2)) - want) <= 1e-5 * abs(want)
+    for l in range(3):                                            # yolo_v4/model.py GetGroudTruth: no transcendental
+        got = oy.get_ground_truth(G["yl_true%d" % l])
+        assert got.shape == G["ggt%d" % l].shape and np.array_equal(got, G["ggt%d" % l])
