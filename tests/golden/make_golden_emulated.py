@@ -191,6 +191,20 @@ def main():
     gstub = types.SimpleNamespace(classes_num=6)
     for l in range(3):
         out["ggt%d" % l] = np.asarray(rm4.YoloV4Model.GetGroudTruth(gstub, y_true[l]))
+    # ---- the reference's own tests/test_anchors.py main(), unmodified: capture what it prints --------------------
+    import tensorflow as tf
+    captured = {}
+
+    def capture(*a, **k):
+        if len(a) == 2 and isinstance(a[0], str):
+            captured[a[0].rstrip(":")] = np.asarray(a[1])
+    tf.print = capture
+    sys.path.insert(0, "/root/reference/AIServer/ai_api/ai_models/tests")
+    import test_anchors as rtest
+    rtest.tf.print = capture
+    rtest.main()
+    for k in ("convert_boxes", "convert_classes_id", "convert_scores"):
+        out["rt_" + k] = captured[k]
     path = os.path.join(HERE, "ref_emulated.npz")
     np.savez_compressed(path, **out)
     print("wrote %s: %d arrays" % (path, len(out)))

@@ -119,3 +119,15 @@ def test_effdet_get_loss_class_focal_loss_and_ground_truth_rows():
     for l in range(3):                                            # yolo_v4/model.py GetGroudTruth: no transcendental
         got = oy.get_ground_truth(G["yl_true%d" % l])
         assert got.shape == G["ggt%d" % l].shape and np.array_equal(got, G["ggt%d" % l])
+
+
+def test_reference_test_anchors_main():
+    """ai_models/tests/test_anchors.py main(), run unmodified: generate_targets -> convert_outputs_boxes -> convert_outputs_one
+    round-trips the two boxes; the oracle does the same."""
+    a = oe.Anchors(0, 0, (10, 10), 3, [(1.0, 1.0)], 3.0)
+    boxes, classes = np.array([[3, 3, 6, 6], [5, 5, 9, 9]], F), np.array([1, 2])
+    tb, tc, tm = a.generate_targets(boxes, classes, 3, iou_threshold=0.5)
+    dec = a.convert_outputs_boxes([t[None] for t in tb])
+    bx, ci, sc = a.convert_outputs_one(0, dec, [t[None] for t in tc])
+    assert ci.tolist() == G["rt_convert_classes_id"].tolist() == [1, 2]
+    close(bx, G["rt_convert_boxes"], atol=2e-5); close(sc, G["rt_convert_scores"])
