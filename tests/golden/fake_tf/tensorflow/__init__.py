@@ -27,6 +27,16 @@ string = str
 _F = _np.float32
 
 
+class _T(_np.ndarray):
+    """ndarray with the one EagerTensor method the reference's unit tests call"""
+    def numpy(self):
+        return _np.asarray(self)
+
+
+def _wrap(a):
+    return _np.asarray(a).view(_T)
+
+
 def _t(x, dtype=None):
     """convert_to_tensor: Python floats -> float32, Python ints -> int32, float64 arrays stay as given unless dtype."""
     if dtype is not None:
@@ -117,6 +127,10 @@ def meshgrid(*xs, **kw):
 
 
 def concat(values, axis):
+    return _wrap(_concat(values, axis))
+
+
+def _concat(values, axis):
     vs = [_t(v) for v in values]
     first = next((v.dtype for v, raw in zip(vs, values) if isinstance(raw, _np.ndarray)), vs[0].dtype)
     # TF converts Python lists / scalars among the inputs to the dtype of the tensors they are concatenated with
@@ -200,7 +214,7 @@ def minimum(a, b):
 
 
 def reduce_sum(x, axis=None, keepdims=False):
-    return _np.sum(x, axis=axis, keepdims=keepdims, dtype=_np.asarray(x).dtype)
+    return _wrap(_np.sum(x, axis=axis, keepdims=keepdims, dtype=_np.asarray(x).dtype))
 
 
 def sigmoid(x):
@@ -308,7 +322,7 @@ class _Loss(object):
 
     def __call__(self, y_true, y_pred):
         v = _np.asarray(self.call(y_true, y_pred))
-        return _np.sum(v, dtype=_F) / _F(v.size) if v.ndim else v
+        return _wrap(_np.sum(v, dtype=_F) / _F(v.size) if v.ndim else v)
 
 
 class _Huber(object):
@@ -329,7 +343,7 @@ def _keras_bce(y_true, y_pred, from_logits=False):
 
 _backend = _mk(
     "tensorflow.keras.backend",
-    dtype=lambda x: _np.asarray(x).dtype, cast=lambda x, d: _np.asarray(x).astype(d), shape=shape, reshape=reshape,
+    dtype=lambda x: _np.asarray(x).dtype, cast=lambda x, d: _wrap(_np.asarray(x).astype(d)), shape=shape, reshape=reshape,
     arange=lambda start, stop=None, step=1, dtype="int32": (_np.arange(int(start), dtype=dtype) if stop is None
                                                             else _np.arange(int(start), int(stop), int(step), dtype=dtype)),
     tile=lambda x, n: _np.tile(x, [int(v) for v in n]),
@@ -348,7 +362,9 @@ keras = _mk(
     activations=_mk("tensorflow.keras.activations"), regularizers=_mk("tensorflow.keras.regularizers"),
     initializers=_mk("tensorflow.keras.initializers"), Model=_Stub, Sequential=_Stub)
 image = _mk("tensorflow.image")
-random = _mk("tensorflow.random")
+_rng = _np.random.default_rng(12345)
+random = _mk("tensorflow.random", uniform=lambda shape, minval=0, maxval=1, dtype=float32, **k: _wrap(
+    (_rng.random(tuple(int(v) for v in shape), dtype=_np.float32) * _F(maxval - minval) + _F(minval)).astype(dtype)))
 data = _mk("tensorflow.data")
 
 

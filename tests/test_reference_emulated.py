@@ -131,3 +131,21 @@ def test_reference_test_anchors_main():
     bx, ci, sc = a.convert_outputs_one(0, dec, [t[None] for t in tc])
     assert ci.tolist() == G["rt_convert_classes_id"].tolist() == [1, 2]
     close(bx, G["rt_convert_boxes"], atol=2e-5); close(sc, G["rt_convert_scores"])
+
+
+REF = "/root/reference/AIServer"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree is only mounted in the build container")
+@pytest.mark.parametrize("name", ["grid_test", "loss_test"])
+def test_reference_unit_tests_pass_under_the_stand_in(name):
+    """The reference's only two unit tests (yolo_v3/unit_test/grid_test.py: grid layout equality; loss_test.py:
+    GetLoss-copy == Yolov4Loss, exact), executed unmodified with the NumPy stand-in as `tensorflow`: they pass, which
+    checks the stand-in itself against the reference's own expectations."""
+    import subprocess
+    import sys
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.path.join(os.path.dirname(__file__), "golden", "fake_tf") + os.pathsep + REF
+    r = subprocess.run([sys.executable, os.path.join(REF, "ai_api/ai_models/yolo_v3/unit_test", name + ".py")], cwd=REF, env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "OK" in r.stdout.splitlines()[-1], r.stdout[-2000:]
