@@ -451,19 +451,18 @@ __global__ void __launch_bounds__(YL_ICHUNK, YL_IMINB) yolo_loss_ignore_kernel(Y
       while (mask) {
         const int g = j0 + __ffs(mask) - 1;
         mask &= mask - 1u;
-        if (!active || hit) continue;
         const float4 c = __ldg(gbox + g);
         const float4 x = __ldg(gaux + g);  // area, atan term, log(area), regular flag
-        if (nice && x.w != 0.0f) {
-          if ((cx1 < c.x) || (c.z < cx0) || (cy1 < c.y) || (c.w < cy0)) continue;
-          if ((sp < x.z + lo_k) || (sp > x.z + hi_k)) continue;
-          const float iw = fminf(fx1, c.z) - fmaxf(fx0, c.x), ih = fminf(fy1, c.w) - fmaxf(fy0, c.y);
-          if ((iw < -1e-5f) || (ih < -1e-5f)) continue;  // disjoint by far more than the decode error
-          if (fast_ok && (iw >= YL_IOU_FLOOR) && (ih >= YL_IOU_FLOOR)) {
-            const float inter = iw * ih;
-            if (inter < thr_lo * (farea + x.x - inter)) continue;
-          }
-        }
+        // all rejects as straight-line predicate arithmetic (bitwise, no short-circuit branches): the warp executes
+        // the tests of every relevant GT anyway, and the divergence bookkeeping of early exits cost more than it saved
+        const float iw = fminf(fx1, c.z) - fmaxf(fx0, c.x), ih = fminf(fy1, c.w) - fmaxf(fy0, c.y);
+        const float inter = iw * ih;
+        const bool cell_rej = (cx1 < c.x) | (c.z < cx0) | (cy1 < c.y) | (c.w < cy0);
+        const bool win_rej = (sp < x.z + lo_k) | (sp > x.z + hi_k);
+        const bool dis_rej = (iw < -1e-5f) | (ih < -1e-5f);  // disjoint by far more than the decode error
+        const bool iou_rej = fast_ok & (iw >= YL_IOU_FLOOR) & (ih >= YL_IOU_FLOOR) & (inter < thr_lo * (farea + x.x - inter));
+        const bool rejected = nice & (x.w != 0.0f) & (cell_rej | win_rej | dis_rej | iou_rej);
+        if (!active | hit | rejected) continue;
         const int slot = atomicAdd(&s_nq, 1);
         if (slot < YL_QCAP) s_q[slot] = (threadIdx.x << 24) | (uint32_t)g;            // drained in phase 2
         else {  // queue full: exact test now.  The logits pass through an opaque asm so that the compiler cannot
