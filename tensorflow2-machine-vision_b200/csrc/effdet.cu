@@ -354,16 +354,15 @@ __global__ void __launch_bounds__(256, 8) effdet_assign_kernel(EfAssignParams p)
           // clamped intersection extents (eiou:58-64); zero overlap -> iou = divide_no_nan(0, union) = +0 exactly
           const float iw = dm_max(0.0f, DM_SUB(dm_min(an.c3, c.w), dm_max(an.c1, c.y)));
           const float ih = dm_max(0.0f, DM_SUB(dm_min(an.c2, c.z), dm_max(an.c0, c.x)));
-          // straight-line: with zero overlap inter = 0 and divide_no_nan(0, union) = +0 exactly, as the reference computes it
-          const float inter = DM_MUL(iw, ih);
-          float v = bm_dnn(inter, DM_SUB(DM_ADD(an.area, s_ga[g]), inter));
-          if (!(iw == iw) | !(ih == ih)) {  // NaN coordinates: the literal formula decides
+          float v = 0.0f;
+          if (iw > 0.0f && ih > 0.0f) {
+            const float inter = DM_MUL(iw, ih);
+            v = bm_dnn(inter, DM_SUB(DM_ADD(an.area, s_ga[g]), inter));
+          } else if (!(iw == iw) || !(ih == ih)) {
             BoxT gb; gb.c0 = c.x; gb.c1 = c.y; gb.c2 = c.z; gb.c3 = c.w; gb.area = s_ga[g]; gb.at = 0.f;
             v = bm_metric(an, gb, B200_METRIC_EFF_IOU);
           }
-          const bool better = v > best;      // tf.argmax: first maximal index
-          best = better ? v : best;
-          best_i = better ? g0 + g : best_i;
+          if (v > best) { best = v; best_i = g0 + g; }  // tf.argmax: first maximal index
         }
       }
     }
