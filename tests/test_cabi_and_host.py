@@ -50,6 +50,16 @@ def test_bad_arguments_are_reported_not_crashed(lib):
     assert lib.b200_yolo_loss_workspace_bytes(hw, 2, 3) > 0
     hw5 = (ctypes.c_int32 * 10)(64, 64, 32, 32, 16, 16, 8, 8, 4, 4)
     assert lib.b200_effdet_table_floats(5, hw5, 9) == 2 * (64 + 32 + 16 + 8 + 4) + 5 * 18
+    # the entry points added for the extensions validate the same way
+    f = ctypes.c_float
+    assert lib.b200_yolo_loss_from_boxes_workspace_bytes(hw, 2, 3, 100) > lib.b200_yolo_loss_workspace_bytes(hw, 2, 3)
+    assert lib.b200_yolo_loss_from_boxes(0, 0, 0, 0, 0, 0, hw, 2, 3, 80, 0, 0, f(0.5), 2, 0, f(2), 0, 0, 0, 0, 0, 0) == -1
+    assert lib.b200_yolo_loss_stages(0, 0, hw, 2, 3, 80, 0, 0, f(0.5), 2, 0, f(2), 0, 0, 0, 0, 0, 0) == -1
+    assert b"stages" in lib.b200_last_error()
+    assert lib.b200_yolo_reset_targets(0, 0, 2, 10, 0, 3, 0, 80, hw, 0, 0) == -1
+    assert lib.b200_unletterbox_boxes(0, 0, 2, 10, 0, 0, 0, 0, 0, 0, 0) == -1
+    assert lib.b200_effdet_assign_targets_indexed(5, hw5, 9, 0, 81, 2, 0, 0, 0, f(0.5), 0, 0, 0, 0) == -1
+    assert lib.b200_focal_box_partial_sums_indexed(5, 0, 81, 0, 0, 0, 0, 0, f(0.25), f(1.5), f(0.1), f(0), 0, 0, 0, 0) == -1
 
 
 def test_reference_assertions_on_iou_type():
