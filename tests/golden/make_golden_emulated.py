@@ -14,8 +14,13 @@ import sys
 
 import numpy as np
 
+import importlib.util
+
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.join(HERE, "fake_tf"))
+# a real TensorFlow, when the image has one, takes precedence over the stand-in (B200_FORCE_TF_STAND_IN=1 overrides)
+REAL_TF = importlib.util.find_spec("tensorflow") is not None and not os.environ.get("B200_FORCE_TF_STAND_IN")
+if not REAL_TF:
+    sys.path.insert(0, os.path.join(HERE, "fake_tf"))
 sys.path.insert(0, "/root/reference/AIServer")
 F = np.float32
 
@@ -207,7 +212,7 @@ def main():
         out["rt_" + k] = captured[k]
     path = os.path.join(HERE, "ref_emulated.npz")
     np.savez_compressed(path, **out)
-    print("wrote %s: %d arrays" % (path, len(out)))
+    print("wrote %s: %d arrays (%s)" % (path, len(out), "real TensorFlow" if REAL_TF else "NumPy stand-in for TensorFlow"))
 
 
 if __name__ == "__main__":
