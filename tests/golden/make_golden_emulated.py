@@ -210,6 +210,15 @@ def main():
     rtest.main()
     for k in ("convert_boxes", "convert_classes_id", "convert_scores"):
         out["rt_" + k] = captured[k]
+    # ---- BASELINE config 1 through the reference's GetNMSBoxes: 416x416, 80 classes, ~5.3 k candidates, cap 500 ----
+    sys.path.insert(0, HERE)
+    import emulated_inputs as ei
+    h416 = ei.yolo_416_heads()
+    for t, thr in (("iou", 0.5), ("diou", 0.45)):
+        r = ryolo.GetNMSBoxes(h416[0], h416[1], h416[2], ei.COCO_ANCHORS, np.array([416, 416], np.int32), 80, 0.5, 0.3, thr, t)
+        out["c1_%s_boxes" % t], out["c1_%s_ids" % t], out["c1_%s_scores" % t] = np.asarray(r[0]), np.asarray(r[1]), np.asarray(r[2])
+        out["c1_%s_conf" % t] = np.asarray(r[4])
+        out["c1_%s_classes_rowsum" % t] = np.asarray(r[3]).sum(-1, dtype=np.float64)   # the (500,80) block as a checksum
     path = os.path.join(HERE, "ref_emulated.npz")
     np.savez_compressed(path, **out)
     print("wrote %s: %d arrays (%s)" % (path, len(out), "real TensorFlow" if REAL_TF else "NumPy stand-in for TensorFlow"))

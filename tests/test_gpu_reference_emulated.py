@@ -89,3 +89,16 @@ def test_effdet(lib, cuda):
     assert abs(float(FocalLoss(0.25, 1.5)([3.0, _t(G["fl_true"], cuda)], _t(G["fl_pred"], cuda))) - want) <= 1e-4 * abs(want)
     want = float(G["bl_loss"])
     assert abs(float(BoxLoss(0.1)([7.0, _t(G["bl_true"], cuda)], _t(G["bl_pred"], cuda))) - want) <= 1e-4 * abs(want)
+
+
+def test_baseline_config1_against_the_reference_get_nms_boxes(lib, cuda):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import emulated_inputs as ei
+    from tfmv_b200.ai_models.utils.tf_yolo_utils import GetNMSBoxes
+    heads = [_t(h, cuda) for h in ei.yolo_416_heads()]
+    for t, thr in (("iou", 0.5), ("diou", 0.45)):
+        r = GetNMSBoxes(heads[0], heads[1], heads[2], ei.COCO_ANCHORS, (416, 416), 80, 0.5, 0.3, thr, t)
+        assert r[1].cpu().tolist() == G["c1_%s_ids" % t].tolist() and len(r[1]) == 500
+        close(r[0], G["c1_%s_boxes" % t]); close(r[2], G["c1_%s_scores" % t]); close(r[4], G["c1_%s_conf" % t])
+        np.testing.assert_allclose(r[3].cpu().numpy().sum(-1, dtype=np.float64), G["c1_%s_classes_rowsum" % t], rtol=1e-5)

@@ -149,3 +149,17 @@ def test_reference_unit_tests_pass_under_the_stand_in(name):
     r = subprocess.run([sys.executable, os.path.join(REF, "ai_api/ai_models/yolo_v3/unit_test", name + ".py")], cwd=REF, env=env,
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0 and "OK" in r.stdout.splitlines()[-1], r.stdout[-2000:]
+
+
+def test_baseline_config1_through_the_reference_get_nms_boxes():
+    """BASELINE config 1 (YOLOv3 416x416, 80 classes, N(0,1) heads, cap 500): the reference's own GetNMSBoxes vs the oracle."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import emulated_inputs as ei
+    heads = ei.yolo_416_heads()
+    for t, thr in (("iou", 0.5), ("diou", 0.45)):
+        r = oy.get_nms_boxes(heads[0], heads[1], heads[2], ei.COCO_ANCHORS, (416, 416), 80, 0.5, 0.3, thr, t)
+        assert len(G["c1_%s_ids" % t]) == 500                                  # the cap was reached
+        assert r[1].tolist() == G["c1_%s_ids" % t].tolist()
+        close(r[0], G["c1_%s_boxes" % t]); close(r[2], G["c1_%s_scores" % t]); close(r[4], G["c1_%s_conf" % t])
+        np.testing.assert_allclose(r[3].sum(-1, dtype=np.float64), G["c1_%s_classes_rowsum" % t], rtol=1e-5)
