@@ -219,6 +219,14 @@ def main():
         out["c1_%s_boxes" % t], out["c1_%s_ids" % t], out["c1_%s_scores" % t] = np.asarray(r[0]), np.asarray(r[1]), np.asarray(r[2])
         out["c1_%s_conf" % t] = np.asarray(r[4])
         out["c1_%s_classes_rowsum" % t] = np.asarray(r[3]).sum(-1, dtype=np.float64)   # the (500,80) block as a checksum
+    # ---- BASELINE config 3 per image through the reference's Anchors: D0 pyramid (49 104 anchors), cap 200 ---------
+    rd0 = RAnchors(**ei.D0)
+    shapes0 = [tuple(np.asarray(b).shape[:3]) for b in rd0.boxes]
+    rel0, cls0 = ei.effdet_d0_heads(shapes0)
+    dec0 = rd0.convert_outputs_boxes(rel0)
+    bx, ci, sc = rd0.convert_outputs_one(0, dec0, cls0)
+    out["c3_boxes"], out["c3_ids"], out["c3_scores"] = np.asarray(bx), np.asarray(ci), np.asarray(sc)
+    out["c3_anchor_checksum"] = np.array([np.asarray(b, dtype=np.float64).sum() for b in rd0.boxes])
     path = os.path.join(HERE, "ref_emulated.npz")
     np.savez_compressed(path, **out)
     print("wrote %s: %d arrays (%s)" % (path, len(out), "real TensorFlow" if REAL_TF else "NumPy stand-in for TensorFlow"))

@@ -102,3 +102,16 @@ def test_baseline_config1_against_the_reference_get_nms_boxes(lib, cuda):
         assert r[1].cpu().tolist() == G["c1_%s_ids" % t].tolist() and len(r[1]) == 500
         close(r[0], G["c1_%s_boxes" % t]); close(r[2], G["c1_%s_scores" % t]); close(r[4], G["c1_%s_conf" % t])
         np.testing.assert_allclose(r[3].cpu().numpy().sum(-1, dtype=np.float64), G["c1_%s_classes_rowsum" % t], rtol=1e-5)
+
+
+def test_baseline_config3_image_against_the_reference_anchors(lib, cuda):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import emulated_inputs as ei
+    from tfmv_b200.ai_models.efficientnet.utils.anchors import Anchors
+    a = Anchors(**ei.D0)
+    rel, cls = ei.effdet_d0_heads([tuple(b.shape[:3]) for b in a.boxes])
+    dec = a.convert_outputs_boxes([_t(r, cuda) for r in rel])
+    bx, ci, sc = a.convert_outputs_one(0, dec, [_t(c, cuda) for c in cls])
+    assert ci.cpu().tolist() == G["c3_ids"].tolist() and len(ci) == 200
+    close(bx, G["c3_boxes"], rtol=3e-6, atol=1e-4); close(sc, G["c3_scores"])

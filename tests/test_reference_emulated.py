@@ -163,3 +163,17 @@ def test_baseline_config1_through_the_reference_get_nms_boxes():
         assert r[1].tolist() == G["c1_%s_ids" % t].tolist()
         close(r[0], G["c1_%s_boxes" % t]); close(r[2], G["c1_%s_scores" % t]); close(r[4], G["c1_%s_conf" % t])
         np.testing.assert_allclose(r[3].sum(-1, dtype=np.float64), G["c1_%s_classes_rowsum" % t], rtol=1e-5)
+
+
+def test_baseline_config3_image_through_the_reference_anchors():
+    """One EfficientDet-D0 image (49 104 anchors, 81 classes, cap 200) through the reference's own Anchors code vs the oracle."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import emulated_inputs as ei
+    a = oe.Anchors(**ei.D0)
+    np.testing.assert_array_equal(np.array([b.astype(np.float64).sum() for b in a.boxes]), G["c3_anchor_checksum"])
+    rel, cls = ei.effdet_d0_heads([b.shape[:3] for b in a.boxes])
+    dec = a.convert_outputs_boxes(rel)
+    bx, ci, sc = a.convert_outputs_one(0, dec, cls)
+    assert len(G["c3_ids"]) == 200 and ci.tolist() == G["c3_ids"].tolist()
+    close(bx, G["c3_boxes"], rtol=3e-6, atol=1e-4); close(sc, G["c3_scores"])
