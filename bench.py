@@ -379,7 +379,7 @@ def run_b200(args, wl):
     roofline["peak_note"] = ("peak is the measured COPY bandwidth (read + write); the write-only zero-fill runs above it, and the "
                              "dense-equivalent figures of the sector-sparse loss kernels are not physical traffic")
     roofline["phases_note"] = ("each kernel timed alone, launched back to back from Python: entries below ~15 us are bounded by "
-                               "the launch interval, their device durations are in profiles/r01_launches_step_v12.csv")
+                               "the launch interval, their device durations are in profiles/r01_launches_step_v13.csv")
     roofline["loss_kernels_dense_equivalent_gbps"] = 2 * n_fill * 4 / sum(p["ms"] for p in phases[2:]) / 1e6
     if dom["kernel"].startswith("yolo_loss"):
         roofline["note"] = ("achieved/frac use SURVEY 8(d)'s dense algorithmic bytes (y_true + y_pred read once); the loss "
