@@ -516,8 +516,12 @@ __global__ void __launch_bounds__(YL_ICHUNK, YL_IMINB) yolo_loss_ignore_kernel(Y
 // K4c: YL_FIN_CTAS CTAs each reduce an interleaved share of the per-CTA partials in fp64 (fixed assignment, fixed
 // order); the CTA that takes the last ticket adds the YL_FIN_CTAS slices in index order and writes parts / loss.
 // Deterministic run to run, and ~3x shorter than one CTA walking all 46 k partials.
+#ifndef YL_FIN_CTAS
 #define YL_FIN_CTAS 32
+#endif
+#ifndef YL_FIN_THREADS
 #define YL_FIN_THREADS 256
+#endif
 
 struct YlFinalize {
   const double* partials; const double* partials_obj;
