@@ -255,7 +255,7 @@ __device__ __forceinline__ int yl_fastdiv(int n, uint32_t magic) {
   return magic == 0u ? n : (int)__umulhi((uint32_t)n, magic);  // magic 0 encodes divisor 1
 }
 
-// Three phases per CTA of 256 records:
+// Three phases per CTA of YL_ICHUNK (128) records:
 //  1. (all lanes, decode-free) each record tests the GTs that can touch its warp's strip of grid cells with the
 //     cell / logit-sum windows and pushes surviving (record, gt) pairs to a shared-memory queue;
 //  2. (dense) the queue is drained with one pair per thread: exact decode of the record (2 sigmoid, 2 exp, atan),
@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(YL_ICHUNK, YL_IMINB) yolo_loss_ignore_kernel(Y
 
 // K4c: YL_FIN_CTAS CTAs each reduce an interleaved share of the per-CTA partials in fp64 (fixed assignment, fixed
 // order); the CTA that takes the last ticket adds the YL_FIN_CTAS slices in index order and writes parts / loss.
-// Deterministic run to run, and ~3x shorter than one CTA walking all 46 k partials.
+// Deterministic run to run, and shorter than a single CTA walking all partials (shapes measured in DESIGN.md section 9).
 #ifndef YL_FIN_CTAS
 #define YL_FIN_CTAS 32
 #endif
