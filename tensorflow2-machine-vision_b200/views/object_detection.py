@@ -1,13 +1,29 @@
-"""The box post-processing of the reference's serving view (views/object_detection.py:70-85, inline code of
-`predict`), as a function: map Predict's normalised boxes on the letterboxed network input back to pixels of the
-original image, clip, drop boxes not larger than 2 px, truncate to int32, and filter the other outputs alike.
-The letterbox resize itself (utils/image_helper.py:293-331, OpenCV INTER_AREA) stays in the reference."""
+"""The image plumbing of the reference's serving view (views/object_detection.py:46-85, inline code of `predict`) as
+two functions around model.Predict:
+  prepare_image        letterbox on black (opencvProportionalResize), BGR->RGB, float32 / 255, batch axis (:50-62)
+  restore_predictions  map Predict's normalised boxes on the letterboxed input back to pixels of the original image,
+                       clip, drop boxes not larger than 2 px, truncate to int32, filter the other outputs alike (:70-85)
+"""
 import ctypes
 
 import numpy as np
 import torch
 
 from .. import _lib, _tensors as T
+from ..ai_models.utils import image_helper
+
+
+def prepare_image(img_old, image_size=(416, 416)):
+  '''
+  Args:
+    img_old: HxWx3 uint8 BGR image as cv2 decodes it (numpy / device tensor / pinned host tensor)
+    image_size: (w,h) of the network input
+  Returns:
+    predict_img (1,h,w,3) float32 RGB in [0,1] on the device, padding (top,bottom,left,right), image_size_old int32 (w,h)
+  '''
+  width, height = image_helper.opencvGetImageSize(img_old)
+  _, img, padding, _ = image_helper.letterbox(img_old, image_size, (0, 0, 0), False, True)
+  return img[None], padding, np.int32([width, height])
 
 
 def restore_predictions(y_boxes, y_classes_id, y_scores, y_classes, y_confidence, image_size, padding, image_size_old):

@@ -58,6 +58,7 @@ def test_bad_arguments_are_reported_not_crashed(lib):
     assert b"stages" in lib.b200_last_error()
     assert lib.b200_yolo_reset_targets(0, 0, 2, 10, 0, 3, 0, 80, hw, 0, 0) == -1
     assert lib.b200_unletterbox_boxes(0, 0, 2, 10, 0, 0, 0, 0, 0, 0, 0) == -1
+    assert lib.b200_letterbox_image(0, 480, 640, 3, 416, 416, 0, 0, 0, 0, 0, 0) == -1
     assert lib.b200_effdet_assign_targets_indexed(5, hw5, 9, 0, 81, 2, 0, 0, 0, f(0.5), 0, 0, 0, 0) == -1
     assert lib.b200_focal_box_partial_sums_indexed(5, 0, 81, 0, 0, 0, 0, 0, f(0.25), f(1.5), f(0.1), f(0), 0, 0, 0, 0) == -1
 
