@@ -25,6 +25,8 @@ equality; GetLoss-copy == Yolov4Loss), not values.  What IS pinned:
     (efficientnet/utils/iou.py:104-111, tests/test_anchors.py:10-15) — which the reference's code reproduces under
     the stand-in as well;
   * utils/mAP.py (pure NumPy) run directly (tests/golden/make_golden_map.py);
+  * utils/image_helper.py opencvProportionalResize (needs only OpenCV, present here) run directly
+    (tests/golden/make_golden_letterbox.py), and oracle/letterbox.py against cv2.resize itself (PINNED row);
   * TF op semantics listed in SURVEY.md §8a (argsort ties, argmax first-max, scatter_nd duplicate
     sums, floor-div, divide_no_nan, boolean_mask order, sigmoid_cross_entropy formula).
 Transcendentals go through the deterministic fp32 header shared with the kernels

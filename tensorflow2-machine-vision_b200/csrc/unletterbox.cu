@@ -1,7 +1,6 @@
 // unletterbox.cu — the box post-processing of the serving path (the part that has a closed form):
 // views/object_detection.py:70-85 maps the boxes Predict returns on the letterboxed image back to the original
-// image, clips them, drops boxes not larger than 2 px and truncates to int32.  (The letterbox resize itself is
-// OpenCV's INTER_AREA, utils/image_helper.py:293-331; OpenCV is absent here, so it is not restated.)
+// image, clips them, drops boxes not larger than 2 px and truncates to int32.  (The letterbox itself: letterbox.cu.)
 //
 //   x' = ((x * W_in - pad_left) / (W_in - pad_left - pad_right)) * W_old      (fp32 step by step, NumPy 1.x casting:
 //   y' = ((y * H_in - pad_top ) / (H_in - pad_top  - pad_bottom)) * H_old       float32 array (op) integer scalar -> float32)
