@@ -108,6 +108,14 @@ def main():
         ms = timed(wrap(lambda: tyu.GetLossAndGrad(y_true, heads, (image, image), anc, 0.5, "ciou")), args.steps, args.warmup)
         report("c2_backward", "YOLOv4 608 B=64: GetLossAndGrad(ciou) = forward + dense d loss/d y_pred (y_true given)", batch, ms,
                3 * 7732620, {"forward_only_ms": ms_f, "note": "bytes: read y_true + read y_pred + write the gradient"})
+    if want("n4_letterbox"):  # the serving view's image pre-processing, one image per call (latency)
+        from tfmv_b200.views.object_detection import prepare_image
+        for (h, w) in ((1080, 1920), (3024, 4032), (480, 640), (240, 320)):
+            img = torch.randint(0, 256, (h, w, 3), device=dev, dtype=torch.uint8, generator=g)
+            fn = wrap(lambda: prepare_image(img, (416, 416))[0])
+            ms = timed(fn, max(args.steps, 50), 10)
+            report("n4_letterbox_%dx%d" % (w, h), "prepare_image: INTER_AREA letterbox to 416x416 + BGR->RGB + /255 (device-resident "
+                   "uint8 frame; L2-resident after the first pass)", 1, ms, h * w * 3 + 416 * 416 * 3 * 4, {"latency_us": ms * 1e3})
     for name, cfgname, batch, with_loss in (("c3_d0_b128", "d0", 128, True), ("c4_d7_b16", "d7", 16, False)):
         if not want(name):
             continue

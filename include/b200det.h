@@ -278,12 +278,12 @@ int b200_unletterbox_boxes(const float* boxes, const int32_t* counts, int B, int
 /* Serving-path image pre-processing: ImageHelper.opencvProportionalResize (utils/image_helper.py:293-325,
  * bg_mode = BORDER_CONSTANT) and, when out_f32 is given, the colour swap and float conversion `predict` applies to its
  * result (views/object_detection.py:50-62).  img [height,width,3] uint8 (device, or pinned host memory); the image is
- * shrunk proportionally with OpenCV's INTER_AREA arithmetic (bit-exact for 8-bit images) to fit
+ * resized proportionally with OpenCV's INTER_AREA arithmetic (bit-exact for 8-bit images) to fit
  * out_width x out_height and centred on bg_color.  out_u8 [out_height,out_width,3] (optional): the letterboxed image in
  * the input's channel order; out_f32 [out_height,out_width,3] (optional): the same with the channels reversed, / 255.
  * padding_out (host) = top,bottom,left,right as the reference returns them; resized_wh_out (host, optional) = size of
- * the image inside the border.  An input smaller than the target in either direction (enlarging: OpenCV's fixed-point
- * bilinear path) returns B200_ERR_UNSUPPORTED; channels != 3 likewise. */
+ * the image inside the border.  An input smaller than the target in either direction takes, as in OpenCV, the 8-bit
+ * bilinear fallback of INTER_AREA (also bit-exact).  channels != 3 returns B200_ERR_UNSUPPORTED. */
 int b200_letterbox_image(const uint8_t* img, int height, int width, int channels, int out_width, int out_height,
                          const uint8_t bg_color[3], uint8_t* out_u8, float* out_f32, int32_t padding_out[4],
                          int32_t resized_wh_out[2], void* stream);

@@ -11,8 +11,9 @@ opencv-python 4.13.0).  Its published algorithm for 8-bit images shrinking in bo
     taps in ascending order, one rounding to uchar at the end.
 Pinned: tests/test_letterbox_oracle.py compares it bit for bit with cv2 itself (same image, here and on the GPU box) and
 with fixtures produced by the reference's own opencvProportionalResize (tests/golden/make_golden_letterbox.py).
-Enlarging (an input smaller than the network size) takes OpenCV's fixed-point bilinear path and is not restated:
-UnsupportedResize is raised, as the CUDA path returns B200_ERR_UNSUPPORTED.
+Enlarging in either direction (an input smaller than the network size) is not an area resize in OpenCV: INTER_AREA
+falls back to its 8-bit bilinear with "area mode" coefficients (11-bit fixed point, two truncating shifts in the vertical
+pass); that path is restated too (linear_coeffs / _resize_bilinear_area_mode).
 """
 import math
 
@@ -70,7 +71,7 @@ def _tap_arrays(taps):
 
 
 def resize_area(img, dsize):
-    """cv2.resize(img, dsize=(w, h), interpolation=cv2.INTER_AREA) for uint8 HxWxC, shrinking (or equal) in both axes."""
+    """cv2.resize(img, dsize=(w, h), interpolation=cv2.INTER_AREA) for uint8 HxWxC."""
     img = np.ascontiguousarray(img, dtype=np.uint8)
     sh, sw = img.shape[:2]
     dw, dh = int(dsize[0]), int(dsize[1])
@@ -78,7 +79,7 @@ def resize_area(img, dsize):
         raise UnsupportedResize("empty destination")
     scale_x, scale_y = 1.0 / (dw / sw), 1.0 / (dh / sh)
     if scale_x < 1.0 or scale_y < 1.0:
-        raise UnsupportedResize("enlarging resize (OpenCV's bilinear path) is not restated")
+        return _resize_bilinear_area_mode(img, dw, dh)
     isx, isy = int(round(scale_x)), int(round(scale_y))  # saturate_cast<int>(double) rounds half to even
     if abs(scale_x - isx) < DBL_EPSILON and abs(scale_y - isy) < DBL_EPSILON:
         blk = img[:dh * isy, :dw * isx].reshape(dh, isy, dw, isx, -1).astype(np.int32).sum(axis=(1, 3))
@@ -98,6 +99,42 @@ def resize_area(img, dsize):
         term = (ya[:, k, None, None] * buf[ys[:, k]]).astype(F)
         acc = np.where(yo[:, k, None, None], (acc + term).astype(F), acc)
     return np.clip(np.rint(acc), 0, 255).astype(np.uint8)
+
+
+def linear_coeffs(ssize, dsize):
+    """cv::resize, INTER_AREA outside its true-area domain ("area_mode" of the bilinear branch): per destination index the
+    left source index and the two 11-bit fixed-point weights."""
+    inv = dsize / ssize
+    scale = 1.0 / inv
+    idx = np.zeros(dsize, np.int64)
+    w = np.zeros((dsize, 2), np.int64)
+    for d in range(dsize):
+        s = math.floor(d * scale)
+        f = F((d + 1) - (s + 1) * inv)
+        f = F(0) if f <= 0 else F(f - F(math.floor(f)))
+        if s < 0:
+            f, s = F(0), 0
+        if s >= ssize - 1:
+            f, s = F(0), ssize - 1
+        idx[d] = s
+        w[d, 0] = int(np.clip(np.rint(F(F(1) - f) * F(2048)), -32768, 32767))  # saturate_cast<short>(cbuf * 2048)
+        w[d, 1] = int(np.clip(np.rint(f * F(2048)), -32768, 32767))
+    return idx, w
+
+
+def _resize_bilinear_area_mode(img, dw, dh):
+    """The 8-bit bilinear of OpenCV (HResizeLinear in int32, VResizeLinear<uchar>: two truncating shifts)."""
+    sh, sw = img.shape[:2]
+    xi, xw = linear_coeffs(sw, dw)
+    yi, yw = linear_coeffs(sh, dh)
+    src = img.astype(np.int64)
+    x1 = np.minimum(xi + 1, sw - 1)
+    hor = src[:, xi, :] * xw[None, :, 0, None] + src[:, x1, :] * xw[None, :, 1, None]   # [sh, dw, C]
+    r0 = np.clip(yi, 0, sh - 1)
+    r1 = np.clip(yi + 1, 0, sh - 1)
+    b0, b1 = yw[:, 0, None, None], yw[:, 1, None, None]
+    v = (((b0 * (hor[r0] >> 4)) >> 16) + ((b1 * (hor[r1] >> 4)) >> 16) + 2) >> 2
+    return (v & 0xFF).astype(np.uint8)
 
 
 def proportional_resize(img, size, bg_color=(128, 128, 128)):

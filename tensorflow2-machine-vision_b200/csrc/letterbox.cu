@@ -2,30 +2,33 @@
 // (utils/image_helper.py:293-325, constant border) and the colour swap / float conversion that `predict` applies to
 // its result (views/object_detection.py:50-62), in one launch.
 //
-// The resize is cv2.resize(..., interpolation=cv2.INTER_AREA) of an 8-bit 3-channel image that shrinks (or keeps its
-// size) in both directions — a serving input is at least as large as the network input.  OpenCV's arithmetic for that
-// case is reproduced bit for bit:
+// The resize is cv2.resize(..., interpolation=cv2.INTER_AREA) of an 8-bit 3-channel image.  OpenCV's arithmetic is
+// reproduced bit for bit.  When the image shrinks (or keeps its size) in both directions — the serving case — it is a
+// true area resize:
 //   * both scale factors integral: int32 block sum, saturate_cast<uchar>(sum * (1.f / area)) (round half to even); the
 //     2x2 block has its own form, (a + b + c + d + 2) >> 2;
 //   * otherwise: per destination index a run of source taps — an optional partial tap, full taps of weight 1/cell, an
 //     optional partial tap — whose fp32 weights come from fp64 interval arithmetic; a horizontal pass accumulates
 //     S * alpha in fp32 in tap order, the vertical pass accumulates beta * row the same way, one rounding at the end.
+// When it grows in either direction OpenCV does not do an area resize at all: INTER_AREA falls back to its 8-bit
+// bilinear with "area mode" coefficients — left neighbour floor(d * scale), weight fx = (d+1) - (s+1) * inv_scale kept
+// to its fractional part, both weights rounded to 11-bit fixed point; the horizontal pass is S0*a0 + S1*a1 in int32 and
+// the vertical pass (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2.
 // Every destination pixel is independent, so a thread recomputes its own taps (a few fp64 operations) instead of
-// reading tables: no host-side table build, no upload, one kernel.  Enlarging takes OpenCV's fixed-point bilinear path
-// and is refused with B200_ERR_UNSUPPORTED.
+// reading tables: no host-side table build, no upload, one kernel.
 //
 // Output: the letterboxed uint8 image in the input's channel order (what opencvProportionalResize returns) and / or
 // the float32 network input with the channels reversed and divided by 255 (predict's cvtColor + astype + / 255).
 #include "detmath.h"
 #include "common.cuh"
 
-enum { LB_GENERIC = 0, LB_BLOCK = 1, LB_BLOCK_2X2 = 2 };
+enum { LB_GENERIC = 0, LB_BLOCK = 1, LB_BLOCK_2X2 = 2, LB_LINEAR = 3 };
 
 struct LbParams {
   const uint8_t* img;  // [sh, sw, 3]
   int sh, sw;
   int rw, rh, top, left, out_w, out_h;
-  double scale_x, scale_y;
+  double scale_x, scale_y, inv_x, inv_y;
   int mode, isx, isy;
   float inv_area;
   int bg0, bg1, bg2;
@@ -58,6 +61,17 @@ __device__ __forceinline__ LbAxis lb_axis(int d, int ssize, double scale) {
 }
 
 __device__ __forceinline__ int lb_saturate(int v) { return min(max(v, 0), 255); }
+
+// one axis of the bilinear fallback: left source index and the two fixed-point weights (INTER_RESIZE_COEF_BITS = 11)
+__device__ __forceinline__ void lb_linear(int d, int ssize, double inv, double scale, int& s, int& w0, int& w1) {
+  s = (int)floor(__dmul_rn((double)d, scale));
+  float f = (float)__dsub_rn((double)(d + 1), __dmul_rn((double)(s + 1), inv));
+  f = (f <= 0.0f) ? 0.0f : DM_SUB(f, floorf(f));
+  if (s < 0) { f = 0.0f; s = 0; }
+  if (s >= ssize - 1) { f = 0.0f; s = ssize - 1; }
+  w0 = min(max(__float2int_rn(DM_MUL(DM_SUB(1.0f, f), 2048.0f)), -32768), 32767);  // saturate_cast<short>
+  w1 = min(max(__float2int_rn(DM_MUL(f, 2048.0f)), -32768), 32767);
+}
 
 __global__ void __launch_bounds__(256) letterbox_kernel(LbParams p) {
   const int ox = blockIdx.x * 32 + (int)(threadIdx.x & 31), oy = blockIdx.y * 8 + (int)(threadIdx.x >> 5);
@@ -97,6 +111,21 @@ __global__ void __launch_bounds__(256) letterbox_kernel(LbParams p) {
         s2 = DM_ADD(s2, DM_MUL(beta, b2));
       }
       v0 = lb_saturate(__float2int_rn(s0)); v1 = lb_saturate(__float2int_rn(s1)); v2 = lb_saturate(__float2int_rn(s2));
+    } else if (p.mode == LB_LINEAR) {
+      int sx, a0, a1, sy, b0, b1;
+      lb_linear(dx, p.sw, p.inv_x, p.scale_x, sx, a0, a1);
+      lb_linear(dy, p.sh, p.inv_y, p.scale_y, sy, b0, b1);
+      const int sx1 = min(sx + 1, p.sw - 1);
+      const uint8_t* R0 = p.img + (size_t)min(max(sy, 0), p.sh - 1) * p.sw * 3;
+      const uint8_t* R1 = p.img + (size_t)min(max(sy + 1, 0), p.sh - 1) * p.sw * 3;
+      int v[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int h0 = (int)__ldg(R0 + sx * 3 + c) * a0 + (int)__ldg(R0 + sx1 * 3 + c) * a1;
+        const int h1 = (int)__ldg(R1 + sx * 3 + c) * a0 + (int)__ldg(R1 + sx1 * 3 + c) * a1;
+        v[c] = ((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2) & 0xff;  // uchar(...) truncates
+      }
+      v0 = v[0]; v1 = v[1]; v2 = v[2];
     } else {
       int s0 = 0, s1 = 0, s2 = 0;
       for (int ky = 0; ky < p.isy; ++ky) {
@@ -143,14 +172,14 @@ extern "C" int b200_letterbox_image(const uint8_t* img, int height, int width, i
                rw, rh);
   LbParams p;
   p.img = img; p.sh = height; p.sw = width; p.rw = rw; p.rh = rh; p.out_w = out_width; p.out_h = out_height;
-  p.scale_x = 1.0 / ((double)rw / (double)width);   // cv::resize: inv_scale = dsize / ssize, scale = 1 / inv_scale
-  p.scale_y = 1.0 / ((double)rh / (double)height);
-  B200_REQUIRE(p.scale_x >= 1.0 && p.scale_y >= 1.0, B200_ERR_UNSUPPORTED,
-               "b200_letterbox_image: input %d x %d is smaller than the network input %d x %d (enlarging: OpenCV's bilinear path)",
-               width, height, out_width, out_height);
+  p.inv_x = (double)rw / (double)width;   // cv::resize: inv_scale = dsize / ssize, scale = 1 / inv_scale
+  p.inv_y = (double)rh / (double)height;
+  p.scale_x = 1.0 / p.inv_x;
+  p.scale_y = 1.0 / p.inv_y;
+  const bool area = p.scale_x >= 1.0 && p.scale_y >= 1.0;  // otherwise INTER_AREA is OpenCV's bilinear fallback
   const int isx = (int)nearbyint(p.scale_x), isy = (int)nearbyint(p.scale_y);
   const bool blocky = fabs(p.scale_x - isx) < 2.220446049250313e-16 && fabs(p.scale_y - isy) < 2.220446049250313e-16;
-  p.mode = !blocky ? LB_GENERIC : ((isx == 2 && isy == 2) ? LB_BLOCK_2X2 : LB_BLOCK);
+  p.mode = !area ? LB_LINEAR : (!blocky ? LB_GENERIC : ((isx == 2 && isy == 2) ? LB_BLOCK_2X2 : LB_BLOCK));
   p.isx = isx; p.isy = isy;
   p.inv_area = 1.0f / (float)(isx * isy);
   p.top = (out_height - rh) / 2;

@@ -15,6 +15,12 @@ CASES = [
     ("noise_tall_500x2000_to_416x416", 2000, 500, (416, 416), "noise"),
     ("noise_wide_to_608", 900, 1600, (608, 608), "noise"),
     ("noise_one_row_short", 417, 416, (416, 416), "noise"),    # scale_x == 1 after int(), scale_y slightly above 1
+    # inputs smaller than the target: INTER_AREA becomes OpenCV's 8-bit bilinear ("area mode" coefficients)
+    ("small_100x80_to_128x128", 80, 100, (128, 128), "noise"),
+    ("small_binary_37x91_to_128x96", 91, 37, (128, 96), "binary"),
+    ("small_320x240_to_416x416", 240, 320, (416, 416), "noise"),
+    ("small_mixed_415x10_to_416x416", 10, 415, (416, 416), "noise"),   # grows along x, scale 1 along y
+    ("small_1x1_to_64x64", 1, 1, (64, 64), "noise"),
 ]
 
 

@@ -81,6 +81,8 @@ def test_letterbox_random_sizes_match_oracle(lib, cuda):
     for it in range(120):
         tw, th = int(rng.integers(8, 200)), int(rng.integers(8, 200))
         h, w = int(rng.integers(th, 6 * th)), int(rng.integers(tw, 6 * tw))
+        if it % 6 == 1:     # smaller than the target in one or both directions: OpenCV's bilinear fallback
+            h, w = int(rng.integers(1, 2 * th)), int(rng.integers(1, tw + 1))
         if it % 5 == 0:     # integral shrink of both sides (block / 2x2 / copy paths)
             k = int(rng.integers(1, 5)); h, w = th * k, tw * k
         if it % 7 == 0:
@@ -89,8 +91,8 @@ def test_letterbox_random_sizes_match_oracle(lib, cuda):
         bg = tuple(int(v) for v in rng.integers(0, 256, 3))
         try:
             want, pad = olb.proportional_resize(img, (tw, th), bg_color=bg)
-        except olb.UnsupportedResize:
-            with pytest.raises(RuntimeError, match="smaller"):
+        except olb.UnsupportedResize:   # the proportional size truncated to 0: cv2.resize raises as well
+            with pytest.raises(ValueError, match="empty"):
                 ih.letterbox(img, (tw, th), bg, True, False)
             continue
         src = img if it % 2 else torch.from_numpy(img).pin_memory()   # pageable numpy / pinned host read in place
@@ -109,8 +111,10 @@ def test_letterbox_points_and_refusals(lib, cuda):
     img = make_image(0, 480, 640, "noise")
     _, pts, _ = ih.opencvProportionalResize(img, np.int32((96, 96)), points=LB_GOLD["points_in"].tolist(), bg_color=(0, 0, 0))
     assert pts.dtype == np.float32 and np.array_equal(pts, LB_GOLD["points_out"])
-    with pytest.raises(RuntimeError, match="smaller"):     # enlarging: OpenCV's bilinear path, not built
-        ih.opencvProportionalResize(np.zeros((100, 100, 3), np.uint8), (416, 416))
+    up, _, pad = ih.opencvProportionalResize(np.full((100, 100, 3), 7, np.uint8), (416, 416))   # enlarging works too
+    assert tuple(up.shape) == (416, 416, 3) and pad == (0, 0, 0, 0) and int(up.min()) == 7 and int(up.max()) == 7
+    with pytest.raises(ValueError, match="empty"):
+        ih.opencvProportionalResize(np.zeros((2, 4000, 3), np.uint8), (416, 416))
     with pytest.raises(RuntimeError, match="3-channel"):
         ih.letterbox(np.zeros((500, 500, 4), np.uint8), (416, 416), (0, 0, 0), True, False)
     with pytest.raises(NotImplementedError):
