@@ -1,5 +1,5 @@
 """Mirror of the one function of the reference's ImageHelper that sits on the serving path:
-opencvProportionalResize (utils/image_helper.py:293-325) — proportional INTER_AREA shrink + constant border — on the
+opencvProportionalResize (utils/image_helper.py:293-325) — proportional INTER_AREA resize + constant border — on the
 device (csrc/letterbox.cu, OpenCV's 8-bit arithmetic bit for bit).  The augmentation options of the reference
 (random background colour, BORDER_REPLICATE) are not part of the serving path and are refused."""
 import ctypes
