@@ -83,6 +83,15 @@ def main():
         fn = wrap(lambda: tyu.GetNMSBoxesBatch(*heads, anc, (416, 416), 80, 0.5, 0.3, 0.5, "iou"))
         ms = timed(fn, args.steps, args.warmup)
         report("c1_b256", "YOLOv3 416 B=256 decode+per-class NMS", 256, ms, 3619980 + 174000)
+    if want("c1_b256_trained"):  # SURVEY 8d second input set: conf ~ N(-4,1.5), 50 planted objects x 5 duplicates per image
+        rng = np.random.default_rng(20261018 + 1)
+        base = synth.yolo_heads_trained_like(rng, 32, 416)
+        heads = [torch.from_numpy(np.tile(h, (8, 1, 1, 1))).to(dev) for h in base]
+        fn = wrap(lambda: tyu.GetNMSBoxesBatch(*heads, anc, (416, 416), 80, 0.5, 0.3, 0.5, "iou"))
+        ms = timed(fn, args.steps, args.warmup)
+        kept = int(tyu.GetNMSBoxesBatch(*heads, anc, (416, 416), 80, 0.5, 0.3, 0.5, "iou")["count"].sum().item())
+        report("c1_b256_trained", "YOLOv3 416 B=256 decode+per-class NMS, trained-like heads (32 generated images tiled x8)", 256, ms,
+               3619980 + 174000, {"kept_boxes_total": kept})
     if want("c5_b64"):  # config 5 per GPU: YOLOv4 608, decode + loss + NMS ('diou'), y_true given
         batch, image = 64, 608
         heads = yolo_heads(batch, image)
