@@ -157,3 +157,30 @@ def test_sharded_loss_exchange_on_gloo_world2():
     assert len({round(r[1], 3) for r in res}) == 1          # both ranks hold the same loss after the all-reduce
     for _, got, want in res:
         assert abs(got - want) <= 1e-4 * abs(want)          # 1e-4 also after the all-reduce
+
+
+def test_product_package_never_touches_the_oracle_or_the_reference():
+    """The oracle is the checker, not the product: nothing under the package (Python or CUDA sources) may import,
+    execute or read oracle/ or /root/reference; importing every product module must not pull `oracle` in either."""
+    import re
+    import subprocess
+    import sys
+    pkg = os.path.join(ROOT, "tensorflow2-machine-vision_b200")
+    bad = []
+    for d, _, files in os.walk(pkg):
+        if os.path.basename(d) in ("build", "__pycache__"):
+            continue
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h")):
+                continue
+            text = open(os.path.join(d, f), encoding="utf-8").read()
+            if re.search(r"^\s*(from|import)\s+oracle\b", text, re.M) or "/root/reference" in text.replace("`/root/reference`", ""):
+                bad.append(os.path.relpath(os.path.join(d, f), ROOT))
+    assert not bad, bad
+    code = ("import sys, pkgutil, importlib; sys.path.insert(0, %r); import tfmv_b200\n"
+            "for m in pkgutil.walk_packages(tfmv_b200.__path__, 'tfmv_b200.'):\n"
+            "    if not m.name.endswith(('.build', '.libb200det')): importlib.import_module(m.name)\n"
+            "assert not [k for k in sys.modules if k == 'oracle' or k.startswith('oracle.')], 'oracle imported by the product'\n"
+            "print('ok')") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
