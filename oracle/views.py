@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE ONLY (see oracle/__init__.py): NumPy restatement of the box post-processing in the reference's
-serving view, views/object_detection.py:70-85.  Parity unpinned (the view is Django code around a TensorFlow model and the reference holds no
-test for it; the image half of the view is oracle/letterbox.py, which is pinned); NumPy 1.x casting of the reference's era is emulated explicitly (float32 array (op) integer scalar ->
+serving view, views/object_detection.py:70-85.  Pinned against the reference's own lines: tests/golden/make_golden_views.py executes lines 71-85 of the
+view verbatim on seeded inputs and tests/test_views_oracle.py holds this file to them (the image half of the view is
+oracle/letterbox.py, pinned against OpenCV); NumPy 1.x casting of the reference's era is emulated explicitly (float32 array (op) integer scalar ->
 float32), because NumPy >= 2 would promote `float32 * np.int32` to float64."""
 import numpy as np
 
