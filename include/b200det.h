@@ -264,6 +264,14 @@ int b200_focal_box_grad(int num_levels, const unsigned long long* anchors_per_le
                         const float* const pred_boxes[], const float* const pred_classes[], float alpha, float gamma,
                         float delta, float label_smoothing, const double* sums, const double* numel_per_level_host,
                         float* const grad_boxes[], float* const grad_classes[], void* stream);
+/* The same with sparse class targets: true_class_index[l] (B,H,W,A) int32 class ids as
+ * b200_effdet_assign_targets_indexed writes them (classes_num >= 4). */
+int b200_focal_box_grad_indexed(int num_levels, const unsigned long long* anchors_per_level, int C,
+                                const float* const true_boxes[], const int32_t* const true_class_index[],
+                                const float* const pred_boxes[], const float* const pred_classes[], float alpha,
+                                float gamma, float delta, float label_smoothing, const double* sums,
+                                const double* numel_per_level_host, float* const grad_boxes[],
+                                float* const grad_classes[], void* stream);
 
 /* Serving-path box post-processing (views/object_detection.py:70-85): boxes [B,max_rows,4] normalised
  * x1,y1,x2,y2 on the letterboxed image (image_size = (w,h) of the network input, padding = (top,bottom,left,right) of

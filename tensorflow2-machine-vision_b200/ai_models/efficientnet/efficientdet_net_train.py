@@ -34,16 +34,23 @@ def get_loss(y_true_boxes, y_true_classes, y_true_masks, y_pred_boxes, y_pred_cl
              '_get_loss')
   if with_grad:
     tb = [T.to_cuda(t) for t in y_true_boxes]
-    tc = [T.to_cuda(t) for t in y_true_classes]
+    # class targets: one-hot float tensors, or integer class ids (generate_targets_batch(class_index=True)) — the same
+    # detection as the forward pass uses
+    indexed = any(not torch.is_floating_point(torch.as_tensor(t)) for t in y_true_classes)
+    tc = [T.to_cuda(t, torch.int32) if indexed else T.to_cuda(t) for t in y_true_classes]
     pb = [T.to_cuda(t) for t in y_pred_boxes]
     pc = [T.to_cuda(t) for t in y_pred_classes]
     gb = [torch.empty_like(t) for t in pb]
     gc = [torch.empty_like(t) for t in pc]
     C = pc[0].shape[-1]
+    for l in range(L):
+      if tc[l].numel() * (C if indexed else 1) != pc[l].numel():
+        raise ValueError('class target / output shapes differ at level %d' % l)
     anc = (ctypes.c_ulonglong * L)(*[t.numel() // C for t in pc])
     arr = lambda ts: (ctypes.c_void_p * L)(*[t.data_ptr() for t in ts])
-    _lib.check(lib.b200_focal_box_grad(L, anc, C, arr(tb), arr(tc), arr(pb), arr(pc), float(alpha), float(gamma),
-                                       float(delta), 0.0, T.ptr(sums), nm, arr(gb), arr(gc), T.stream_ptr()),
+    grad = lib.b200_focal_box_grad_indexed if indexed else lib.b200_focal_box_grad
+    _lib.check(grad(L, anc, C, arr(tb), arr(tc), arr(pb), arr(pc), float(alpha), float(gamma),
+                    float(delta), 0.0, T.ptr(sums), nm, arr(gb), arr(gc), T.stream_ptr()),
                '_get_loss backward')
     return loss, tuple(gb), tuple(gc)
   return (loss, parts, npos) if return_parts else loss

@@ -209,6 +209,8 @@ __global__ void focal_box_finalize_kernel(ElFinalize f) {
 struct ElGradParams {
   int num_levels;
   const float4* cls_pred[EL_MAX_LEVELS]; const float4* cls_true[EL_MAX_LEVELS]; float4* cls_grad[EL_MAX_LEVELS];
+  const int32_t* cls_index[EL_MAX_LEVELS];  // sparse-target mode: class id per anchor instead of cls_true
+  int C;
   unsigned long long cls_vec[EL_MAX_LEVELS];
   int cls_tail[EL_MAX_LEVELS];  // floats after the last whole float4
   const float4* box_pred[EL_MAX_LEVELS]; const float4* box_true[EL_MAX_LEVELS]; float4* box_grad[EL_MAX_LEVELS];
@@ -254,9 +256,26 @@ __global__ void __launch_bounds__(EL_THREADS) focal_box_grad_kernel(ElGradParams
   if (p.cls_grad[l]) {
     const unsigned long long nv = p.cls_vec[l];
 #pragma unroll 2
+    const int32_t* __restrict__ ci = p.cls_index[l];
     for (unsigned long long i = (unsigned long long)cta * EL_THREADS + threadIdx.x; i < nv; i += stride) {
       const float4 x = __ldcs(p.cls_pred[l] + i);
-      const float4 y = __ldcs(p.cls_true[l] + i);
+      float4 y;
+      if (ci) {
+        // the one-hot row generate_targets would have written: 1 at the anchor's class id, ids outside [0, C) -> zeros
+        const unsigned long long e = i * 4ull, a0 = e / (unsigned long long)p.C;
+        const int c0 = (int)(e - a0 * (unsigned long long)p.C);
+        const int id0 = __ldg(ci + a0);
+        const int id1 = (c0 + 3 >= p.C) ? __ldg(ci + a0 + 1) : 0;  // a float4 may straddle two anchors (C >= 4 here)
+        float yy[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = c0 + k;
+          yy[k] = (c < p.C) ? ((c == id0) ? 1.0f : 0.0f) : ((c - p.C == id1) ? 1.0f : 0.0f);
+        }
+        y = make_float4(yy[0], yy[1], yy[2], yy[3]);
+      } else {
+        y = __ldcs(p.cls_true[l] + i);
+      }
       float4 g;
       g.x = cs * el_focal_grad(y.x, x.x, p.alpha, p.gamma, p.label_smoothing);
       g.y = cs * el_focal_grad(y.y, x.y, p.alpha, p.gamma, p.label_smoothing);
@@ -266,9 +285,15 @@ __global__ void __launch_bounds__(EL_THREADS) focal_box_grad_kernel(ElGradParams
     }
     if (cta == 0 && (int)threadIdx.x < p.cls_tail[l]) {
       const unsigned long long e = nv * 4ull + threadIdx.x;
+      float yt;
+      if (p.cls_index[l]) {
+        const unsigned long long a = e / (unsigned long long)p.C;
+        yt = ((int)(e - a * (unsigned long long)p.C) == __ldg(p.cls_index[l] + a)) ? 1.0f : 0.0f;
+      } else {
+        yt = reinterpret_cast<const float*>(p.cls_true[l])[e];
+      }
       reinterpret_cast<float*>(p.cls_grad[l])[e] =
-          cs * el_focal_grad(reinterpret_cast<const float*>(p.cls_true[l])[e], reinterpret_cast<const float*>(p.cls_pred[l])[e],
-                             p.alpha, p.gamma, p.label_smoothing);
+          cs * el_focal_grad(yt, reinterpret_cast<const float*>(p.cls_pred[l])[e], p.alpha, p.gamma, p.label_smoothing);
     }
   }
   if (p.box_grad[l]) {
@@ -434,29 +459,35 @@ extern "C" int b200_focal_box_finalize(int num_levels, const double* sums, const
 
 // d loss / d pred_classes[l] and d loss / d pred_boxes[l] (either array entry may be NULL).  `sums` is the device
 // array b200_focal_box_partial_sums produced (after the all-reduce, if any); numel_per_level_host as in finalize.
-extern "C" int b200_focal_box_grad(int num_levels, const unsigned long long* anchors_per_level, int C,
-                                   const float* const true_boxes[], const float* const true_classes[],
-                                   const float* const pred_boxes[], const float* const pred_classes[], float alpha,
-                                   float gamma, float delta, float label_smoothing, const double* sums,
-                                   const double* numel_per_level_host, float* const grad_boxes[],
-                                   float* const grad_classes[], void* stream) {
+static int el_grad_impl(int num_levels, const unsigned long long* anchors_per_level, int C,
+                        const float* const true_boxes[], const float* const true_classes[],
+                        const int32_t* const true_class_index[],
+                        const float* const pred_boxes[], const float* const pred_classes[], float alpha,
+                        float gamma, float delta, float label_smoothing, const double* sums,
+                        const double* numel_per_level_host, float* const grad_boxes[],
+                        float* const grad_classes[], void* stream) {
   B200_REQUIRE(num_levels >= 1 && num_levels <= EL_MAX_LEVELS && C >= 1 && anchors_per_level && sums && numel_per_level_host,
                B200_ERR_BAD_ARG, "b200_focal_box_grad: bad argument");
+  B200_REQUIRE(!true_class_index || C >= 4, B200_ERR_UNSUPPORTED, "b200_focal_box_grad_indexed: needs classes_num >= 4");
   ElGradParams p;
+  p.C = C;
   unsigned long long plan[EL_MAX_LEVELS];
   p.num_levels = num_levels;
   for (int l = 0; l < EL_MAX_LEVELS; ++l) {
     p.cls_pred[l] = p.cls_true[l] = nullptr; p.cls_grad[l] = nullptr; p.box_pred[l] = p.box_true[l] = nullptr; p.box_grad[l] = nullptr;
+    p.cls_index[l] = nullptr;
     p.cls_vec[l] = 0; p.cls_tail[l] = 0; p.anchors[l] = 0; p.numel[l] = 1.0; plan[l] = 0;
     if (l >= num_levels) continue;
     p.numel[l] = numel_per_level_host[l];
     if (grad_classes && grad_classes[l]) {
-      B200_REQUIRE(true_classes && pred_classes && true_classes[l] && pred_classes[l], B200_ERR_BAD_ARG, "b200_focal_box_grad: null class tensors at level %d", l);
+      const void* tcl = true_class_index ? (const void*)true_class_index[l] : (true_classes ? (const void*)true_classes[l] : nullptr);
+      B200_REQUIRE(tcl && pred_classes && pred_classes[l], B200_ERR_BAD_ARG, "b200_focal_box_grad: null class tensors at level %d", l);
       const unsigned long long n = anchors_per_level[l] * (unsigned long long)C;
-      const uintptr_t al = reinterpret_cast<uintptr_t>(true_classes[l]) | reinterpret_cast<uintptr_t>(pred_classes[l]) | reinterpret_cast<uintptr_t>(grad_classes[l]);
+      const uintptr_t al = (true_class_index ? 0 : reinterpret_cast<uintptr_t>(tcl)) | reinterpret_cast<uintptr_t>(pred_classes[l]) | reinterpret_cast<uintptr_t>(grad_classes[l]);
       B200_REQUIRE((al & 15) == 0, B200_ERR_BAD_ARG, "b200_focal_box_grad: level %d class tensors must be 16-byte aligned", l);
       p.cls_pred[l] = reinterpret_cast<const float4*>(pred_classes[l]);
-      p.cls_true[l] = reinterpret_cast<const float4*>(true_classes[l]);
+      p.cls_true[l] = true_class_index ? nullptr : reinterpret_cast<const float4*>(tcl);
+      p.cls_index[l] = true_class_index ? true_class_index[l] : nullptr;
       p.cls_grad[l] = reinterpret_cast<float4*>(grad_classes[l]);
       p.cls_vec[l] = n / 4ull;
       p.cls_tail[l] = (int)(n - p.cls_vec[l] * 4ull);
@@ -479,4 +510,27 @@ extern "C" int b200_focal_box_grad(int num_levels, const unsigned long long* anc
   focal_box_grad_kernel<<<n_cta, EL_THREADS, 0, (cudaStream_t)stream>>>(p);
   B200_LAUNCH_CHECK();
   return B200_OK;
+}
+
+extern "C" int b200_focal_box_grad(int num_levels, const unsigned long long* anchors_per_level, int C,
+                                   const float* const true_boxes[], const float* const true_classes[],
+                                   const float* const pred_boxes[], const float* const pred_classes[], float alpha,
+                                   float gamma, float delta, float label_smoothing, const double* sums,
+                                   const double* numel_per_level_host, float* const grad_boxes[],
+                                   float* const grad_classes[], void* stream) {
+  return el_grad_impl(num_levels, anchors_per_level, C, true_boxes, true_classes, nullptr, pred_boxes, pred_classes, alpha, gamma,
+                      delta, label_smoothing, sums, numel_per_level_host, grad_boxes, grad_classes, stream);
+}
+
+// Sparse-target mode of the backward pass: true_class_index[l] (B,H,W,A) int32 class ids, as
+// b200_focal_box_partial_sums_indexed takes them (the one-hot row is rebuilt in registers).
+extern "C" int b200_focal_box_grad_indexed(int num_levels, const unsigned long long* anchors_per_level, int C,
+                                           const float* const true_boxes[], const int32_t* const true_class_index[],
+                                           const float* const pred_boxes[], const float* const pred_classes[], float alpha,
+                                           float gamma, float delta, float label_smoothing, const double* sums,
+                                           const double* numel_per_level_host, float* const grad_boxes[],
+                                           float* const grad_classes[], void* stream) {
+  B200_REQUIRE(true_class_index, B200_ERR_BAD_ARG, "b200_focal_box_grad_indexed: null argument");
+  return el_grad_impl(num_levels, anchors_per_level, C, true_boxes, nullptr, true_class_index, pred_boxes, pred_classes, alpha,
+                      gamma, delta, label_smoothing, sums, numel_per_level_host, grad_boxes, grad_classes, stream);
 }

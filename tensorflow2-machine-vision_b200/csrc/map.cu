@@ -81,7 +81,9 @@ __global__ void __launch_bounds__(MAP_THREADS) map_kernel(MapParams p) {
         const double iw = fmax(fmin(gx2, px2) - fmax(gx1, px1), 0.0), ih = fmax(fmin(gy2, py2) - fmax(gy1, py1), 0.0);
         const double inter = iw * ih;
         const double iou = inter / (ga + (px2 - px1) * (py2 - py1) - inter);
-        if (q == 0 || iou > bv) { bv = iou; best = q; }
+        // np.argmax (mAP.py:53): the first maximal index, and a NaN (0/0: zero-area boxes) counts as maximal — the
+        // first NaN freezes the choice, and `NaN >= thresh` is False, so that ground-truth box claims nothing
+        if (q == 0 || (bv == bv && (iou > bv || iou != iou))) { bv = iou; best = q; }
       }
       if (bv >= p.thresh) s_tp[best] = 1;
     }

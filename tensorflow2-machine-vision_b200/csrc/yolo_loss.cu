@@ -15,7 +15,8 @@
 //      object_loss = obj*bce + (1-obj)*bce*ignore (tyu:111-114).  The trailing CTAs of its grid instead take a warp per
 //      object and produce the xy, wh and class terms (tyu:107-118) from the full y_true / y_pred records.
 //  K4c yolo_loss_finalize_kernel  fixed-order fp64 reduction of the per-CTA partials -> parts[3][4] / batch,
-//      loss = sum_l ((xy+wh)+obj)+cls in fp32 in the reference's order (tyu:120-125).  Deterministic run to run.
+//      loss = sum_l ((xy+wh)+obj)+cls in fp32 in the reference's order (tyu:120-125).  Deterministic run to run (the object lists are
+//      put into ascending record order by K4a' before anything is summed over them).
 //
 // ignore = float(best < thr) with best = max_g metric(pred, gt_g) is evaluated as "no g with metric >= thr or
 // metric NaN": tf.reduce_max propagates NaN and NaN < thr is False, so a NaN pair clears the ignore bit.
@@ -132,12 +133,29 @@ __global__ void __launch_bounds__(YL_CHUNK) yolo_loss_scan_kernel(YlParams p) {
 
 // K4a': one thread per object: the prepared GT box of the ignore mask (corners of (t_xy, t_wh), tyu:68-71; area,
 // atan(w/h), log area, "regular" flag).  One CTA per (level, image).
+#define YL_SORT_CAP 2048
 __global__ void __launch_bounds__(128) yolo_loss_gtprep_kernel(YlParams p) {
+  __shared__ int s_idx[YL_SORT_CAP];
   const int l = blockIdx.x / p.B, img = blockIdx.x - l * p.B;
   const int rpi = p.lv.rec_per_img[l];
   const float* yt = p.sp_t ? nullptr : p.lv.y_true[l] + ((size_t)img * rpi) * p.RF;
   const int n = p.gt_count[img * YL_LEVELS + l];
   const size_t gbase = (size_t)img * p.n_img + p.lv.anchor_base[l];
+  // The scan kernel appended the object records with atomics, i.e. in a run-dependent order; the xy / wh / class terms
+  // are summed in list order (fp64, then one fp32 cast), so the list is put into ascending record order first: the
+  // loss is then bit-reproducible run to run (lists longer than YL_SORT_CAP keep the atomic order).  The sparse-target
+  // path builds its list in box order already.
+  if (!p.sp_t && n > 1 && n <= YL_SORT_CAP) {
+    for (int k = threadIdx.x; k < n; k += 128) s_idx[k] = p.obj_index[gbase + k];
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += 128) {
+      const int mine = s_idx[k];
+      int rank = 0;
+      for (int j = 0; j < n; ++j) rank += (s_idx[j] < mine) ? 1 : 0;  // record indices are unique
+      p.obj_index[gbase + rank] = mine;
+    }
+    __syncthreads();
+  }
   for (int k = threadIdx.x; k < n; k += 128) {
     float tx, ty, tw, th;
     if (p.sp_t) {
@@ -322,7 +340,9 @@ __global__ void __launch_bounds__(YL_ICHUNK, YL_IMINB) yolo_loss_ignore_kernel(Y
   const float4* gaux = p.gt_aux + (size_t)img * p.n_img + p.lv.anchor_base[l];
   const int W = p.lv.w[l], H = p.lv.h[l];
   float obj = 0.f, tx = 0.f, ty = 0.f, tw = 0.f, th = 0.f, pobj = 0.f;
-  const bool aligned = (reinterpret_cast<uintptr_t>(p.lv.y_pred[l]) & 15) == 0;  // block-uniform
+  // block-uniform.  The two aligned 16-byte loads cover floats [f0 & ~3, (f0 & ~3) + 8): inside the tensor only when a
+  // record holds at least 8 floats (C >= 3); narrower records take the scalar path
+  const bool aligned = ((reinterpret_cast<uintptr_t>(p.lv.y_pred[l]) & 15) == 0) && (p.RF >= 8);
   if (active) {
     if (p.obj_bits) {
       const int bit = p.lv.anchor_base[l] + rin;
@@ -701,16 +721,50 @@ __global__ void __launch_bounds__(128) yolo_loss_assign_sparse_kernel(YtParams t
     keys[i] = yt_assign(t, i, layer, rin, nx, ny, nw, nh) ? p.lv.anchor_base[layer] + rin : -1;
   }
   __syncthreads();
+  // boxes that collide on a record are dropped (all of them): decide for every box first, then retire the keys
+  bool dup_mine[8];  // up to 8 * 128 boxes per image in registers; beyond that the flag is recomputed below
+  {
+    int u = 0;
+    for (int i = beg + (int)threadIdx.x; i < end; i += 128, ++u) {
+      const int key = keys[i];
+      bool dup = false;
+      if (key >= 0) for (int j = beg; j < end; ++j) dup |= (j != i) && (keys[j] == key);
+      if (u < 8) dup_mine[u] = dup;
+    }
+  }
+  __syncthreads();
+  if (end - beg <= 8 * 128) {
+    int u = 0;
+    for (int i = beg + (int)threadIdx.x; i < end; i += 128, ++u) if (dup_mine[u]) keys[i] = -1;
+  } else {
+    // rare (more than 1024 boxes in one image): mark duplicates with a sentinel that still compares equal among themselves
+    // is not possible in place, so fall back to a serial pass by one thread
+    if (threadIdx.x == 0) {
+      for (int i = beg; i < end; ++i) {
+        const int key = keys[i];
+        if (key < 0) continue;
+        bool dup = false;
+        for (int j = i + 1; j < end; ++j) if (keys[j] == key) { keys[j] = -2; dup = true; }
+        if (dup) keys[i] = -2;
+      }
+    }
+  }
+  __syncthreads();
   for (int i = beg + (int)threadIdx.x; i < end; i += 128) {
     const int key = keys[i];
     if (key < 0) continue;
-    bool dup = false;
-    for (int j = beg; j < end; ++j) dup |= (j != i) && (keys[j] == key);
-    if (dup) continue;
     int layer, rin;
     float nx, ny, nw, nh;
     yt_assign(t, i, layer, rin, nx, ny, nw, nh);
-    const int slot = atomicAdd(&s_cnt[layer], 1);
+    // slot = number of surviving boxes of the same layer with a smaller record index (ascending record order, as the
+    // dense path's sorted object list): deterministic run to run, no atomics on the slot
+    const int lo_key = p.lv.anchor_base[layer];
+    int slot = 0;
+    for (int j = beg; j < end; ++j) {
+      const int kj = keys[j];
+      slot += (kj >= lo_key && kj < key) ? 1 : 0;
+    }
+    atomicAdd(&s_cnt[layer], 1);
     const size_t gi = (size_t)img * p.n_img + p.lv.anchor_base[layer] + slot;
     p.obj_index[gi] = rin;
     sp_t[gi] = make_float4(nx, ny, nw, nh);

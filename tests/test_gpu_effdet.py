@@ -255,3 +255,32 @@ def test_get_loss_gradient_matches_oracle(lib, cuda):
     for l in range(L):
         np.testing.assert_allclose(gc[l].cpu().numpy(), wc[l], rtol=2e-4, atol=1e-12)
         np.testing.assert_allclose(gb[l].cpu().numpy(), wb[l], rtol=2e-4, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_gradient_with_class_index_targets_equals_one_hot(lib, cuda):
+    """get_loss(with_grad=True) on sparse class-id targets (generate_targets_batch(class_index=True)): the gradient must
+    equal the gradient against the one-hot rows those ids stand for, including ids outside [0, C) (all-zero row)."""
+    import torch
+    from tfmv_b200 import synth
+    from tfmv_b200.ai_models.efficientnet.efficientdet_net_train import get_loss_and_grad
+    a, o = _pair("small")
+    rng = np.random.default_rng(53)
+    batch, C = 3, 81
+    boxes, classes, off = synth.gt_batch(rng, batch, (128, 128), max_boxes=20, order="yxyx")
+    classes = (classes % 80 + 1).astype(np.int32)
+    classes[::7] = 200  # tf.one_hot: out of range -> zeros
+    d_b, d_c, d_o = _t(boxes, cuda), _t(classes, cuda), _t(off, cuda)
+    tb, tc, tm = a.generate_targets_batch(d_b, d_c, d_o, C)
+    ib, ic, im = a.generate_targets_batch(d_b, d_c, d_o, C, class_index=True)
+    g = torch.Generator(device=cuda).manual_seed(5)
+    pb = [torch.randn(t.shape, device=cuda, generator=g) * 0.25 for t in tb]
+    pc = [torch.randn(t.shape, device=cuda, generator=g) for t in tc]
+    loss_d, gb_d, gc_d = get_loss_and_grad(tb, tc, tm, pb, pc)
+    loss_i, gb_i, gc_i = get_loss_and_grad(ib, ic, im, pb, pc)
+    assert abs(float(loss_d) - float(loss_i)) <= 1e-5 * abs(float(loss_d))
+    for l in range(len(tb)):
+        assert torch.equal(gc_d[l], gc_i[l]), l     # same arithmetic on the same y values: identical bits
+        assert torch.equal(gb_d[l], gb_i[l]), l
+    with pytest.raises(ValueError):
+        get_loss_and_grad(ib, [t[..., :1] for t in tc], im, pb, pc)

@@ -61,3 +61,32 @@ def test_gpu_map_matches_oracle_on_nms_output(lib, cuda):
     got = float(Get_mAP_one(gt, pred, 80, 0.5))
     want = om.get_map_one(gt.cpu().numpy(), pred.cpu().numpy(), 80, 0.5)
     assert abs(got - want) < 1e-12
+
+
+def _degenerate_case():
+    # a zero-area ground-truth box and an identical zero-area prediction give IoU = 0/0 = NaN; np.argmax picks the first
+    # NaN as the maximum and `NaN >= thresh` is False, so that ground-truth box claims nothing (mAP.py:53-56)
+    gt = np.array([[10, 10, 10, 10, 0], [0, 0, 20, 20, 0]], dtype=np.float64)
+    pr = np.array([[0, 0, 20, 20, 0, 0.9], [10, 10, 10, 10, 0, 0.8], [1, 1, 19, 19, 0, 0.7]], dtype=np.float64)
+    return gt, pr
+
+
+def test_oracle_nan_iou_follows_np_argmax():
+    from oracle import map as om
+    gt, pr = _degenerate_case()
+    tp, n_gt = om.get_tpfp_one(gt, pr, 0, 0.5)
+    # GT 0: IoU column = [0, NaN, 0] -> argmax = 1 (first NaN) -> no true positive; GT 1 claims prediction 0
+    assert n_gt == 2 and tp[:, 0].tolist() == [1.0, 0.0, 0.0]
+
+
+@pytest.mark.gpu
+def test_gpu_map_nan_iou_follows_np_argmax(lib, cuda):
+    import torch
+    from oracle import map as om
+    from tfmv_b200.ai_models.utils.mAP import Get_mAP_one
+    gt, pr = _degenerate_case()
+    # put the NaN pair first in the prediction list as well: the kernel must freeze on the first NaN it meets
+    for order in ([0, 1, 2], [1, 0, 2], [2, 1, 0]):
+        p = pr[order]
+        got = float(Get_mAP_one(torch.from_numpy(gt).to(cuda), torch.from_numpy(p).to(cuda), 3, 0.5))
+        assert abs(got - om.get_map_one(gt, p, 3, 0.5)) < 1e-12, order
