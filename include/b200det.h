@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define B200DET_VERSION 100
+#define B200DET_VERSION 200
 
 #define B200_OK 0
 #define B200_ERR_BAD_ARG (-1)
@@ -295,6 +295,58 @@ int b200_unletterbox_boxes(const float* boxes, const int32_t* counts, int B, int
 int b200_letterbox_image(const uint8_t* img, int height, int width, int channels, int out_width, int out_height,
                          const uint8_t bg_color[3], uint8_t* out_u8, float* out_f32, int32_t padding_out[4],
                          int32_t resized_wh_out[2], void* stream);
+
+/* ---- the collective of the path ------------------------------------------
+ * Data parallel over images: the only inter-GPU traffic is the sum of a handful of per-GPU partial loss terms (YOLO:
+ * 12 floats; EfficientDet: 2L+1 doubles).  The reference's only collective site is the MirroredStrategy reduce of
+ * facenet/facenet_model.py:297,318-322 (strategy.reduce(SUM, per_replica_losses)); its YOLO / EfficientDet train
+ * steps are single-replica.  Two transports, both stream-ordered and CUDA-graph capturable:
+ *
+ * (1) peer mailboxes over NVLink (one process per GPU, CUDA IPC).  Each rank creates a mailbox, hands the 64-byte
+ *     handle to its peers by any host channel (torch.distributed, MPI, a file), and maps theirs.  The *_dp entry
+ *     points below then do the exchange INSIDE their finalize kernel (peer stores + release/acquire flags, sum in rank
+ *     order: identical bits on every rank, no separate collective launch).  mailboxes[r] = rank r's mailbox as mapped
+ *     in this process (own one included), world <= 8, n <= 32 values.  A peer that never arrives is reported through
+ *     b200_peer_mailbox_status(errors) after 20 s instead of hanging the GPU. */
+size_t b200_peer_mailbox_bytes(void);
+int b200_peer_mailbox_create(void** mailbox_out, void* ipc_handle_out /* 64 bytes, may be NULL */);
+int b200_peer_mailbox_open(const void* ipc_handle /* 64 bytes */, void** mapped_out);
+int b200_peer_mailbox_close(void* mapped);
+int b200_peer_mailbox_destroy(void* mailbox);
+int b200_peer_mailbox_status(const void* own_mailbox, unsigned long long* epoch_out, unsigned int* errors_out); /* synchronous */
+/* stand-alone exchange (one warp): values[n] <- sum over ranks, in place */
+int b200_allreduce_loss_peer(float* partials, int n, int rank, int world, void* const mailboxes[], void* stream);
+int b200_allreduce_sums_peer(double* sums, int n, int rank, int world, void* const mailboxes[], void* stream);
+/* protocol self-test on one device: `world` CTAs of one grid play the ranks; out [world, rounds, n] */
+int b200_peer_exchange_selftest(int world, int rounds, int n, void* workspace, size_t workspace_bytes, float* out, void* stream);
+/* GetLoss / GetLossFromBoxes on one rank's images with the exchange fused into the finalize kernel: batch divisor =
+ * global_batch, out_parts / out_loss = the GLOBAL values on every rank (tyu:120-125 order of additions). */
+int b200_yolo_loss_dp(const float* const y_true[3], const float* const y_pred[3], const int32_t hw[6], int B, int A,
+                      int C, const float* anchors_wh_host, const float* image_wh_host, float iou_thresh, int metric,
+                      int variant, float global_batch, float* out_parts, float* out_loss, void* workspace,
+                      size_t workspace_bytes, int rank, int world, void* const mailboxes[], void* stream);
+int b200_yolo_loss_from_boxes_dp(const float* boxes, const int32_t* classes, const int32_t* offsets, int total_boxes,
+                                 const float* assign_anchors_wh_host, const float* const y_pred[3], const int32_t hw[6],
+                                 int B, int A, int C, const float* anchors_wh_host, const float* image_wh_host,
+                                 float iou_thresh, int metric, int variant, float global_batch, float* out_parts,
+                                 float* out_loss, void* workspace, size_t workspace_bytes, int rank, int world,
+                                 void* const mailboxes[], void* stream);
+/* _get_loss (edt:41-52) data parallel: sums = this rank's b200_focal_box_partial_sums on entry, the global sums on
+ * return; numel_per_level_host = GLOBAL element counts. */
+int b200_focal_box_finalize_dp(int num_levels, double* sums, const double* numel_per_level_host, float* out_parts,
+                               float* out_loss, float* out_num_positives, int rank, int world, void* const mailboxes[],
+                               void* stream);
+
+/* (2) NCCL.  `comm` is an ncclComm_t (passed as void*): the caller's own, or one made by b200_nccl_comm_init from a
+ *     128-byte ncclUniqueId that rank 0 obtains with b200_nccl_unique_id and broadcasts.  libnccl.so.2 is opened with
+ *     dlopen on first use (env B200_NCCL_LIB overrides the name); ncclAllReduce(sum) in place on `stream`. */
+int b200_nccl_unique_id(void* id128_out);
+int b200_nccl_comm_init(void** comm_out, int world, int rank, const void* id128);
+int b200_nccl_comm_destroy(void* comm);
+int b200_allreduce_loss(void* comm /* ncclComm_t */, float* partials, int n, void* stream);
+int b200_allreduce_sums(void* comm /* ncclComm_t */, double* sums, int n, void* stream);
+/* loss = sum_l ((xy_l + wh_l) + obj_l) + cls_l from the 12 all-reduced terms, the reference's order (tyu:120-125). */
+int b200_yolo_loss_combine(const float* parts, float* out_loss, void* stream);
 
 #ifdef __cplusplus
 }

@@ -57,6 +57,25 @@ SIGNATURES = {
     "b200_row_positions": (c_i, [c_p, ctypes.c_longlong, c_p, c_p, c_p, c_sz, c_p]),
     "b200_gather_rows": (c_i, [c_p, c_i, c_p, c_p, ctypes.c_longlong, c_p, c_p]),
     "b200_yolo_ground_truth_rows": (c_i, [c_p, ctypes.c_longlong, c_i, c_p, c_p, c_p]),
+    "b200_peer_mailbox_bytes": (c_sz, []),
+    "b200_peer_mailbox_create": (c_i, [c_p, c_p]),
+    "b200_peer_mailbox_open": (c_i, [c_p, c_p]),
+    "b200_peer_mailbox_close": (c_i, [c_p]),
+    "b200_peer_mailbox_destroy": (c_i, [c_p]),
+    "b200_peer_mailbox_status": (c_i, [c_p, c_p, c_p]),
+    "b200_allreduce_loss_peer": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p]),
+    "b200_allreduce_sums_peer": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p]),
+    "b200_peer_exchange_selftest": (c_i, [c_i, c_i, c_i, c_p, c_sz, c_p, c_p]),
+    "b200_yolo_loss_dp": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_f, c_i, c_i, c_f, c_p, c_p, c_p, c_sz, c_i, c_i, c_p, c_p]),
+    "b200_yolo_loss_from_boxes_dp": (c_i, [c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_f, c_i, c_i, c_f, c_p, c_p,
+                                           c_p, c_sz, c_i, c_i, c_p, c_p]),
+    "b200_focal_box_finalize_dp": (c_i, [c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p]),
+    "b200_nccl_unique_id": (c_i, [c_p]),
+    "b200_nccl_comm_init": (c_i, [c_p, c_i, c_i, c_p]),
+    "b200_nccl_comm_destroy": (c_i, [c_p]),
+    "b200_allreduce_loss": (c_i, [c_p, c_p, c_i, c_p]),
+    "b200_allreduce_sums": (c_i, [c_p, c_p, c_i, c_p]),
+    "b200_yolo_loss_combine": (c_i, [c_p, c_p, c_p]),
     "b200_map_per_image": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, ctypes.c_double, c_p, c_p]),
 }
 

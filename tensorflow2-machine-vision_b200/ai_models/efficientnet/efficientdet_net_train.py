@@ -11,18 +11,25 @@ from ..losses.focal_loss import _partial_sums
 
 
 def get_loss(y_true_boxes, y_true_classes, y_true_masks, y_pred_boxes, y_pred_classes, alpha=0.25, gamma=1.5,
-             delta=0.1, global_batch_scale=1, group=None, return_parts=False, with_grad=False):
+             delta=0.1, global_batch_scale=1, group=None, return_parts=False, with_grad=False, exchange=None):
   '''sum over levels of (50 * box_loss + focal_loss) with num_positives = sum(masks) + 1.
 
-  Data parallel: every rank passes its shard; the 2L+1 fp64 partial sums are all-reduced once (NCCL) before the
-  normalisation.  `global_batch_scale` = world size when the per-level element count of the Keras mean must refer
+  Data parallel: every rank passes its shard; the 2L+1 fp64 partial sums are all-reduced once before the
+  normalisation — inside the finalize kernel over NVLink peer mailboxes (exchange=runtime.PeerExchange), by the
+  library's ncclAllReduce (runtime.NcclExchange), or by torch.distributed on `group` (exchange=None).  `global_batch_scale` = world size when the per-level element count of the Keras mean must refer
   to the global batch.
   '''
   lib = _lib.load()
   sums, numel = _partial_sums(list(y_true_boxes), list(y_true_classes), list(y_true_masks), list(y_pred_boxes),
                               list(y_pred_classes), alpha, gamma, delta, 0.0)
   import torch.distributed as dist
-  if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+  peer = exchange is not None and hasattr(exchange, 'mailboxes')
+  if exchange is not None:
+    # runtime.NcclExchange: ncclAllReduce issued by the library; runtime.PeerExchange: summed inside the finalize kernel
+    if not peer:
+      exchange.allreduce_(sums)
+    global_batch_scale = exchange.world
+  elif dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
     dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
     global_batch_scale = dist.get_world_size(group)
   L = len(numel)
@@ -30,8 +37,13 @@ def get_loss(y_true_boxes, y_true_classes, y_true_masks, y_pred_boxes, y_pred_cl
   parts = torch.empty((L, 2), dtype=torch.float32, device=sums.device)
   loss = torch.empty((), dtype=torch.float32, device=sums.device)
   npos = torch.empty((), dtype=torch.float32, device=sums.device)
-  _lib.check(lib.b200_focal_box_finalize(L, T.ptr(sums), nm, T.ptr(parts), T.ptr(loss), T.ptr(npos), T.stream_ptr()),
-             '_get_loss')
+  if peer:
+    rank, world, boxes_ = exchange.args()
+    _lib.check(lib.b200_focal_box_finalize_dp(L, T.ptr(sums), nm, T.ptr(parts), T.ptr(loss), T.ptr(npos), rank, world, boxes_,
+                                              T.stream_ptr()), '_get_loss (data parallel)')
+  else:
+    _lib.check(lib.b200_focal_box_finalize(L, T.ptr(sums), nm, T.ptr(parts), T.ptr(loss), T.ptr(npos), T.stream_ptr()),
+               '_get_loss')
   if with_grad:
     tb = [T.to_cuda(t) for t in y_true_boxes]
     # class targets: one-hot float tensors, or integer class ids (generate_targets_batch(class_index=True)) — the same

@@ -157,7 +157,10 @@ def GetNMSBoxes(y1, y2, y3, anchors_wh, image_wh, classes_num,
 
 
 def _loss_call(y_true, y_pred, image_wh, anchors_wh, iou_thresh, iou_type, variant, batch_divisor=None,
-               return_parts=False, workspace=None, ignore_out=None, with_grad=False):
+               return_parts=False, workspace=None, ignore_out=None, with_grad=False, exchange=None):
+  """exchange: a runtime.PeerExchange (the 12 terms are summed over the ranks inside the finalize kernel, NVLink peer
+  stores) or a runtime.NcclExchange (b200_allreduce_loss + b200_yolo_loss_combine behind the loss); batch_divisor must
+  then be the GLOBAL batch.  Forward only."""
   lib = _lib.load()
   if len(y_true) != 3 or len(y_pred) != 3:
     raise ValueError('y_true and y_pred must each hold 3 levels')
@@ -196,11 +199,21 @@ def _loss_call(y_true, y_pred, image_wh, anchors_wh, iou_thresh, iou_type, varia
                                        _lib.METRIC_YOLO[iou_type], variant, div, T.ptr(parts), T.ptr(loss), gp,
                                        T.ptr(workspace), ws_bytes, T.stream_ptr()), 'GetLoss')
     return loss, parts, grads
+  if exchange is not None and hasattr(exchange, 'mailboxes'):
+    rank, world, boxes_ = exchange.args()
+    _lib.check(lib.b200_yolo_loss_dp(tp, pp, hw, B, A, RF - 5, anc.ctypes.data_as(ctypes.c_void_p),
+                                     img.ctypes.data_as(ctypes.c_void_p), float(iou_thresh), _lib.METRIC_YOLO[iou_type],
+                                     variant, div, T.ptr(parts), T.ptr(loss), T.ptr(workspace), ws_bytes, rank, world, boxes_,
+                                     T.stream_ptr()), 'GetLoss (data parallel)')
+    return (loss, parts) if return_parts else loss
   _lib.check(lib.b200_yolo_loss(tp, pp, hw, B, A, RF - 5, anc.ctypes.data_as(ctypes.c_void_p),
                                 img.ctypes.data_as(ctypes.c_void_p), float(iou_thresh), _lib.METRIC_YOLO[iou_type],
                                 variant, div, T.ptr(parts), T.ptr(loss), T.ptr(ignore_out), T.ptr(workspace), ws_bytes,
                                 T.stream_ptr()),
              'GetLoss')
+  if exchange is not None:  # NCCL transport: all-reduce the 12 terms in place, then the reference's order of additions
+    exchange.allreduce_(parts)
+    _lib.check(lib.b200_yolo_loss_combine(T.ptr(parts), T.ptr(loss), T.stream_ptr()), 'GetLoss (data parallel)')
   return (loss, parts) if return_parts else loss
 
 
@@ -299,14 +312,20 @@ def shard_range(batch, rank, world):
 
 
 def GetLossSharded(y_true, y_pred, image_wh, anchors_wh, iou_thresh=0.5, iou_type='iou', global_batch=None,
-                   group=None):
+                   group=None, exchange=None):
   '''Data-parallel GetLoss: every rank passes its own images; the 12 per-level terms (already divided by the
-  global batch) are summed with ONE NCCL all-reduce and re-added in the reference's order (tyu:120-125).'''
+  global batch) are summed over the ranks and re-added in the reference's order (tyu:120-125).
+  exchange = runtime.PeerExchange: the sum happens inside the loss's finalize kernel over NVLink peer stores (no
+  collective launch; CUDA-graph capturable); runtime.NcclExchange: b200_allreduce_loss (ncclAllReduce issued by the
+  library on the current stream); None: torch.distributed.all_reduce on `group` (any backend, e.g. gloo in CPU tests).'''
   import torch.distributed as dist
   assert iou_type in ['iou','diou','ciou']
-  world = dist.get_world_size(group) if dist.is_initialized() else 1
+  world = exchange.world if exchange is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
   if global_batch is None:
     global_batch = T.to_cuda(y_true[0]).shape[0] * world
+  if exchange is not None:
+    return _loss_call(y_true, y_pred, image_wh, anchors_wh, iou_thresh, iou_type, 0, batch_divisor=global_batch,
+                      exchange=exchange)
   loss, parts = _loss_call(y_true, y_pred, image_wh, anchors_wh, iou_thresh, iou_type, 0,
                            batch_divisor=global_batch, return_parts=True)
   if world > 1:

@@ -14,6 +14,7 @@
 //        loss = sum_l (50 box_l + focal_l) in fp32 in the reference's order.
 #include "common.cuh"
 #include "detmath.h"
+#include "exchange.cuh"
 
 #define EL_MAX_LEVELS 8
 #define EL_THREADS 256
@@ -184,11 +185,23 @@ __global__ void __launch_bounds__(256) focal_box_reduce_kernel(ElReduce r) {
   }
 }
 
-struct ElFinalize { const double* sums; int num_levels; double numel[EL_MAX_LEVELS]; float* parts; float* loss; float* num_pos; };
+struct ElFinalize {
+  double* sums; int num_levels; double numel[EL_MAX_LEVELS]; float* parts; float* loss; float* num_pos;
+  B200Exchange xchg;  // data parallel: the 2L+1 sums are added over the ranks here first (world 1: no-op)
+};
 
-__global__ void focal_box_finalize_kernel(ElFinalize f) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(32) focal_box_finalize_kernel(ElFinalize f) {
   const int L = f.num_levels;
+  if (f.xchg.world > 1) {
+    // num_positives is a batch-wide count (edt:43-46): the un-normalised sums of every rank are added (fp64, rank order)
+    // before anything is divided; the global sums are written back for the backward pass
+    const int lane = threadIdx.x, n = 2 * L + 1;
+    double v = lane < n ? f.sums[lane] : 0.0;
+    v = xchg_allreduce_warp<double>(f.xchg, v, n);
+    if (lane < n) f.sums[lane] = v;
+    __syncwarp();
+  }
+  if (threadIdx.x != 0) return;
   const float npos = DM_ADD((float)f.sums[2 * L], 1.0f);         // edt:43-46
   if (f.num_pos) *f.num_pos = npos;
   float loss = 0.0f;
@@ -445,16 +458,37 @@ extern "C" int b200_focal_box_partial_sums_indexed(int num_levels, const unsigne
 }
 
 // numel_per_level[l] = GLOBAL element count B_global*H*W*A*C of level l (the Keras mean divisor)
-extern "C" int b200_focal_box_finalize(int num_levels, const double* sums, const double* numel_per_level_host,
-                                       float* out_parts, float* out_loss, float* out_num_positives, void* stream) {
+int b200_fill_exchange(B200Exchange& x, int rank, int world, void* const mailboxes[], const char* who);
+
+static int el_finalize_impl(int num_levels, double* sums, const double* numel_per_level_host, float* out_parts, float* out_loss,
+                            float* out_num_positives, const B200Exchange& x, void* stream) {
   B200_REQUIRE(num_levels >= 1 && num_levels <= EL_MAX_LEVELS && sums && numel_per_level_host && out_loss, B200_ERR_BAD_ARG,
                "b200_focal_box_finalize: bad argument");
   ElFinalize f;
   f.sums = sums; f.num_levels = num_levels; f.parts = out_parts; f.loss = out_loss; f.num_pos = out_num_positives;
+  f.xchg = x;
   for (int l = 0; l < EL_MAX_LEVELS; ++l) f.numel[l] = l < num_levels ? numel_per_level_host[l] : 1.0;
   focal_box_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f);
   B200_LAUNCH_CHECK();
   return B200_OK;
+}
+
+extern "C" int b200_focal_box_finalize(int num_levels, const double* sums, const double* numel_per_level_host,
+                                       float* out_parts, float* out_loss, float* out_num_positives, void* stream) {
+  B200Exchange x;
+  b200_fill_exchange(x, 0, 1, nullptr, "b200_focal_box_finalize");
+  return el_finalize_impl(num_levels, const_cast<double*>(sums), numel_per_level_host, out_parts, out_loss, out_num_positives, x, stream);
+}
+
+// Data-parallel finalize: `sums` holds THIS rank's partial sums on entry and the global sums on return (all-reduced
+// inside the kernel through the peer mailboxes); numel_per_level_host = GLOBAL element counts.
+extern "C" int b200_focal_box_finalize_dp(int num_levels, double* sums, const double* numel_per_level_host, float* out_parts,
+                                          float* out_loss, float* out_num_positives, int rank, int world,
+                                          void* const mailboxes[], void* stream) {
+  B200Exchange x;
+  const int rc = b200_fill_exchange(x, rank, world, mailboxes, "b200_focal_box_finalize_dp");
+  if (rc != B200_OK) return rc;
+  return el_finalize_impl(num_levels, sums, numel_per_level_host, out_parts, out_loss, out_num_positives, x, stream);
 }
 
 // d loss / d pred_classes[l] and d loss / d pred_boxes[l] (either array entry may be NULL).  `sums` is the device

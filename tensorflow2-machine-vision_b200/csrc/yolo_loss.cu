@@ -21,6 +21,7 @@
 // ignore = float(best < thr) with best = max_g metric(pred, gt_g) is evaluated as "no g with metric >= thr or
 // metric NaN": tf.reduce_max propagates NaN and NaN < thr is False, so a NaN pair clears the ignore bit.
 #include "yolo_targets.cuh"
+#include "exchange.cuh"
 
 #define YL_LEVELS 3
 #define YL_CHUNK 256
@@ -549,6 +550,7 @@ struct YlFinalize {
   float batch_divisor; float* parts; float* loss;
   double* slices;          // [YL_FIN_CTAS][12]
   unsigned int* ticket;    // zero on entry; reset by the last CTA
+  B200Exchange xchg;       // data parallel: the 12 terms are summed over the ranks inside this kernel (world 1: no-op)
 };
 
 __global__ void __launch_bounds__(YL_FIN_THREADS) yolo_loss_finalize_kernel(YlFinalize f) {
@@ -592,8 +594,11 @@ __global__ void __launch_bounds__(YL_FIN_THREADS) yolo_loss_finalize_kernel(YlFi
       double s = 0.0;
       for (int g = 0; g < YL_FIN_CTAS; ++g) s += __ldcg(f.slices + g * 12 + lane);
       v = DM_DIV((float)s, f.batch_divisor);  // reduce_sum(...) / batch_size_float, tyu:120-123
-      if (f.parts) f.parts[lane] = v;
     }
+    // data parallel: batch_divisor is the GLOBAL batch, so the per-rank terms simply add up; the sum runs over
+    // NVLink peer stores inside this warp, in rank order on every rank (exchange.cuh)
+    v = xchg_allreduce_warp<float>(f.xchg, v, 12);
+    if (lane < 12 && f.parts) f.parts[lane] = v;
     float total = 0.0f;
     for (int l = 0; l < 3; ++l) {
       const float t0_ = __shfl_sync(0xffffffffu, v, l * 4 + 0), t1 = __shfl_sync(0xffffffffu, v, l * 4 + 1);
@@ -839,7 +844,8 @@ static int yolo_loss_impl(const float* const y_true[3], const float* const y_pre
                           int A, int C, const float* anchors_wh_host, const float* image_wh_host,
                           float iou_thresh, int metric, int variant, float batch_divisor, float* out_parts,
                           float* out_loss, unsigned char* out_ignore, float* const out_grad[3], void* workspace,
-                          size_t workspace_bytes, void* stream_, const YlSparseIn* sparse = nullptr, int stages = 0xf) {
+                          size_t workspace_bytes, void* stream_, const YlSparseIn* sparse = nullptr, int stages = 0xf,
+                          const B200Exchange* xchg = nullptr) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_REQUIRE((y_true || sparse) && y_pred && hw && anchors_wh_host && image_wh_host && out_loss, B200_ERR_BAD_ARG, "b200_yolo_loss: null argument");
   B200_REQUIRE(B >= 1 && A >= 1 && A <= 8 && C >= 0, B200_ERR_BAD_ARG, "b200_yolo_loss: unsupported shape B=%d A=%d C=%d", B, A, C);
@@ -936,6 +942,8 @@ static int yolo_loss_impl(const float* const y_true[3], const float* const y_pre
   f.batch_divisor = batch_divisor; f.parts = out_parts; f.loss = out_loss;
   f.slices = reinterpret_cast<double*>(wsb + ws.fin);
   f.ticket = reinterpret_cast<unsigned int*>(wsb + ws.cnt) + (size_t)B * YL_LEVELS;
+  if (xchg) f.xchg = *xchg;
+  else { f.xchg.rank = 0; f.xchg.world = 1; for (int r = 0; r < B200_XCHG_MAX_WORLD; ++r) f.xchg.mailbox[r] = nullptr; }
   yolo_loss_finalize_kernel<<<YL_FIN_CTAS, YL_FIN_THREADS, 0, stream>>>(f);
   B200_LAUNCH_CHECK();
   if (out_grad) {
@@ -1010,4 +1018,56 @@ extern "C" int b200_yolo_loss_grad(const float* const y_true[3], const float* co
   B200_REQUIRE(out_grad, B200_ERR_BAD_ARG, "b200_yolo_loss_grad: null out_grad");
   return yolo_loss_impl(y_true, y_pred, hw, B, A, C, anchors_wh_host, image_wh_host, iou_thresh, metric, variant,
                         batch_divisor, out_parts, out_loss, nullptr, out_grad, workspace, workspace_bytes, stream_);
+}
+
+// Data-parallel forms: every rank passes its own images and batch_divisor = the GLOBAL batch; the 12
+// per-level terms are summed over the ranks inside the finalize kernel through the peer mailboxes
+// (b200_peer_mailbox_*), so out_parts / out_loss are the global values on every rank and the step has no separate
+// collective launch.  y_true == NULL selects the sparse-target form (boxes / classes / offsets as in
+// b200_yolo_loss_from_boxes); world == 1 degenerates to the plain calls.
+int b200_fill_exchange(B200Exchange& x, int rank, int world, void* const mailboxes[], const char* who);
+
+extern "C" int b200_yolo_loss_dp(const float* const y_true[3], const float* const y_pred[3], const int32_t hw[6], int B,
+                                 int A, int C, const float* anchors_wh_host, const float* image_wh_host,
+                                 float iou_thresh, int metric, int variant, float global_batch, float* out_parts,
+                                 float* out_loss, void* workspace, size_t workspace_bytes, int rank, int world,
+                                 void* const mailboxes[], void* stream_) {
+  B200Exchange x;
+  const int rc = b200_fill_exchange(x, rank, world, mailboxes, "b200_yolo_loss_dp");
+  if (rc != B200_OK) return rc;
+  return yolo_loss_impl(y_true, y_pred, hw, B, A, C, anchors_wh_host, image_wh_host, iou_thresh, metric, variant,
+                        global_batch, out_parts, out_loss, nullptr, nullptr, workspace, workspace_bytes, stream_, nullptr, 0xf, &x);
+}
+
+extern "C" int b200_yolo_loss_from_boxes_dp(const float* boxes, const int32_t* classes, const int32_t* offsets, int total_boxes,
+                                            const float* assign_anchors_wh_host, const float* const y_pred[3], const int32_t hw[6],
+                                            int B, int A, int C, const float* anchors_wh_host, const float* image_wh_host,
+                                            float iou_thresh, int metric, int variant, float global_batch, float* out_parts,
+                                            float* out_loss, void* workspace, size_t workspace_bytes, int rank, int world,
+                                            void* const mailboxes[], void* stream_) {
+  B200Exchange x;
+  const int rc = b200_fill_exchange(x, rank, world, mailboxes, "b200_yolo_loss_from_boxes_dp");
+  if (rc != B200_OK) return rc;
+  YlSparseIn sp;
+  sp.boxes = boxes; sp.classes = classes; sp.offsets = offsets; sp.total_boxes = total_boxes;
+  sp.assign_anchors_wh_host = assign_anchors_wh_host;
+  return yolo_loss_impl(nullptr, y_pred, hw, B, A, C, anchors_wh_host, image_wh_host, iou_thresh, metric, variant,
+                        global_batch, out_parts, out_loss, nullptr, nullptr, workspace, workspace_bytes, stream_, &sp, 0xf, &x);
+}
+
+// loss = sum_l ((xy_l + wh_l) + obj_l) + cls_l from the 12 (all-reduced) terms, in the reference's order of additions
+// (tyu:120-125) — the step after b200_allreduce_loss when the NCCL transport is used.
+__global__ void yolo_loss_combine_kernel(const float* __restrict__ parts, float* __restrict__ loss) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float total = 0.0f;
+  for (int l = 0; l < 3; ++l)
+    total = DM_ADD(total, DM_ADD(DM_ADD(DM_ADD(parts[l * 4 + 0], parts[l * 4 + 1]), parts[l * 4 + 2]), parts[l * 4 + 3]));
+  *loss = total;
+}
+
+extern "C" int b200_yolo_loss_combine(const float* parts, float* out_loss, void* stream) {
+  B200_REQUIRE(parts && out_loss, B200_ERR_BAD_ARG, "b200_yolo_loss_combine: null argument");
+  yolo_loss_combine_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(parts, out_loss);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
 }

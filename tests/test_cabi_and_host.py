@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(lib):
         assert hasattr(lib, n), "libb200det.so does not export %s" % n
         assert n in _lib.SIGNATURES, "ctypes binding missing for %s" % n
     assert sorted(_lib.SIGNATURES) == names  # and nothing is bound that the header does not declare
-    assert lib.b200_version() == 100
+    assert lib.b200_version() == 200
 
 
 def test_no_cpu_fallback_without_device(lib):

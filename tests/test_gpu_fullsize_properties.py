@@ -143,3 +143,32 @@ def test_config4_effdet_d7_postprocess_topk_regime(lib, cuda):
         mx, am = flat[sel].max(-1)
         assert torch.equal(am, r["classes_id"][k])
         assert torch.allclose(torch.sigmoid(mx), s[k], rtol=1e-5)
+
+
+def test_config4_effdet_d7_image_matches_oracle(lib, cuda):
+    """One full D7 image (441 936 anchors, ~436 k candidates: the multi-CTA pivot / pre-gather window path) through the
+    oracle's convert_outputs_one (efficientnet/utils/anchors.py:161-202, nms.py:5-61) — ids bit-exact, boxes and
+    scores equal.  The oracle needs a few seconds for its 200 NMS iterations over 436 k boxes."""
+    import torch
+    from oracle import effdet as oe
+    from tfmv_b200 import synth
+    from tfmv_b200.ai_models.efficientnet.utils.anchors import Anchors
+    c = synth.EFFDET_CONFIGS["d7"]
+    args = (c["min_level"], c["max_level"], c["image_size"], c["num_scales"], c["aspect_ratios"], c["anchor_scale"])
+    a, o = Anchors(*args), oe.Anchors(*args)
+    rng = np.random.default_rng(20261018 + 4)
+    rel, cls = synth.effdet_heads(rng, 1, c["image_size"])
+    d = lambda xs: [torch.from_numpy(x).to(cuda) for x in xs]
+    dec = a.convert_outputs_boxes(d(rel))
+    want_dec = o.convert_outputs_boxes(rel)
+    for l in range(len(rel)):
+        assert np.array_equal(dec[l].cpu().numpy(), want_dec[l])
+    r = a.convert_outputs_batch(dec, d(cls), with_indices=True)
+    want = o.convert_outputs_one_ex(0, want_dec, cls)
+    k = int(r["count"][0])
+    assert k == len(want["selected"]) == 200
+    assert r["sel_idx"][0, :k].cpu().tolist() == want["selected"].tolist()          # NMS indices: bit-exact
+    assert r["sel_anchor"][0, :k].cpu().tolist() == want["cand_anchor"][want["selected"]].tolist()
+    assert r["classes_id"][0, :k].cpu().tolist() == want["classes_id"].tolist()
+    assert np.array_equal(r["boxes"][0, :k].cpu().numpy(), want["boxes"])
+    assert np.array_equal(r["scores"][0, :k].cpu().numpy(), want["scores"])
