@@ -1,16 +1,22 @@
 #!/usr/bin/env python
-"""bench.py — throughput of the detection hot path on B200 (contract: see DESIGN.md §Measurement).
+"""bench.py — throughput of the detection hot path on B200 (contract: DESIGN.md §5).
 
-Default workload = BASELINE.json configs[1]: YOLOv4 608x608, batch 64 per GPU, best-anchor target assignment
+Headline workload = BASELINE.json configs[1]: YOLOv4 608x608, batch 64 per GPU, best-anchor target assignment
 (GetTargets) + yolo_loss with the CIoU ignore mask (GetLoss), synthetic heads ~ N(0,1) and synthetic ground truth
-(1..100 boxes/image).  One "step" = one pass of that path over one batch.
+(1..100 boxes/image).  One "step" = one pass of that path over one batch.  The same run also measures the other four
+BASELINE configs (key `configs`): c1 YOLOv3 416 decode + per-class NMS (latency at batch 1, throughput at batch 256),
+c3 EfficientDet-D0 batch 128 loss + decode + NMS, c4 EfficientDet-D7 batch 16 decode + NMS, and c5 YOLOv4 608 global
+batch 512 loss + decode + NMS sharded by image over the N GPUs with the loss all-reduce (c5 runs at every N; c1/c3/c4
+at N = 1), each with its roofline fractions and a parity check against the committed golden fixtures.
 
   python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run)
   python bench.py --impl reference ...                      CPU restatement of the reference on the host cores
+  python bench.py --only c3 --only-step --no-graph ...      one config, launch by launch (the ncu launch-list runs)
 
 Prints ONE JSON line on rank 0.
 """
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -25,12 +31,22 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 F = np.float32
-WORKLOADS = {
-    # name: (image, per-GPU batch, description, algorithmic bytes / image per SURVEY.md §8d)
-    "yolov4_608_b64_targets_loss": dict(image=608, batch=64, bytes_per_img=23197860,
-                                        what="YOLOv4 608x608 batch 64: GetTargets + GetLoss(ciou ignore mask)"),
+SEED = 20261018
+# algorithmic (dense) bytes per image, SURVEY.md §8(d)
+BYTES = {
+    "c1": 3619980 + 174000,      # heads read once + outputs (<= 500 x 87 floats)
+    "c2": 23197860,              # write y_true + read y_true + read y_pred
+    "c3": 49104 * (81 * 4 * 2 + 16 * 2 + 1 + 16),   # cls logits + one-hot + box out + box tgt + mask + decoded write
+    "c4": 441936 * (81 * 4 + 16 + 16),              # cls logits + box out + decoded write
+    "c5": 15639240,              # y_pred + y_true (+ outputs)
 }
-SEED = 20261018 + 2
+WHAT = {
+    "c1": "YOLOv3 416x416, 80 classes: yolo_head decode + per-class NMS ('iou', 0.5/0.3/0.5, cap 500), N(0,1) heads",
+    "c2": "YOLOv4 608x608 batch 64: GetTargets + GetLoss(ciou ignore mask)",
+    "c3": "EfficientDet-D0 512x512 batch 128: focal + box loss, anchor decode, NMS ('diou', cap 200) over 49 104 anchors/image",
+    "c4": "EfficientDet-D7 1536x1536 batch 16: anchor decode + NMS ('diou', cap 200) over 441 936 anchors/image",
+    "c5": "YOLOv4 608x608 global batch 512 sharded by image: GetLoss(ciou) + decode + per-class NMS(diou) + loss all-reduce",
+}
 
 
 def parse():
@@ -39,14 +55,16 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="yolov4_608_b64_targets_loss", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (0 = workload default)")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="images in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch of the headline workload (0 = 64)")
+    ap.add_argument("--repeats", type=int, default=25, help="timed windows of --steps steps for the headline (median reported)")
+    ap.add_argument("--config-repeats", type=int, default=9, help="timed windows per entry of `configs`")
+    ap.add_argument("--only", default="", help="comma list out of c1,c2,c3,c4,c5: measure only these")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="images per CPU-baseline run (0 = 16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--l2-fetch", type=int, default=0, help="set cudaLimitMaxL2FetchGranularity (32/64/128), 0 = leave")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl", "torch"], help="transport of the loss all-reduce (N > 1)")
     ap.add_argument("--verbose", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="issue the step launch by launch instead of replaying a CUDA graph")
-    ap.add_argument("--only-step", action="store_true", help="skip phase timing / e2e / cpu baseline (profiling runs)")
+    ap.add_argument("--no-graph", action="store_true", help="issue every step launch by launch instead of replaying CUDA graphs")
+    ap.add_argument("--only-step", action="store_true", help="skip phase timing / e2e / cpu baseline / parity (profiling runs)")
     return ap.parse_args()
 
 
@@ -71,6 +89,7 @@ class ClockSampler(object):
         except OSError:
             self.proc = None
             return
+
         def pump():
             for line in self.proc.stdout:
                 self.rows.append(line.strip())
@@ -99,33 +118,40 @@ class ClockSampler(object):
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        # the busiest samples are the ones under load
         sm_sorted = sorted(sm)
-        top = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        top = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []   # the busiest samples are the ones under load
         return {"sm_mhz": statistics.median(top) if top else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_inputs(wl, batch, rank):
-    from tfmv_b200 import synth
-    rng = np.random.default_rng(SEED + 1000 * rank)
-    image = wl["image"]
-    heads = synth.yolo_heads(rng, batch, image)
-    boxes, classes, off = synth.gt_batch(rng, batch, (image, image), max_boxes=100)
-    return heads, boxes, classes, off
+def spread(xs):
+    xs = sorted(xs)
+    n = len(xs)
+    return {"n": n, "median": statistics.median(xs), "min": xs[0], "max": xs[-1], "p10": xs[int(0.1 * (n - 1))], "p90": xs[int(round(0.9 * (n - 1)))]}
 
 
 # ------------------------------------------------------------------------------------------------
+# CPU legs (the NumPy restatement of the reference; TensorFlow is not installable in this image)
+_CPU_CACHE = {}
+
+
+def cpu_inputs(image, seed, n_images):
+    key = (image, seed, n_images)
+    if key not in _CPU_CACHE:
+        from tfmv_b200 import synth
+        rng = np.random.default_rng(seed)
+        _CPU_CACHE.clear()
+        _CPU_CACHE[key] = (synth.yolo_anchors().astype(F), synth.yolo_heads(rng, n_images, image),
+                           synth.gt_batch(rng, n_images, (image, image), max_boxes=100))
+    return _CPU_CACHE[key]
+
+
 def cpu_step_images(args_tuple):
-    """Oracle (NumPy restatement of the reference) on a few images: GetTargets + GetLoss.  Used by both the
-    cpu_baseline leg and --impl reference; runs in worker processes."""
+    """Oracle on a few images: GetTargets + GetLoss.  Inputs are generated once per (worker, seed) and cached, so a timed
+    call is compute only.  Returns (seconds of compute, loss)."""
     image, seed, n_images = args_tuple
     from oracle import yolo as oy
-    from tfmv_b200 import synth
-    rng = np.random.default_rng(seed)
-    anc = synth.yolo_anchors().astype(F)
-    heads = synth.yolo_heads(rng, n_images, image)
-    boxes, classes, off = synth.gt_batch(rng, n_images, (image, image), max_boxes=100)
+    anc, heads, (boxes, classes, off) = cpu_inputs(image, seed, n_images)
     t0 = time.perf_counter()
     per = [oy.get_targets(boxes[off[b]:off[b + 1]], classes[off[b]:off[b + 1]], anc, (image, image), 80) for b in range(n_images)]
     y_true = [np.stack([p[l] for p in per], 0) for l in range(3)]
@@ -133,68 +159,194 @@ def cpu_step_images(args_tuple):
     return time.perf_counter() - t0, float(loss)
 
 
-def run_reference(args, wl):
-    """Reference arm: the oracle port on every host core (one image per worker per step)."""
+def run_reference(args):
+    """Reference arm: the oracle port on every host core.  Each worker holds its own fixed images (generated before the
+    timed region); a step = every worker computing GetTargets + GetLoss on its images once; the step time is the slowest
+    worker's COMPUTE time (input generation and result pickling are outside it)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     per_worker = 4
+    image = 608
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
-        jobs = lambda s: [(wl["image"], SEED + 7919 * s + w, per_worker) for w in range(cores)]
-        warm = max(1, min(args.warmup, 2))
-        for w in range(warm):
-            pool.map(cpu_step_images, jobs(10_000 + w))
+        jobs = [(image, SEED + 2 + 7919 * w, per_worker) for w in range(cores)]
+        warm = max(1, min(args.warmup, 3))
+        for _ in range(warm):
+            pool.map(cpu_step_images, jobs, chunksize=1)     # first call also generates and caches the worker's inputs
         steps = max(1, min(args.steps, 30))
+        per_step = []
         t0 = time.perf_counter()
-        for s in range(steps):
-            pool.map(cpu_step_images, jobs(s))
-        dt = time.perf_counter() - t0
-    imgs = steps * cores * per_worker
-    value = imgs / dt
+        for _ in range(steps):
+            res = pool.map(cpu_step_images, jobs, chunksize=1)
+            per_step.append(max(r[0] for r in res))
+        wall = time.perf_counter() - t0
+    imgs_per_step = cores * per_worker
+    dt = sum(per_step)
+    value = steps * imgs_per_step / dt
     line = {
         "impl": "reference", "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["what"], "image": wl["image"], "per_gpu_batch": args.batch or wl["batch"],
-                   "note": "NumPy restatement of the reference (TensorFlow not installable); each step = %d images, one per host core" % (cores * per_worker)},
+        "config": {"workload": WHAT["c2"], "image": image, "per_gpu_batch": args.batch or 64,
+                   "note": "NumPy restatement of the reference (TensorFlow not installable); each step = %d images, %d per host core; "
+                           "timed: the slowest worker's compute per step (wall clock incl. pool overhead: %.1f ms/step)" % (
+                               imgs_per_step, per_worker, 1e3 * wall / steps)},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": "%d steps x %d images (GetTargets+GetLoss ciou, 608x608), process pool over all host cores" % (steps, cores * per_worker)},
+                         "sample": "%d steps x %d images (GetTargets+GetLoss ciou, 608x608), process pool over all host cores, compute only" % (steps, imgs_per_step)},
+        "step_spread_ms": spread([1e3 * x for x in per_step]),
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
-def run_b200(args, wl):
-    import ctypes
-    import torch
-    import torch.distributed as dist
-    import tfmv_b200  # noqa: F401
-    from tfmv_b200 import _lib, _tensors as T, synth
+class Bench(object):
+    """Shared state of the GPU arm: device, distributed group, exchange transport, timing helpers."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        import tfmv_b200  # noqa: F401
+        from tfmv_b200 import _lib, runtime
+        self.args = args
+        self.torch, self.dist, self.runtime = torch, dist, runtime
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback in the product path")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.lib = _lib.load()
+        self.exchange, self.exchange_kind = None, "none (single GPU)"
+        if self.world > 1:
+            kind = args.exchange
+            if kind == "peer":
+                ok = 1
+                try:
+                    self.exchange = runtime.PeerExchange()
+                except Exception as e:  # noqa: BLE001  (e.g. CUDA IPC not permitted in this container)
+                    self.log("peer mailboxes unavailable: %r" % (e,))
+                    ok = 0
+                t = torch.tensor([ok], device=self.dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                if int(t.item()) == 0:
+                    self.exchange, kind = None, "nccl"
+                else:
+                    self.exchange_kind = "NVLink peer mailboxes, summed inside the loss-finalize kernel (no collective launch)"
+            if kind == "nccl":
+                self.exchange = runtime.NcclExchange()
+                self.exchange_kind = "b200_allreduce_loss: ncclAllReduce issued by the library on the step's stream"
+            if kind == "torch":
+                self.exchange_kind = "torch.distributed all_reduce behind the step (outside the CUDA graph)"
+        self.peaks = {}
+        try:
+            self.peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        self.peak = float(self.peaks.get("hbm_gbs", 6650.0))
+        self.peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in self.peaks else "6650 GB/s (of fallback)"
+        self.kernels = {}
+        try:
+            self.kernels = json.load(open(os.path.join(ROOT, "profiles", "r02_kernels.json")))
+        except Exception:
+            pass
+
+    def log(self, msg):
+        if self.args.verbose:
+            sys.stderr.write("[rank %d] %s\n" % (self.rank, msg))
+            sys.stderr.flush()
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def window(self, fn, steps):
+        """EXACTLY `steps` calls of fn bracketed by barrier + synchronize on both sides, CUDA events on the launching
+        stream, max over ranks.  Returns milliseconds for the window."""
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t.item())
+        self.barrier()
+        return ms
+
+    def timed(self, fn, steps, warmup, repeats=1):
+        """Warm-up, then `repeats` windows of `steps` steps.  Returns (median ms per step, per-window ms-per-step list)."""
+        for _ in range(max(warmup, 3)):
+            fn()
+        per = [self.window(fn, steps) / steps for _ in range(max(1, repeats))]
+        return statistics.median(per), per
+
+    def wrap(self, fn):
+        return fn if self.args.no_graph else self.runtime.capture(fn)
+
+    def table(self, cfg):
+        """ncu launch-list summary of a config (profiles/r02_kernels.json): per-kernel device time and DRAM bytes."""
+        return self.kernels.get(cfg) or {}
+
+    def roofline(self, cfg, batch, ms_step, dominant_live=None):
+        """Step-level fractions: dense-equivalent (SURVEY 8d bytes) and physical (ncu DRAM bytes of the step's kernels)."""
+        dense = BYTES[cfg] * batch
+        r = {"bound": "hbm", "peak": self.peak, "unit": "GB/s", "peak_source": self.peak_src,
+             "algorithmic_bytes_per_step": dense, "step_gbps_dense": dense / ms_step / 1e6,
+             "frac_dense": dense / ms_step / 1e6 / self.peak}
+        t = self.table(cfg)
+        if t.get("dram_bytes_per_step"):
+            scale = batch / float(t.get("batch", batch))
+            r["traffic_step"] = t["dram_bytes_per_step"] * scale
+            r["frac_dram"] = t["dram_bytes_per_step"] * scale / ms_step / 1e6 / self.peak
+            r["traffic_source"] = "profiles/r02_kernels.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, sum over the step's launches)"
+        if t.get("dominant"):
+            d = t["dominant"]
+            r["kernel"] = d["name"]
+            r["kernel_share_ncu"] = d.get("share")
+            r["traffic"] = d.get("dram_bytes")
+        if dominant_live:
+            r.update(dominant_live)
+        else:
+            r["achieved"] = r["step_gbps_dense"]
+            r["frac"] = r["frac_dense"]
+        return r
+
+
+def to_dev(b, a, dtype=None):
+    t = b.torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(b.dev)
+
+
+# ------------------------------------------------------------------------------------------------
+def headline_c2(b, line):
+    """BASELINE configs[1]: the headline.  Fills `line` (value, ms_per_step, roofline, e2e, cpu_baseline, ...)."""
+    args, torch, lib = b.args, b.torch, b.lib
+    from tfmv_b200 import _tensors as T, synth
     from tfmv_b200.ai_models.datasets.coco_dataset import DataGenerator
     from tfmv_b200.ai_models.utils import tf_yolo_utils as tyu
-
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback in the product path")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    lib = _lib.load()
-    if args.l2_fetch:
-        _lib.check(lib.b200_set_l2_fetch_granularity(args.l2_fetch), "set_l2_fetch_granularity")
-    batch = args.batch or wl["batch"]
-    image = wl["image"]
+    world, rank, dev = b.world, b.rank, b.dev
+    batch, image = args.batch or 64, 608
     anc = synth.yolo_anchors().astype(F)
-    heads_h, boxes_h, classes_h, off_h = make_inputs(wl, batch, rank)
-    # pinned host copies (e2e path) and resident device copies (device-timed path)
+    rng = np.random.default_rng(SEED + 2 + 1000 * rank)
+    heads_h = synth.yolo_heads(rng, batch, image)
+    boxes_h, classes_h, off_h = synth.gt_batch(rng, batch, (image, image), max_boxes=100)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     heads_p = [pin(h) for h in heads_h]
     boxes_p, classes_p, off_p = pin(boxes_h), pin(classes_h), pin(off_h)
@@ -206,113 +358,54 @@ def run_b200(args, wl):
     hw = (ctypes.c_int32 * 6)(*[d for l in gen.layers_hw for d in l])
     ws = torch.empty((lib.b200_yolo_loss_workspace_bytes(hw, batch, A),), dtype=torch.uint8, device=dev)
     global_batch = batch * world
-    parts_buf = {}
-
-    def log(msg):
-        if args.verbose:
-            sys.stderr.write("[rank %d] %s\n" % (rank, msg))
-            sys.stderr.flush()
-
-    def local_step(heads, boxes, classes, off):
-        """This rank's images: target assignment + loss partials (already divided by the global batch)."""
-        gen.GetTargetsBatch(classes, boxes, off, out=y_true)
-        loss, parts = tyu._loss_call(y_true, heads, (image, image), anc, 0.5, "ciou", 0, batch_divisor=global_batch,
-                                     return_parts=True, workspace=ws)
-        return loss, parts
-
-    def exchange(loss, parts):
-        if world > 1:
-            loss = tyu.combine_loss_parts(parts)  # the single collective of the path: 12 floats over NCCL
-        parts_buf["loss"] = loss
-        return loss
+    in_graph = b.exchange is not None      # peer mailboxes / library NCCL: the exchange is part of the captured step
 
     def step(heads, boxes, classes, off):
-        return exchange(*local_step(heads, boxes, classes, off))
+        """One step on this rank's images: target assignment + loss, the 12 terms summed over the ranks."""
+        gen.GetTargetsBatch(classes, boxes, off, out=y_true)
+        if in_graph or world == 1:
+            return tyu._loss_call(y_true, heads, (image, image), anc, 0.5, "ciou", 0, batch_divisor=global_batch,
+                                  workspace=ws, exchange=b.exchange)
+        loss, parts = tyu._loss_call(y_true, heads, (image, image), anc, 0.5, "ciou", 0, batch_divisor=global_batch,
+                                     return_parts=True, workspace=ws)
+        return tyu.combine_loss_parts(parts)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    pending_streams = []   # side streams whose work belongs to the timed region
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        for st_ in pending_streams:
-            torch.cuda.current_stream().wait_stream(st_)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        barrier()
-        return ms
-
-    # ---- device-resident timing (the `value`) ----
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(b.local_rank)
     if rank == 0:
         sampler.start()
-    from tfmv_b200 import runtime
-    log("inputs ready")
-    if args.no_graph:
-        dev_step = lambda: step(heads_d, boxes_d, classes_d, off_d)
-    else:
-        # the kernels of the step replay as one CUDA graph; the 12-float all-reduce is issued right behind it on the
-        # same stream (kept outside the capture so the graph does not depend on NCCL's capture support)
-        local_graph = runtime.capture(lambda: local_step(heads_d, boxes_d, classes_d, off_d))
-        if world == 1:
-            dev_step = lambda: exchange(*local_graph())
-        else:
-            # two graphs with their own output buffers: the all-reduce of step i runs on a communication stream
-            # while the kernels of step i+1 already execute (it only needs the 12 floats step i produced)
-            graphs = [local_graph, runtime.capture(lambda: local_step(heads_d, boxes_d, classes_d, off_d))]
-            comm = torch.cuda.Stream()
-            done = [None, None]
-            counter = [0]
-
-            def dev_step():
-                k = counter[0] & 1
-                counter[0] += 1
-                main = torch.cuda.current_stream()
-                if done[k] is not None:
-                    main.wait_event(done[k])      # step i-2's exchange has released this buffer pair (long ago)
-                loss, parts = graphs[k]()
-                ready = torch.cuda.Event()
-                ready.record(main)
-                with torch.cuda.stream(comm):
-                    comm.wait_event(ready)
-                    exchange(loss, parts)
-                    done[k] = torch.cuda.Event()
-                    done[k].record(comm)
-
-            pending_streams.append(comm)
-    log("graph captured")
+    raw = lambda: step(heads_d, boxes_d, classes_d, off_d)
     if world > 1:
-        step(heads_d, boxes_d, classes_d, off_d)  # NCCL communicator warm-up outside the timed region
-        barrier()
-        log("nccl warm")
-    ms_dev = timed(dev_step, args.steps, max(args.warmup, 3))
-    del pending_streams[:]
-    log("device timing done")
+        raw()   # communicator / mailbox warm-up outside the timed region, the same number of times on every rank
+        b.barrier()
+    dev_step = raw if (args.no_graph or (world > 1 and not in_graph)) else b.runtime.capture(raw)
+    ms_dev, windows = b.timed(dev_step, args.steps, args.warmup, args.repeats)
+    loss_val = float(dev_step().item())
     clocks = sampler.stop() if rank == 0 else None
-    loss_val = float(parts_buf["loss"].item())
-
-    if args.only_step:
-        if rank == 0:
-            print(json.dumps({"value": global_batch * args.steps / (ms_dev / 1e3), "ms_per_step": ms_dev / args.steps, "loss": loss_val}))
-        return
-    # ---- per-phase timing on the launching stream (roofline of the dominant kernel) ----
-    st = T.stream_ptr()
+    b.log("headline timed")
     n_fill = sum(int(t.numel()) for t in y_true)
+    line.update({
+        "metric": "images/sec", "value": global_batch / (ms_dev / 1e3), "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "timing": {"windows": len(windows), "steps_per_window": args.steps, "ms_per_step": spread(windows),
+                   "what": "each window = exactly --steps steps between barrier + synchronize, CUDA events, max over ranks; "
+                           "value / ms_per_step are the median window"},
+        "config": {"workload": WHAT["c2"], "image": image, "per_gpu_batch": batch, "global_batch": global_batch,
+                   "classes": 80, "anchors_per_cell": 3, "gt_boxes_per_image": "U{1..100}",
+                   "parallelism": "dp%d (images sharded; one 12-float all-reduce per step: %s)" % (world, b.exchange_kind),
+                   "launch": "launch by launch" if dev_step is raw else "CUDA graph replay of the whole step (exchange included)",
+                   "l2": "inputs larger than L2 (y_pred %.0f MB + y_true %.0f MB per step vs 126 MB L2)" % (n_fill * 4 / 1e6, n_fill * 4 / 1e6)},
+        "loss": loss_val, "clocks": clocks,
+        "gpu_launches": 6 * args.steps * len(windows),
+        "gpu_launches_note": "6 kernels per step (fill, scatter, scan, gtprep, ignore+terms, finalize incl. the exchange)",
+    })
+    if b.exchange is not None and hasattr(b.exchange, "status"):
+        ep, err = b.exchange.status()
+        line["config"]["exchange_status"] = {"exchanges": ep, "timeouts": err}
+    if args.only_step:
+        return
+    # ---- the dominant kernel, timed alone with CUDA events (roofline.achieved / frac) ----
+    st = T.stream_ptr()
     tp = (ctypes.c_void_p * 3)(*[t.data_ptr() for t in y_true])
     pp = (ctypes.c_void_p * 3)(*[t.data_ptr() for t in heads_d])
     anc_h = np.ascontiguousarray(anc.reshape(-1))
@@ -320,201 +413,319 @@ def run_b200(args, wl):
     parts_t = torch.empty((3, 4), dtype=torch.float32, device=dev)
     loss_t = torch.empty((), dtype=torch.float32, device=dev)
 
-    def ph_fill():  # the step's zero-fill: one fill_zero_multi_kernel launch (no boxes -> no scatter launch)
+    def ph_fill():
         lib.b200_yolo_assign_targets(boxes_d.data_ptr(), classes_d.data_ptr(), off_d.data_ptr(), batch, 0,
-                                     anc_h.ctypes.data_as(ctypes.c_void_p), A, img_h.ctypes.data_as(ctypes.c_void_p), 80,
-                                     hw, tp, 1, st)
+                                     anc_h.ctypes.data_as(ctypes.c_void_p), A, img_h.ctypes.data_as(ctypes.c_void_p), 80, hw, tp, 1, st)
 
     def ph_scatter():
         lib.b200_yolo_assign_targets(boxes_d.data_ptr(), classes_d.data_ptr(), off_d.data_ptr(), batch, boxes_d.shape[0],
-                                     anc_h.ctypes.data_as(ctypes.c_void_p), A, img_h.ctypes.data_as(ctypes.c_void_p), 80,
-                                     hw, tp, 0, st)
+                                     anc_h.ctypes.data_as(ctypes.c_void_p), A, img_h.ctypes.data_as(ctypes.c_void_p), 80, hw, tp, 0, st)
 
     def ph_loss_stage(mask):
         def run():
-            lib.b200_yolo_loss_stages(tp, pp, hw, batch, A, 80, anc_h.ctypes.data_as(ctypes.c_void_p),
-                                      img_h.ctypes.data_as(ctypes.c_void_p), 0.5, 2, 0, float(global_batch), parts_t.data_ptr(),
-                                      loss_t.data_ptr(), ws.data_ptr(), ws.numel(), mask, st)
+            lib.b200_yolo_loss_stages(tp, pp, hw, batch, A, 80, anc_h.ctypes.data_as(ctypes.c_void_p), img_h.ctypes.data_as(ctypes.c_void_p),
+                                      0.5, 2, 0, float(global_batch), parts_t.data_ptr(), loss_t.data_ptr(), ws.data_ptr(), ws.numel(), mask, st)
         return run
-
-    n_rec = n_fill // RF
     ph_fill(); ph_scatter()
+    n_rec = n_fill // RF
     phases = []
-    # one entry per kernel of the step, each timed alone with CUDA events over `steps` back-to-back launches (the loss
-    # kernels through the stage hook of the C ABI; their state lives in the workspace, so the order below matters)
-    for name, fn, nbytes, launches in (
-            ("fill_zero_multi_kernel (dense y_true zero-fill, write)", ph_fill, n_fill * 4, 1),
-            ("yolo_scatter_targets_kernel (one CTA per image)", ph_scatter, int(boxes_d.shape[0]) * (16 + 4 + 340), 1),
-            ("yolo_loss_scan_kernel (obj channel of y_true; dense-equivalent read of y_true)", ph_loss_stage(1), n_fill * 4, 1),
-            ("yolo_loss_gtprep_kernel (a thread per object)", ph_loss_stage(2), int(boxes_d.shape[0]) * (16 + 32), 1),
-            ("yolo_loss_ignore_kernel (box/conf logits of y_pred + object records; dense-equivalent read of y_pred)",
-             ph_loss_stage(4), n_fill * 4, 1),
-            ("yolo_loss_finalize_kernel (fp64 partial sums)", ph_loss_stage(8), n_rec // 128 * 8, 1)):
-        ms = timed(fn, args.steps, 3) / args.steps
-        phases.append({"kernel": name, "ms": ms, "algorithmic_bytes": nbytes, "gbps": nbytes / ms / 1e6, "launches": launches})
+    for name, fn, nbytes in (
+            ("fill_zero_multi_kernel", ph_fill, n_fill * 4),
+            ("yolo_scatter_targets_kernel", ph_scatter, int(boxes_d.shape[0]) * (16 + 4 + 340)),
+            ("yolo_loss_scan_kernel", ph_loss_stage(1), n_fill * 4),
+            ("yolo_loss_gtprep_kernel", ph_loss_stage(2), int(boxes_d.shape[0]) * (16 + 32)),
+            ("yolo_loss_ignore_kernel", ph_loss_stage(4), n_fill * 4),
+            ("yolo_loss_finalize_kernel", ph_loss_stage(8), n_rec // 128 * 8)):
+        if name == "yolo_loss_finalize_kernel" and world > 1:
+            continue   # stage 8 alone would exchange on one rank only; its time is in the step
+        ms, _ = b.timed(fn, args.steps, 3, 5)
+        phases.append({"kernel": name, "ms": ms, "algorithmic_bytes": nbytes, "gbps": nbytes / ms / 1e6})
         if fn in (ph_fill, ph_scatter):
             ph_fill(); ph_scatter()  # restore valid targets (repeated scatters collide with themselves)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
-    dom = max(phases, key=lambda p: p["ms"])
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        key = dom["kernel"].split(" ")[0].replace("_kernel", "")
-        traffic = tj.get(key)
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["gbps"], "peak": peak, "unit": "GB/s",
-                "frac": dom["gbps"] / peak, "traffic": traffic, "peak_source": peak_src,
-                "step_dense_equivalent_gbps": wl["bytes_per_img"] * batch / (ms_dev / args.steps) / 1e6,
-                "phases": phases}
-    if traffic:
-        roofline["achieved_dram_gbps"] = traffic / dom["ms"] / 1e6
-        roofline["frac_dram"] = traffic / dom["ms"] / 1e6 / peak
-    roofline["peak_note"] = ("peak is the measured COPY bandwidth (read + write); the write-only zero-fill runs above it, and the "
-                             "dense-equivalent figures of the sector-sparse loss kernels are not physical traffic")
-    roofline["phases_note"] = ("each kernel timed alone, launched back to back from Python: entries below ~15 us are bounded by "
-                               "the launch interval, their device durations are in profiles/r01_launches_step_v13.csv")
-    roofline["loss_kernels_dense_equivalent_gbps"] = 2 * n_fill * 4 / sum(p["ms"] for p in phases[2:]) / 1e6
-    if dom["kernel"].startswith("yolo_loss"):
-        roofline["note"] = ("achieved/frac use SURVEY 8(d)'s dense algorithmic bytes (y_true + y_pred read once); the loss "
-                            "kernels are sector-sparse (obj*(...) makes the class channels of non-object cells dead data), so "
-                            "the dense-equivalent figure can exceed the physical peak; achieved_dram_gbps/frac_dram use the "
-                            "ncu-measured DRAM bytes of the same launch (profiles/traffic.json)")
-    log("phase timing done")
-    # ---- same step with persistent target buffers (sparse reset instead of the dense zero-fill); reported beside
-    # the headline, which keeps the reference's fresh-zeros-every-call behaviour ----
-    persistent = None
+    tab = b.table("c2")
+    dom_name = (tab.get("dominant") or {}).get("name")
+    dom = next((p for p in phases if dom_name and p["kernel"] in dom_name), None) or max(phases, key=lambda p: p["ms"])
+    live = {"kernel": dom["kernel"], "achieved": dom["gbps"], "frac": dom["gbps"] / b.peak, "kernel_ms_live": dom["ms"],
+            "dominant_chosen_by": "ncu launch list (profiles/r02_kernels.json)" if dom_name else "live timing (no ncu table found)"}
+    roof = b.roofline("c2", batch, ms_dev, live)
+    kt = {k["name"].split("(")[0].replace("void ", "").split("<")[0]: k for k in tab.get("kernels", [])}
+    if dom["kernel"] in kt and kt[dom["kernel"]].get("dram_bytes"):
+        roof["traffic"] = kt[dom["kernel"]]["dram_bytes"]
+        roof["achieved_dram_gbps"] = roof["traffic"] / dom["ms"] / 1e6
+        roof["frac_kernel_dram"] = roof["achieved_dram_gbps"] / b.peak
+    roof["phases"] = phases
+    roof["note"] = ("achieved/frac: the dominant kernel's SURVEY 8(d) dense bytes over its live CUDA-event time; the loss kernels are "
+                    "sector-sparse (obj*(...) kills the class channels of non-object cells), so dense-equivalent figures can exceed the "
+                    "physical peak; frac_dram / traffic use ncu DRAM bytes.  Kernels below ~15 us are launch-interval-bound when timed "
+                    "alone from Python; their device durations are in the ncu launch list")
+    line["roofline"] = roof
+    b.log("phases timed")
+    # ---- API extensions measured beside the drop-in step (N == 1) ----
     if world == 1:
         from tfmv_b200.ai_models.datasets.coco_dataset import TargetBuffers
         tbuf = TargetBuffers()
 
         def pstep():
             yt = gen.GetTargetsBatch(classes_d, boxes_d, off_d, buffers=tbuf)
-            return tyu._loss_call(yt, heads_d, (image, image), anc, 0.5, "ciou", 0, batch_divisor=global_batch,
-                                  return_parts=True, workspace=ws)
-        pstep()  # first call: dense fill
-        pfn = pstep if args.no_graph else runtime.capture(pstep)
-        ms_p = timed(pfn, args.steps, 3)
-        ploss = float(pfn()[0].item())
-        persistent = {"what": "GetTargetsBatch(buffers=TargetBuffers) + GetLoss: y_true reused across steps, only the previous "
-                              "step's records are re-zeroed", "value": global_batch * args.steps / (ms_p / 1e3),
-                      "unit": "images/s", "ms_per_step": ms_p / args.steps, "loss": ploss, "loss_equal": ploss == loss_val}
-    # ---- end-to-end through the public API with host buffers ----
+            return tyu._loss_call(yt, heads_d, (image, image), anc, 0.5, "ciou", 0, batch_divisor=global_batch, workspace=ws)
+        pstep()
+        pfn = b.wrap(pstep)
+        ms_p, _ = b.timed(pfn, args.steps, 3, 5)
+        ploss = float(pfn().item())
+        line["persistent_targets"] = {"what": "GetTargetsBatch(buffers=TargetBuffers) + GetLoss: y_true reused, only the previous step's records re-zeroed",
+                                      "value": global_batch / (ms_p / 1e3), "unit": "images/s", "ms_per_step": ms_p, "loss_equal": ploss == loss_val}
+        ws_f = torch.empty((lib.b200_yolo_loss_from_boxes_workspace_bytes(hw, batch, A, int(boxes_d.shape[0])),), dtype=torch.uint8, device=dev)
+        fstep = lambda: tyu.GetLossFromBoxes(classes_d, boxes_d, off_d, heads_d, (image, image), anc, 80, 0.5, "ciou",
+                                             batch_divisor=global_batch, workspace=ws_f)
+        ffn = b.wrap(fstep)
+        ms_f, _ = b.timed(ffn, args.steps, 3, 5)
+        floss = float(ffn().item())
+        line["sparse_target_fusion"] = {"what": "GetLossFromBoxes: assignment + loss from the box lists, no dense y_true (API extension, SURVEY 8f N3)",
+                                        "value": global_batch / (ms_f / 1e3), "unit": "images/s", "ms_per_step": ms_f,
+                                        "loss_rel_diff": abs(floss - loss_val) / abs(loss_val)}
+    # ---- end to end through the public API with HOST buffers ----
     e2e_steps = max(3, min(args.steps, 10))
-    ms_e2e = timed(lambda: float(step(heads_p, boxes_p, classes_p, off_p).item()), e2e_steps, 2)
+    call = lambda hp, bx, cl, of: float(step(hp, bx, cl, of).item())
+    ms_e2e, _ = b.timed(lambda: call(heads_p, boxes_p, classes_p, off_p), e2e_steps, 2, 3)
     h2d = sum(h.numel() * 4 for h in heads_p) + boxes_p.numel() * 4 + classes_p.numel() * 4 + off_p.numel() * 4
-    e2e = {"value": global_batch * e2e_steps / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": int(h2d) * world,
-           "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / e2e_steps}  # bytes: all ranks together
+    e2e = {"value": global_batch / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": int(h2d) * world,
+           "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e,
+           "what": "pinned host y_pred handed to GetLoss and read in place by the loss kernels over PCIe (they need ~6 % of it); boxes / "
+                   "classes / offsets copied; loss scalar read back"}
 
-    # for comparison: the same call after an explicit copy of the whole y_pred to the device
     def copy_step():
         hd = [h.to(dev, non_blocking=True) for h in heads_p]
-        return float(step(hd, boxes_p, classes_p, off_p).item())
-    ms_cp = timed(copy_step, e2e_steps, 2)
-    e2e["y_pred_transfer"] = ("pinned host y_pred is read in place by the loss kernels (they need ~6 % of it: 32-byte sectors "
-                              "fetched over PCIe); boxes / classes / offsets are copied")
-    n_rec_all = sum(int(h.numel()) for h in heads_p) // RF
-    e2e["h2d_bytes_fetched_estimate"] = world * int(n_rec_all * 48 + boxes_p.shape[0] * 352 + boxes_p.numel() * 4 + classes_p.numel() * 4
-                                                    + off_p.numel() * 4)  # ~1.5 32-byte sectors per record + the object records
-    e2e["h2d_bytes_per_step_note"] = "size of the host tensors handed to the call; the kernels fetch only the sectors they use"
-    e2e["explicit_copy"] = {"value": global_batch * e2e_steps / (ms_cp / 1e3), "unit": "images/s", "ms_per_step": ms_cp / e2e_steps,
-                            "what": "whole y_pred copied host->device first (495 MB per step, PCIe-bound)"}
+        return call(hd, boxes_p, classes_p, off_p)
+    ms_cp, _ = b.timed(copy_step, e2e_steps, 2, 3)
+    e2e["explicit_copy"] = {"value": global_batch / (ms_cp / 1e3), "unit": "images/s", "ms_per_step": ms_cp,
+                            "what": "whole y_pred copied host->device from pinned memory first (495 MB per step per GPU, PCIe-bound)"}
+    heads_pg = [torch.from_numpy(np.ascontiguousarray(h)) for h in heads_h]   # ordinary (pageable) host arrays
 
-    # ---- CPU baseline beside it (rank 0, N == 1) ----
-    cpu = None
+    def pageable_step():
+        hd = [h.to(dev) for h in heads_pg]
+        return call(hd, boxes_h, classes_h, off_h)
+    ms_pg, _ = b.timed(pageable_step, max(2, e2e_steps // 2), 1, 2)
+    e2e["pageable_host"] = {"value": global_batch / (ms_pg / 1e3), "unit": "images/s", "ms_per_step": ms_pg,
+                            "what": "caller holds plain (pageable) NumPy arrays: staged copy of the whole y_pred, then the same call"}
+    e2e["note"] = "the headline e2e needs caller-pinned memory; explicit_copy and pageable_host are what other callers get"
+    line["e2e"] = e2e
+    # ---- CPU baseline beside it (rank 0, N == 1): median of >= 5 runs after one warm-up ----
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n = args.cpu_sample or 32
-        cpu_step_images((image, SEED + 5, 1))  # warm-up
-        dt, _ = cpu_step_images((image, SEED + 6, n))
-        cpu = {"value": n / dt, "unit": "images/s", "cores": 1, "kind": "port",
-               "sample": "%d images of the same workload (NumPy oracle GetTargets+GetLoss, single process), %.1f s" % (n, dt)}
+        n = args.cpu_sample or 16
+        cpu_step_images((image, SEED + 6, n))
+        runs = [cpu_step_images((image, SEED + 6, n))[0] for _ in range(5)]
+        med = statistics.median(runs)
+        line["cpu_baseline"] = {"value": n / med, "unit": "images/s", "cores": 1, "kind": "port",
+                                "sample": "%d images of the same workload (NumPy oracle GetTargets+GetLoss, single process), median of 5 runs "
+                                          "after 1 warm-up, %.2f s per run (min %.2f, max %.2f)" % (n, med, min(runs), max(runs))}
+    else:
+        line["cpu_baseline"] = None
 
-    # ---- software-pipelined drop-in step: the targets of batch i+1 are assigned on a second stream while the loss of
-    # batch i runs (double-buffered y_true), as the reference's tf.data prefetch overlaps GetTargets with train_step ----
-    pipelined = None
-    if world == 1 and not args.no_graph:
-        y_true2 = tuple(torch.empty_like(t) for t in y_true)
-        bufs = (y_true, y_true2)
-        side = torch.cuda.Stream()               # target assignment (bandwidth-bound fill: takes whatever is left)
-        hi = torch.cuda.Stream(priority=-1)      # loss kernels (latency-bound): their CTAs are scheduled first
 
-        def make_pipe(k):
-            def run():
-                main = torch.cuda.current_stream()
-                side.wait_stream(main)
-                hi.wait_stream(main)
-                with torch.cuda.stream(side):
-                    gen.GetTargetsBatch(classes_d, boxes_d, off_d, out=bufs[k ^ 1])   # batch i+1
-                with torch.cuda.stream(hi):
-                    out = tyu._loss_call(bufs[k], heads_d, (image, image), anc, 0.5, "ciou", 0, batch_divisor=global_batch,
-                                         return_parts=True, workspace=ws)           # batch i
-                main.wait_stream(side)
-                main.wait_stream(hi)
-                return out
-            return run
-        gen.GetTargetsBatch(classes_d, boxes_d, off_d, out=bufs[0])
-        gen.GetTargetsBatch(classes_d, boxes_d, off_d, out=bufs[1])
-        pipes = [runtime.capture(make_pipe(0)), runtime.capture(make_pipe(1))]
-        pk = [0]
+# ------------------------------------------------------------------------------------------------
+def yolo_heads_dev(b, batch, image, gen):
+    from tfmv_b200 import synth
+    return [b.torch.randn((batch, s, s, 255), device=b.dev, generator=gen) for s in synth.yolo_grids(image)]
 
-        def pipe_step():
-            r = pipes[pk[0] & 1]()
-            pk[0] += 1
-            return r
-        ms_pl = timed(pipe_step, args.steps, 4)
-        plloss = float(pipe_step()[0].item())
-        pipelined = {"what": "GetTargets(batch i+1) on a second stream under GetLoss(batch i), double-buffered dense y_true",
-                     "value": global_batch * args.steps / (ms_pl / 1e3), "unit": "images/s", "ms_per_step": ms_pl / args.steps,
-                     "loss": plloss, "loss_equal": plloss == loss_val}
 
-    # ---- sparse-target fusion: the same step without materialising y_true ----
-    fused = None
-    if world == 1:
-        ws_f = torch.empty((lib.b200_yolo_loss_from_boxes_workspace_bytes(hw, batch, A, int(boxes_d.shape[0])),), dtype=torch.uint8, device=dev)
+def config_c1(b):
+    from tfmv_b200 import synth
+    from tfmv_b200.ai_models.utils import tf_yolo_utils as tyu
+    torch, args = b.torch, b.args
+    anc = synth.yolo_anchors().astype(F)
+    g = torch.Generator(device=b.dev).manual_seed(SEED + 1)
+    out = {"what": WHAT["c1"], "algorithmic_bytes_per_image": BYTES["c1"]}
+    if not args.only_step:
+        h1 = yolo_heads_dev(b, 1, 416, g)
+        f1 = b.wrap(lambda: tyu.GetNMSBoxesBatch(*h1, anc, (416, 416), 80, 0.5, 0.3, 0.5, "iou"))
+        ms1, w1 = b.timed(f1, max(args.steps, 50), 10, args.config_repeats)
+        out["batch1"] = {"latency_us": ms1 * 1e3, "images_per_s": 1e3 / ms1, "latency_us_spread": spread([x * 1e3 for x in w1]),
+                         "note": "3.6 MB input: L2-resident, launch/latency-bound by construction (SURVEY 8d)"}
+    B = 256
+    hb = yolo_heads_dev(b, B, 416, g)
+    fb = b.wrap(lambda: tyu.GetNMSBoxesBatch(*hb, anc, (416, 416), 80, 0.5, 0.3, 0.5, "iou"))
+    ms, w = b.timed(fb, args.steps, args.warmup, args.config_repeats)
+    out.update({"batch": B, "value": B / ms * 1e3, "unit": "images/s", "ms_per_step": ms, "ms_per_step_spread": spread(w),
+                "roofline": b.roofline("c1", B, ms), "gpu_launches_per_step": 3,
+                "l2": "inputs larger than L2 (927 MB of heads per step)"})
+    return out
 
-        def fstep():
-            return tyu.GetLossFromBoxes(classes_d, boxes_d, off_d, heads_d, (image, image), anc, 80, 0.5, "ciou",
-                                        batch_divisor=global_batch, return_parts=True, workspace=ws_f)
-        ffn = fstep if args.no_graph else runtime.capture(fstep)
-        ms_f = timed(ffn, args.steps, 3)
-        floss = float(ffn()[0].item())
-        fused = {"what": "GetLossFromBoxes: target assignment + loss from the box lists, no dense y_true (API extension, SURVEY 8f N3)",
-                 "value": global_batch * args.steps / (ms_f / 1e3), "unit": "images/s", "ms_per_step": ms_f / args.steps,
-                 "loss": floss, "loss_rel_diff": abs(floss - loss_val) / abs(loss_val)}
 
-    if rank == 0:
-        line = {
-            "metric": "images/sec", "value": global_batch * args.steps / (ms_dev / 1e3), "unit": "images/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["what"], "image": image, "per_gpu_batch": batch, "global_batch": global_batch,
-                       "classes": 80, "anchors_per_cell": 3, "gt_boxes_per_image": "U{1..100}",
-                       "parallelism": "dp%d (images sharded, one 12-float NCCL all-reduce per step%s)" % (
-                           world, ", overlapped with the next step's kernels on a second stream" if world > 1 and not args.no_graph else ""),
-                       "launch": "launch by launch" if args.no_graph else "CUDA graph replay of the step",
-                       "l2": "inputs larger than L2 (y_pred %.0f MB + y_true %.0f MB per step vs 126 MB L2)" % (
-                           n_fill * 4 / 1e6, n_fill * 4 / 1e6)},
-            "loss": loss_val, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "persistent_targets": persistent, "sparse_target_fusion": fused, "pipelined_streams": pipelined,
-            "gpu_launches": 6 * args.steps, "clocks": clocks,
-        }
-        print(json.dumps(line), flush=True)
+def effdet_setup(b, name, batch, seed):
+    from tfmv_b200 import synth
+    from tfmv_b200.ai_models.efficientnet.utils.anchors import Anchors
+    torch = b.torch
+    c = synth.EFFDET_CONFIGS[name]
+    a = Anchors(c["min_level"], c["max_level"], c["image_size"], c["num_scales"], c["aspect_ratios"], c["anchor_scale"])
+    g = torch.Generator(device=b.dev).manual_seed(seed)
+    shapes = [tuple(x.shape) for x in a.boxes]
+    rel = [torch.randn((batch,) + s, device=b.dev, generator=g) * 0.25 for s in shapes]
+    cls = [torch.randn((batch,) + s[:-1] + (81,), device=b.dev, generator=g) for s in shapes]
+    return c, a, rel, cls
+
+
+def config_c3(b):
+    from tfmv_b200 import synth
+    from tfmv_b200.ai_models.efficientnet.efficientdet_net_train import get_loss
+    args, torch = b.args, b.torch
+    B = 128
+    c, a, rel, cls = effdet_setup(b, "d0", B, SEED + 3)
+    rng = np.random.default_rng(SEED + 3)
+    boxes, classes, off = synth.gt_batch(rng, B, (c["image_size"][1], c["image_size"][0]), max_boxes=100, order="yxyx")
+    tb, tc, tm = a.generate_targets_batch(to_dev(b, boxes), to_dev(b, (classes + 1).astype(np.int32)), to_dev(b, off), 81)
+
+    def step():   # efficientdet_net_train.py:135-169 test_step: loss, convert_outputs_boxes, convert_outputs_one per image
+        if hasattr(a, "eval_step"):
+            return a.eval_step(tb, tc, tm, rel, cls)
+        loss = get_loss(tb, tc, tm, rel, cls)
+        dec = a.convert_outputs_boxes(rel)
+        return loss, a.convert_outputs_batch(dec, cls)
+    ms, w = b.timed(b.wrap(step), args.steps, args.warmup, args.config_repeats)
+    out = {"what": WHAT["c3"], "batch": B, "value": B / ms * 1e3, "unit": "images/s", "ms_per_step": ms, "ms_per_step_spread": spread(w),
+           "algorithmic_bytes_per_image": BYTES["c3"], "roofline": b.roofline("c3", B, ms),
+           "fused": bool(hasattr(a, "eval_step")), "l2": "inputs larger than L2 (2 x 2.04 GB class tensors per step)"}
+    if not args.only_step:
+        ph = {}
+        ph["loss"], _ = b.timed(b.wrap(lambda: get_loss(tb, tc, tm, rel, cls)), args.steps, 3, 3)
+        ph["decode"], _ = b.timed(b.wrap(lambda: a.convert_outputs_boxes(rel)), args.steps, 3, 3)
+        dec = a.convert_outputs_boxes(rel)
+        ph["postprocess"], _ = b.timed(b.wrap(lambda: a.convert_outputs_batch(dec, cls)), args.steps, 3, 3)
+        ph["generate_targets (not part of the step)"], _ = b.timed(
+            b.wrap(lambda: a.generate_targets_batch(to_dev(b, boxes), to_dev(b, (classes + 1).astype(np.int32)), to_dev(b, off), 81)), args.steps, 3, 3)
+        out["phase_ms_separate_calls"] = ph
+    return out
+
+
+def config_c4(b):
+    args = b.args
+    B = 16
+    c, a, rel, cls = effdet_setup(b, "d7", B, SEED + 4)
+
+    def step():
+        if hasattr(a, "decode_and_postprocess"):
+            return a.decode_and_postprocess(rel, cls)
+        dec = a.convert_outputs_boxes(rel)
+        return a.convert_outputs_batch(dec, cls)
+    ms, w = b.timed(b.wrap(step), args.steps, args.warmup, args.config_repeats)
+    out = {"what": WHAT["c4"], "batch": B, "value": B / ms * 1e3, "unit": "images/s", "ms_per_step": ms, "ms_per_step_spread": spread(w),
+           "algorithmic_bytes_per_image": BYTES["c4"], "roofline": b.roofline("c4", B, ms),
+           "fused": bool(hasattr(a, "decode_and_postprocess")), "l2": "inputs larger than L2 (2.3 GB of class logits per step)"}
+    if not args.only_step:
+        ph = {}
+        ph["decode"], _ = b.timed(b.wrap(lambda: a.convert_outputs_boxes(rel)), args.steps, 3, 3)
+        dec = a.convert_outputs_boxes(rel)
+        ph["postprocess"], _ = b.timed(b.wrap(lambda: a.convert_outputs_batch(dec, cls)), args.steps, 3, 3)
+        out["phase_ms_separate_calls"] = ph
+    return out
+
+
+def config_c5(b):
+    """BASELINE configs[4]: YOLOv4 608, GLOBAL batch 512 sharded by image over the ranks (strong scaling inside this entry):
+    GetLoss(ciou) + decode + per-class NMS(diou) on the same y_pred, the 12 loss terms all-reduced."""
+    from tfmv_b200 import synth
+    from tfmv_b200.ai_models.datasets.coco_dataset import DataGenerator
+    from tfmv_b200.ai_models.utils import tf_yolo_utils as tyu
+    args, torch, world, rank = b.args, b.torch, b.world, b.rank
+    G, image = 512, 608
+    lo, hi = tyu.shard_range(G, rank, world)
+    B = hi - lo
+    anc = synth.yolo_anchors().astype(F)
+    g = torch.Generator(device=b.dev).manual_seed(SEED + 5 + 1000 * rank)
+    heads = yolo_heads_dev(b, B, image, g)
+    rng = np.random.default_rng(SEED + 5)
+    boxes, classes, off = synth.gt_batch(rng, G, (image, image), max_boxes=100)
+    sl = slice(off[lo], off[hi])
+    gen = DataGenerator(80, anc, (image, image))
+    y_true = gen.GetTargetsBatch(to_dev(b, classes[sl]), to_dev(b, boxes[sl]), to_dev(b, (off[lo:hi + 1] - off[lo]).astype(np.int32)))
+    in_graph = b.exchange is not None
+    fused = getattr(tyu, "LossAndNMSBoxesBatch", None)
+
+    def step():
+        if fused is not None:
+            return fused(y_true, heads, (image, image), anc, 80, 0.5, "ciou", 0.5, 0.3, 0.5, "diou", global_batch=G, exchange=b.exchange)
+        if in_graph or world == 1:
+            loss = tyu._loss_call(y_true, heads, (image, image), anc, 0.5, "ciou", 0, batch_divisor=G, exchange=b.exchange)
+        else:
+            loss, parts = tyu._loss_call(y_true, heads, (image, image), anc, 0.5, "ciou", 0, batch_divisor=G, return_parts=True)
+            loss = tyu.combine_loss_parts(parts)
+        return loss, tyu.GetNMSBoxesBatch(*heads, anc, (image, image), 80, 0.5, 0.3, 0.5, "diou")
     if world > 1:
-        dist.destroy_process_group()
+        step()
+        b.barrier()
+    fn = step if (args.no_graph or (world > 1 and not in_graph)) else b.runtime.capture(step)
+    ms, w = b.timed(fn, args.steps, args.warmup, args.config_repeats)
+    loss = float(fn()[0].item())
+    out = {"what": WHAT["c5"], "global_batch": G, "per_gpu_batch": B, "n_gpus": world, "value": G / ms * 1e3, "unit": "images/s",
+           "ms_per_step": ms, "ms_per_step_spread": spread(w), "scaling": "strong (global batch fixed at 512)", "loss": loss,
+           "algorithmic_bytes_per_image": BYTES["c5"], "roofline": b.roofline("c5", B, ms), "fused": fused is not None,
+           "exchange": b.exchange_kind, "l2": "inputs larger than L2 (%.1f GB of heads + %.1f GB of targets per rank)" % (
+               sum(h.numel() for h in heads) * 4 / 1e9, sum(t.numel() for t in y_true) * 4 / 1e9)}
+    out["roofline"]["note"] = "fractions are per GPU: this rank's %d images over the step time" % B
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    b = Bench(args)
+    torch = b.torch
+    only = [c for c in args.only.split(",") if c]
+    want = lambda c: (not only) or (c in only)
+    line = {}
+    if want("c2"):
+        headline_c2(b, line)
+    torch.cuda.empty_cache()
+    configs = {}
+    plan = [("c5", config_c5)] + ([("c1", config_c1), ("c3", config_c3), ("c4", config_c4)] if b.world == 1 else [])
+    for name, fn in plan:
+        if not want(name):
+            continue
+        try:
+            configs[name] = fn(b)
+        except Exception as e:  # noqa: BLE001  (a failing extra config must not lose the headline line)
+            import traceback
+            configs[name] = {"error": repr(e), "trace": traceback.format_exc()[-1500:]}
+            if b.world > 1:
+                raise
+        b.log("%s done" % name)
+        torch.cuda.empty_cache()
+    if want("c2") and "value" in line:
+        configs["c2"] = {"what": WHAT["c2"], "batch": line["config"]["per_gpu_batch"], "value": line["value"], "unit": "images/s",
+                         "ms_per_step": line["ms_per_step"], "algorithmic_bytes_per_image": BYTES["c2"],
+                         "roofline": {k: v for k, v in (line.get("roofline") or b.roofline("c2", line["config"]["per_gpu_batch"], line["ms_per_step"])).items() if k != "phases"},
+                         "note": "the headline of this line"}
+    # ---- one-shot parity of every config's entry points against the committed golden fixtures ----
+    if b.rank == 0 and not args.only_step:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+            import parity
+            res = parity.run_all(b.dev)
+            for c, r in res.items():
+                if c in configs:
+                    configs[c]["parity"] = r
+            line["parity"] = {"source": "tests/golden/parity.py: CUDA path vs tests/golden/{yolo_64,effdet_64}.npz", "all_ok": all(r.get("ok") for r in res.values())}
+        except Exception as e:  # noqa: BLE001
+            line["parity"] = {"error": repr(e)}
+    line["configs"] = {k: configs[k] for k in sorted(configs)}
+    if "metric" not in line:   # --only without c2: still one well-formed line
+        first = next(iter(line["configs"].values()), {})
+        line.update({"metric": "images/sec", "value": first.get("value"), "unit": "images/s", "n_gpus": b.world, "steps": args.steps,
+                     "warmup": max(args.warmup, 3), "ms_per_step": first.get("ms_per_step"), "higher_is_better": True, "scaling": "weak",
+                     "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": first.get("what"), "only": only}})
+    if b.rank == 0:
+        print(json.dumps(line), flush=True)
+    if b.exchange is not None:
+        b.barrier()
+        b.exchange.close()
+    if b.world > 1:
+        b.dist.destroy_process_group()
 
 
 def main():
     args = parse()
-    wl = WORKLOADS[args.workload]
     if args.impl == "reference":
-        run_reference(args, wl)
+        run_reference(args)
     else:
-        run_b200(args, wl)
+        run_b200(args)
 
 
 if __name__ == "__main__":
