@@ -572,7 +572,8 @@ def config_c3(b):
     c, a, rel, cls = effdet_setup(b, "d0", B, SEED + 3)
     rng = np.random.default_rng(SEED + 3)
     boxes, classes, off = synth.gt_batch(rng, B, (c["image_size"][1], c["image_size"][0]), max_boxes=100, order="yxyx")
-    tb, tc, tm = a.generate_targets_batch(to_dev(b, boxes), to_dev(b, (classes + 1).astype(np.int32)), to_dev(b, off), 81)
+    d_boxes, d_cls, d_off = to_dev(b, boxes), to_dev(b, (classes + 1).astype(np.int32)), to_dev(b, off)
+    tb, tc, tm = a.generate_targets_batch(d_boxes, d_cls, d_off, 81)
 
     def step():   # efficientdet_net_train.py:135-169 test_step: loss, convert_outputs_boxes, convert_outputs_one per image
         if hasattr(a, "eval_step"):
@@ -590,8 +591,7 @@ def config_c3(b):
         ph["decode"], _ = b.timed(b.wrap(lambda: a.convert_outputs_boxes(rel)), args.steps, 3, 3)
         dec = a.convert_outputs_boxes(rel)
         ph["postprocess"], _ = b.timed(b.wrap(lambda: a.convert_outputs_batch(dec, cls)), args.steps, 3, 3)
-        ph["generate_targets (not part of the step)"], _ = b.timed(
-            b.wrap(lambda: a.generate_targets_batch(to_dev(b, boxes), to_dev(b, (classes + 1).astype(np.int32)), to_dev(b, off), 81)), args.steps, 3, 3)
+        ph["generate_targets (not part of the step)"], _ = b.timed(b.wrap(lambda: a.generate_targets_batch(d_boxes, d_cls, d_off, 81)), args.steps, 3, 3)
         out["phase_ms_separate_calls"] = ph
     return out
 

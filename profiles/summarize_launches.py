@@ -56,13 +56,18 @@ def summarize(path, calls, batch):
         kernels.append({"name": k["name"], "launches_per_step": k["launches"] / calls, "us": k["us_sum"] / k["launches"],
                         "dram_bytes": k["bytes_sum"] / k["launches"], "us_per_step": k["us_sum"] / calls,
                         "dram_bytes_per_step": k["bytes_sum"] / calls})
+    # kernels that ran less than once per step are input preparation (target assignment, anchor tables): listed, not summed
+    setup = [k for k in kernels if k["launches_per_step"] < 0.9]
+    kernels = [k for k in kernels if k["launches_per_step"] >= 0.9]
     tot_us = sum(k["us_per_step"] for k in kernels) or 1.0
     for k in kernels:
         k["share"] = k["us_per_step"] / tot_us
+    for k in setup:
+        k["share"] = 0.0
     kernels.sort(key=lambda k: -k["us_per_step"])
     return {"source": os.path.basename(path), "calls": calls, "batch": batch, "us_per_step_sum": tot_us,
             "dram_bytes_per_step": sum(k["dram_bytes_per_step"] for k in kernels), "dominant": kernels[0] if kernels else None,
-            "kernels": kernels}
+            "kernels": kernels, "setup_kernels_not_in_step": setup}
 
 
 def main():

@@ -601,7 +601,8 @@ extern "C" int b200_effdet_postprocess(int num_levels, const int32_t* hw, int A,
     pp.count = reinterpret_cast<int*>(wsb + ws.pre_count);
     pp.eligible = reinterpret_cast<int*>(wsb + ws.pre_elig);
     pp.khi = reinterpret_cast<unsigned long long*>(wsb + ws.pre_khi);
-    effdet_nms_pivot_kernel<<<num_images, NMS_THREADS, (size_t)NMS_PRE_SAMPLES * 8, stream>>>(pp);
+    B200_CUDA(cudaFuncSetAttribute(effdet_nms_pivot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NMS_PIVOT_SMEM));
+    effdet_nms_pivot_kernel<<<num_images, NMS_THREADS, NMS_PIVOT_SMEM, stream>>>(pp);
     B200_LAUNCH_CHECK();
     effdet_nms_pregather_kernel<<<num_images * slices, 512, 0, stream>>>(pp);
     B200_LAUNCH_CHECK();

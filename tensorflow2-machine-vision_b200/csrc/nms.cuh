@@ -9,11 +9,15 @@
 // (DESCENDING) does; candidate j is emitted iff no earlier *emitted* i suppresses it; at most max_out emitted.
 //
 // Algorithm (B200: one 1024-thread CTA per image, everything after the score read lives in shared memory):
-//   1. top-window selection: 2048 strided samples of the 64-bit key (~ordered(score) << 32 | order_id) are
-//      sorted to pick a pivot that should admit ~2048 candidates; ONE pass over the scores gathers every eligible
-//      key below the pivot into shared memory (if the count leaves [1024, 4096] the pivot is rescaled from the
-//      samples, then bisected on the key value — rare); a bitonic sort of the gathered window gives the exact
-//      global order of its members.  Segments with <= 4096 candidates are gathered whole;
+//   1. top-window selection by radix buckets of the 64-bit key (~ordered(score) << 32 | order_id): one pass finds
+//      the range of the eligible keys, a second one histograms them into 2048 buckets of that range (monotone in the
+//      key), a prefix scan picks the bucket where the cumulative count reaches the window target, a third pass
+//      gathers every key up to that bucket into shared memory — an exact top-k cut with no sorting at all.  The
+//      gathered window (<= 4096 keys) is then ordered in place by the same trick applied to its own range: 2048
+//      buckets, a per-bucket chain, rank inside the chain (chains hold ~1-2 keys), exclusive scan -> the exact global
+//      order of its members as an index array.  (The sampled-pivot + bitonic path of round 1 — 66 + 78 barrier stages
+//      — is kept only as the fallback for a bucket that alone overflows the window, e.g. thousands of equal scores.)
+//      Segments with <= 4096 candidates are gathered whole;
 //   2. the sorted window is consumed lazily in tiles of 64 candidates: a tile is first tested against every box
 //      emitted so far (kept list in shared memory; 64 x n_kept pairs spread over the 1024 threads), then resolved
 //      internally with a 64x64 ballot bitmask and a one-warp sweep (skipped when the tile has no internal
@@ -115,6 +119,115 @@ __device__ __forceinline__ void nms_bitonic(unsigned long long* sK, uint32_t* sP
   }
 }
 
+#define NMS_BINS 2048
+
+// bucket of a descending-score key inside [dmin, dmax]: monotone non-decreasing in d (int->float rounding, the
+// multiplication by a positive constant and the truncation all are), so bucket(a) < bucket(b) implies a < b
+__device__ __forceinline__ int nms_bin(uint32_t d, uint32_t dmin, float scale) {
+  const int b = (int)((float)(d - dmin) * scale);
+  return b < NMS_BINS - 1 ? b : NMS_BINS - 1;
+}
+__device__ __forceinline__ float nms_bin_scale(uint32_t dmin, uint32_t dmax) {
+  return (float)NMS_BINS / ((float)(dmax - dmin) + 1.0f);
+}
+
+// CTA-wide (min, max, sum) of three per-thread values; red = 3 * 32 uint32 of scratch.  All threads get the result.
+template <int THREADS>
+__device__ __forceinline__ void nms_block_minmaxsum(uint32_t& mn, uint32_t& mx, int& sum, uint32_t* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  }
+  if (lane == 0) { red[warp] = mn; red[32 + warp] = mx; red[64 + warp] = (uint32_t)sum; }
+  __syncthreads();
+  mn = 0xffffffffu; mx = 0u; sum = 0;
+#pragma unroll
+  for (int w = 0; w < THREADS / 32; ++w) { mn = min(mn, red[w]); mx = max(mx, red[32 + w]); sum += (int)red[64 + w]; }
+  __syncthreads();
+}
+
+// In-place exclusive prefix sum of hist[NMS_BINS] by the whole CTA.  Returns the total; when `target` > 0 also reports
+// through *cut_out (shared) the first bucket whose inclusive count reaches target (NMS_BINS - 1 when none does).
+template <int THREADS>
+__device__ __forceinline__ int nms_block_scan_bins(int* hist, uint32_t* red, int target, int* cut_out) {
+  constexpr int PER = NMS_BINS / THREADS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int v[PER], local = 0;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) { v[k] = hist[threadIdx.x * PER + k]; local += v[k]; }
+  int incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) red[warp] = (uint32_t)incl;
+  if (threadIdx.x == 0 && cut_out) *cut_out = NMS_BINS - 1;
+  __syncthreads();
+  int base = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < THREADS / 32; ++w) { const int t = (int)red[w]; if (w < warp) base += t; total += t; }
+  int run = base + incl - local;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    hist[threadIdx.x * PER + k] = run;
+    if (cut_out && target > 0 && run < target && run + v[k] >= target) *cut_out = threadIdx.x * PER + k;
+    run += v[k];
+  }
+  __syncthreads();
+  return total;
+}
+
+// Exact ascending order of keys[0..n) (n <= NMS_WINDOW, 64-bit keys in shared memory; ties by position) as an index array:
+// ord[r] = position of the r-th smallest key.  bins: 2 * NMS_BINS ints of scratch (ord may alias its first half),
+// nxt: n ints of scratch, red: 96 uint32.  Cost: a handful of barriers and O(chain length) per key.
+template <int THREADS>
+__device__ __forceinline__ void nms_bucket_order(const unsigned long long* keys, int n, int* bins, int* nxt, uint32_t* red,
+                                                 unsigned short* ord) {
+  constexpr int PER = NMS_WINDOW / THREADS;
+  int* hist = bins;
+  int* head = bins + NMS_BINS;
+  uint32_t mn = 0xffffffffu, mx = 0u;
+  int dummy = 0;
+  for (int t = threadIdx.x; t < n; t += THREADS) {
+    const uint32_t d = (uint32_t)(keys[t] >> 32);
+    mn = min(mn, d); mx = max(mx, d);
+  }
+  for (int b = threadIdx.x; b < NMS_BINS; b += THREADS) { hist[b] = 0; head[b] = -1; }
+  nms_block_minmaxsum<THREADS>(mn, mx, dummy, red);   // its barriers also publish the cleared bins
+  const float scale = nms_bin_scale(mn, mx);
+  for (int t = threadIdx.x; t < n; t += THREADS) {
+    const int b = nms_bin((uint32_t)(keys[t] >> 32), mn, scale);
+    atomicAdd(&hist[b], 1);
+    nxt[t] = atomicExch(&head[b], t);
+  }
+  __syncthreads();
+  nms_block_scan_bins<THREADS>(hist, red, 0, nullptr);
+  int dst[PER];
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    const int t = (int)threadIdx.x + u * THREADS;
+    dst[u] = 0;
+    if (t < n) {
+      const unsigned long long K = keys[t];
+      const int b = nms_bin((uint32_t)(K >> 32), mn, scale);
+      int r = 0;
+      for (int j = head[b]; j >= 0; j = nxt[j]) {  // equal keys (only the ineligible-sample sentinel repeats) order by position
+        const unsigned long long Kj = keys[j];
+        r += (Kj < K || (Kj == K && j < t)) ? 1 : 0;
+      }
+      dst[u] = hist[b] + r;
+    }
+  }
+  __syncthreads();   // every chain walk is finished: the bins may be overwritten by ord
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    const int t = (int)threadIdx.x + u * THREADS;
+    if (t < n) ord[dst[u]] = (unsigned short)t;
+  }
+  __syncthreads();
+}
+
 // Runs NMS for one segment with the whole CTA (blockDim.x == THREADS).  out_pos receives the local
 // positions (0..n-1) of emitted candidates in emit order; returns the number emitted (uniform across threads).
 // How a candidate's box is obtained when it enters the window: by default a read of seg.boxes; a caller may decode
@@ -159,7 +272,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
   unsigned long long* sMask = reinterpret_cast<unsigned long long*>(misc_addr);  // [64]
   uint32_t* sSupp = reinterpret_cast<uint32_t*>(sMask + 64);                    // [32]
   unsigned long long* sKeptMask = reinterpret_cast<unsigned long long*>(sSupp + 32);
-  int* sScalar = reinterpret_cast<int*>(sKeptMask + 1);  // [0]=gathered [1]=eligible [2]=nk
+  int* sScalar = reinterpret_cast<int*>(sKeptMask + 1);  // [0]=gathered [1]=eligible [2]=nk [3]=cut bucket
 
   if (tid < 256) sHead[tid] = -1;
   const int n = seg.n;
@@ -171,99 +284,169 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
   unsigned long long klo = 0ull;  // inclusive lower bound of not-yet-consumed keys
   bool exhausted = (n <= 0);
 
+  int* sBins = reinterpret_cast<int*>(sS);                    // [2 * NMS_BINS]: bucket counts / starts, chain heads
+  unsigned short* sOrd = reinterpret_cast<unsigned short*>(sS);  // [NMS_WINDOW] order of the window (aliases the counts)
+  int* sNext = reinterpret_cast<int*>(cC0);                    // [NMS_WINDOW] bucket chains (the candidate tile is idle then)
+  uint32_t* sRed = reinterpret_cast<uint32_t*>(sMask);        // 96 words of reduction scratch (64 x 8 bytes available)
   while (!exhausted && n_kept < cfg.max_out) {
     // ---------------- 1. choose and gather the window [klo, khi) ----------------
-    const bool take_all = (n <= NMS_WINDOW);
     unsigned long long khi = ~0ull;   // exclusive upper bound; ~0 = everything that is left
-    unsigned long long rank = 0;
-    int n_samp = 256;  // enough samples for a pivot rank of >= ~48 (relative spread of the admitted count <= ~15 %)
-    while (n_samp < NMS_SAMPLES && (long long)n_samp * target < 48ll * n) n_samp <<= 1;
-    const bool pre_ok = pre && klo == 0ull && (*pre->eligible > 0) && (*pre->count <= NMS_WINDOW) &&
-                        (*pre->count >= min_win || *pre->count >= *pre->eligible);
-    if (!take_all && !pre_ok) {
-      for (int t = tid; t < n_samp; t += THREADS) {
-        const int i = (int)(((long long)t * n) / n_samp);
-        const float s = seg.scores[i];
-        const uint32_t oid = seg.order_id ? seg.order_id[i] : (uint32_t)i;
-        const unsigned long long K = ((unsigned long long)nms_dkey(s) << 32) | oid;
-        const bool el = !(cfg.use_score_thr && (s < cfg.score_thr)) && (K >= klo);
-        sS[t] = el ? K : ~0ull;
-      }
-      __syncthreads();
-      nms_bitonic<THREADS>(sS, nullptr, n_samp);
-      rank = ((unsigned long long)target * (unsigned long long)n_samp) / (unsigned long long)n;
-      if (rank < 2ull) rank = 2ull;
-      khi = rank >= (unsigned long long)n_samp ? ~0ull : sS[rank];
-    }
-    unsigned long long b_lo = klo, b_hi = ~0ull;  // bisection bounds: khi <= b_lo admits too few, khi >= b_hi too many
     int n_win = 0;
-    bool from_pre = false;
-    if (pre && klo == 0ull) {
+    bool gathered = false, fallback = false, sorted_in_place = false;
+    if (pre && klo == 0ull) {   // first window of a large segment, gathered by several CTAs beforehand
       const int c = *pre->count, e = *pre->eligible;
-      if (e > 0 && c <= NMS_WINDOW && (c >= min_win || c >= e)) {
+      if (e == 0) { exhausted = true; break; }
+      if (c <= NMS_WINDOW && (c >= min_win || c >= e)) {
         for (int t = tid; t < c; t += THREADS) { sK[t] = pre->keys[t]; sPos[t] = pre->pos[t]; }
         n_win = c;
         khi = (c >= e) ? ~0ull : *pre->khi;
-        from_pre = true;
+        gathered = true;
         __syncthreads();
-      } else if (e == 0) {
-        exhausted = true;
-        break;
       }
     }
-    for (int attempt = 0; attempt < 80 && !from_pre; ++attempt) {
-      if (tid == 0) { sScalar[0] = 0; sScalar[1] = 0; }
-      __syncthreads();
-      int my_el = 0;
+    if (!gathered) {
+      // G1: range and number of the eligible keys that are left
+      uint32_t dmin = 0xffffffffu, dmax = 0u;
+      int n_el = 0;
       for (int i = tid; i < n; i += THREADS) {
         const float s = seg.scores[i];
         if (cfg.use_score_thr && (s < cfg.score_thr)) continue;
-        const uint32_t oid = seg.order_id ? seg.order_id[i] : (uint32_t)i;
-        const unsigned long long K = ((unsigned long long)nms_dkey(s) << 32) | oid;
-        if (K < klo) continue;
-        ++my_el;
-        if (khi == ~0ull || K < khi) {
-          const int slot = atomicAdd(&sScalar[0], 1);
-          if (slot < NMS_WINDOW) { sK[slot] = K; sPos[slot] = (uint32_t)i; }
+        const uint32_t d = nms_dkey(s);
+        if (klo != 0ull) {
+          const uint32_t oid = seg.order_id ? seg.order_id[i] : (uint32_t)i;
+          if ((((unsigned long long)d << 32) | oid) < klo) continue;
         }
+        ++n_el; dmin = min(dmin, d); dmax = max(dmax, d);
       }
-      my_el = warp_sum_i(my_el);
-      if (lane == 0 && my_el) atomicAdd(&sScalar[1], my_el);
-      __syncthreads();
-      const int c = sScalar[0], e = sScalar[1];
-      __syncthreads();
-      if (e == 0) { n_win = 0; break; }
-      const bool too_many = c > NMS_WINDOW;
-      const bool too_few = (c < min_win) && (c < e);
-      if (!too_many && !too_few) {
-        n_win = c;
-        if (c >= e) khi = ~0ull;  // the window holds everything that was left
-        break;
+      nms_block_minmaxsum<THREADS>(dmin, dmax, n_el, sRed);
+      if (n_el == 0) { exhausted = true; break; }
+      const float scale = nms_bin_scale(dmin, dmax);
+      int cut = NMS_BINS - 1;
+      if (n_el > NMS_WINDOW) {
+        // G2: histogram of the buckets; G3: the bucket where the cumulative count reaches the target
+        for (int b = tid; b < NMS_BINS; b += THREADS) sBins[b] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += THREADS) {
+          const float s = seg.scores[i];
+          if (cfg.use_score_thr && (s < cfg.score_thr)) continue;
+          const uint32_t d = nms_dkey(s);
+          if (klo != 0ull) {
+            const uint32_t oid = seg.order_id ? seg.order_id[i] : (uint32_t)i;
+            if ((((unsigned long long)d << 32) | oid) < klo) continue;
+          }
+          atomicAdd(&sBins[nms_bin(d, dmin, scale)], 1);
+        }
+        __syncthreads();
+        nms_block_scan_bins<THREADS>(sBins, sRed, target, &sScalar[3]);
+        cut = sScalar[3];
+        const int upto = (cut + 1 < NMS_BINS) ? sBins[cut + 1] : n_el;   // keys in buckets 0..cut
+        fallback = upto > NMS_WINDOW;   // one bucket alone overflows the window (masses of near-equal scores)
+        __syncthreads();
       }
-      // adjust the pivot: rescale the sample rank first, then bisect on the key value
-      if (too_many) b_hi = khi; else b_lo = khi;
-      unsigned long long next = 0ull;
-      bool have = false;
-      if (attempt < 3 && !take_all) {
-        unsigned long long r2 = c > 0 ? (rank * (unsigned long long)target) / (unsigned long long)c : rank * 8ull;
-        if (too_few && r2 <= rank) r2 = rank + 1ull;
-        if (too_many && r2 >= rank) r2 = rank > 0ull ? rank - 1ull : 0ull;
-        rank = r2;
-        next = rank >= (unsigned long long)n_samp ? ~0ull : sS[rank];
-        have = (next > b_lo) && (next < b_hi || b_hi == ~0ull) && (next != khi);
+      if (!fallback) {
+        // G4: gather buckets 0..cut (unordered)
+        if (tid == 0) sScalar[0] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += THREADS) {
+          const float s = seg.scores[i];
+          if (cfg.use_score_thr && (s < cfg.score_thr)) continue;
+          const uint32_t d = nms_dkey(s);
+          const uint32_t oid = seg.order_id ? seg.order_id[i] : (uint32_t)i;
+          const unsigned long long K = ((unsigned long long)d << 32) | oid;
+          if (K < klo || nms_bin(d, dmin, scale) > cut) continue;
+          const int slot = atomicAdd(&sScalar[0], 1);
+          sK[slot] = K; sPos[slot] = (uint32_t)i;
+        }
+        __syncthreads();
+        n_win = sScalar[0];
+        gathered = true;
+        if (n_win < n_el) khi = 1ull;   // placeholder: the real bound (largest key of the window + 1) is set after ordering
+        __syncthreads();
       }
-      if (!have) next = b_lo + ((b_hi - b_lo) >> 1);
-      if (next == khi || next <= b_lo) next = b_lo + 1ull;  // keys are unique: a one-key step cannot skip the band
-      khi = next;
+    }
+    if (!gathered) {
+      // fallback of round 1: pivot from sorted samples, rescale / bisect until the window fits, bitonic sort
+      const bool take_all = (n <= NMS_WINDOW);
+      unsigned long long rank = 0;
+      int n_samp = 256;  // enough samples for a pivot rank of >= ~48 (relative spread of the admitted count <= ~15 %)
+      while (n_samp < NMS_SAMPLES && (long long)n_samp * target < 48ll * n) n_samp <<= 1;
+      khi = ~0ull;
+      if (!take_all) {
+        for (int t = tid; t < n_samp; t += THREADS) {
+          const int i = (int)(((long long)t * n) / n_samp);
+          const float s = seg.scores[i];
+          const uint32_t oid = seg.order_id ? seg.order_id[i] : (uint32_t)i;
+          const unsigned long long K = ((unsigned long long)nms_dkey(s) << 32) | oid;
+          const bool el = !(cfg.use_score_thr && (s < cfg.score_thr)) && (K >= klo);
+          sS[t] = el ? K : ~0ull;
+        }
+        __syncthreads();
+        nms_bitonic<THREADS>(sS, nullptr, n_samp);
+        rank = ((unsigned long long)target * (unsigned long long)n_samp) / (unsigned long long)n;
+        if (rank < 2ull) rank = 2ull;
+        khi = rank >= (unsigned long long)n_samp ? ~0ull : sS[rank];
+      }
+      unsigned long long b_lo = klo, b_hi = ~0ull;  // bisection bounds: khi <= b_lo admits too few, khi >= b_hi too many
+      for (int attempt = 0; attempt < 80; ++attempt) {
+        if (tid == 0) { sScalar[0] = 0; sScalar[1] = 0; }
+        __syncthreads();
+        int my_el = 0;
+        for (int i = tid; i < n; i += THREADS) {
+          const float s = seg.scores[i];
+          if (cfg.use_score_thr && (s < cfg.score_thr)) continue;
+          const uint32_t oid = seg.order_id ? seg.order_id[i] : (uint32_t)i;
+          const unsigned long long K = ((unsigned long long)nms_dkey(s) << 32) | oid;
+          if (K < klo) continue;
+          ++my_el;
+          if (khi == ~0ull || K < khi) {
+            const int slot = atomicAdd(&sScalar[0], 1);
+            if (slot < NMS_WINDOW) { sK[slot] = K; sPos[slot] = (uint32_t)i; }
+          }
+        }
+        my_el = warp_sum_i(my_el);
+        if (lane == 0 && my_el) atomicAdd(&sScalar[1], my_el);
+        __syncthreads();
+        const int c = sScalar[0], e = sScalar[1];
+        __syncthreads();
+        if (e == 0) { n_win = 0; break; }
+        const bool too_many = c > NMS_WINDOW;
+        const bool too_few = (c < min_win) && (c < e);
+        if (!too_many && !too_few) {
+          n_win = c;
+          if (c >= e) khi = ~0ull;  // the window holds everything that was left
+          break;
+        }
+        // adjust the pivot: rescale the sample rank first, then bisect on the key value
+        if (too_many) b_hi = khi; else b_lo = khi;
+        unsigned long long next = 0ull;
+        bool have = false;
+        if (attempt < 3 && !take_all) {
+          unsigned long long r2 = c > 0 ? (rank * (unsigned long long)target) / (unsigned long long)c : rank * 8ull;
+          if (too_few && r2 <= rank) r2 = rank + 1ull;
+          if (too_many && r2 >= rank) r2 = rank > 0ull ? rank - 1ull : 0ull;
+          rank = r2;
+          next = rank >= (unsigned long long)n_samp ? ~0ull : sS[rank];
+          have = (next > b_lo) && (next < b_hi || b_hi == ~0ull) && (next != khi);
+        }
+        if (!have) next = b_lo + ((b_hi - b_lo) >> 1);
+        if (next == khi || next <= b_lo) next = b_lo + 1ull;  // keys are unique: a one-key step cannot skip the band
+        khi = next;
+      }
+      sorted_in_place = n_win > 0;
     }
     if (n_win == 0) { exhausted = true; break; }
-    {
+    if (sorted_in_place) {
       int npad = 64;
       while (npad < n_win) npad <<= 1;
       for (int t = tid; t < npad; t += THREADS)
         if (t >= n_win) { sK[t] = ~0ull; sPos[t] = 0xffffffffu; }
       __syncthreads();
       nms_bitonic<THREADS>(sK, sPos, npad);
+      for (int t = tid; t < n_win; t += THREADS) sOrd[t] = (unsigned short)t;
+      __syncthreads();
+    } else {
+      nms_bucket_order<THREADS>(sK, n_win, sBins, sNext, sRed, sOrd);
+      if (khi == 1ull) khi = sK[sOrd[n_win - 1]] + 1ull;   // everything not gathered has a larger key (bucket > cut)
     }
 
     // ---------------- 2. consume the window in tiles of 64 sorted candidates, lazily ----------------
@@ -273,7 +456,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
     for (int w0 = 0; w0 < n_win && n_kept < cfg.max_out; w0 += NMS_CHUNK) {
       const int n_chunk = min(NMS_CHUNK, n_win - w0);
       for (int ct = tid; ct < n_chunk; ct += THREADS) {
-        const uint32_t p = sPos[w0 + ct];
+        const uint32_t p = sPos[sOrd[w0 + ct]];
         const float4 b = load_box(seg, p);
         const BoxT mine = bm_prep(b.x, b.y, b.z, b.w, METRIC);
         cC0[ct] = mine.c0; cC1[ct] = mine.c1; cC2[ct] = mine.c2; cC3[ct] = mine.c3;
@@ -382,7 +565,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
           const int slot = n_kept + __popcll(keptmask & ((1ull << tid) - 1ull));
           kC0[slot] = cC0[gi]; kC1[slot] = cC1[gi]; kC2[slot] = cC2[gi]; kC3[slot] = cC3[gi];
           kAr[slot] = cAr[gi]; kAt[slot] = cAt[gi]; kCl[slot] = cCl[gi];
-          out_pos[slot] = (int32_t)sPos[w0 + gi];
+          out_pos[slot] = (int32_t)sPos[sOrd[w0 + gi]];
           if (mode == B200_NMS_BY_CLASS) kNext[slot] = atomicExch(&sHead[(uint32_t)cCl[gi] & 255u], slot);
         }
         n_kept += nk;
@@ -410,6 +593,7 @@ struct NmsPreselectParams {
 };
 
 #define NMS_PRE_SAMPLES 4096
+#define NMS_PIVOT_SMEM ((size_t)NMS_PRE_SAMPLES * 8 + 2 * NMS_BINS * 4 + NMS_PRE_SAMPLES * 4 + 512)
 
 // One CTA per segment: pivot = the sample whose rank should admit ~NMS_TARGET candidates (up to 4096 strided samples,
 // so the admitted count has a relative spread of ~1/sqrt(rank) and stays inside [1024, 4096] with high probability).
@@ -433,10 +617,16 @@ static __device__ void nms_pivot_body(const NmsPreselectParams& p, unsigned char
       sS[t] = (p.use_score_thr && (s < p.score_thr)) ? ~0ull : K;
     }
     __syncthreads();
-    nms_bitonic(sS, nullptr, ns);
+    // rank-th smallest sample by bucket ordering (ineligible samples carry the largest key and sort last; they share
+    // one key, so their mutual order is arbitrary, which is harmless: only eligible ranks are ever looked up)
+    int* bins = reinterpret_cast<int*>(sS + NMS_PRE_SAMPLES);
+    int* nxt = bins + 2 * NMS_BINS;
+    uint32_t* red = reinterpret_cast<uint32_t*>(nxt + NMS_PRE_SAMPLES);
+    unsigned short* ord = reinterpret_cast<unsigned short*>(bins);
+    nms_bucket_order<NMS_THREADS>(sS, ns, bins, nxt, red, ord);
     unsigned long long rank = ((unsigned long long)NMS_TARGET * (unsigned long long)ns) / (unsigned long long)n;
     if (rank < 2ull) rank = 2ull;
-    khi = rank >= (unsigned long long)ns ? ~0ull : sS[rank];
+    khi = rank >= (unsigned long long)ns ? ~0ull : sS[ord[rank]];
   }
   if (tid == 0) p.khi[seg] = khi;
 }
