@@ -296,6 +296,27 @@ int b200_letterbox_image(const uint8_t* img, int height, int width, int channels
                          const uint8_t bg_color[3], uint8_t* out_u8, float* out_f32, int32_t padding_out[4],
                          int32_t resized_wh_out[2], void* stream);
 
+/* test_step of EfficientDetNetTrain (efficientnet/efficientdet_net_train.py:135-169) in ONE pass over the heads: focal +
+ * Huber partial sums (:141-151; sums_out [2L+1] fp64 as b200_focal_box_partial_sums writes them -> b200_focal_box_finalize
+ * / _dp), convert_outputs_boxes (:153, out_decoded[l] (B,H,W,A,4), entries may be NULL) and convert_outputs_one for every
+ * image (:156-157; outputs as b200_effdet_postprocess).  The class logits are read once instead of twice.  true_classes
+ * are the dense one-hot targets.  b200_effdet_decode_postprocess is the same stream without targets (anchors.py:141-202).
+ * Workspace: b200_effdet_eval_workspace_bytes (256-byte aligned). */
+size_t b200_effdet_eval_workspace_bytes(int num_levels, const int32_t* hw, int A, int num_images, int max_out);
+int b200_effdet_eval_step(int num_levels, const int32_t* hw, int A, const float* table_dev, int C, int B,
+                          const float* const true_boxes[], const float* const true_classes[],
+                          const unsigned char* const true_masks[], const float* const pred_boxes[],
+                          const float* const pred_classes[], float alpha, float gamma, float delta, float label_smoothing,
+                          double* sums_out, float* const out_decoded[], int max_out, float iou_thr, float score_thr,
+                          int metric, float* out_boxes, long long* out_class_id, float* out_score, int32_t* out_sel_idx,
+                          int32_t* out_sel_anchor, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
+int b200_effdet_decode_postprocess(int num_levels, const int32_t* hw, int A, const float* table_dev, int C, int B,
+                                   const float* const pred_boxes[], const float* const pred_classes[],
+                                   float* const out_decoded[], int max_out, float iou_thr, float score_thr, int metric,
+                                   float* out_boxes, long long* out_class_id, float* out_score, int32_t* out_sel_idx,
+                                   int32_t* out_sel_anchor, int32_t* out_count, void* workspace, size_t workspace_bytes,
+                                   void* stream);
+
 /* ---- the collective of the path ------------------------------------------
  * Data parallel over images: the only inter-GPU traffic is the sum of a handful of per-GPU partial loss terms (YOLO:
  * 12 floats; EfficientDet: 2L+1 doubles).  The reference's only collective site is the MirroredStrategy reduce of

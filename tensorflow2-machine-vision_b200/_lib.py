@@ -76,6 +76,11 @@ SIGNATURES = {
     "b200_allreduce_loss": (c_i, [c_p, c_p, c_i, c_p]),
     "b200_allreduce_sums": (c_i, [c_p, c_p, c_i, c_p]),
     "b200_yolo_loss_combine": (c_i, [c_p, c_p, c_p]),
+    "b200_effdet_eval_workspace_bytes": (c_sz, [c_i, c_p, c_i, c_i, c_i]),
+    "b200_effdet_eval_step": (c_i, [c_i, c_p, c_i, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_f, c_p, c_p, c_i, c_f, c_f,
+                                    c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "b200_effdet_decode_postprocess": (c_i, [c_i, c_p, c_i, c_p, c_i, c_i, c_p, c_p, c_p, c_i, c_f, c_f, c_i, c_p, c_p, c_p, c_p, c_p,
+                                             c_p, c_p, c_sz, c_p]),
     "b200_map_per_image": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, ctypes.c_double, c_p, c_p]),
 }
 

@@ -208,6 +208,105 @@ class Anchors(object):
                                            T.ptr(ws), ws_bytes, T.stream_ptr()), 'convert_outputs_one')
     return out
 
+  # -- fused passes (one read of the class logits) -----------------------------------------------------------
+  def _post_outputs(self, n, K, dev, with_indices):
+    out = {
+      'boxes': torch.empty((n, K, 4), dtype=torch.float32, device=dev),
+      'classes_id': torch.empty((n, K), dtype=torch.int64, device=dev),
+      'scores': torch.empty((n, K), dtype=torch.float32, device=dev),
+      'count': torch.zeros((n,), dtype=torch.int32, device=dev),
+    }
+    if with_indices:
+      out['sel_idx'] = torch.empty((n, K), dtype=torch.int32, device=dev)
+      out['sel_anchor'] = torch.empty((n, K), dtype=torch.int32, device=dev)
+    return out
+
+  def decode_and_postprocess(self, outputs_boxes, outputs_classes, max_output_size=200, iou_threshold=0.5,
+                             score_threshold=0.0001, iou_type='diou', with_indices=False):
+    '''convert_outputs_boxes followed by convert_outputs_one for every image of the batch (anchors.py:141-202) in one
+    pass over the heads.  Returns (decoded boxes per level, dict as convert_outputs_batch).'''
+    assert iou_type in ('iou', 'giou', 'diou', 'ciou')
+    lib = _lib.load()
+    tab = self._dev_table()
+    rel = [T.to_cuda(t) for t in outputs_boxes]
+    cl = [T.to_cuda(t) for t in outputs_classes]
+    L = self._num_levels
+    if len(rel) != L or len(cl) != L:
+      raise ValueError('expected %d levels' % L)
+    B, C, K = cl[0].shape[0], cl[0].shape[-1], int(max_output_size)
+    for t, c, (h, w) in zip(rel, cl, self._level_hw):
+      if tuple(t.shape) != (B, h, w, self._A, 4) or tuple(c.shape) != (B, h, w, self._A, C):
+        raise ValueError('level shapes %r / %r do not match (B,%d,%d,%d,4|C)' % (tuple(t.shape), tuple(c.shape), h, w, self._A))
+    dev = cl[0].device
+    dec = [torch.empty_like(t) for t in rel]
+    out = self._post_outputs(B, K, dev, with_indices)
+    ws_bytes = lib.b200_effdet_eval_workspace_bytes(L, self._hw, self._A, B, K)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    arr = lambda ts: (ctypes.c_void_p * L)(*[t.data_ptr() for t in ts])
+    _lib.check(lib.b200_effdet_decode_postprocess(L, self._hw, self._A, T.ptr(tab), C, B, arr(rel), arr(cl), arr(dec), K,
+                                                  float(iou_threshold), float(score_threshold), _lib.METRIC_EFF[iou_type],
+                                                  T.ptr(out['boxes']), T.ptr(out['classes_id']), T.ptr(out['scores']),
+                                                  T.ptr(out.get('sel_idx')), T.ptr(out.get('sel_anchor')), T.ptr(out['count']),
+                                                  T.ptr(ws), ws_bytes, T.stream_ptr()), 'decode_and_postprocess')
+    return tuple(dec), out
+
+  def eval_step(self, y_true_boxes, y_true_classes, y_true_masks, y_pred_boxes, y_pred_classes, alpha=0.25, gamma=1.5,
+                delta=0.1, max_output_size=200, iou_threshold=0.5, score_threshold=0.0001, iou_type='diou',
+                with_indices=False, exchange=None, return_parts=False):
+    '''EfficientDetNetTrain.test_step (efficientdet_net_train.py:135-169) without the backbone and the L2 term: the
+    _get_loss value, convert_outputs_boxes and convert_outputs_one for every image, reading the class logits ONCE.
+    Returns (loss, decoded boxes per level, dict as convert_outputs_batch).  exchange: runtime.PeerExchange /
+    NcclExchange for the data-parallel sum of the 2L+1 loss terms.'''
+    assert iou_type in ('iou', 'giou', 'diou', 'ciou')
+    lib = _lib.load()
+    tab = self._dev_table()
+    L = self._num_levels
+    tb = [T.to_cuda(t) for t in y_true_boxes]
+    tc = [T.to_cuda(t) for t in y_true_classes]
+    tm = [T.to_cuda(t, torch.bool) for t in y_true_masks]
+    rel = [T.to_cuda(t) for t in y_pred_boxes]
+    cl = [T.to_cuda(t) for t in y_pred_classes]
+    if not (len(tb) == len(tc) == len(tm) == len(rel) == len(cl) == L):
+      raise ValueError('expected %d levels' % L)
+    B, C, K = cl[0].shape[0], cl[0].shape[-1], int(max_output_size)
+    for l, (h, w) in enumerate(self._level_hw):
+      if tuple(rel[l].shape) != (B, h, w, self._A, 4) or tuple(cl[l].shape) != (B, h, w, self._A, C):
+        raise ValueError('prediction shapes of level %d do not match (B,%d,%d,%d,4|C)' % (l, h, w, self._A))
+      if tb[l].shape != rel[l].shape or tc[l].shape != cl[l].shape or tm[l].numel() != rel[l].numel() // 4:
+        raise ValueError('target shapes of level %d differ from the predictions (dense one-hot class targets expected)' % l)
+    dev = cl[0].device
+    dec = [torch.empty_like(t) for t in rel]
+    out = self._post_outputs(B, K, dev, with_indices)
+    sums = torch.empty((2 * L + 1,), dtype=torch.float64, device=dev)
+    ws_bytes = lib.b200_effdet_eval_workspace_bytes(L, self._hw, self._A, B, K)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    arr = lambda ts: (ctypes.c_void_p * L)(*[t.data_ptr() for t in ts])
+    _lib.check(lib.b200_effdet_eval_step(L, self._hw, self._A, T.ptr(tab), C, B, arr(tb), arr(tc), arr(tm), arr(rel), arr(cl),
+                                         float(alpha), float(gamma), float(delta), 0.0, T.ptr(sums), arr(dec), K,
+                                         float(iou_threshold), float(score_threshold), _lib.METRIC_EFF[iou_type],
+                                         T.ptr(out['boxes']), T.ptr(out['classes_id']), T.ptr(out['scores']),
+                                         T.ptr(out.get('sel_idx')), T.ptr(out.get('sel_anchor')), T.ptr(out['count']),
+                                         T.ptr(ws), ws_bytes, T.stream_ptr()), 'eval_step')
+    scale = 1
+    peer = exchange is not None and hasattr(exchange, 'mailboxes')
+    if exchange is not None:
+      if not peer:
+        exchange.allreduce_(sums)
+      scale = exchange.world
+    nm = (ctypes.c_double * L)(*[float(t.numel()) * scale for t in cl])
+    parts = torch.empty((L, 2), dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    npos = torch.empty((), dtype=torch.float32, device=dev)
+    if peer:
+      rank, world, boxes_ = exchange.args()
+      _lib.check(lib.b200_focal_box_finalize_dp(L, T.ptr(sums), nm, T.ptr(parts), T.ptr(loss), T.ptr(npos), rank, world, boxes_,
+                                                T.stream_ptr()), 'eval_step (data parallel)')
+    else:
+      _lib.check(lib.b200_focal_box_finalize(L, T.ptr(sums), nm, T.ptr(parts), T.ptr(loss), T.ptr(npos), T.stream_ptr()), 'eval_step')
+    if return_parts:
+      return loss, tuple(dec), out, parts, npos
+    return loss, tuple(dec), out
+
   def convert_outputs_one(self, batch_index, outputs_boxes, outputs_classes):
     '''One image of the batch: (nms_boxes [K,4], nms_classes_id [K] int64, nms_scores [K]); K <= 200.'''
     r = self.convert_outputs_batch(outputs_boxes, outputs_classes, first_image=int(batch_index), num_images=1)

@@ -12,6 +12,7 @@
 // then centre/size re-derived from those corners (anc:204-217) — so results are bit-identical to reading
 // Anchors.boxes while saving 0.8 MB (D0) / 7 MB (D7) of reads per image.
 #include "nms.cuh"
+#include "effdet_focal.cuh"
 
 #define EF_MAX_LEVELS 8
 #define EF_STAGES 2
@@ -520,6 +521,54 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) effdet_nms_pivot_kernel(NmsPre
 }
 __global__ void __launch_bounds__(512) effdet_nms_pregather_kernel(NmsPreselectParams p) { nms_pregather_body(p); }
 
+// The NMS tail shared by b200_effdet_postprocess and the fused entry points: (large segments) pivot + multi-CTA
+// pre-gather of the first window, then one CTA per image.
+static int ef_launch_nms(const EfFilterParams& fp, const EfWs& ws, unsigned char* wsb, int num_images, int n_img, int max_out,
+                         float iou_thr, float score_thr, int metric, float* out_boxes, long long* out_class_id, float* out_score,
+                         int32_t* out_sel_idx, int32_t* out_sel_anchor, int32_t* out_count, cudaStream_t stream) {
+  EfFinalizeParams np;
+  np.NB = num_images; np.n_img = n_img;
+  np.cfg.metric = metric; np.cfg.mode = B200_NMS_AGNOSTIC; np.cfg.iou_thr = iou_thr; np.cfg.score_thr = score_thr;
+  np.cfg.use_score_thr = 1; np.cfg.max_out = max_out;
+  np.cand_box = fp.cand_box; np.cand_score = fp.cand_score; np.cand_cls = fp.cand_cls; np.cand_aidx = fp.cand_aidx;
+  np.counts = fp.counts; np.bitmap = fp.bitmap; np.bitmap_words = ws.bitmap_words;
+  np.nms_pos = reinterpret_cast<int32_t*>(wsb + ws.pos);
+  np.pre_keys = nullptr; np.pre_pos = nullptr; np.pre_count = nullptr; np.pre_elig = nullptr; np.pre_khi = nullptr;
+  if (n_img > 32768) {
+    // large segments: several CTAs per image gather the first NMS window so the single NMS CTA does not have to
+    // scan hundreds of thousands of scores alone
+    NmsPreselectParams pp;
+    int slices = (4 * b200_sm_count() + num_images - 1) / num_images;
+    if (slices < 1) slices = 1;
+    if (slices > 32) slices = 32;
+    pp.scores = fp.cand_score; pp.order_id = fp.cand_aidx; pp.counts = fp.counts; pp.stride = n_img; pp.slices = slices;
+    pp.use_score_thr = 1; pp.score_thr = score_thr;
+    pp.keys = reinterpret_cast<unsigned long long*>(wsb + ws.pre_keys);
+    pp.pos = reinterpret_cast<uint32_t*>(wsb + ws.pre_pos);
+    pp.count = reinterpret_cast<int*>(wsb + ws.pre_count);
+    pp.eligible = reinterpret_cast<int*>(wsb + ws.pre_elig);
+    pp.khi = reinterpret_cast<unsigned long long*>(wsb + ws.pre_khi);
+    B200_CUDA(cudaFuncSetAttribute(effdet_nms_pivot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NMS_PIVOT_SMEM));
+    effdet_nms_pivot_kernel<<<num_images, NMS_THREADS, NMS_PIVOT_SMEM, stream>>>(pp);
+    B200_LAUNCH_CHECK();
+    effdet_nms_pregather_kernel<<<num_images * slices, 512, 0, stream>>>(pp);
+    B200_LAUNCH_CHECK();
+    np.pre_keys = pp.keys; np.pre_pos = pp.pos; np.pre_count = pp.count; np.pre_elig = pp.eligible; np.pre_khi = pp.khi;
+  }
+  np.out_boxes = out_boxes; np.out_cls = out_class_id; np.out_score = out_score; np.out_sel_idx = out_sel_idx;
+  np.out_sel_anchor = out_sel_anchor; np.out_count = out_count;
+  size_t smem2 = nms_smem_bytes(max_out);
+  if (smem2 < (size_t)ws.bitmap_words * 4) smem2 = (size_t)ws.bitmap_words * 4;
+  B200_REQUIRE(smem2 <= 220 * 1024, B200_ERR_UNSUPPORTED, "b200_effdet_postprocess: too many anchors per image for the rank table");
+#define EF_LAUNCH(M)                                                                                                     \
+  B200_CUDA(cudaFuncSetAttribute(effdet_nms_finalize_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
+  effdet_nms_finalize_kernel<M><<<num_images, NMS_THREADS, smem2, stream>>>(np)
+  NMS_DISPATCH_METRIC(metric, EF_LAUNCH)
+#undef EF_LAUNCH
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
 extern "C" size_t b200_effdet_postprocess_workspace_bytes(int num_levels, const int32_t* hw, int A, int num_images, int max_out) {
   int n_img = 0;
   for (int l = 0; l < num_levels; ++l) n_img += hw[2 * l] * hw[2 * l + 1] * A;
@@ -579,47 +628,8 @@ extern "C" int b200_effdet_postprocess(int num_levels, const int32_t* hw, int A,
   effdet_filter_kernel<<<grid, warps * 32, smem1, stream>>>(fp);
   B200_LAUNCH_CHECK();
 
-  EfFinalizeParams np;
-  np.NB = num_images; np.n_img = n_img;
-  np.cfg.metric = metric; np.cfg.mode = B200_NMS_AGNOSTIC; np.cfg.iou_thr = iou_thr; np.cfg.score_thr = score_thr;
-  np.cfg.use_score_thr = 1; np.cfg.max_out = max_out;
-  np.cand_box = fp.cand_box; np.cand_score = fp.cand_score; np.cand_cls = fp.cand_cls; np.cand_aidx = fp.cand_aidx;
-  np.counts = fp.counts; np.bitmap = fp.bitmap; np.bitmap_words = ws.bitmap_words;
-  np.nms_pos = reinterpret_cast<int32_t*>(wsb + ws.pos);
-  np.pre_keys = nullptr; np.pre_pos = nullptr; np.pre_count = nullptr; np.pre_elig = nullptr; np.pre_khi = nullptr;
-  if (n_img > 32768) {
-    // large segments: several CTAs per image gather the first NMS window so the single NMS CTA does not have to
-    // scan hundreds of thousands of scores alone
-    NmsPreselectParams pp;
-    int slices = (4 * b200_sm_count() + num_images - 1) / num_images;
-    if (slices < 1) slices = 1;
-    if (slices > 32) slices = 32;
-    pp.scores = fp.cand_score; pp.order_id = fp.cand_aidx; pp.counts = fp.counts; pp.stride = n_img; pp.slices = slices;
-    pp.use_score_thr = 1; pp.score_thr = score_thr;
-    pp.keys = reinterpret_cast<unsigned long long*>(wsb + ws.pre_keys);
-    pp.pos = reinterpret_cast<uint32_t*>(wsb + ws.pre_pos);
-    pp.count = reinterpret_cast<int*>(wsb + ws.pre_count);
-    pp.eligible = reinterpret_cast<int*>(wsb + ws.pre_elig);
-    pp.khi = reinterpret_cast<unsigned long long*>(wsb + ws.pre_khi);
-    B200_CUDA(cudaFuncSetAttribute(effdet_nms_pivot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NMS_PIVOT_SMEM));
-    effdet_nms_pivot_kernel<<<num_images, NMS_THREADS, NMS_PIVOT_SMEM, stream>>>(pp);
-    B200_LAUNCH_CHECK();
-    effdet_nms_pregather_kernel<<<num_images * slices, 512, 0, stream>>>(pp);
-    B200_LAUNCH_CHECK();
-    np.pre_keys = pp.keys; np.pre_pos = pp.pos; np.pre_count = pp.count; np.pre_elig = pp.eligible; np.pre_khi = pp.khi;
-  }
-  np.out_boxes = out_boxes; np.out_cls = out_class_id; np.out_score = out_score; np.out_sel_idx = out_sel_idx;
-  np.out_sel_anchor = out_sel_anchor; np.out_count = out_count;
-  size_t smem2 = nms_smem_bytes(max_out);
-  if (smem2 < (size_t)ws.bitmap_words * 4) smem2 = (size_t)ws.bitmap_words * 4;
-  B200_REQUIRE(smem2 <= 220 * 1024, B200_ERR_UNSUPPORTED, "b200_effdet_postprocess: too many anchors per image for the rank table");
-#define EF_LAUNCH(M)                                                                                                     \
-  B200_CUDA(cudaFuncSetAttribute(effdet_nms_finalize_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
-  effdet_nms_finalize_kernel<M><<<num_images, NMS_THREADS, smem2, stream>>>(np)
-  NMS_DISPATCH_METRIC(metric, EF_LAUNCH)
-#undef EF_LAUNCH
-  B200_LAUNCH_CHECK();
-  return B200_OK;
+  return ef_launch_nms(fp, ws, wsb, num_images, n_img, max_out, iou_thr, score_thr, metric, out_boxes, out_class_id, out_score,
+                       out_sel_idx, out_sel_anchor, out_count, stream);
 }
 
 static int ef_assign_impl(int num_levels, const int32_t* hw, int A, const float* table_dev, int C, int B,
@@ -671,4 +681,331 @@ extern "C" int b200_effdet_assign_targets_indexed(int num_levels, const int32_t*
   B200_REQUIRE(out_class, B200_ERR_BAD_ARG, "b200_effdet_assign_targets_indexed: null argument");
   return ef_assign_impl(num_levels, hw, A, table_dev, C, B, gt_boxes, gt_classes, gt_offsets, iou_thr, out_boxes, nullptr,
                         out_class, out_mask, stream);
+}
+
+// ---- fused eval-step stream (test_step, efficientnet/efficientdet_net_train.py:135-169) ----------------------------
+// The reference's test_step reads the class logits twice: FocalLoss (:150) and, after convert_outputs_boxes (:153), the
+// per-image argmax / max of convert_outputs_one (anchors.py:172-174).  Here ONE pass over every level does
+//   * focal loss of the tile's logits against the one-hot targets (flat 128-bit streaming loads, both tensors),
+//   * argmax / max over each anchor's C logits (the tile also goes to shared memory; four lanes per anchor),
+//   * box decode from the head offsets and the anchor table (anchors.py:245-274) -> the dense decoded tensor,
+//   * Huber box loss + positive count (box_loss.py:17-29), and
+//   * the append of every non-background anchor to its image's candidate list (anchors.py:179-189).
+// WITH_LOSS = false is the same stream without targets: convert_outputs_boxes + the filter of convert_outputs_one.
+#define EFU_TILE 64      // anchors per tile
+#define EFU_THREADS 256
+#define EFU_INFLIGHT 3   // float4 of each class tensor a thread has in flight
+
+struct EfFusedParams {
+  EfLevels lv;
+  int B, C, n_img;
+  const float* cls[EF_MAX_LEVELS];        // (B,H,W,A,C) logits
+  const float* cls_true[EF_MAX_LEVELS];   // (B,H,W,A,C) targets (WITH_LOSS)
+  const float4* rel[EF_MAX_LEVELS];       // (B,H,W,A,4) head offsets ty,tx,th,tw
+  const float4* box_true[EF_MAX_LEVELS];  // (WITH_LOSS)
+  const unsigned char* mask[EF_MAX_LEVELS];
+  float4* dec[EF_MAX_LEVELS];             // decoded boxes out
+  long long tile_base[EF_MAX_LEVELS + 1];
+  float4* cand_box; float* cand_score; int32_t* cand_cls; uint32_t* cand_aidx; int32_t* counts;
+  uint32_t* bitmap; int bitmap_words;
+  float alpha, gamma, delta, label_smoothing;
+  double* partials;                       // [gridDim.x][num_levels][3] focal, huber, positives
+};
+
+template <bool WITH_LOSS, bool G15>
+__global__ void __launch_bounds__(EFU_THREADS, 4) effdet_stream_kernel(EfFusedParams p) {
+  extern __shared__ __align__(16) unsigned char efu_smem[];
+  float* tile = reinterpret_cast<float*>(efu_smem);                 // [EFU_TILE * C]
+  __shared__ double s_part[EF_MAX_LEVELS][3];
+  __shared__ double s_red[EFU_THREADS / 32][3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = p.C;
+  if (tid < EF_MAX_LEVELS * 3) s_part[tid / 3][tid % 3] = 0.0;
+  const long long n_tiles = p.tile_base[p.lv.num_levels];
+  double focal = 0.0;
+  float hub = 0.f;
+  unsigned int pos = 0;
+  int cur_level = -1;
+  auto flush = [&](int level) {   // block-reduce this thread's running sums into the level's slot
+    double v0 = warp_sum_d(focal), v1 = warp_sum_d((double)hub), v2 = warp_sum_d((double)pos);
+    if (lane == 0) { s_red[warp][0] = v0; s_red[warp][1] = v1; s_red[warp][2] = v2; }
+    __syncthreads();
+    if (tid < 3) {
+      double sacc = 0.0;
+      for (int w = 0; w < EFU_THREADS / 32; ++w) sacc += s_red[w][tid];
+      s_part[level][tid] += sacc;
+    }
+    __syncthreads();
+    focal = 0.0; hub = 0.f; pos = 0;
+  };
+  const int a_in_tile = tid >> 2, part = tid & 3;
+  const int q = (C + 3) >> 2;
+  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < EF_MAX_LEVELS; ++k) if (k < p.lv.num_levels && t >= p.tile_base[k]) l = k;
+    if (WITH_LOSS && l != cur_level) {
+      if (cur_level >= 0) flush(cur_level);
+      cur_level = l;
+    }
+    const int api = p.lv.anc_per_img[l];
+    const long long rec0 = (t - p.tile_base[l]) * EFU_TILE;
+    const long long remain = (long long)p.B * api - rec0;
+    const int nrec = remain < EFU_TILE ? (int)remain : EFU_TILE;
+    // per-anchor inputs of the box half, issued first so that they travel with the class stream
+    const bool boxer = (part == 0) && (a_in_tile < nrec);
+    const long long rec = rec0 + a_in_tile;
+    float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f), t4 = r4;
+    unsigned char mk = 0;
+    if (boxer) {
+      r4 = __ldcs(p.rel[l] + rec);
+      if (WITH_LOSS) { t4 = __ldcs(p.box_true[l] + rec); mk = p.mask[l][rec]; }
+    }
+    // ---- phase 1: flat stream of the tile's logits (and targets): focal terms + copy to shared memory ----
+    const float* xg = p.cls[l] + rec0 * C;
+    const float* yg = WITH_LOSS ? p.cls_true[l] + rec0 * C : nullptr;
+    const int n_el = nrec * C;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(xg) | (WITH_LOSS ? reinterpret_cast<uintptr_t>(yg) : 0)) & 15) == 0;
+    const int n_vec = vec_ok ? (n_el >> 2) : 0;
+    float f0 = 0.f, f1 = 0.f;
+    for (int i0 = 0; i0 < n_vec; i0 += EFU_THREADS * EFU_INFLIGHT) {
+      float4 x[EFU_INFLIGHT], y[EFU_INFLIGHT];
+#pragma unroll
+      for (int u = 0; u < EFU_INFLIGHT; ++u) {
+        const int i = i0 + u * EFU_THREADS + tid;
+        if (i < n_vec) {
+          x[u] = __ldcs(reinterpret_cast<const float4*>(xg) + i);
+          if (WITH_LOSS) y[u] = __ldcs(reinterpret_cast<const float4*>(yg) + i);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < EFU_INFLIGHT; ++u) {
+        const int i = i0 + u * EFU_THREADS + tid;
+        if (i < n_vec) {
+          reinterpret_cast<float4*>(tile)[i] = x[u];
+          if (WITH_LOSS) {
+            f0 += el_focal<G15>(y[u].x, x[u].x, p.alpha, p.gamma, p.label_smoothing) + el_focal<G15>(y[u].y, x[u].y, p.alpha, p.gamma, p.label_smoothing);
+            f1 += el_focal<G15>(y[u].z, x[u].z, p.alpha, p.gamma, p.label_smoothing) + el_focal<G15>(y[u].w, x[u].w, p.alpha, p.gamma, p.label_smoothing);
+          }
+        }
+      }
+    }
+    for (int e = (n_vec << 2) + tid; e < n_el; e += EFU_THREADS) {   // unaligned level / ragged tail: scalar
+      const float xv = __ldg(xg + e);
+      tile[e] = xv;
+      if (WITH_LOSS) f0 += el_focal<G15>(__ldg(yg + e), xv, p.alpha, p.gamma, p.label_smoothing);
+    }
+    if (WITH_LOSS) focal += (double)f0 + (double)f1;
+    __syncthreads();
+    // ---- phase 2: four lanes per anchor: tf.argmax (first maximal index) / reduce_max over the C logits ----
+    float m = -INFINITY;
+    int mi = -1;
+    if (a_in_tile < nrec) {
+      const float* r = tile + a_in_tile * C;
+      int c0 = part * q;
+      const int c1 = min(C, c0 + q);
+      if (part == 0) { m = r[0]; mi = 0; c0 = 1; }   // the scan starts from element 0 exactly as a serial one (NaN there sticks)
+      for (int c = c0; c < c1; ++c) { const float v = r[c]; if (v > m) { m = v; mi = c; } }
+    }
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {   // fold parts 1..3 into part 0 in ascending index order: ties keep the lower index
+      const float vk = __shfl_sync(0xffffffffu, m, (lane & ~3) + k);
+      const int ik = __shfl_sync(0xffffffffu, mi, (lane & ~3) + k);
+      if (part == 0 && vk > m) { m = vk; mi = ik; }
+    }
+    bool pass = false;
+    int img = 0;
+    uint32_t aidx = 0;
+    float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (boxer) {
+      img = (int)(rec / api);
+      const int rin = (int)(rec - (long long)img * api);
+      int y, x, an_i;
+      ef_split(p.lv, l, rin, y, x, an_i);
+      const AnchorBox an = ef_anchor(p.lv, l, y, x, an_i);
+      // _boxes_decoder, anc:245-274 (the arithmetic of effdet_decode_kernel)
+      const float yca = DM_DIV(DM_ADD(an.y2, an.y1), 2.0f), xca = DM_DIV(DM_ADD(an.x2, an.x1), 2.0f);
+      const float ha = DM_SUB(an.y2, an.y1), wa = DM_SUB(an.x2, an.x1);
+      const float w = DM_MUL(dm_expf(r4.w), wa), h = DM_MUL(dm_expf(r4.z), ha);
+      const float yc = DM_ADD(DM_MUL(r4.x, ha), yca), xc = DM_ADD(DM_MUL(r4.y, wa), xca);
+      const float hh = DM_DIV(h, 2.0f), hw = DM_DIV(w, 2.0f);
+      d4 = make_float4(DM_SUB(yc, hh), DM_SUB(xc, hw), DM_ADD(yc, hh), DM_ADD(xc, hw));
+      if (p.dec[l]) __stcs(p.dec[l] + rec, d4);
+      if (WITH_LOSS) {
+        hub += el_huber(t4.x, r4.x, p.delta) + el_huber(t4.y, r4.y, p.delta) + el_huber(t4.z, r4.z, p.delta) + el_huber(t4.w, r4.w, p.delta);
+        pos += mk ? 1u : 0u;
+      }
+      if (mi != 0) {   // classes_mask = classes_id != 0 (anc:179)
+        pass = true;
+        aidx = (uint32_t)(p.lv.anchor_base[l] + rin);
+      }
+    }
+    // warp-aggregated append, one atomic per (warp, image)
+    uint32_t todo = __ballot_sync(0xffffffffu, pass);
+    while (todo) {
+      const int leader = __ffs(todo) - 1;
+      const int limg = __shfl_sync(0xffffffffu, img, leader);
+      const uint32_t grp = __ballot_sync(0xffffffffu, pass && img == limg);
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&p.counts[limg], __popc(grp));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (pass && img == limg) {
+        const size_t slot = (size_t)limg * p.n_img + base + __popc(grp & ((1u << lane) - 1u));
+        p.cand_box[slot] = d4; p.cand_score[slot] = m; p.cand_cls[slot] = mi; p.cand_aidx[slot] = aidx;
+        if (p.bitmap) atomicOr(&p.bitmap[(size_t)limg * p.bitmap_words + (aidx >> 5)], 1u << (aidx & 31u));
+      }
+      todo &= ~grp;
+    }
+    __syncthreads();   // the tile is consumed: the next iteration may overwrite it
+  }
+  if (WITH_LOSS) {
+    if (cur_level >= 0) flush(cur_level);
+    __syncthreads();
+    if (tid < p.lv.num_levels * 3)
+      p.partials[((size_t)blockIdx.x * p.lv.num_levels + tid / 3) * 3 + tid % 3] = s_part[tid / 3][tid % 3];
+  }
+}
+
+// sums layout of effdet_loss.cu: [0..L) focal_l, [L..2L) huber_l, [2L] positives
+__global__ void __launch_bounds__(256) effdet_stream_reduce_kernel(const double* __restrict__ partials, int n_cta, int L, double* __restrict__ sums) {
+  __shared__ double s_red[8][3];
+  const int l = blockIdx.x;
+  double a[3] = {0.0, 0.0, 0.0};
+  for (int c = threadIdx.x; c < n_cta; c += 256) {
+    const double* q = partials + ((size_t)c * L + l) * 3;
+    a[0] += q[0]; a[1] += q[1]; a[2] += q[2];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { const double v = warp_sum_d(a[k]); if (lane == 0) s_red[warp][k] = v; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sacc[3] = {0.0, 0.0, 0.0};
+    for (int w = 0; w < 8; ++w) for (int k = 0; k < 3; ++k) sacc[k] += s_red[w][k];
+    sums[l] = sacc[0];
+    sums[L + l] = sacc[1];
+    atomicAdd(&sums[2 * L], sacc[2]);  // integer-valued: exact and order-independent
+  }
+}
+
+#define EFU_GRID_PER_SM 16
+
+static size_t efu_partials_bytes(int num_levels) {
+  return b200_align_up(sizeof(double) * 3 * (size_t)num_levels * (size_t)b200_sm_count() * EFU_GRID_PER_SM, 256);
+}
+
+extern "C" size_t b200_effdet_eval_workspace_bytes(int num_levels, const int32_t* hw, int A, int num_images, int max_out) {
+  return b200_effdet_postprocess_workspace_bytes(num_levels, hw, A, num_images, max_out) + efu_partials_bytes(num_levels);
+}
+
+static int efu_impl(bool with_loss, int num_levels, const int32_t* hw, int A, const float* table_dev, int C, int B,
+                    const float* const true_boxes[], const float* const true_classes[], const unsigned char* const true_masks[],
+                    const float* const pred_boxes[], const float* const pred_classes[], float alpha, float gamma, float delta,
+                    float label_smoothing, double* sums_out, float* const out_decoded[], int max_out, float iou_thr,
+                    float score_thr, int metric, float* out_boxes, long long* out_class_id, float* out_score,
+                    int32_t* out_sel_idx, int32_t* out_sel_anchor, int32_t* out_count, void* workspace, size_t workspace_bytes,
+                    void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const char* who = with_loss ? "b200_effdet_eval_step" : "b200_effdet_decode_postprocess";
+  EfFusedParams p;
+  B200_REQUIRE(hw && table_dev && pred_boxes && pred_classes, B200_ERR_BAD_ARG, "%s: null argument", who);
+  B200_REQUIRE(!with_loss || (true_boxes && true_classes && true_masks && sums_out), B200_ERR_BAD_ARG, "%s: null target argument", who);
+  const int n_img = ef_fill_levels(p.lv, num_levels, hw, A, table_dev);
+  B200_REQUIRE(n_img >= 0, B200_ERR_BAD_ARG, "%s: bad level spec", who);
+  B200_REQUIRE(C >= 1 && C <= 400, B200_ERR_UNSUPPORTED, "%s: classes_num %d outside [1,400]", who, C);
+  B200_REQUIRE(B >= 0, B200_ERR_BAD_ARG, "%s: negative batch", who);
+  B200_REQUIRE(metric >= B200_METRIC_EFF_IOU && metric <= B200_METRIC_EFF_CIOU, B200_ERR_BAD_ARG, "%s: iou_type must be iou/giou/diou/ciou", who);
+  B200_REQUIRE(max_out >= 1 && max_out <= NMS_MAX_OUT_LIMIT, B200_ERR_UNSUPPORTED, "%s: max_out %d outside [1,%d]", who, max_out, NMS_MAX_OUT_LIMIT);
+  if (B == 0) return B200_OK;
+  B200_REQUIRE(out_boxes && out_class_id && out_score && out_count, B200_ERR_BAD_ARG, "%s: null output", who);
+  EfWs ws = ef_ws_layout(B, n_img, max_out);
+  const size_t part_bytes = efu_partials_bytes(num_levels);
+  B200_REQUIRE(workspace && workspace_bytes >= ws.total + part_bytes, B200_ERR_WORKSPACE, "%s: workspace %zu < required %zu", who, workspace_bytes, ws.total + part_bytes);
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, B200_ERR_BAD_ARG, "%s: workspace not 256-byte aligned", who);
+  unsigned char* wsb = static_cast<unsigned char*>(workspace);
+  p.B = B; p.C = C; p.n_img = n_img;
+  long long tb = 0;
+  for (int l = 0; l < EF_MAX_LEVELS; ++l) {
+    p.tile_base[l] = tb;
+    p.cls[l] = nullptr; p.cls_true[l] = nullptr; p.rel[l] = nullptr; p.box_true[l] = nullptr; p.mask[l] = nullptr; p.dec[l] = nullptr;
+    if (l >= num_levels) continue;
+    B200_REQUIRE(pred_boxes[l] && pred_classes[l], B200_ERR_BAD_ARG, "%s: null level %d", who, l);
+    B200_REQUIRE(!with_loss || (true_boxes[l] && true_classes[l] && true_masks[l]), B200_ERR_BAD_ARG, "%s: null target level %d", who, l);
+    uintptr_t al = reinterpret_cast<uintptr_t>(pred_boxes[l]) | (out_decoded && out_decoded[l] ? reinterpret_cast<uintptr_t>(out_decoded[l]) : 0);
+    if (with_loss) al |= reinterpret_cast<uintptr_t>(true_boxes[l]);
+    B200_REQUIRE((al & 15) == 0, B200_ERR_BAD_ARG, "%s: box tensors of level %d must be 16-byte aligned", who, l);
+    p.cls[l] = pred_classes[l];
+    p.rel[l] = reinterpret_cast<const float4*>(pred_boxes[l]);
+    p.dec[l] = out_decoded ? reinterpret_cast<float4*>(out_decoded[l]) : nullptr;
+    if (with_loss) {
+      p.cls_true[l] = true_classes[l];
+      p.box_true[l] = reinterpret_cast<const float4*>(true_boxes[l]);
+      p.mask[l] = true_masks[l];
+    }
+    tb += ((long long)B * p.lv.anc_per_img[l] + EFU_TILE - 1) / EFU_TILE;
+  }
+  for (int l = num_levels; l <= EF_MAX_LEVELS; ++l) p.tile_base[l] = tb;
+  p.cand_box = reinterpret_cast<float4*>(wsb + ws.box);
+  p.cand_score = reinterpret_cast<float*>(wsb + ws.score);
+  p.cand_cls = reinterpret_cast<int32_t*>(wsb + ws.cls);
+  p.cand_aidx = reinterpret_cast<uint32_t*>(wsb + ws.aidx);
+  p.counts = reinterpret_cast<int32_t*>(wsb + ws.counts);
+  p.bitmap = out_sel_idx ? reinterpret_cast<uint32_t*>(wsb + ws.bitmap) : nullptr;
+  p.bitmap_words = ws.bitmap_words;
+  p.alpha = alpha; p.gamma = gamma; p.delta = delta; p.label_smoothing = label_smoothing;
+  p.partials = reinterpret_cast<double*>(wsb + ws.total);
+  B200_CUDA(cudaMemsetAsync(wsb, 0, out_sel_idx ? ws.box : ws.bitmap, stream));
+  const size_t smem = (size_t)EFU_TILE * C * sizeof(float);
+  long long want = tb;
+  const long long cap = (long long)b200_sm_count() * EFU_GRID_PER_SM;
+  const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+#define EFU_LAUNCH(WL, G)                                                                                                  \
+  do {                                                                                                                     \
+    B200_CUDA(cudaFuncSetAttribute(effdet_stream_kernel<WL, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    effdet_stream_kernel<WL, G><<<grid, EFU_THREADS, smem, stream>>>(p);                                                  \
+  } while (0)
+  if (!with_loss) EFU_LAUNCH(false, false);
+  else if (gamma == 1.5f) EFU_LAUNCH(true, true);
+  else EFU_LAUNCH(true, false);
+#undef EFU_LAUNCH
+  B200_LAUNCH_CHECK();
+  if (with_loss) {
+    B200_CUDA(cudaMemsetAsync(sums_out, 0, sizeof(double) * (2 * num_levels + 1), stream));
+    effdet_stream_reduce_kernel<<<num_levels, 256, 0, stream>>>(p.partials, grid, num_levels, sums_out);
+    B200_LAUNCH_CHECK();
+  }
+  // the NMS tail reads the candidate store through the filter-parameter view
+  EfFilterParams fp;
+  fp.lv = p.lv; fp.B0 = 0; fp.NB = B; fp.C = C; fp.B = B; fp.n_img = n_img;
+  fp.cand_box = p.cand_box; fp.cand_score = p.cand_score; fp.cand_cls = p.cand_cls; fp.cand_aidx = p.cand_aidx;
+  fp.counts = p.counts; fp.bitmap = p.bitmap; fp.bitmap_words = p.bitmap_words;
+  return ef_launch_nms(fp, ws, wsb, B, n_img, max_out, iou_thr, score_thr, metric, out_boxes, out_class_id, out_score, out_sel_idx,
+                       out_sel_anchor, out_count, stream);
+}
+
+// test_step in one call: sums_out [2L+1] fp64 (un-normalised focal_l, huber_l, positives: feed b200_focal_box_finalize or
+// its _dp form), out_decoded[l] = convert_outputs_boxes, then convert_outputs_one for every image of the batch.
+extern "C" int b200_effdet_eval_step(int num_levels, const int32_t* hw, int A, const float* table_dev, int C, int B,
+                                     const float* const true_boxes[], const float* const true_classes[],
+                                     const unsigned char* const true_masks[], const float* const pred_boxes[],
+                                     const float* const pred_classes[], float alpha, float gamma, float delta,
+                                     float label_smoothing, double* sums_out, float* const out_decoded[], int max_out,
+                                     float iou_thr, float score_thr, int metric, float* out_boxes, long long* out_class_id,
+                                     float* out_score, int32_t* out_sel_idx, int32_t* out_sel_anchor, int32_t* out_count,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  return efu_impl(true, num_levels, hw, A, table_dev, C, B, true_boxes, true_classes, true_masks, pred_boxes, pred_classes, alpha,
+                  gamma, delta, label_smoothing, sums_out, out_decoded, max_out, iou_thr, score_thr, metric, out_boxes, out_class_id,
+                  out_score, out_sel_idx, out_sel_anchor, out_count, workspace, workspace_bytes, stream);
+}
+
+// convert_outputs_boxes + convert_outputs_one of the whole batch in one pass over the heads (no targets, no loss).
+extern "C" int b200_effdet_decode_postprocess(int num_levels, const int32_t* hw, int A, const float* table_dev, int C, int B,
+                                              const float* const pred_boxes[], const float* const pred_classes[],
+                                              float* const out_decoded[], int max_out, float iou_thr, float score_thr, int metric,
+                                              float* out_boxes, long long* out_class_id, float* out_score, int32_t* out_sel_idx,
+                                              int32_t* out_sel_anchor, int32_t* out_count, void* workspace, size_t workspace_bytes,
+                                              void* stream) {
+  return efu_impl(false, num_levels, hw, A, table_dev, C, B, nullptr, nullptr, nullptr, pred_boxes, pred_classes, 0.f, 0.f, 0.f, 0.f,
+                  nullptr, out_decoded, max_out, iou_thr, score_thr, metric, out_boxes, out_class_id, out_score, out_sel_idx,
+                  out_sel_anchor, out_count, workspace, workspace_bytes, stream);
 }

@@ -284,3 +284,69 @@ def test_gradient_with_class_index_targets_equals_one_hot(lib, cuda):
         assert torch.equal(gb_d[l], gb_i[l]), l
     with pytest.raises(ValueError):
         get_loss_and_grad(ib, [t[..., :1] for t in tc], im, pb, pc)
+
+
+@pytest.mark.parametrize("name,batch,C,iou_type", [("small", 3, 81, "diou"), ("rect", 2, 7, "ciou"), ("d0", 2, 81, "diou"), ("small", 5, 6, "giou")])
+def test_fused_eval_step_matches_oracle_and_separate_calls(lib, cuda, name, batch, C, iou_type):
+    """test_step in one pass (b200_effdet_eval_step / b200_effdet_decode_postprocess): the class logits are read once for
+    the focal loss and the argmax filter.  Against the oracle: decoded boxes, NMS indices / anchors / class ids / boxes /
+    scores bit-exact, loss <= 1e-4; against the separate drop-in calls: identical outputs, loss equal to 1e-6."""
+    import torch
+    from oracle import effdet as oe
+    from tfmv_b200 import synth
+    from tfmv_b200.ai_models.efficientnet.efficientdet_net_train import get_loss
+    a, o = _pair(name)
+    rng = np.random.default_rng(600 + batch + C)
+    hw = CFGS[name]["image_size"]
+    boxes, classes, off = synth.gt_batch(rng, batch, (hw[1], hw[0]), max_boxes=20, order="yxyx")
+    classes = (classes % (C - 1) + 1).astype(np.int32)
+    per = [o.generate_targets(boxes[off[b]:off[b + 1]], classes[off[b]:off[b + 1]], C) for b in range(batch)]
+    L = len(o.boxes)
+    tb = [np.stack([p[0][l] for p in per], 0) for l in range(L)]
+    tc = [np.stack([p[1][l] for p in per], 0) for l in range(L)]
+    tm = [np.stack([p[2][l] for p in per], 0) for l in range(L)]
+    rel = [(rng.standard_normal(t.shape, dtype=F) * F(0.25)) for t in tb]
+    cls = [rng.standard_normal(t.shape, dtype=F) for t in tc]
+    cls[0][0, 0, 0, :, :] = 0.5          # ties across classes -> argmax 0 -> background, dropped
+    cls[0][0, 0, 1, :, C - 1] = 3.0      # exact score ties between anchors -> lower index first
+    cls[0][1, 0, 0, 0, 0] = np.nan       # NaN in channel 0 sticks (serial scan from element 0): background
+    cls[0][1, 0, 0, 1, 3] = np.nan       # NaN elsewhere is skipped by `v > m`
+    rel[0][0, 0, 0, 0, 2] = 120.0        # exp overflow -> inf box (anc:266)
+    d = lambda xs: [_t(x, cuda) for x in xs]
+    loss, dec, r = a.eval_step(d(tb), d(tc), d(tm), d(rel), d(cls), iou_type=iou_type, with_indices=True)
+    dec2, r2 = a.decode_and_postprocess(d(rel), d(cls), iou_type=iou_type, with_indices=True)
+    dec_w = o.convert_outputs_boxes(rel)
+    for l in range(L):
+        assert_bits_equal(dec[l].cpu().numpy(), dec_w[l])
+        assert_bits_equal(dec2[l].cpu().numpy(), dec_w[l])
+    rn = {k: v.cpu().numpy() for k, v in r.items()}
+    assert sorted(rn) == sorted(r2)
+    for b in range(batch):
+        # the image with planted NaN logits is compared with the separate calls only (np.argmax and the serial `v > m`
+        # scan of the kernels differ on NaN; non-finite logits are outside the parity contract, DESIGN.md section 8)
+        w = None if np.isnan(cls[0][b]).any() else o.convert_outputs_one_ex(b, dec_w, cls, iou_type=iou_type)
+        k = int(rn["count"][b])
+        assert k == int(r2["count"][b])
+        for key in ("sel_idx", "sel_anchor", "classes_id", "boxes", "scores"):
+            assert np.array_equal(rn[key][b, :k], r2[key][b, :k].cpu().numpy(), equal_nan=True), (b, key)
+        if w is None:
+            continue
+        assert k == w["selected"].shape[0] and k > 0
+        assert rn["sel_idx"][b, :k].tolist() == w["selected"].tolist()
+        assert rn["sel_anchor"][b, :k].tolist() == w["cand_anchor"][w["selected"]].tolist()
+        assert rn["classes_id"][b, :k].tolist() == w["classes_id"].tolist()
+        assert_bits_equal(rn["boxes"][b, :k], w["boxes"])
+        assert_bits_equal(rn["scores"][b, :k], w["scores"])
+    # the separate drop-in calls give the same post-processing result, NaN rows included
+    rs = a.convert_outputs_batch(a.convert_outputs_boxes(d(rel)), d(cls), iou_type=iou_type, with_indices=True)
+    for b in range(batch):
+        k = int(rn["count"][b])
+        assert k == int(rs["count"][b])
+        for key in ("sel_idx", "sel_anchor", "classes_id", "boxes", "scores"):
+            assert np.array_equal(rn[key][b, :k], rs[key][b, :k].cpu().numpy(), equal_nan=True), (b, key)
+    cls_l = [np.nan_to_num(c, nan=0.0) for c in cls]           # the loss itself on NaN-free logits
+    loss2, _, _ = a.eval_step(d(tb), d(tc), d(tm), d(rel), d(cls_l), iou_type=iou_type)
+    want = float(oe.get_loss(tb, tc, tm, rel, cls_l))
+    assert abs(float(loss2) - want) <= LOSS_RTOL * abs(want)
+    sep = float(get_loss(d(tb), d(tc), d(tm), d(rel), d(cls_l)))
+    assert abs(float(loss2) - sep) <= 2e-6 * abs(sep)
