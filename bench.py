@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--repeats", type=int, default=25, help="timed windows of --steps steps for the headline (median reported)")
     ap.add_argument("--config-repeats", type=int, default=9, help="timed windows per entry of `configs`")
     ap.add_argument("--only", default="", help="comma list out of c1,c2,c3,c4,c5: measure only these")
+    ap.add_argument("--c5-global-batch", type=int, default=512, help="global batch of configs.c5 (512 = BASELINE configs[4])")
     ap.add_argument("--cpu-sample", type=int, default=0, help="images per CPU-baseline run (0 = 16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl", "torch"], help="transport of the loss all-reduce (N > 1)")
@@ -626,7 +627,7 @@ def config_c5(b):
     from tfmv_b200.ai_models.datasets.coco_dataset import DataGenerator
     from tfmv_b200.ai_models.utils import tf_yolo_utils as tyu
     args, torch, world, rank = b.args, b.torch, b.world, b.rank
-    G, image = 512, 608
+    G, image = args.c5_global_batch, 608
     lo, hi = tyu.shard_range(G, rank, world)
     B = hi - lo
     anc = synth.yolo_anchors().astype(F)
@@ -656,7 +657,7 @@ def config_c5(b):
     ms, w = b.timed(fn, args.steps, args.warmup, args.config_repeats)
     loss = float(fn()[0].item())
     out = {"what": WHAT["c5"], "global_batch": G, "per_gpu_batch": B, "n_gpus": world, "value": G / ms * 1e3, "unit": "images/s",
-           "ms_per_step": ms, "ms_per_step_spread": spread(w), "scaling": "strong (global batch fixed at 512)", "loss": loss,
+           "ms_per_step": ms, "ms_per_step_spread": spread(w), "scaling": "strong (global batch fixed at %d)" % G, "loss": loss,
            "algorithmic_bytes_per_image": BYTES["c5"], "roofline": b.roofline("c5", B, ms), "fused": fused is not None,
            "exchange": b.exchange_kind, "l2": "inputs larger than L2 (%.1f GB of heads + %.1f GB of targets per rank)" % (
                sum(h.numel() for h in heads) * 4 / 1e9, sum(t.numel() for t in y_true) * 4 / 1e9)}

@@ -285,6 +285,48 @@ def GetLossFromBoxes(classes, boxes, offsets, y_pred, image_wh, anchors_wh, clas
   return (loss, parts) if return_parts else loss
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+  key = (dev.type, dev.index)
+  if key not in _SIDE_STREAMS:
+    _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+  return _SIDE_STREAMS[key]
+
+
+def LossAndNMSBoxesBatch(y_true, y_pred, image_wh, anchors_wh, classes_num, iou_thresh=0.5, iou_type='iou',
+                         confidence_thresh=0.5, scores_thresh=0.3, nms_iou_thresh=0.5, nms_iou_type='iou',
+                         max_output_size=NMS_MAX_OUTPUT, global_batch=None, exchange=None, with_classes=True,
+                         with_indices=False, loss_anchors_wh=None, workspace=None):
+  '''
+  GetLoss and GetNMSBoxes on the SAME y_pred (an evaluation step that also reports the loss; BASELINE config 5).  The two
+  are independent given y_pred, so they run as two concurrent chains: decode filter -> NMS -> class rows on a second
+  stream, object scan -> GT preparation -> ignore mask / terms -> finalize (+ the data-parallel exchange) on the
+  current one.  The persistent decode filter (one CTA per SM, issue-bound) and the latency-bound loss kernels share the
+  SMs, and the per-image NMS CTAs run beside the loss instead of behind it.  CUDA-graph capturable (the fork / join
+  become graph branches).  Returns (loss, dict as GetNMSBoxesBatch).
+
+  loss_anchors_wh: the anchors GetLoss takes when they differ in units from the ones GetNMSBoxes takes (default: the same).
+  '''
+  assert iou_type in ['iou','diou','ciou'] and nms_iou_type in ['iou','diou','ciou']
+  heads = [T.to_cuda(t) for t in y_pred]
+  dev = heads[0].device
+  main = torch.cuda.current_stream(dev)
+  side = _side_stream(dev)
+  side.wait_stream(main)
+  with torch.cuda.stream(side):
+    r = GetNMSBoxesBatch(heads[0], heads[1], heads[2], anchors_wh, image_wh, classes_num, confidence_thresh, scores_thresh,
+                         nms_iou_thresh, nms_iou_type, max_output_size, with_classes, with_indices)
+  B = heads[0].shape[0]
+  loss = _loss_call(y_true, heads, image_wh, anchors_wh if loss_anchors_wh is None else loss_anchors_wh, iou_thresh, iou_type, 0,
+                    batch_divisor=B if global_batch is None else global_batch, workspace=workspace, exchange=exchange)
+  main.wait_stream(side)
+  for t in r.values():
+    t.record_stream(main)   # allocated on the side stream, consumed by the caller on the current one
+  return loss, r
+
+
 def GetLossAndGrad(y_true, y_pred, image_wh, anchors_wh, iou_thresh=0.5, iou_type='iou'):
   '''GetLoss plus d loss / d y_pred (list of 3 tensors shaped like y_pred) for an upstream gradient of 1 —
   what tf.GradientTape derives from the reference's GetLoss.  Wrap with tf.custom_gradient.'''

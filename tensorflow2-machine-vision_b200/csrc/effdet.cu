@@ -13,6 +13,7 @@
 // Anchors.boxes while saving 0.8 MB (D0) / 7 MB (D7) of reads per image.
 #include "nms.cuh"
 #include "effdet_focal.cuh"
+#include "bulkcopy.cuh"
 
 #define EF_MAX_LEVELS 8
 #define EF_STAGES 2
@@ -534,7 +535,7 @@ static int ef_launch_nms(const EfFilterParams& fp, const EfWs& ws, unsigned char
   np.counts = fp.counts; np.bitmap = fp.bitmap; np.bitmap_words = ws.bitmap_words;
   np.nms_pos = reinterpret_cast<int32_t*>(wsb + ws.pos);
   np.pre_keys = nullptr; np.pre_pos = nullptr; np.pre_count = nullptr; np.pre_elig = nullptr; np.pre_khi = nullptr;
-  if (n_img > 32768) {
+  if (n_img > NMS_PRE_MIN_N) {
     // large segments: several CTAs per image gather the first NMS window so the single NMS CTA does not have to
     // scan hundreds of thousands of scores alone
     NmsPreselectParams pp;
@@ -694,7 +695,9 @@ extern "C" int b200_effdet_assign_targets_indexed(int num_levels, const int32_t*
 // WITH_LOSS = false is the same stream without targets: convert_outputs_boxes + the filter of convert_outputs_one.
 #define EFU_TILE 64      // anchors per tile
 #define EFU_THREADS 256
-#define EFU_INFLIGHT 3   // float4 of each class tensor a thread has in flight
+#ifndef EFU_INFLIGHT
+#define EFU_INFLIGHT 4   // float4 of each class tensor a stream thread has in flight
+#endif
 
 struct EfFusedParams {
   EfLevels lv;
@@ -712,15 +715,38 @@ struct EfFusedParams {
   double* partials;                       // [gridDim.x][num_levels][3] focal, huber, positives
 };
 
+// Warp roles inside a CTA (tile = 64 anchors):
+//   warps 2-7 (CLASS stream, 192 threads): the tile's logits (and one-hot targets) arrive in shared memory by 1-D bulk
+//     asynchronous copies (cp.async.bulk + mbarrier, two stages: the copy of the CTA's next tile is in flight while this
+//     one is processed); focal terms from flat 128-bit shared-memory reads, then the per-anchor argmax with three lanes
+//     per anchor (partial (max, first index) per third of the C logits -> shared memory);
+//   warps 0-1 (BOX half, lane <-> anchor): head offsets / box targets / mask straight from global memory, decode, Huber,
+//     and — behind the tile's single CTA barrier — the fold of the three argmax partials and the candidate append.
+// Both halves are ~600-800 instructions per warp and tile and independent, so they run side by side.
+#define EFU_BOX_WARPS 2
+#define EFU_STREAM_THREADS (EFU_THREADS - 32 * EFU_BOX_WARPS)
+#define EFU_STAGES 2
+
 template <bool WITH_LOSS, bool G15>
-__global__ void __launch_bounds__(EFU_THREADS, 4) effdet_stream_kernel(EfFusedParams p) {
-  extern __shared__ __align__(16) unsigned char efu_smem[];
-  float* tile = reinterpret_cast<float*>(efu_smem);                 // [EFU_TILE * C]
-  __shared__ double s_part[EF_MAX_LEVELS][3];
-  __shared__ double s_red[EFU_THREADS / 32][3];
+__global__ void __launch_bounds__(EFU_THREADS, WITH_LOSS ? 2 : 4) effdet_stream_kernel(EfFusedParams p) {
+  extern __shared__ __align__(128) unsigned char efu_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = p.C;
+  const uint32_t tile_bytes = (uint32_t)EFU_TILE * (uint32_t)C * 4u;
+  // stage s: [x tile][y tile (WITH_LOSS)]
+  const uint32_t stage_bytes = tile_bytes * (WITH_LOSS ? 2u : 1u);
+  __shared__ __align__(8) uint64_t s_bar[EFU_STAGES];
+  __shared__ double s_part[EF_MAX_LEVELS][3];
+  __shared__ double s_red[EFU_THREADS / 32][3];
+  __shared__ float s_m[2][EFU_TILE][3];
+  __shared__ int s_mi[2][EFU_TILE][3];
   if (tid < EF_MAX_LEVELS * 3) s_part[tid / 3][tid % 3] = 0.0;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < EFU_STAGES; ++s) bc_mbar_init(&s_bar[s], 1);
+    bc_fence_mbar_init();
+  }
+  __syncthreads();
   const long long n_tiles = p.tile_base[p.lv.num_levels];
   double focal = 0.0;
   float hub = 0.f;
@@ -738,125 +764,168 @@ __global__ void __launch_bounds__(EFU_THREADS, 4) effdet_stream_kernel(EfFusedPa
     __syncthreads();
     focal = 0.0; hub = 0.f; pos = 0;
   };
-  const int a_in_tile = tid >> 2, part = tid & 3;
-  const int q = (C + 3) >> 2;
-  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    int l = 0;
+  // (level, first anchor, anchors, bulk-copyable) of a tile
+  auto locate = [&](long long t, int& l, long long& rec0, int& nrec) {
+    l = 0;
 #pragma unroll
     for (int k = 1; k < EF_MAX_LEVELS; ++k) if (k < p.lv.num_levels && t >= p.tile_base[k]) l = k;
+    rec0 = (t - p.tile_base[l]) * EFU_TILE;
+    const long long remain = (long long)p.B * p.lv.anc_per_img[l] - rec0;
+    nrec = remain < EFU_TILE ? (int)remain : EFU_TILE;
+  };
+  auto bulk_ok = [&](int l, long long rec0, int nrec) {
+    const uintptr_t ax = reinterpret_cast<uintptr_t>(p.cls[l] + rec0 * C);
+    const uintptr_t ay = WITH_LOSS ? reinterpret_cast<uintptr_t>(p.cls_true[l] + rec0 * C) : 0;
+    return (((ax | ay) & 15) == 0) && ((((uint32_t)nrec * (uint32_t)C * 4u) & 15u) == 0u);
+  };
+  auto issue = [&](long long t, int s) {   // one thread: start the copies of tile t into stage s
+    int l, nrec; long long rec0;
+    locate(t, l, rec0, nrec);
+    if (!bulk_ok(l, rec0, nrec)) return;   // ragged / unaligned tile: read straight from global memory when it is consumed
+    const uint32_t bytes = (uint32_t)nrec * (uint32_t)C * 4u;
+    unsigned char* dst = efu_smem + (size_t)s * stage_bytes;
+    bc_fence_proxy_async();
+    bc_mbar_expect_tx(&s_bar[s], bytes * (WITH_LOSS ? 2u : 1u));
+    bc_bulk_g2s(dst, p.cls[l] + rec0 * C, bytes, &s_bar[s]);
+    if (WITH_LOSS) bc_bulk_g2s(dst + tile_bytes, p.cls_true[l] + rec0 * C, bytes, &s_bar[s]);
+  };
+  const bool box_warp = warp < EFU_BOX_WARPS;
+  const int st = tid - 32 * EFU_BOX_WARPS;   // index among the stream threads
+  const int q3 = (C + 2) / 3;
+  if (tid == 32 * EFU_BOX_WARPS) {
+#pragma unroll
+    for (int s = 0; s < EFU_STAGES; ++s) {
+      const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
+      if (t < n_tiles) issue(t, s);
+    }
+  }
+  uint32_t phase_bits = 0;   // parity of each stage's barrier
+  int j = 0;
+  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++j) {
+    const int s = j & (EFU_STAGES - 1), pb = j & 1;
+    int l, nrec; long long rec0;
+    locate(t, l, rec0, nrec);
     if (WITH_LOSS && l != cur_level) {
       if (cur_level >= 0) flush(cur_level);
       cur_level = l;
     }
     const int api = p.lv.anc_per_img[l];
-    const long long rec0 = (t - p.tile_base[l]) * EFU_TILE;
-    const long long remain = (long long)p.B * api - rec0;
-    const int nrec = remain < EFU_TILE ? (int)remain : EFU_TILE;
-    // per-anchor inputs of the box half, issued first so that they travel with the class stream
-    const bool boxer = (part == 0) && (a_in_tile < nrec);
-    const long long rec = rec0 + a_in_tile;
-    float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f), t4 = r4;
-    unsigned char mk = 0;
-    if (boxer) {
-      r4 = __ldcs(p.rel[l] + rec);
-      if (WITH_LOSS) { t4 = __ldcs(p.box_true[l] + rec); mk = p.mask[l][rec]; }
-    }
-    // ---- phase 1: flat stream of the tile's logits (and targets): focal terms + copy to shared memory ----
-    const float* xg = p.cls[l] + rec0 * C;
-    const float* yg = WITH_LOSS ? p.cls_true[l] + rec0 * C : nullptr;
-    const int n_el = nrec * C;
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(xg) | (WITH_LOSS ? reinterpret_cast<uintptr_t>(yg) : 0)) & 15) == 0;
-    const int n_vec = vec_ok ? (n_el >> 2) : 0;
-    float f0 = 0.f, f1 = 0.f;
-    for (int i0 = 0; i0 < n_vec; i0 += EFU_THREADS * EFU_INFLIGHT) {
-      float4 x[EFU_INFLIGHT], y[EFU_INFLIGHT];
-#pragma unroll
-      for (int u = 0; u < EFU_INFLIGHT; ++u) {
-        const int i = i0 + u * EFU_THREADS + tid;
-        if (i < n_vec) {
-          x[u] = __ldcs(reinterpret_cast<const float4*>(xg) + i);
-          if (WITH_LOSS) y[u] = __ldcs(reinterpret_cast<const float4*>(yg) + i);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < EFU_INFLIGHT; ++u) {
-        const int i = i0 + u * EFU_THREADS + tid;
-        if (i < n_vec) {
-          reinterpret_cast<float4*>(tile)[i] = x[u];
-          if (WITH_LOSS) {
-            f0 += el_focal<G15>(y[u].x, x[u].x, p.alpha, p.gamma, p.label_smoothing) + el_focal<G15>(y[u].y, x[u].y, p.alpha, p.gamma, p.label_smoothing);
-            f1 += el_focal<G15>(y[u].z, x[u].z, p.alpha, p.gamma, p.label_smoothing) + el_focal<G15>(y[u].w, x[u].w, p.alpha, p.gamma, p.label_smoothing);
-          }
-        }
-      }
-    }
-    for (int e = (n_vec << 2) + tid; e < n_el; e += EFU_THREADS) {   // unaligned level / ragged tail: scalar
-      const float xv = __ldg(xg + e);
-      tile[e] = xv;
-      if (WITH_LOSS) f0 += el_focal<G15>(__ldg(yg + e), xv, p.alpha, p.gamma, p.label_smoothing);
-    }
-    if (WITH_LOSS) focal += (double)f0 + (double)f1;
-    __syncthreads();
-    // ---- phase 2: four lanes per anchor: tf.argmax (first maximal index) / reduce_max over the C logits ----
-    float m = -INFINITY;
-    int mi = -1;
-    if (a_in_tile < nrec) {
-      const float* r = tile + a_in_tile * C;
-      int c0 = part * q;
-      const int c1 = min(C, c0 + q);
-      if (part == 0) { m = r[0]; mi = 0; c0 = 1; }   // the scan starts from element 0 exactly as a serial one (NaN there sticks)
-      for (int c = c0; c < c1; ++c) { const float v = r[c]; if (v > m) { m = v; mi = c; } }
-    }
-#pragma unroll
-    for (int k = 1; k < 4; ++k) {   // fold parts 1..3 into part 0 in ascending index order: ties keep the lower index
-      const float vk = __shfl_sync(0xffffffffu, m, (lane & ~3) + k);
-      const int ik = __shfl_sync(0xffffffffu, mi, (lane & ~3) + k);
-      if (part == 0 && vk > m) { m = vk; mi = ik; }
-    }
-    bool pass = false;
+    const long long total = (long long)p.B * api;
+    const bool bulk = bulk_ok(l, rec0, nrec);
     int img = 0;
     uint32_t aidx = 0;
     float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (boxer) {
-      img = (int)(rec / api);
-      const int rin = (int)(rec - (long long)img * api);
-      int y, x, an_i;
-      ef_split(p.lv, l, rin, y, x, an_i);
-      const AnchorBox an = ef_anchor(p.lv, l, y, x, an_i);
-      // _boxes_decoder, anc:245-274 (the arithmetic of effdet_decode_kernel)
-      const float yca = DM_DIV(DM_ADD(an.y2, an.y1), 2.0f), xca = DM_DIV(DM_ADD(an.x2, an.x1), 2.0f);
-      const float ha = DM_SUB(an.y2, an.y1), wa = DM_SUB(an.x2, an.x1);
-      const float w = DM_MUL(dm_expf(r4.w), wa), h = DM_MUL(dm_expf(r4.z), ha);
-      const float yc = DM_ADD(DM_MUL(r4.x, ha), yca), xc = DM_ADD(DM_MUL(r4.y, wa), xca);
-      const float hh = DM_DIV(h, 2.0f), hw = DM_DIV(w, 2.0f);
-      d4 = make_float4(DM_SUB(yc, hh), DM_SUB(xc, hw), DM_ADD(yc, hh), DM_ADD(xc, hw));
-      if (p.dec[l]) __stcs(p.dec[l] + rec, d4);
-      if (WITH_LOSS) {
-        hub += el_huber(t4.x, r4.x, p.delta) + el_huber(t4.y, r4.y, p.delta) + el_huber(t4.z, r4.z, p.delta) + el_huber(t4.w, r4.w, p.delta);
-        pos += mk ? 1u : 0u;
-      }
-      if (mi != 0) {   // classes_mask = classes_id != 0 (anc:179)
-        pass = true;
+    if (box_warp) {
+      // ---- box half: lane <-> anchor ----
+      if (tid < nrec) {
+        const long long rec = rec0 + tid;
+        const float4 r4 = __ldcs(p.rel[l] + rec);
+        float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        unsigned char mk = 0;
+        if (WITH_LOSS) { t4 = __ldcs(p.box_true[l] + rec); mk = p.mask[l][rec]; }
+        int rin;
+        if (total < 0x7fffffffLL) { img = (int)((uint32_t)rec / (uint32_t)api); rin = (int)((uint32_t)rec - (uint32_t)img * (uint32_t)api); }
+        else { img = (int)(rec / api); rin = (int)(rec - (long long)img * api); }
+        int y, x, an_i;
+        ef_split(p.lv, l, rin, y, x, an_i);
+        const AnchorBox an = ef_anchor(p.lv, l, y, x, an_i);
+        // _boxes_decoder, anc:245-274 (the arithmetic of effdet_decode_kernel)
+        const float yca = DM_DIV(DM_ADD(an.y2, an.y1), 2.0f), xca = DM_DIV(DM_ADD(an.x2, an.x1), 2.0f);
+        const float ha = DM_SUB(an.y2, an.y1), wa = DM_SUB(an.x2, an.x1);
+        const float w = DM_MUL(dm_expf(r4.w), wa), h = DM_MUL(dm_expf(r4.z), ha);
+        const float yc = DM_ADD(DM_MUL(r4.x, ha), yca), xc = DM_ADD(DM_MUL(r4.y, wa), xca);
+        const float hh = DM_DIV(h, 2.0f), hw = DM_DIV(w, 2.0f);
+        d4 = make_float4(DM_SUB(yc, hh), DM_SUB(xc, hw), DM_ADD(yc, hh), DM_ADD(xc, hw));
+        if (p.dec[l]) __stcs(p.dec[l] + rec, d4);
+        if (WITH_LOSS) {
+          hub += el_huber(t4.x, r4.x, p.delta) + el_huber(t4.y, r4.y, p.delta) + el_huber(t4.z, r4.z, p.delta) + el_huber(t4.w, r4.w, p.delta);
+          pos += mk ? 1u : 0u;
+        }
         aidx = (uint32_t)(p.lv.anchor_base[l] + rin);
       }
-    }
-    // warp-aggregated append, one atomic per (warp, image)
-    uint32_t todo = __ballot_sync(0xffffffffu, pass);
-    while (todo) {
-      const int leader = __ffs(todo) - 1;
-      const int limg = __shfl_sync(0xffffffffu, img, leader);
-      const uint32_t grp = __ballot_sync(0xffffffffu, pass && img == limg);
-      int base = 0;
-      if (lane == leader) base = atomicAdd(&p.counts[limg], __popc(grp));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (pass && img == limg) {
-        const size_t slot = (size_t)limg * p.n_img + base + __popc(grp & ((1u << lane) - 1u));
-        p.cand_box[slot] = d4; p.cand_score[slot] = m; p.cand_cls[slot] = mi; p.cand_aidx[slot] = aidx;
-        if (p.bitmap) atomicOr(&p.bitmap[(size_t)limg * p.bitmap_words + (aidx >> 5)], 1u << (aidx & 31u));
+    } else {
+      // ---- class stream ----
+      float* xs = reinterpret_cast<float*>(efu_smem + (size_t)s * stage_bytes);
+      const float* ys = reinterpret_cast<const float*>(efu_smem + (size_t)s * stage_bytes + tile_bytes);
+      const int n_el = nrec * C;
+      float f0 = 0.f, f1 = 0.f;
+      if (bulk) {
+        bc_mbar_wait(&s_bar[s], (phase_bits >> s) & 1u);
+        if (WITH_LOSS) {
+          const int n_vec = n_el >> 2;
+#pragma unroll 2
+          for (int i = st; i < n_vec; i += EFU_STREAM_THREADS) {
+            const float4 x = reinterpret_cast<const float4*>(xs)[i];
+            const float4 y = reinterpret_cast<const float4*>(ys)[i];
+            f0 += el_focal<G15>(y.x, x.x, p.alpha, p.gamma, p.label_smoothing) + el_focal<G15>(y.y, x.y, p.alpha, p.gamma, p.label_smoothing);
+            f1 += el_focal<G15>(y.z, x.z, p.alpha, p.gamma, p.label_smoothing) + el_focal<G15>(y.w, x.w, p.alpha, p.gamma, p.label_smoothing);
+          }
+        }
+      } else {
+        // ragged tail of a level or an unaligned tensor: plain loads; the logits still go to the stage for the argmax
+        const float* xg = p.cls[l] + rec0 * C;
+        const float* yg = WITH_LOSS ? p.cls_true[l] + rec0 * C : nullptr;
+        for (int e = st; e < n_el; e += EFU_STREAM_THREADS) {
+          const float xv = __ldg(xg + e);
+          xs[e] = xv;
+          if (WITH_LOSS) f0 += el_focal<G15>(__ldg(yg + e), xv, p.alpha, p.gamma, p.label_smoothing);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(EFU_STREAM_THREADS) : "memory");   // stream warps only: the tile is complete
       }
-      todo &= ~grp;
+      if (WITH_LOSS) focal += (double)f0 + (double)f1;
+      // per-anchor argmax, three lanes per anchor: tf.argmax (first maximal index) / reduce_max over a third of the C
+      // logits each; the box warps fold the three partials in ascending index order
+      const int a = st / 3, part = st - a * 3;
+      float m = -INFINITY;
+      int mi = -1;
+      if (a < nrec) {
+        const float* r = xs + a * C;
+        const int c0 = part * q3, c1 = min(C, c0 + q3);
+        int c = c0;
+        if (part == 0) { m = r[0]; mi = 0; c = 1; }   // the scan starts from element 0 exactly as a serial one (NaN there sticks)
+        for (; c + 4 <= c1; c += 4) {                  // loads first, then the dependent compare / select chain
+          const float v0 = r[c], v1 = r[c + 1], v2 = r[c + 2], v3 = r[c + 3];
+          if (v0 > m) { m = v0; mi = c; }
+          if (v1 > m) { m = v1; mi = c + 1; }
+          if (v2 > m) { m = v2; mi = c + 2; }
+          if (v3 > m) { m = v3; mi = c + 3; }
+        }
+        for (; c < c1; ++c) { const float v = r[c]; if (v > m) { m = v; mi = c; } }
+      }
+      s_m[pb][a][part] = m;
+      s_mi[pb][a][part] = mi;
     }
-    __syncthreads();   // the tile is consumed: the next iteration may overwrite it
+    __syncthreads();   // the tile's single CTA barrier: the stage is consumed, the argmax partials are published
+    if (bulk) phase_bits ^= (1u << s);
+    if (tid == 32 * EFU_BOX_WARPS) {
+      const long long tn = t + (long long)EFU_STAGES * gridDim.x;
+      if (tn < n_tiles) issue(tn, s);
+    }
+    if (box_warp) {
+      // ---- fold the partials, candidate append (anc:179-189), one atomic per (warp, image) ----
+      float m = s_m[pb][tid][0];
+      int mi = s_mi[pb][tid][0];
+#pragma unroll
+      for (int k = 1; k < 3; ++k) { const float vk = s_m[pb][tid][k]; if (vk > m) { m = vk; mi = s_mi[pb][tid][k]; } }
+      const bool pass = (tid < nrec) && (mi != 0);   // classes_mask = classes_id != 0 (anc:179)
+      uint32_t todo = __ballot_sync(0xffffffffu, pass);
+      while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int limg = __shfl_sync(0xffffffffu, img, leader);
+        const uint32_t grp = __ballot_sync(0xffffffffu, pass && img == limg);
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&p.counts[limg], __popc(grp));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (pass && img == limg) {
+          const size_t slot = (size_t)limg * p.n_img + base + __popc(grp & ((1u << lane) - 1u));
+          p.cand_box[slot] = d4; p.cand_score[slot] = m; p.cand_cls[slot] = mi; p.cand_aidx[slot] = aidx;
+          if (p.bitmap) atomicOr(&p.bitmap[(size_t)limg * p.bitmap_words + (aidx >> 5)], 1u << (aidx & 31u));
+        }
+        todo &= ~grp;
+      }
+    }
+    // the partial buffers alternate by tile parity: the stream warps write buffer pb again only two tiles later, behind
+    // the next tile's barrier, which the box warps reach after this append
   }
   if (WITH_LOSS) {
     if (cur_level >= 0) flush(cur_level);
@@ -955,7 +1024,8 @@ static int efu_impl(bool with_loss, int num_levels, const int32_t* hw, int A, co
   p.alpha = alpha; p.gamma = gamma; p.delta = delta; p.label_smoothing = label_smoothing;
   p.partials = reinterpret_cast<double*>(wsb + ws.total);
   B200_CUDA(cudaMemsetAsync(wsb, 0, out_sel_idx ? ws.box : ws.bitmap, stream));
-  const size_t smem = (size_t)EFU_TILE * C * sizeof(float);
+  B200_REQUIRE(C <= 128, B200_ERR_UNSUPPORTED, "%s: the fused pass stages %d-anchor tiles in shared memory: classes_num %d > 128 (use the separate calls)", who, EFU_TILE, C);
+  const size_t smem = (size_t)EFU_STAGES * EFU_TILE * C * sizeof(float) * (with_loss ? 2 : 1);
   long long want = tb;
   const long long cap = (long long)b200_sm_count() * EFU_GRID_PER_SM;
   const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);

@@ -68,9 +68,13 @@ __host__ __device__ inline size_t nms_smem_bytes(int max_out) {
   return (size_t)NMS_WINDOW * 12 + (size_t)NMS_SAMPLES * 8 + NMS_CHUNK * 28 + 256 * 4 + (size_t)max_out * 32 + 1024;
 }
 
-// Large segments pay a full gather pass per extra window, so they keep the big window.
+// Large segments pay full passes over their scores per extra window, so they take big windows (ordering a window by
+// buckets is cheap, and only the part that is needed is ever consumed).
+#define NMS_PRE_MIN_N 65536      // segments above this get their first window from the multi-CTA pre-selection
+#define NMS_TARGET_LARGE 3072
 __host__ __device__ inline int nms_window_target(int max_out, int n) {
-  if (n > 32768) return NMS_TARGET;
+  if (n > NMS_PRE_MIN_N) return NMS_TARGET_LARGE;
+  if (n > 16384) return NMS_TARGET;
   int t = max_out + (max_out >> 1);
   if (t < 512) t = 512;
   if (t > NMS_TARGET) t = NMS_TARGET;
@@ -608,7 +612,7 @@ static __device__ void nms_pivot_body(const NmsPreselectParams& p, unsigned char
   if (n > NMS_WINDOW) {
     // enough samples for a pivot rank of >= ~32 (relative spread of the admitted count <= ~18 %)
     int ns = 512;
-    while (ns < NMS_PRE_SAMPLES && (long long)ns * NMS_TARGET < 32ll * n) ns <<= 1;
+    while (ns < NMS_PRE_SAMPLES && (long long)ns * NMS_TARGET_LARGE < 32ll * n) ns <<= 1;
     for (int t = tid; t < ns; t += NMS_THREADS) {
       const int i = (int)(((long long)t * n) / ns);
       const float s = scores[i];
@@ -624,7 +628,7 @@ static __device__ void nms_pivot_body(const NmsPreselectParams& p, unsigned char
     uint32_t* red = reinterpret_cast<uint32_t*>(nxt + NMS_PRE_SAMPLES);
     unsigned short* ord = reinterpret_cast<unsigned short*>(bins);
     nms_bucket_order<NMS_THREADS>(sS, ns, bins, nxt, red, ord);
-    unsigned long long rank = ((unsigned long long)NMS_TARGET * (unsigned long long)ns) / (unsigned long long)n;
+    unsigned long long rank = ((unsigned long long)NMS_TARGET_LARGE * (unsigned long long)ns) / (unsigned long long)n;
     if (rank < 2ull) rank = 2ull;
     khi = rank >= (unsigned long long)ns ? ~0ull : sS[ord[rank]];
   }

@@ -217,14 +217,60 @@ def reduce_sum(x, axis=None, keepdims=False):
     return _wrap(_np.sum(x, axis=axis, keepdims=keepdims, dtype=_np.asarray(x).dtype))
 
 
+# ---- transcendental back end --------------------------------------------------------------------------------
+# FAKE_TF_MATH=libm (default): NumPy's float32 ufuncs (glibc / NumPy SIMD loops).
+# FAKE_TF_MATH=torch: the same functions through PyTorch's CPU kernels (SLEEF-vectorised; torch.sigmoid is a fused
+# kernel like Eigen's logistic) — an independent second implementation, used by tests/golden/tf_numerics_risk.py to
+# measure how often a few-ulp difference in exp / sigmoid / atan / log flips a DISCRETE output (NMS order, ignore bit,
+# target cell), since TensorFlow's own Eigen kernels cannot be run here.
+import os as _os
+_MATH = _os.environ.get("FAKE_TF_MATH", "libm")
+if _MATH == "torch":
+    import torch as _torch
+
+    def _via_torch(fn):
+        def run(x, *rest):
+            a = _np.ascontiguousarray(_np.asarray(x, dtype=_F))
+            with _np.errstate(all="ignore"):
+                return fn(_torch.from_numpy(a.reshape(-1)), *rest).numpy().reshape(a.shape).astype(_F)
+        return run
+    _exp, _log, _log1p, _atan_f, _sigmoid_f = (_via_torch(_torch.exp), _via_torch(_torch.log), _via_torch(_torch.log1p),
+                                               _via_torch(_torch.atan), _via_torch(_torch.sigmoid))
+
+    def _pow(a, b):
+        a, b = _np.broadcast_arrays(_np.asarray(a, dtype=_F), _np.asarray(b, dtype=_F))
+        return _torch.pow(_torch.from_numpy(_np.ascontiguousarray(a)), _torch.from_numpy(_np.ascontiguousarray(b))).numpy().astype(_F)
+else:
+    def _exp(x):
+        with _np.errstate(all="ignore"):
+            return _np.exp(_np.asarray(x, dtype=_F)).astype(_F)
+
+    def _log(x):
+        with _np.errstate(all="ignore"):
+            return _np.log(_np.asarray(x, dtype=_F)).astype(_F)
+
+    def _log1p(x):
+        with _np.errstate(all="ignore"):
+            return _np.log1p(_np.asarray(x, dtype=_F)).astype(_F)
+
+    def _atan_f(x):
+        return _np.arctan(_np.asarray(x, dtype=_F)).astype(_F)
+
+    def _sigmoid_f(x):
+        x = _np.asarray(x, dtype=_F)
+        with _np.errstate(all="ignore"):
+            return (_F(1) / (_F(1) + _np.exp(-x))).astype(_F)
+
+    def _pow(a, b):
+        return _np.power(_t(a), _t(b))
+
+
 def sigmoid(x):
-    x = _np.asarray(x, dtype=_F)
-    with _np.errstate(all="ignore"):
-        return (_F(1) / (_F(1) + _np.exp(-x))).astype(_F)
+    return _sigmoid_f(x)
 
 
 def atan(x):
-    return _np.arctan(_np.asarray(x, dtype=_F)).astype(_F)
+    return _atan_f(x)
 
 
 def print(*a, **k):  # noqa: A001
@@ -286,7 +332,7 @@ def _bce_logits(z, x):
     """max(x,0) - x z + log1p(exp(-|x|)), sigmoid_cross_entropy_with_logits"""
     z, x = _np.asarray(z, dtype=_F), _np.asarray(x, dtype=_F)
     with _np.errstate(all="ignore"):
-        return (_np.maximum(x, _F(0)) - x * z + _np.log1p(_np.exp(-_np.abs(x)))).astype(_F)
+        return (_np.maximum(x, _F(0)) - x * z + _log1p(_exp(-_np.abs(x)))).astype(_F)
 
 
 def _mk(name, **attrs):
@@ -303,12 +349,12 @@ with _np.errstate(all="ignore"):
 math = _mk(
     "tensorflow.math",
     maximum=maximum, minimum=minimum, square=lambda x: _np.square(_t(x)), reduce_sum=reduce_sum, reduce_max=_reduce_max,
-    atan=atan, log=lambda x: _np.log(_np.asarray(x, dtype=_F)).astype(_F), exp=lambda x: _np.exp(_np.asarray(x, dtype=_F)).astype(_F),
+    atan=atan, log=lambda x: _log(x), exp=lambda x: _exp(x),
     sigmoid=sigmoid, tanh=lambda x: _np.tanh(x), is_inf=_np.isinf, is_nan=_np.isnan, logical_and=_np.logical_and,
     logical_not=_np.logical_not, logical_or=_np.logical_or, not_equal=_np.not_equal, equal=_np.equal, greater=_np.greater,
     greater_equal=_np.greater_equal, less=_np.less, less_equal=_np.less_equal, floor=_np.floor,
     argmax=lambda x, axis=-1, output_type=_np.int64: _np.argmax(x, axis=axis).astype(output_type), divide_no_nan=_divide_no_nan,
-    abs=_np.abs, sqrt=_np.sqrt, pow=lambda a, b: _np.power(_t(a), _t(b)))
+    abs=_np.abs, sqrt=_np.sqrt, pow=lambda a, b: _pow(a, b))
 reduce_max = _reduce_max
 linalg = _mk("tensorflow.linalg", norm=lambda x, axis=None: _np.sqrt(_np.sum(_np.square(x), axis=axis, dtype=_np.asarray(x).dtype)))
 nn = _mk("tensorflow.nn", sigmoid_cross_entropy_with_logits=lambda labels=None, logits=None: _bce_logits(labels, logits))
