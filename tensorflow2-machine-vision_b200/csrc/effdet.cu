@@ -95,7 +95,9 @@ struct EfFilterParams {
   int B;
   int n_img;                     // anchors per image
   const float* cls[EF_MAX_LEVELS];    // (B,H,W,A,C) logits
-  const float4* boxes[EF_MAX_LEVELS]; // (B,H,W,A,4) decoded
+  const float4* boxes[EF_MAX_LEVELS]; // (B,H,W,A,4) decoded, or null: decode here from rel (lv.table must be set)
+  const float4* rel[EF_MAX_LEVELS];   // (B,H,W,A,4) head offsets ty,tx,th,tw (fused decode mode)
+  float4* dec[EF_MAX_LEVELS];         // fused decode mode: the dense decoded tensor is written here (may be null)
   long long tile_base[EF_MAX_LEVELS + 1];  // tiles of 32 anchors over the NB images of each level
   float4* cand_box; float* cand_score; int32_t* cand_cls; uint32_t* cand_aidx;  // [NB, n_img]
   int32_t* counts;               // [NB]
@@ -166,18 +168,37 @@ __global__ void __launch_bounds__(256, 1) effdet_filter_kernel(EfFilterParams p)
     uint32_t aidx = 0;
     float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
     if (lane < nrec) {
+      const long long rec = rec0 + lane;
+      const int api = p.lv.anc_per_img[l];
+      const long long total = (long long)p.NB * api;
+      int rin;
+      if (total < 0x7fffffffLL) { img = (int)((uint32_t)rec / (uint32_t)api); rin = (int)((uint32_t)rec - (uint32_t)img * (uint32_t)api); }
+      else { img = (int)(rec / api); rin = (int)(rec - (long long)img * api); }
+      const long long grec = (long long)(p.B0 + img) * api + rin;
+      const bool fused_decode = p.rel[l] != nullptr;   // block-uniform
+      float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (fused_decode) r4 = __ldcs(p.rel[l] + grec);   // issued before the class scan: coalesced, 16 bytes per lane
       // tf.math.argmax: first maximal index; reduce_max: the maximum (anc:172-174)
       float m = r[0];
       int mi = 0;
       for (int c = 1; c < C; ++c) { const float v = r[c]; if (v > m) { m = v; mi = c; } }
+      if (fused_decode) {
+        // convert_outputs_boxes (_boxes_decoder, anc:245-274) for every anchor: the dense decoded tensor is an output
+        int y, x, an_i;
+        ef_split(p.lv, l, rin, y, x, an_i);
+        const AnchorBox an = ef_anchor(p.lv, l, y, x, an_i);
+        const float yca = DM_DIV(DM_ADD(an.y2, an.y1), 2.0f), xca = DM_DIV(DM_ADD(an.x2, an.x1), 2.0f);
+        const float ha = DM_SUB(an.y2, an.y1), wa = DM_SUB(an.x2, an.x1);
+        const float w = DM_MUL(dm_expf(r4.w), wa), h = DM_MUL(dm_expf(r4.z), ha);
+        const float yc = DM_ADD(DM_MUL(r4.x, ha), yca), xc = DM_ADD(DM_MUL(r4.y, wa), xca);
+        const float hh = DM_DIV(h, 2.0f), hw = DM_DIV(w, 2.0f);
+        box = make_float4(DM_SUB(yc, hh), DM_SUB(xc, hw), DM_ADD(yc, hh), DM_ADD(xc, hw));
+        if (p.dec[l]) __stcs(p.dec[l] + grec, box);
+      }
       if (mi != 0) {  // classes_mask = classes_id != 0 (anc:179)
-        const long long rec = rec0 + lane;
-        const int api = p.lv.anc_per_img[l];
-        img = (int)(rec / api);
-        const int rin = (int)(rec - (long long)img * api);
         pass = true; cls = mi; score = m;
         aidx = (uint32_t)(p.lv.anchor_base[l] + rin);
-        box = __ldg(p.boxes[l] + (long long)(p.B0 + img) * api + rin);
+        if (!fused_decode) box = __ldg(p.boxes[l] + grec);
       }
     }
     uint32_t todo = __ballot_sync(0xffffffffu, pass);
@@ -227,7 +248,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) effdet_nms_finalize_kernel(EfF
   int32_t* pos = p.nms_pos + (size_t)img * p.cfg.max_out;
   NmsPre pre;
   if (p.pre_keys) {
-    pre.keys = p.pre_keys + (size_t)img * NMS_WINDOW; pre.pos = p.pre_pos + (size_t)img * NMS_WINDOW;
+    pre.keys = p.pre_keys + (size_t)img * NMS_PRE_CAP; pre.pos = p.pre_pos + (size_t)img * NMS_PRE_CAP;
     pre.count = p.pre_count + img; pre.eligible = p.pre_elig + img; pre.khi = p.pre_khi + img;
   }
   const int kept = nms_run_segment<METRIC>(seg, p.cfg, pos, nms_smem, p.pre_keys ? &pre : nullptr);
@@ -510,8 +531,8 @@ static EfWs ef_ws_layout(int NB, int n_img, int max_out) {
   w.aidx = o; o = b200_align_up(o + sizeof(uint32_t) * (size_t)NB * n_img, 256);
   w.pos = o; o = b200_align_up(o + sizeof(int32_t) * (size_t)NB * max_out, 256);
   w.pre_khi = o; o = b200_align_up(o + sizeof(unsigned long long) * NB, 256);
-  w.pre_keys = o; o = b200_align_up(o + sizeof(unsigned long long) * (size_t)NB * NMS_WINDOW, 256);
-  w.pre_pos = o; o = b200_align_up(o + sizeof(uint32_t) * (size_t)NB * NMS_WINDOW, 256);
+  w.pre_keys = o; o = b200_align_up(o + sizeof(unsigned long long) * (size_t)NB * NMS_PRE_CAP, 256);
+  w.pre_pos = o; o = b200_align_up(o + sizeof(uint32_t) * (size_t)NB * NMS_PRE_CAP, 256);
   w.total = o;
   return w;
 }
@@ -576,16 +597,18 @@ extern "C" size_t b200_effdet_postprocess_workspace_bytes(int num_levels, const 
   return ef_ws_layout(num_images, n_img, max_out).total;
 }
 
-extern "C" int b200_effdet_postprocess(int num_levels, const int32_t* hw, int A, int C, int B, int first_image,
-                                       int num_images, const float* const boxes[], const float* const classes[],
-                                       int max_out, float iou_thr, float score_thr, int metric, float* out_boxes,
-                                       long long* out_class_id, float* out_score, int32_t* out_sel_idx,
-                                       int32_t* out_sel_anchor, int32_t* out_count, void* workspace,
-                                       size_t workspace_bytes, void* stream_) {
+// boxes: decoded boxes (the drop-in convert_outputs_one), or null with rel / table_dev given: decode inside the filter
+// pass (convert_outputs_boxes + convert_outputs_one in one sweep; dec_out[l] receives the dense decoded tensor)
+static int ef_post_impl(int num_levels, const int32_t* hw, int A, const float* table_dev, int C, int B, int first_image,
+                        int num_images, const float* const boxes[], const float* const rel[], float* const dec_out[],
+                        const float* const classes[], int max_out, float iou_thr, float score_thr, int metric, float* out_boxes,
+                        long long* out_class_id, float* out_score, int32_t* out_sel_idx,
+                        int32_t* out_sel_anchor, int32_t* out_count, void* workspace,
+                        size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   EfFilterParams fp;
-  B200_REQUIRE(hw && boxes && classes, B200_ERR_BAD_ARG, "b200_effdet_postprocess: null argument");
-  const int n_img = ef_fill_levels(fp.lv, num_levels, hw, A, nullptr);
+  B200_REQUIRE(hw && (boxes || (rel && table_dev)) && classes, B200_ERR_BAD_ARG, "b200_effdet_postprocess: null argument");
+  const int n_img = ef_fill_levels(fp.lv, num_levels, hw, A, table_dev);
   B200_REQUIRE(n_img >= 0, B200_ERR_BAD_ARG, "b200_effdet_postprocess: bad level spec");
   B200_REQUIRE(C >= 1 && C <= 400, B200_ERR_UNSUPPORTED, "b200_effdet_postprocess: classes_num %d outside [1,400]", C);
   B200_REQUIRE(first_image >= 0 && num_images >= 0 && first_image + num_images <= B, B200_ERR_BAD_ARG, "b200_effdet_postprocess: image range outside the batch");
@@ -602,12 +625,16 @@ extern "C" int b200_effdet_postprocess(int num_levels, const int32_t* hw, int A,
   for (int l = 0; l < EF_MAX_LEVELS; ++l) {
     fp.tile_base[l] = tb;
     if (l < num_levels) {
-      B200_REQUIRE(boxes[l] && classes[l], B200_ERR_BAD_ARG, "b200_effdet_postprocess: null level %d", l);
-      B200_REQUIRE((reinterpret_cast<uintptr_t>(boxes[l]) & 15) == 0, B200_ERR_BAD_ARG, "b200_effdet_postprocess: boxes level %d not 16-byte aligned", l);
+      const float* bl = boxes ? boxes[l] : rel[l];
+      B200_REQUIRE(bl && classes[l], B200_ERR_BAD_ARG, "b200_effdet_postprocess: null level %d", l);
+      B200_REQUIRE(((reinterpret_cast<uintptr_t>(bl) | (dec_out && dec_out[l] ? reinterpret_cast<uintptr_t>(dec_out[l]) : 0)) & 15) == 0, B200_ERR_BAD_ARG,
+                   "b200_effdet_postprocess: boxes level %d not 16-byte aligned", l);
       fp.cls[l] = classes[l];
-      fp.boxes[l] = reinterpret_cast<const float4*>(boxes[l]);
+      fp.boxes[l] = boxes ? reinterpret_cast<const float4*>(boxes[l]) : nullptr;
+      fp.rel[l] = boxes ? nullptr : reinterpret_cast<const float4*>(rel[l]);
+      fp.dec[l] = (!boxes && dec_out) ? reinterpret_cast<float4*>(dec_out[l]) : nullptr;
       tb += ((long long)num_images * fp.lv.anc_per_img[l] + 31) / 32;
-    } else { fp.cls[l] = nullptr; fp.boxes[l] = nullptr; }
+    } else { fp.cls[l] = nullptr; fp.boxes[l] = nullptr; fp.rel[l] = nullptr; fp.dec[l] = nullptr; }
   }
   for (int l = num_levels; l <= EF_MAX_LEVELS; ++l) fp.tile_base[l] = tb;
   fp.cand_box = reinterpret_cast<float4*>(wsb + ws.box);
@@ -631,6 +658,18 @@ extern "C" int b200_effdet_postprocess(int num_levels, const int32_t* hw, int A,
 
   return ef_launch_nms(fp, ws, wsb, num_images, n_img, max_out, iou_thr, score_thr, metric, out_boxes, out_class_id, out_score,
                        out_sel_idx, out_sel_anchor, out_count, stream);
+}
+
+extern "C" int b200_effdet_postprocess(int num_levels, const int32_t* hw, int A, int C, int B, int first_image,
+                                       int num_images, const float* const boxes[], const float* const classes[],
+                                       int max_out, float iou_thr, float score_thr, int metric, float* out_boxes,
+                                       long long* out_class_id, float* out_score, int32_t* out_sel_idx,
+                                       int32_t* out_sel_anchor, int32_t* out_count, void* workspace,
+                                       size_t workspace_bytes, void* stream_) {
+  B200_REQUIRE(boxes, B200_ERR_BAD_ARG, "b200_effdet_postprocess: null argument");
+  return ef_post_impl(num_levels, hw, A, nullptr, C, B, first_image, num_images, boxes, nullptr, nullptr, classes, max_out, iou_thr,
+                      score_thr, metric, out_boxes, out_class_id, out_score, out_sel_idx, out_sel_anchor, out_count, workspace,
+                      workspace_bytes, stream_);
 }
 
 static int ef_assign_impl(int num_levels, const int32_t* hw, int A, const float* table_dev, int C, int B,
@@ -1075,7 +1114,10 @@ extern "C" int b200_effdet_decode_postprocess(int num_levels, const int32_t* hw,
                                               float* out_boxes, long long* out_class_id, float* out_score, int32_t* out_sel_idx,
                                               int32_t* out_sel_anchor, int32_t* out_count, void* workspace, size_t workspace_bytes,
                                               void* stream) {
-  return efu_impl(false, num_levels, hw, A, table_dev, C, B, nullptr, nullptr, nullptr, pred_boxes, pred_classes, 0.f, 0.f, 0.f, 0.f,
-                  nullptr, out_decoded, max_out, iou_thr, score_thr, metric, out_boxes, out_class_id, out_score, out_sel_idx,
-                  out_sel_anchor, out_count, workspace, workspace_bytes, stream);
+  // without targets the per-warp bulk-copy filter (lane <-> anchor, no CTA barriers) is the faster stream: the decode rides
+  // on it (one coalesced 16-byte load and store per lane); the CTA-tiled kernel above pays off only with the focal terms
+  B200_REQUIRE(pred_boxes && table_dev, B200_ERR_BAD_ARG, "b200_effdet_decode_postprocess: null argument");
+  return ef_post_impl(num_levels, hw, A, table_dev, C, B, 0, B, nullptr, pred_boxes, out_decoded, pred_classes, max_out, iou_thr,
+                      score_thr, metric, out_boxes, out_class_id, out_score, out_sel_idx, out_sel_anchor, out_count, workspace,
+                      workspace_bytes, stream);
 }

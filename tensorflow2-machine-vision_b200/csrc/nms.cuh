@@ -47,9 +47,9 @@ struct NmsSegment {
 // Optional pre-gathered first window of a segment (produced by nms_preselect_kernel with several CTAs per
 // segment, for segments too large for one CTA to scan quickly).  Ignored unless its counters show a valid window.
 struct NmsPre {
-  const unsigned long long* keys;  // [NMS_WINDOW]
-  const uint32_t* pos;             // [NMS_WINDOW]
-  const int* count;                // gathered (may exceed NMS_WINDOW: then invalid)
+  const unsigned long long* keys;  // [NMS_PRE_CAP]
+  const uint32_t* pos;             // [NMS_PRE_CAP]
+  const int* count;                // gathered (may exceed NMS_PRE_CAP: then invalid)
   const int* eligible;             // eligible candidates in the whole segment
   const unsigned long long* khi;   // pivot used
 };
@@ -72,6 +72,7 @@ __host__ __device__ inline size_t nms_smem_bytes(int max_out) {
 // buckets is cheap, and only the part that is needed is ever consumed).
 #define NMS_PRE_MIN_N 65536      // segments above this get their first window from the multi-CTA pre-selection
 #define NMS_TARGET_LARGE 3072
+#define NMS_PRE_CAP 8192          // capacity of a pre-gathered list (keys below a sampled pivot aiming at NMS_TARGET_LARGE)
 __host__ __device__ inline int nms_window_target(int max_out, int n) {
   if (n > NMS_PRE_MIN_N) return NMS_TARGET_LARGE;
   if (n > 16384) return NMS_TARGET;
@@ -297,29 +298,33 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
     unsigned long long khi = ~0ull;   // exclusive upper bound; ~0 = everything that is left
     int n_win = 0;
     bool gathered = false, fallback = false, sorted_in_place = false;
-    if (pre && klo == 0ull) {   // first window of a large segment, gathered by several CTAs beforehand
+    // Source of the selection passes: the whole segment, or — first window of a large segment — the list that several
+    // CTAs pre-gathered below a sampled pivot (all eligible keys < *pre->khi: a superset of the true top of the segment,
+    // whose size varies with the sample; up to NMS_PRE_CAP keys, so a generous pivot never overflows).
+    bool use_pre = false;
+    int src_n = n;
+    if (pre && klo == 0ull) {
       const int c = *pre->count, e = *pre->eligible;
       if (e == 0) { exhausted = true; break; }
-      if (c <= NMS_WINDOW && (c >= min_win || c >= e)) {
-        for (int t = tid; t < c; t += THREADS) { sK[t] = pre->keys[t]; sPos[t] = pre->pos[t]; }
-        n_win = c;
-        khi = (c >= e) ? ~0ull : *pre->khi;
-        gathered = true;
-        __syncthreads();
-      }
+      if (c >= 1 && c <= NMS_PRE_CAP) { use_pre = true; src_n = c; }
     }
-    if (!gathered) {
+    // one (key, eligible) fetch for both kinds of source
+    auto fetch = [&](int i, unsigned long long& K) -> bool {
+      if (use_pre) { K = pre->keys[i]; return true; }
+      const float s = seg.scores[i];
+      if (cfg.use_score_thr && (s < cfg.score_thr)) return false;
+      const uint32_t oid = seg.order_id ? seg.order_id[i] : (uint32_t)i;
+      K = ((unsigned long long)nms_dkey(s) << 32) | oid;
+      return K >= klo;
+    };
+    {
       // G1: range and number of the eligible keys that are left
       uint32_t dmin = 0xffffffffu, dmax = 0u;
       int n_el = 0;
-      for (int i = tid; i < n; i += THREADS) {
-        const float s = seg.scores[i];
-        if (cfg.use_score_thr && (s < cfg.score_thr)) continue;
-        const uint32_t d = nms_dkey(s);
-        if (klo != 0ull) {
-          const uint32_t oid = seg.order_id ? seg.order_id[i] : (uint32_t)i;
-          if ((((unsigned long long)d << 32) | oid) < klo) continue;
-        }
+      for (int i = tid; i < src_n; i += THREADS) {
+        unsigned long long K;
+        if (!fetch(i, K)) continue;
+        const uint32_t d = (uint32_t)(K >> 32);
         ++n_el; dmin = min(dmin, d); dmax = max(dmax, d);
       }
       nms_block_minmaxsum<THREADS>(dmin, dmax, n_el, sRed);
@@ -330,15 +335,10 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
         // G2: histogram of the buckets; G3: the bucket where the cumulative count reaches the target
         for (int b = tid; b < NMS_BINS; b += THREADS) sBins[b] = 0;
         __syncthreads();
-        for (int i = tid; i < n; i += THREADS) {
-          const float s = seg.scores[i];
-          if (cfg.use_score_thr && (s < cfg.score_thr)) continue;
-          const uint32_t d = nms_dkey(s);
-          if (klo != 0ull) {
-            const uint32_t oid = seg.order_id ? seg.order_id[i] : (uint32_t)i;
-            if ((((unsigned long long)d << 32) | oid) < klo) continue;
-          }
-          atomicAdd(&sBins[nms_bin(d, dmin, scale)], 1);
+        for (int i = tid; i < src_n; i += THREADS) {
+          unsigned long long K;
+          if (!fetch(i, K)) continue;
+          atomicAdd(&sBins[nms_bin((uint32_t)(K >> 32), dmin, scale)], 1);
         }
         __syncthreads();
         nms_block_scan_bins<THREADS>(sBins, sRed, target, &sScalar[3]);
@@ -346,25 +346,27 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
         const int upto = (cut + 1 < NMS_BINS) ? sBins[cut + 1] : n_el;   // keys in buckets 0..cut
         fallback = upto > NMS_WINDOW;   // one bucket alone overflows the window (masses of near-equal scores)
         __syncthreads();
+        if (fallback && use_pre) {      // cannot happen short of thousands of tied scores: redo on the whole segment
+          use_pre = false; src_n = n; fallback = true;
+        }
       }
       if (!fallback) {
         // G4: gather buckets 0..cut (unordered)
         if (tid == 0) sScalar[0] = 0;
         __syncthreads();
-        for (int i = tid; i < n; i += THREADS) {
-          const float s = seg.scores[i];
-          if (cfg.use_score_thr && (s < cfg.score_thr)) continue;
-          const uint32_t d = nms_dkey(s);
-          const uint32_t oid = seg.order_id ? seg.order_id[i] : (uint32_t)i;
-          const unsigned long long K = ((unsigned long long)d << 32) | oid;
-          if (K < klo || nms_bin(d, dmin, scale) > cut) continue;
+        for (int i = tid; i < src_n; i += THREADS) {
+          unsigned long long K;
+          if (!fetch(i, K)) continue;
+          if (nms_bin((uint32_t)(K >> 32), dmin, scale) > cut) continue;
           const int slot = atomicAdd(&sScalar[0], 1);
-          sK[slot] = K; sPos[slot] = (uint32_t)i;
+          sK[slot] = K; sPos[slot] = use_pre ? pre->pos[i] : (uint32_t)i;
         }
         __syncthreads();
         n_win = sScalar[0];
         gathered = true;
-        if (n_win < n_el) khi = 1ull;   // placeholder: the real bound (largest key of the window + 1) is set after ordering
+        // the window holds everything that is left only if nothing was cut here AND the pre-gathered list was complete
+        const bool complete = (n_win >= n_el) && (!use_pre || *pre->count >= *pre->eligible);
+        if (!complete) khi = 1ull;   // placeholder: the real bound (largest key of the window + 1) is set after ordering
         __syncthreads();
       }
     }
@@ -468,6 +470,108 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
       }
       if (tid < 2) sSupp[tid] = 0u;
       __syncthreads();
+      if (mode == B200_NMS_BY_CLASS) {
+        // ---- per-class NMS: classes never interact, so the chunk is split by class bucket and every bucket is resolved
+        // by its own warp (greedy in rank order inside the bucket); the survivors are then emitted in global rank order.
+        // Exact: a candidate is dropped iff an EMITTED better-ranked box of its class suppresses it, and every surviving
+        // better-ranked box inside the cap is emitted.  No tile loop: ~8 CTA barriers per 1024 candidates.
+        unsigned short* sTab = reinterpret_cast<unsigned short*>(sK);          // [32 blocks][256 buckets] counts -> offsets
+        unsigned short* sMem = sTab + 32 * 256;                                 // [NMS_CHUNK] members, bucket-major, rank order
+        int* sBase = reinterpret_cast<int*>(sMem + NMS_CHUNK);                  // [257] bucket starts
+        unsigned char* sAlive = reinterpret_cast<unsigned char*>(sBase + 260);  // [NMS_CHUNK]
+        constexpr int NW = THREADS / 32;
+        // (1) against the boxes kept by earlier chunks / windows; clear the count table
+        for (int ct = tid; ct < n_chunk; ct += THREADS) {
+          bool supp = false;
+          if (n_kept > 0) {
+            const int ccls = cCl[ct];
+            BoxT cb; cb.c0 = cC0[ct]; cb.c1 = cC1[ct]; cb.c2 = cC2[ct]; cb.c3 = cC3[ct]; cb.area = cAr[ct]; cb.at = cAt[ct];
+            for (int k = sHead[(uint32_t)ccls & 255u]; k >= 0; k = kNext[k]) {
+              if (kCl[k] != ccls) continue;
+              BoxT kb; kb.c0 = kC0[k]; kb.c1 = kC1[k]; kb.c2 = kC2[k]; kb.c3 = kC3[k]; kb.area = kAr[k]; kb.at = kAt[k];
+              if (nms_suppresses<METRIC>(kb, ccls, cb, ccls, mode, thr)) { supp = true; break; }
+            }
+          }
+          sAlive[ct] = supp ? 0 : 1;
+        }
+        for (int i = tid; i < 32 * 256 / 2; i += THREADS) reinterpret_cast<uint32_t*>(sTab)[i] = 0u;
+        __syncthreads();
+        // (2) stable split by bucket: 32-candidate blocks in rank order; intra-block rank by match_any, block counts in sTab
+        const int n_blk = (n_chunk + 31) >> 5;
+        for (int blk = warp; blk < n_blk; blk += NW) {
+          const int ct = (blk << 5) + lane;
+          const uint32_t bucket = ct < n_chunk ? ((uint32_t)cCl[ct] & 255u) : 0xffffu;
+          const uint32_t peers = __match_any_sync(0xffffffffu, bucket);
+          if (ct < n_chunk && (peers & ((1u << lane) - 1u)) == 0u) sTab[blk * 256 + bucket] = (unsigned short)__popc(peers);
+        }
+        __syncthreads();
+        for (int b = tid; b < 256; b += THREADS) {   // per bucket: exclusive prefix over the blocks, total into sBase[b + 1]
+          int run = 0;
+          for (int blk = 0; blk < n_blk; ++blk) { const int t = sTab[blk * 256 + b]; sTab[blk * 256 + b] = (unsigned short)run; run += t; }
+          sBase[b + 1] = run;
+        }
+        __syncthreads();
+        if (warp == 0) {   // bucket starts: exclusive prefix of the 256 totals
+          int v[8], local = 0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { v[k] = sBase[lane * 8 + k + 1]; local += v[k]; }
+          int incl = local;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+          int run = incl - local;
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { sBase[lane * 8 + k] = run; run += v[k]; }
+          if (lane == 31) sBase[256] = run;
+        }
+        __syncthreads();
+        for (int blk = warp; blk < n_blk; blk += NW) {
+          const int ct = (blk << 5) + lane;
+          const uint32_t bucket = ct < n_chunk ? ((uint32_t)cCl[ct] & 255u) : 0xffffu;
+          const uint32_t peers = __match_any_sync(0xffffffffu, bucket);
+          if (ct < n_chunk) sMem[sBase[bucket] + sTab[blk * 256 + bucket] + __popc(peers & ((1u << lane) - 1u))] = (unsigned short)ct;
+        }
+        __syncthreads();
+        // (3) a warp per bucket: greedy in rank order; state lives in shared memory (sAlive), broadcast reads of box i
+        for (int b = warp; b < 256; b += NW) {
+          const int base = sBase[b], m = sBase[b + 1] - base;
+          for (int i = 0; i + 1 < m; ++i) {
+            const int ci = sMem[base + i];
+            if (!sAlive[ci]) continue;                   // warp-uniform
+            BoxT bi; bi.c0 = cC0[ci]; bi.c1 = cC1[ci]; bi.c2 = cC2[ci]; bi.c3 = cC3[ci]; bi.area = cAr[ci]; bi.at = cAt[ci];
+            const int cls_i = cCl[ci];
+            for (int j = i + 1 + lane; j < m; j += 32) {
+              const int cj = sMem[base + j];
+              if (!sAlive[cj] || cCl[cj] != cls_i) continue;   // classes sharing a bucket (ids 256 apart) do not interact
+              BoxT bj; bj.c0 = cC0[cj]; bj.c1 = cC1[cj]; bj.c2 = cC2[cj]; bj.c3 = cC3[cj]; bj.area = cAr[cj]; bj.at = cAt[cj];
+              if (nms_suppresses<METRIC>(bi, cls_i, bj, cls_i, mode, thr)) sAlive[cj] = 0;
+            }
+            __syncwarp();
+          }
+        }
+        __syncthreads();
+        // (4) emit the survivors in rank order, up to the cap
+        for (int c0 = 0; c0 < n_chunk && n_kept < cfg.max_out; c0 += THREADS) {
+          const int ct = c0 + tid;
+          const bool a = ct < n_chunk && sAlive[ct];
+          const uint32_t bal = __ballot_sync(0xffffffffu, a);
+          if (lane == 0) sRed[warp] = (uint32_t)__popc(bal);
+          __syncthreads();
+          int before = 0, total = 0;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) { const int t = (int)sRed[w]; if (w < warp) before += t; total += t; }
+          const int slot = n_kept + before + __popc(bal & ((1u << lane) - 1u));
+          if (a && slot < cfg.max_out) {
+            kC0[slot] = cC0[ct]; kC1[slot] = cC1[ct]; kC2[slot] = cC2[ct]; kC3[slot] = cC3[ct];
+            kAr[slot] = cAr[ct]; kAt[slot] = cAt[ct]; kCl[slot] = cCl[ct];
+            out_pos[slot] = (int32_t)sPos[sOrd[w0 + ct]];
+            kNext[slot] = atomicExch(&sHead[(uint32_t)cCl[ct] & 255u], slot);
+          }
+          n_kept = min(cfg.max_out, n_kept + total);
+          __syncthreads();
+        }
+        continue;
+      }
       const int n_tiles = (n_chunk + 63) >> 6;
       for (int T = 0; T < n_tiles && n_kept < cfg.max_out; ++T) {
         const int t0 = T << 6;
@@ -592,7 +696,7 @@ struct NmsPreselectParams {
   int stride;                   // elements between segments
   int slices;                   // CTAs per segment
   int use_score_thr; float score_thr;
-  unsigned long long* keys; uint32_t* pos;  // [num_segments, NMS_WINDOW]
+  unsigned long long* keys; uint32_t* pos;  // [num_segments, NMS_PRE_CAP]
   int* count; int* eligible; unsigned long long* khi;  // [num_segments] (count/eligible zeroed by the caller)
 };
 
@@ -672,9 +776,9 @@ static __device__ void nms_pregather_body(const NmsPreselectParams& p) {
         base = __shfl_sync(0xffffffffu, base, 0);
         if (take) {
           const int slot = base + __popc(bal & ((1u << lane) - 1u));
-          if (slot < NMS_WINDOW) {
-            p.keys[(size_t)seg * NMS_WINDOW + slot] = K;
-            p.pos[(size_t)seg * NMS_WINDOW + slot] = (uint32_t)i;
+          if (slot < NMS_PRE_CAP) {
+            p.keys[(size_t)seg * NMS_PRE_CAP + slot] = K;
+            p.pos[(size_t)seg * NMS_PRE_CAP + slot] = (uint32_t)i;
           }
         }
       }
