@@ -63,6 +63,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="images per CPU-baseline run (0 = 16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl", "torch"], help="transport of the loss all-reduce (N > 1)")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: keep the whole exchange inside the step's finalize kernel (no second stream)")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every step launch by launch instead of replaying CUDA graphs")
     ap.add_argument("--only-step", action="store_true", help="skip phase timing / e2e / cpu baseline / parity (profiling runs)")
@@ -123,6 +124,15 @@ class ClockSampler(object):
         top = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []   # the busiest samples are the ones under load
         return {"sm_mhz": statistics.median(top) if top else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def spread(xs):
@@ -200,7 +210,7 @@ def run_reference(args):
         "step_spread_ms": spread([1e3 * x for x in per_step]),
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -225,6 +235,7 @@ class Bench(object):
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
         self.lib = _lib.load()
+        self.tail_hooks = []
         self.exchange, self.exchange_kind = None, "none (single GPU)"
         if self.world > 1:
             kind = args.exchange
@@ -279,6 +290,8 @@ class Bench(object):
         e0.record()
         for _ in range(steps):
             fn()
+        for hook in self.tail_hooks:   # side streams whose work belongs to the timed region join before the stop event
+            hook()
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -376,11 +389,50 @@ def headline_c2(b, line):
         sampler.start()
     raw = lambda: step(heads_d, boxes_d, classes_d, off_d)
     if world > 1:
-        raw()   # communicator / mailbox warm-up outside the timed region, the same number of times on every rank
+        raw(); raw()   # communicator / mailbox warm-up outside the timed region, the same number of times on every rank
         b.barrier()
-    dev_step = raw if (args.no_graph or (world > 1 and not in_graph)) else b.runtime.capture(raw)
+    peer = b.exchange is not None and hasattr(b.exchange, "mailboxes")
+    overlapped = False
+    if args.no_graph or (world > 1 and not in_graph):
+        dev_step = raw
+    elif world > 1 and peer and not args.no_overlap:
+        # The step's graph ends with the PUBLISH half of the exchange (peer stores, no wait); the collect half of step i
+        # runs on a second stream under the kernels of step i+1.  Two graphs with their own result buffers alternate; the
+        # graph of step i waits for the collect of step i-2 (the rule of the four slot sets, csrc/exchange.cuh).
+        overlapped = True
+        comm = torch.cuda.Stream()
+        res = [dict(parts=torch.empty((3, 4), dtype=torch.float32, device=dev), loss=torch.zeros((), dtype=torch.float32, device=dev), done=None) for _ in range(2)]
+
+        def pub_step():
+            gen.GetTargetsBatch(classes_d, boxes_d, off_d, out=y_true)
+            return tyu._loss_call(y_true, heads_d, (image, image), anc, 0.5, "ciou", 0, batch_divisor=global_batch, workspace=ws,
+                                  exchange=b.exchange, defer_collect=True)
+        graphs = [b.runtime.capture(pub_step, warmup=0), b.runtime.capture(pub_step, warmup=0)]
+        counter = [0]
+
+        def dev_step():
+            k = counter[0] & 1
+            counter[0] += 1
+            main = torch.cuda.current_stream()
+            if res[k]["done"] is not None:
+                main.wait_event(res[k]["done"])
+            graphs[k]()
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ready)
+                b.exchange.collect_yolo(res[k]["parts"], res[k]["loss"])
+                res[k]["done"] = torch.cuda.Event()
+                res[k]["done"].record(comm)
+            return res[k]["loss"]
+        b.tail_hooks.append(lambda: torch.cuda.current_stream().wait_stream(comm))
+    else:
+        dev_step = b.runtime.capture(raw)
     ms_dev, windows = b.timed(dev_step, args.steps, args.warmup, args.repeats)
-    loss_val = float(dev_step().item())
+    last = dev_step()
+    torch.cuda.synchronize()
+    loss_val = float(last.item())
+    del b.tail_hooks[:]
     clocks = sampler.stop() if rank == 0 else None
     b.log("headline timed")
     n_fill = sum(int(t.numel()) for t in y_true)
@@ -394,7 +446,9 @@ def headline_c2(b, line):
         "config": {"workload": WHAT["c2"], "image": image, "per_gpu_batch": batch, "global_batch": global_batch,
                    "classes": 80, "anchors_per_cell": 3, "gt_boxes_per_image": "U{1..100}",
                    "parallelism": "dp%d (images sharded; one 12-float all-reduce per step: %s)" % (world, b.exchange_kind),
-                   "launch": "launch by launch" if dev_step is raw else "CUDA graph replay of the whole step (exchange included)",
+                   "launch": "launch by launch" if dev_step is raw else (
+                       "CUDA graph replay of the step up to the publish half of the exchange; the collect half of step i runs on a second "
+                       "stream under step i+1" if overlapped else "CUDA graph replay of the whole step (exchange included)"),
                    "l2": "inputs larger than L2 (y_pred %.0f MB + y_true %.0f MB per step vs 126 MB L2)" % (n_fill * 4 / 1e6, n_fill * 4 / 1e6)},
         "loss": loss_val, "clocks": clocks,
         "gpu_launches": 6 * args.steps * len(windows),
@@ -713,7 +767,7 @@ def run_b200(args):
                      "warmup": max(args.warmup, 3), "ms_per_step": first.get("ms_per_step"), "higher_is_better": True, "scaling": "weak",
                      "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": first.get("what"), "only": only}})
     if b.rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if b.exchange is not None:
         b.barrier()
         b.exchange.close()
@@ -722,6 +776,12 @@ def run_b200(args):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: whatever libraries print to file descriptor 1 (NCCL's version banner ...) goes to
+    # stderr instead; the line itself is written to a private duplicate of the original stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         run_reference(args)

@@ -346,6 +346,16 @@ int b200_yolo_loss_dp(const float* const y_true[3], const float* const y_pred[3]
                       int C, const float* anchors_wh_host, const float* image_wh_host, float iou_thresh, int metric,
                       int variant, float global_batch, float* out_parts, float* out_loss, void* workspace,
                       size_t workspace_bytes, int rank, int world, void* const mailboxes[], void* stream);
+/* The exchange split in two halves so that the wait can be hidden: b200_yolo_loss_dp_publish ends with the publish half
+ * (peer stores, no wait; out_parts / out_loss = this rank's own terms); b200_yolo_loss_collect_peer — on any stream ordered
+ * behind it, e.g. a second stream running under the next step — waits for the peers' flags in the local mailbox, sums in
+ * rank order and writes the global parts [12] (may be NULL) and loss.  Rule: the publish of step f must be ordered after
+ * this rank's own collect of step f-2 (four slot sets; see csrc/exchange.cuh), i.e. one collect may run under the next step. */
+int b200_yolo_loss_dp_publish(const float* const y_true[3], const float* const y_pred[3], const int32_t hw[6], int B, int A,
+                              int C, const float* anchors_wh_host, const float* image_wh_host, float iou_thresh, int metric,
+                              int variant, float global_batch, float* out_parts, float* out_loss, void* workspace,
+                              size_t workspace_bytes, int rank, int world, void* const mailboxes[], void* stream);
+int b200_yolo_loss_collect_peer(float* out_parts, float* out_loss, int rank, int world, void* const mailboxes[], void* stream);
 int b200_yolo_loss_from_boxes_dp(const float* boxes, const int32_t* classes, const int32_t* offsets, int total_boxes,
                                  const float* assign_anchors_wh_host, const float* const y_pred[3], const int32_t hw[6],
                                  int B, int A, int C, const float* anchors_wh_host, const float* image_wh_host,

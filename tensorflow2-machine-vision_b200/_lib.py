@@ -67,6 +67,8 @@ SIGNATURES = {
     "b200_allreduce_sums_peer": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p]),
     "b200_peer_exchange_selftest": (c_i, [c_i, c_i, c_i, c_p, c_sz, c_p, c_p]),
     "b200_yolo_loss_dp": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_f, c_i, c_i, c_f, c_p, c_p, c_p, c_sz, c_i, c_i, c_p, c_p]),
+    "b200_yolo_loss_dp_publish": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_f, c_i, c_i, c_f, c_p, c_p, c_p, c_sz, c_i, c_i, c_p, c_p]),
+    "b200_yolo_loss_collect_peer": (c_i, [c_p, c_p, c_i, c_i, c_p, c_p]),
     "b200_yolo_loss_from_boxes_dp": (c_i, [c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_f, c_i, c_i, c_f, c_p, c_p,
                                            c_p, c_sz, c_i, c_i, c_p, c_p]),
     "b200_focal_box_finalize_dp": (c_i, [c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p]),

@@ -157,10 +157,11 @@ def GetNMSBoxes(y1, y2, y3, anchors_wh, image_wh, classes_num,
 
 
 def _loss_call(y_true, y_pred, image_wh, anchors_wh, iou_thresh, iou_type, variant, batch_divisor=None,
-               return_parts=False, workspace=None, ignore_out=None, with_grad=False, exchange=None):
+               return_parts=False, workspace=None, ignore_out=None, with_grad=False, exchange=None, defer_collect=False):
   """exchange: a runtime.PeerExchange (the 12 terms are summed over the ranks inside the finalize kernel, NVLink peer
   stores) or a runtime.NcclExchange (b200_allreduce_loss + b200_yolo_loss_combine behind the loss); batch_divisor must
-  then be the GLOBAL batch.  Forward only."""
+  then be the GLOBAL batch.  Forward only.  defer_collect (PeerExchange only): the call ends with the publish half of the
+  exchange and returns this rank's own terms; exchange.collect_yolo(parts, loss) on another stream finishes it."""
   lib = _lib.load()
   if len(y_true) != 3 or len(y_pred) != 3:
     raise ValueError('y_true and y_pred must each hold 3 levels')
@@ -201,7 +202,8 @@ def _loss_call(y_true, y_pred, image_wh, anchors_wh, iou_thresh, iou_type, varia
     return loss, parts, grads
   if exchange is not None and hasattr(exchange, 'mailboxes'):
     rank, world, boxes_ = exchange.args()
-    _lib.check(lib.b200_yolo_loss_dp(tp, pp, hw, B, A, RF - 5, anc.ctypes.data_as(ctypes.c_void_p),
+    entry = lib.b200_yolo_loss_dp_publish if (defer_collect and world > 1) else lib.b200_yolo_loss_dp
+    _lib.check(entry(tp, pp, hw, B, A, RF - 5, anc.ctypes.data_as(ctypes.c_void_p),
                                      img.ctypes.data_as(ctypes.c_void_p), float(iou_thresh), _lib.METRIC_YOLO[iou_type],
                                      variant, div, T.ptr(parts), T.ptr(loss), T.ptr(workspace), ws_bytes, rank, world, boxes_,
                                      T.stream_ptr()), 'GetLoss (data parallel)')

@@ -100,6 +100,34 @@ static int xchg_launch(T* values, int n, int rank, int world, void* const mailbo
   return B200_OK;
 }
 
+// The collect half alone (the publish half ran inside a *_dp_publish call): values[n] <- sum over ranks; with loss_out the
+// 12 YOLO terms are also folded in the reference's order (tyu:120-125).
+__global__ void __launch_bounds__(32) xchg_collect_kernel(B200Exchange x, float* values, int n, float* loss_out) {
+  const int lane = threadIdx.x;
+  const float v = xchg_collect_warp<float>(x, n);
+  if (lane < n && values) values[lane] = v;
+  if (loss_out) {
+    float total = 0.0f;
+    for (int l = 0; l < 3; ++l) {
+      const float t0 = __shfl_sync(0xffffffffu, v, l * 4 + 0), t1 = __shfl_sync(0xffffffffu, v, l * 4 + 1);
+      const float t2 = __shfl_sync(0xffffffffu, v, l * 4 + 2), t3 = __shfl_sync(0xffffffffu, v, l * 4 + 3);
+      total = __fadd_rn(total, __fadd_rn(__fadd_rn(__fadd_rn(t0, t1), t2), t3));
+    }
+    if (lane == 0) *loss_out = total;
+  }
+}
+
+extern "C" int b200_yolo_loss_collect_peer(float* out_parts, float* out_loss, int rank, int world, void* const mailboxes[], void* stream) {
+  B200Exchange x;
+  const int rc = b200_fill_exchange(x, rank, world, mailboxes, "b200_yolo_loss_collect_peer");
+  if (rc != B200_OK) return rc;
+  B200_REQUIRE(world > 1, B200_ERR_BAD_ARG, "b200_yolo_loss_collect_peer: nothing was published (world 1)");
+  B200_REQUIRE(out_loss, B200_ERR_BAD_ARG, "b200_yolo_loss_collect_peer: null output");
+  xchg_collect_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(x, out_parts, 12, out_loss);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
 extern "C" int b200_allreduce_loss_peer(float* partials, int n, int rank, int world, void* const mailboxes[], void* stream) {
   return xchg_launch<float>(partials, n, rank, world, mailboxes, stream, "b200_allreduce_loss_peer");
 }

@@ -4,12 +4,15 @@
 //
 // B200-first form: no separate collective launch.  Every rank owns a small "mailbox" in its HBM that its peers map
 // through CUDA IPC (NVLink 5 / NVSwitch peer stores).  The last CTA of the loss-finalize kernel
-//   1. stores its n <= 32 partial terms into slot [epoch & 1][rank] of EVERY rank's mailbox (plain peer stores),
+//   1. stores its n <= 32 partial terms into slot [epoch % 4][rank] of EVERY rank's mailbox (plain peer stores),
 //   2. fences (system scope) and release-stores the epoch number into the slot's flag,
 //   3. acquire-spins on the `world` flags of its OWN mailbox (local HBM, no link traffic while waiting),
 //   4. adds the `world` payloads in rank order — the same order on every rank, so every rank gets the same bits.
-// Two slot sets alternate by epoch parity: a rank can be at most one exchange ahead of its slowest peer (it needs
-// that peer's flag of epoch e to leave epoch e), so set (e & 1) is never overwritten while somebody still reads it.
+// Four slot sets are used round robin.  Fused form: a rank can be at most one exchange ahead of its slowest peer (it
+// needs that peer's flag of epoch e to leave epoch e), so a set is never overwritten while somebody still reads it.
+// Split form (publish now, collect later on another stream): rule "publish(f) is ordered after this rank's own
+// collect(f - 2)".  Then rank A's publish(f) implies A collected f-2, hence peer B published f-2, hence (B's rule) B
+// collected f-4 — exactly the epoch whose slot set publish(f) overwrites in B's mailbox.
 // A wall-clock bound (%globaltimer) turns a missing peer into an error flag instead of a hung GPU.
 #pragma once
 #include <stdint.h>
@@ -18,7 +21,8 @@
 #define B200_XCHG_MAX_VALUES 32
 #define B200_XCHG_SLOT_BYTES 512   // 32 x 8-byte payload + flag, padded
 #define B200_XCHG_HEADER_BYTES 256
-#define B200_XCHG_MAILBOX_BYTES (B200_XCHG_HEADER_BYTES + 2 * B200_XCHG_MAX_WORLD * B200_XCHG_SLOT_BYTES)
+#define B200_XCHG_SLOT_SETS 4      // slot sets, used round robin by epoch
+#define B200_XCHG_MAILBOX_BYTES (B200_XCHG_HEADER_BYTES + B200_XCHG_SLOT_SETS * B200_XCHG_MAX_WORLD * B200_XCHG_SLOT_BYTES)
 #ifndef B200_XCHG_TIMEOUT_NS
 #define B200_XCHG_TIMEOUT_NS 20000000000ull  // 20 s
 #endif
@@ -30,7 +34,7 @@ struct B200Exchange {
 };
 
 #ifdef __CUDACC__
-struct XchgHeader { unsigned long long epoch; unsigned int errors; unsigned int pad; };
+struct XchgHeader { unsigned long long epoch; unsigned int errors; unsigned int pad; unsigned long long pub_epoch; };  // epoch = exchanges collected
 
 __device__ __forceinline__ unsigned char* xchg_slot(unsigned char* mailbox, unsigned par, int r) {
   return mailbox + B200_XCHG_HEADER_BYTES + ((size_t)par * B200_XCHG_MAX_WORLD + (size_t)r) * B200_XCHG_SLOT_BYTES;
@@ -49,31 +53,44 @@ __device__ __forceinline__ unsigned long long xchg_globaltimer() {
   return t;
 }
 
-// All-reduce(sum) of one value per lane (lanes >= n pass 0 and get 0 back) over the ranks of `x`, executed by ONE full
-// warp of one CTA per rank.  T = float or double.  Returns the sum on every lane < n; world <= 1 returns v unchanged.
+// The exchange in two halves, so that a caller may overlap the wait with other work (publish at the end of step i on
+// the compute stream, collect on a second stream while step i+1 already runs).  Each half keeps its own epoch counter in
+// the header; both advance by one per exchange.  The caller orders publish(f) after its own collect(f - 2) (stream /
+// event order; see the slot-set argument at the top); the fused form below is trivially safe.
+//
+// publish: one value per lane (lanes >= n pass anything) into slot [epoch % 4][rank] of every rank's mailbox.
 template <typename T>
-__device__ __forceinline__ T xchg_allreduce_warp(const B200Exchange& x, T v, int n) {
-  if (x.world <= 1) return v;
+__device__ __forceinline__ void xchg_publish_warp(const B200Exchange& x, T v, int n) {
   const int lane = threadIdx.x & 31;
-  unsigned char* mine = x.mailbox[x.rank];
-  XchgHeader* hdr = reinterpret_cast<XchgHeader*>(mine);
+  XchgHeader* hdr = reinterpret_cast<XchgHeader*>(x.mailbox[x.rank]);
   unsigned long long epoch = 0;
-  if (lane == 0) epoch = *reinterpret_cast<volatile unsigned long long*>(&hdr->epoch) + 1ull;
+  if (lane == 0) epoch = *reinterpret_cast<volatile unsigned long long*>(&hdr->pub_epoch) + 1ull;
   epoch = __shfl_sync(0xffffffffu, epoch, 0);
-  const unsigned par = (unsigned)(epoch & 1ull);
-  // 1. payload into every rank's mailbox (own one too: the sum below then reads all ranks the same way)
+  const unsigned par = (unsigned)(epoch % B200_XCHG_SLOT_SETS);
   if (lane < n) {
-    for (int r = 0; r < x.world; ++r) {
+    for (int r = 0; r < x.world; ++r) {   // own mailbox too: the sum then reads all ranks the same way
       volatile T* dst = reinterpret_cast<volatile T*>(xchg_slot(x.mailbox[r], par, x.rank));
       dst[lane] = v;
     }
   }
   __threadfence_system();
   __syncwarp();
-  // 2. publish
   if (lane < x.world)
     xchg_st_release_sys(reinterpret_cast<unsigned long long*>(xchg_slot(x.mailbox[lane], par, x.rank) + 8 * B200_XCHG_MAX_VALUES), epoch);
-  // 3. wait for every rank's flag of this epoch in the local mailbox
+  if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(&hdr->pub_epoch) = epoch;
+}
+
+// collect: waits for every rank's flag of the next epoch in the LOCAL mailbox (no link traffic while waiting) and adds the
+// payloads in rank order — the same order on every rank.  Returns the sum on lanes < n.
+template <typename T>
+__device__ __forceinline__ T xchg_collect_warp(const B200Exchange& x, int n) {
+  const int lane = threadIdx.x & 31;
+  unsigned char* mine = x.mailbox[x.rank];
+  XchgHeader* hdr = reinterpret_cast<XchgHeader*>(mine);
+  unsigned long long epoch = 0;
+  if (lane == 0) epoch = *reinterpret_cast<volatile unsigned long long*>(&hdr->epoch) + 1ull;
+  epoch = __shfl_sync(0xffffffffu, epoch, 0);
+  const unsigned par = (unsigned)(epoch % B200_XCHG_SLOT_SETS);
   bool ok = true;
   if (lane < x.world) {
     const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(xchg_slot(mine, par, lane) + 8 * B200_XCHG_MAX_VALUES);
@@ -85,7 +102,6 @@ __device__ __forceinline__ T xchg_allreduce_warp(const B200Exchange& x, T v, int
   }
   ok = __all_sync(0xffffffffu, ok);
   __threadfence_system();
-  // 4. the same rank order everywhere
   T acc = (T)0;
   if (lane < n) {
     for (int r = 0; r < x.world; ++r) {
@@ -98,5 +114,14 @@ __device__ __forceinline__ T xchg_allreduce_warp(const B200Exchange& x, T v, int
     *reinterpret_cast<volatile unsigned long long*>(&hdr->epoch) = epoch;
   }
   return acc;
+}
+
+// All-reduce(sum) of one value per lane (lanes >= n pass 0 and get 0 back) over the ranks of `x`, executed by ONE full
+// warp of one CTA per rank.  T = float or double.  Returns the sum on every lane < n; world <= 1 returns v unchanged.
+template <typename T>
+__device__ __forceinline__ T xchg_allreduce_warp(const B200Exchange& x, T v, int n) {
+  if (x.world <= 1) return v;
+  xchg_publish_warp<T>(x, v, n);
+  return xchg_collect_warp<T>(x, n);
 }
 #endif

@@ -308,25 +308,47 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
       if (e == 0) { exhausted = true; break; }
       if (c >= 1 && c <= NMS_PRE_CAP) { use_pre = true; src_n = c; }
     }
-    // one (key, eligible) fetch for both kinds of source
-    auto fetch = [&](int i, unsigned long long& K) -> bool {
-      if (use_pre) { K = pre->keys[i]; return true; }
-      const float s = seg.scores[i];
-      if (cfg.use_score_thr && (s < cfg.score_thr)) return false;
-      const uint32_t oid = seg.order_id ? seg.order_id[i] : (uint32_t)i;
-      K = ((unsigned long long)nms_dkey(s) << 32) | oid;
-      return K >= klo;
+    // one sweep over the source: body(i, K) for every eligible key that is left; four independent loads in flight per
+    // thread (a plain strided loop serialises on the L2 latency: 48 dependent round trips per pass at 49 k candidates)
+    auto for_each_key = [&](auto&& body) {
+      for (int i0 = tid; i0 < src_n; i0 += 4 * THREADS) {
+        unsigned long long K[4];
+        bool ok[4];
+        if (use_pre) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * THREADS;
+            ok[u] = i < src_n;
+            K[u] = ok[u] ? pre->keys[i] : 0ull;
+          }
+        } else {
+          float sv[4];
+          uint32_t ov[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * THREADS;
+            sv[u] = (i < src_n) ? seg.scores[i] : 0.0f;
+            ov[u] = (i < src_n && seg.order_id) ? seg.order_id[i] : (uint32_t)i;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * THREADS;
+            K[u] = ((unsigned long long)nms_dkey(sv[u]) << 32) | ov[u];
+            ok[u] = (i < src_n) && !(cfg.use_score_thr && (sv[u] < cfg.score_thr)) && (K[u] >= klo);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (ok[u]) body(i0 + u * THREADS, K[u]);
+      }
     };
     {
       // G1: range and number of the eligible keys that are left
       uint32_t dmin = 0xffffffffu, dmax = 0u;
       int n_el = 0;
-      for (int i = tid; i < src_n; i += THREADS) {
-        unsigned long long K;
-        if (!fetch(i, K)) continue;
+      for_each_key([&](int, unsigned long long K) {
         const uint32_t d = (uint32_t)(K >> 32);
         ++n_el; dmin = min(dmin, d); dmax = max(dmax, d);
-      }
+      });
       nms_block_minmaxsum<THREADS>(dmin, dmax, n_el, sRed);
       if (n_el == 0) { exhausted = true; break; }
       const float scale = nms_bin_scale(dmin, dmax);
@@ -335,11 +357,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
         // G2: histogram of the buckets; G3: the bucket where the cumulative count reaches the target
         for (int b = tid; b < NMS_BINS; b += THREADS) sBins[b] = 0;
         __syncthreads();
-        for (int i = tid; i < src_n; i += THREADS) {
-          unsigned long long K;
-          if (!fetch(i, K)) continue;
-          atomicAdd(&sBins[nms_bin((uint32_t)(K >> 32), dmin, scale)], 1);
-        }
+        for_each_key([&](int, unsigned long long K) { atomicAdd(&sBins[nms_bin((uint32_t)(K >> 32), dmin, scale)], 1); });
         __syncthreads();
         nms_block_scan_bins<THREADS>(sBins, sRed, target, &sScalar[3]);
         cut = sScalar[3];
@@ -354,13 +372,11 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
         // G4: gather buckets 0..cut (unordered)
         if (tid == 0) sScalar[0] = 0;
         __syncthreads();
-        for (int i = tid; i < src_n; i += THREADS) {
-          unsigned long long K;
-          if (!fetch(i, K)) continue;
-          if (nms_bin((uint32_t)(K >> 32), dmin, scale) > cut) continue;
+        for_each_key([&](int i, unsigned long long K) {
+          if (nms_bin((uint32_t)(K >> 32), dmin, scale) > cut) return;
           const int slot = atomicAdd(&sScalar[0], 1);
           sK[slot] = K; sPos[slot] = use_pre ? pre->pos[i] : (uint32_t)i;
-        }
+        });
         __syncthreads();
         n_win = sScalar[0];
         gathered = true;

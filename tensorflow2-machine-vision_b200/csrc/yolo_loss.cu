@@ -551,6 +551,7 @@ struct YlFinalize {
   double* slices;          // [YL_FIN_CTAS][12]
   unsigned int* ticket;    // zero on entry; reset by the last CTA
   B200Exchange xchg;       // data parallel: the 12 terms are summed over the ranks inside this kernel (world 1: no-op)
+  int publish_only;        // 1: store this rank's terms into the peers' mailboxes and return (b200_yolo_loss_collect_peer finishes)
 };
 
 __global__ void __launch_bounds__(YL_FIN_THREADS) yolo_loss_finalize_kernel(YlFinalize f) {
@@ -597,7 +598,8 @@ __global__ void __launch_bounds__(YL_FIN_THREADS) yolo_loss_finalize_kernel(YlFi
     }
     // data parallel: batch_divisor is the GLOBAL batch, so the per-rank terms simply add up; the sum runs over
     // NVLink peer stores inside this warp, in rank order on every rank (exchange.cuh)
-    v = xchg_allreduce_warp<float>(f.xchg, v, 12);
+    if (f.publish_only && f.xchg.world > 1) xchg_publish_warp<float>(f.xchg, v, 12);
+    else v = xchg_allreduce_warp<float>(f.xchg, v, 12);
     if (lane < 12 && f.parts) f.parts[lane] = v;
     float total = 0.0f;
     for (int l = 0; l < 3; ++l) {
@@ -845,7 +847,7 @@ static int yolo_loss_impl(const float* const y_true[3], const float* const y_pre
                           float iou_thresh, int metric, int variant, float batch_divisor, float* out_parts,
                           float* out_loss, unsigned char* out_ignore, float* const out_grad[3], void* workspace,
                           size_t workspace_bytes, void* stream_, const YlSparseIn* sparse = nullptr, int stages = 0xf,
-                          const B200Exchange* xchg = nullptr) {
+                          const B200Exchange* xchg = nullptr, int publish_only = 0) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_REQUIRE((y_true || sparse) && y_pred && hw && anchors_wh_host && image_wh_host && out_loss, B200_ERR_BAD_ARG, "b200_yolo_loss: null argument");
   B200_REQUIRE(B >= 1 && A >= 1 && A <= 8 && C >= 0, B200_ERR_BAD_ARG, "b200_yolo_loss: unsupported shape B=%d A=%d C=%d", B, A, C);
@@ -942,6 +944,7 @@ static int yolo_loss_impl(const float* const y_true[3], const float* const y_pre
   f.batch_divisor = batch_divisor; f.parts = out_parts; f.loss = out_loss;
   f.slices = reinterpret_cast<double*>(wsb + ws.fin);
   f.ticket = reinterpret_cast<unsigned int*>(wsb + ws.cnt) + (size_t)B * YL_LEVELS;
+  f.publish_only = publish_only;
   if (xchg) f.xchg = *xchg;
   else { f.xchg.rank = 0; f.xchg.world = 1; for (int r = 0; r < B200_XCHG_MAX_WORLD; ++r) f.xchg.mailbox[r] = nullptr; }
   yolo_loss_finalize_kernel<<<YL_FIN_CTAS, YL_FIN_THREADS, 0, stream>>>(f);
@@ -1037,6 +1040,22 @@ extern "C" int b200_yolo_loss_dp(const float* const y_true[3], const float* cons
   if (rc != B200_OK) return rc;
   return yolo_loss_impl(y_true, y_pred, hw, B, A, C, anchors_wh_host, image_wh_host, iou_thresh, metric, variant,
                         global_batch, out_parts, out_loss, nullptr, nullptr, workspace, workspace_bytes, stream_, nullptr, 0xf, &x);
+}
+
+// The same with the exchange split in two: this call ends with the PUBLISH half (out_parts / out_loss hold this rank's
+// own terms); b200_yolo_loss_collect_peer, enqueued on any stream ordered behind it, waits for the peers and writes the
+// global parts / loss — e.g. on a second stream, under the kernels of the next step.  The publish of step f must be
+// ordered after this rank's collect of step f-2 (four slot sets, exchange.cuh).
+extern "C" int b200_yolo_loss_dp_publish(const float* const y_true[3], const float* const y_pred[3], const int32_t hw[6], int B,
+                                         int A, int C, const float* anchors_wh_host, const float* image_wh_host,
+                                         float iou_thresh, int metric, int variant, float global_batch, float* out_parts,
+                                         float* out_loss, void* workspace, size_t workspace_bytes, int rank, int world,
+                                         void* const mailboxes[], void* stream_) {
+  B200Exchange x;
+  const int rc = b200_fill_exchange(x, rank, world, mailboxes, "b200_yolo_loss_dp_publish");
+  if (rc != B200_OK) return rc;
+  return yolo_loss_impl(y_true, y_pred, hw, B, A, C, anchors_wh_host, image_wh_host, iou_thresh, metric, variant,
+                        global_batch, out_parts, out_loss, nullptr, nullptr, workspace, workspace_bytes, stream_, nullptr, 0xf, &x, 1);
 }
 
 extern "C" int b200_yolo_loss_from_boxes_dp(const float* boxes, const int32_t* classes, const int32_t* offsets, int total_boxes,

@@ -98,6 +98,14 @@ class PeerExchange(object):
         _lib.check(fn(t.data_ptr(), t.numel(), self.rank, self.world, self.mailboxes, T.stream_ptr()), "PeerExchange.allreduce_")
         return t
 
+    def collect_yolo(self, parts_out, loss_out):
+        """Second half of a deferred GetLoss exchange (_loss_call(..., defer_collect=True)): waits for the peers' terms,
+        writes the global parts (3,4) / loss.  Enqueue it on a stream ordered behind the publishing call; the publish of
+        step f must in turn be ordered behind the collect of step f-2 (four slot sets)."""
+        from . import _lib, _tensors as T
+        _lib.check(self.lib.b200_yolo_loss_collect_peer(T.ptr(parts_out), T.ptr(loss_out), self.rank, self.world, self.mailboxes,
+                                                        T.stream_ptr()), "PeerExchange.collect_yolo")
+
     def close(self):
         for m in self.mapped:
             self.lib.b200_peer_mailbox_close(m)

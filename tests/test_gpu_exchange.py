@@ -82,6 +82,27 @@ def _worker(rank, world, port, q):
         vals = [float(step()) for _ in range(5)]
         res["peer_graph"] = vals
         res["peer_status"] = peer.status()
+        # split exchange: publish inside the loss call, collect on a second stream one step later (bench.py's N > 1 mode)
+        from tfmv_b200.ai_models.utils import tf_yolo_utils as tyu
+        comm = torch.cuda.Stream()
+        outs = [dict(parts=torch.empty((3, 4), device=dev), loss=torch.zeros((), device=dev), done=None) for _ in range(2)]
+        got = []
+        for i in range(6):
+            k = i & 1
+            main = torch.cuda.current_stream()
+            if outs[k]["done"] is not None:
+                main.wait_event(outs[k]["done"])          # publish(f) behind the own collect(f - 2)
+                got.append(float(outs[k]["loss"]))
+            tyu._loss_call(yt, yp, (image, image), anc, 0.5, "ciou", 0, batch_divisor=batch, exchange=peer, defer_collect=True)
+            ready = torch.cuda.Event(); ready.record(main)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ready)
+                peer.collect_yolo(outs[k]["parts"], outs[k]["loss"])
+                outs[k]["done"] = torch.cuda.Event(); outs[k]["done"].record(comm)
+        torch.cuda.synchronize()
+        got += [float(outs[0]["loss"]), float(outs[1]["loss"])]
+        res["peer_deferred"] = got
+        res["peer_status"] = peer.status()
         nccl = runtime.NcclExchange()
         res["nccl"] = float(GetLossSharded(yt, yp, (image, image), anc, 0.5, "ciou", global_batch=batch, exchange=nccl))
         res["torch"] = float(GetLossSharded(yt, yp, (image, image), anc, 0.5, "ciou", global_batch=batch))
@@ -122,5 +143,6 @@ def test_sharded_loss_over_peer_mailboxes_and_nccl(lib, cuda):
         assert abs(v["peer"] - want) <= 1e-4 * abs(want), v
         assert v["peer"] == res[0]["peer"]                       # rank-ordered sum: identical bits on every rank
         assert all(x == v["peer"] for x in v["peer_graph"]), v   # graph replays reproduce the eager value
-        assert v["peer_status"][1] == 0 and v["peer_status"][0] >= 6
+        assert v["peer_status"][1] == 0 and v["peer_status"][0] >= 12
+        assert all(x == v["peer"] for x in v["peer_deferred"]), v   # the split exchange gives the same bits
         assert abs(v["nccl"] - want) <= 1e-4 * abs(want) and abs(v["torch"] - want) <= 1e-4 * abs(want)
