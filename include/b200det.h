@@ -73,6 +73,12 @@ int b200_detmath_eval(int op, const float* x, const float* y, float* out, size_t
 int b200_pairwise_iou(const float* b1, int n1, const float* b2, int n2, int metric, float* out, void* stream);
 int b200_elementwise_iou(const float* b1, const float* b2, size_t n, int metric, float* out, void* stream);
 
+/* _get_v (efficientnet/utils/iou.py:5-24): the aspect-ratio term of the EfficientDet CIoU and the hand-written gradient
+ * its tf.custom_gradient returns for the second box's (height, width) given an upstream dv.  Elementwise over n; v_out or
+ * the gradient outputs may be NULL. */
+int b200_ciou_v_grad(const float* b1_height, const float* b1_width, const float* b2_height, const float* b2_width,
+                     const float* dv, size_t n, float* v_out, float* grad_height_out, float* grad_width_out, void* stream);
+
 /* GetIOUNMS tiu:67-108, GetIOUNMSByClasses tiu:110-157, get_nms enms:5-61 — batched over segments.
  * boxes [total,4] (16-byte aligned), scores [total], classes [total] int32 or NULL, order_id [total] or NULL
  * (unique ids giving the tie order; NULL = position), seg_offsets [num_segments+1] int32 (device).

@@ -95,6 +95,16 @@ def get_iou(boxes1, boxes2, iou_type="iou"):
     return diou_v - alpha * v
 
 
+def get_v_grad(b1_height, b1_width, b2_height, b2_width, dv):
+    """efficientnet/utils/iou.py:5-24 _get_v with its custom gradient: (v, gdh, gdw) for the second box's (height, width)."""
+    h1, w1, h2, w2, dv = [np.asarray(x, F) for x in (b1_height, b1_width, b2_height, b2_width, dv)]
+    arct = (dm.atan(_dnn(w1, h1)) - dm.atan(_dnn(w2, h2))).astype(F)
+    v = (F(4) * np.square(arct / F(math.pi))).astype(F)
+    gdw = (dv * F(8) * arct * h2 / F(math.pi ** 2)).astype(F)
+    gdh = (-dv * F(8) * arct * w2 / F(math.pi ** 2)).astype(F)
+    return v, gdh, gdw
+
+
 def get_nms(boxes, scores, max_output_size, iou_threshold=0.5, score_threshold=float("-inf"), iou_type="diou"):
     """efficientnet/utils/nms.py:5-61 get_nms: class-agnostic greedy, stop at first top score < score_threshold."""
     boxes = np.asarray(boxes, F).reshape(-1, 4)

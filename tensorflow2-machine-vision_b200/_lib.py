@@ -21,6 +21,7 @@ SIGNATURES = {
     "b200_detmath_eval": (c_i, [c_i, c_p, c_p, c_p, c_sz, c_p]),
     "b200_pairwise_iou": (c_i, [c_p, c_i, c_p, c_i, c_i, c_p, c_p]),
     "b200_elementwise_iou": (c_i, [c_p, c_p, c_sz, c_i, c_p, c_p]),
+    "b200_ciou_v_grad": (c_i, [c_p, c_p, c_p, c_p, c_p, c_sz, c_p, c_p, c_p, c_p]),
     "b200_nms": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_i, c_f, c_i, c_p, c_p, c_p]),
     "b200_yolo_decode_nms_workspace_bytes": (c_sz, [c_p, c_i, c_i, c_i]),
     "b200_yolo_decode_nms": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_f, c_f, c_f, c_i, c_i,

@@ -4,6 +4,25 @@ import torch
 from .... import _lib, _tensors as T
 
 
+def _get_v(b1_height, b1_width, b2_height, b2_width, dv=None):
+  """Aspect-ratio term of the CIoU (reference :5-24).  With `dv` (the upstream gradient) also returns the gradient the
+  reference's tf.custom_gradient hands back for (b2_height, b2_width): (v, grad_height, grad_width) — what a
+  tf.custom_gradient wrapper around the drop-in passes on."""
+  lib = _lib.load()
+  ts = torch.broadcast_tensors(*[T.to_cuda(t) for t in (b1_height, b1_width, b2_height, b2_width)])
+  h1, w1, h2, w2 = [t.contiguous() for t in ts]
+  v = torch.empty_like(h1)
+  if dv is None:
+    _lib.check(lib.b200_ciou_v_grad(T.ptr(h1), T.ptr(w1), T.ptr(h2), T.ptr(w2), None, v.numel(), T.ptr(v), None, None,
+                                    T.stream_ptr()), '_get_v')
+    return v
+  d = torch.broadcast_to(T.to_cuda(dv), h1.shape).contiguous()
+  gh, gw = torch.empty_like(h1), torch.empty_like(h1)
+  _lib.check(lib.b200_ciou_v_grad(T.ptr(h1), T.ptr(w1), T.ptr(h2), T.ptr(w2), T.ptr(d), v.numel(), T.ptr(v), T.ptr(gh), T.ptr(gw),
+                                  T.stream_ptr()), '_get_v')
+  return v, gh, gw
+
+
 def get_iou(boxes1, boxes2, iou_type = 'iou'):
   """
   Args:

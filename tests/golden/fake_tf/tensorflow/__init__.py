@@ -279,7 +279,9 @@ def print(*a, **k):  # noqa: A001
 
 def custom_gradient(fn):
     def wrapped(*args):
-        return fn(*args)[0]
+        out, grad = fn(*args)
+        custom_gradient.last_grad = grad   # kept so that the golden generator can evaluate the hand-written gradient too
+        return out
     return wrapped
 
 

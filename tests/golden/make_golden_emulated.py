@@ -227,6 +227,17 @@ def main():
     bx, ci, sc = rd0.convert_outputs_one(0, dec0, cls0)
     out["c3_boxes"], out["c3_ids"], out["c3_scores"] = np.asarray(bx), np.asarray(ci), np.asarray(sc)
     out["c3_anchor_checksum"] = np.array([np.asarray(b, dtype=np.float64).sum() for b in rd0.boxes])
+    # ---- efficientnet/utils/iou.py:5-24 _get_v and the gradient its tf.custom_gradient returns (drawn last: every array
+    # above keeps its values) ----------------------------------------------------------------------------------------
+    if not REAL_TF:
+        import tensorflow as tfs
+        vh1, vw1, vh2, vw2 = [np.exp(rng.uniform(np.log(2.0), np.log(200.0), 64)).astype(F) for _ in range(4)]
+        vh2[5] = 0.0; vw1[9] = 0.0          # divide_no_nan branches
+        vdv = rng.standard_normal(64).astype(F)
+        out["cv_h1"], out["cv_w1"], out["cv_h2"], out["cv_w2"], out["cv_dv"] = vh1, vw1, vh2, vw2, vdv
+        out["cv_v"] = np.asarray(reiou._get_v(vh1, vw1, vh2, vw2), dtype=F)
+        (gdh, gdw), _ = tfs.custom_gradient.last_grad(vdv, [])
+        out["cv_gdh"], out["cv_gdw"] = np.asarray(gdh, dtype=F), np.asarray(gdw, dtype=F)
     path = os.environ.get("B200_EMULATED_OUT") or os.path.join(HERE, "ref_emulated.npz")   # the risk study writes elsewhere
     np.savez_compressed(path, **out)
     print("wrote %s: %d arrays (%s)" % (path, len(out), "real TensorFlow" if REAL_TF else "NumPy stand-in for TensorFlow"))

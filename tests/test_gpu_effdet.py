@@ -350,3 +350,23 @@ def test_fused_eval_step_matches_oracle_and_separate_calls(lib, cuda, name, batc
     assert abs(float(loss2) - want) <= LOSS_RTOL * abs(want)
     sep = float(get_loss(d(tb), d(tc), d(tm), d(rel), d(cls_l)))
     assert abs(float(loss2) - sep) <= 2e-6 * abs(sep)
+
+
+def test_ciou_v_custom_gradient_bitwise(lib, cuda):
+    """_get_v + the gradient of its tf.custom_gradient (efficientnet/utils/iou.py:5-24) against the oracle, bit for bit
+    (same detmath atan, same operation order)."""
+    from oracle import effdet as oe
+    from tfmv_b200.ai_models.efficientnet.utils.iou import _get_v
+    rng = np.random.default_rng(91)
+    n = 5000
+    h1, w1, h2, w2 = [np.exp(rng.uniform(np.log(0.5), np.log(500.0), n)).astype(F) for _ in range(4)]
+    h2[::97] = 0.0
+    w1[::89] = 0.0
+    h1[::83] = 0.0
+    dv = rng.standard_normal(n).astype(F)
+    v, gh, gw = _get_v(_t(h1, cuda), _t(w1, cuda), _t(h2, cuda), _t(w2, cuda), _t(dv, cuda))
+    wv, wgh, wgw = oe.get_v_grad(h1, w1, h2, w2, dv)
+    assert_bits_equal(v.cpu().numpy(), wv)
+    assert_bits_equal(gh.cpu().numpy(), wgh)
+    assert_bits_equal(gw.cpu().numpy(), wgw)
+    assert_bits_equal(_get_v(_t(h1, cuda), _t(w1, cuda), _t(h2, cuda), _t(w2, cuda)).cpu().numpy(), wv)

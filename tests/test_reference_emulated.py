@@ -177,3 +177,19 @@ def test_baseline_config3_image_through_the_reference_anchors():
     bx, ci, sc = a.convert_outputs_one(0, dec, cls)
     assert len(G["c3_ids"]) == 200 and ci.tolist() == G["c3_ids"].tolist()
     close(bx, G["c3_boxes"], rtol=3e-6, atol=1e-4); close(sc, G["c3_scores"])
+
+
+def test_ciou_v_custom_gradient_matches_reference_source():
+    """efficientnet/utils/iou.py:5-24: _get_v and the hand-written gradient its tf.custom_gradient returns, evaluated by
+    the reference's own code under the stand-in.  atan(w1/h1) - atan(w2/h2) cancels, so the comparison is absolute on the
+    scale of the operands (libm vs detmath atan differ by an ulp of a value near 1)."""
+    from oracle import effdet as oe
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_emulated.npz"))
+    v, gdh, gdw = oe.get_v_grad(g["cv_h1"], g["cv_w1"], g["cv_h2"], g["cv_w2"], g["cv_dv"])
+    np.testing.assert_allclose(v, g["cv_v"], rtol=1e-5, atol=2e-7)
+    scale_h = np.abs(g["cv_dv"]) * 8 * g["cv_w2"] / np.pi ** 2
+    scale_w = np.abs(g["cv_dv"]) * 8 * g["cv_h2"] / np.pi ** 2
+    assert np.all(np.abs(gdh - g["cv_gdh"]) <= 4e-7 * scale_h + 1e-12)
+    assert np.all(np.abs(gdw - g["cv_gdw"]) <= 4e-7 * scale_w + 1e-12)
+    # sign convention and the divide_no_nan branches (h2 == 0 -> atan(0)); the gradient is NOT the true derivative: no 1/(w^2+h^2)
+    assert np.sign(gdh[0]) == -np.sign(gdw[0]) or gdh[0] == 0
