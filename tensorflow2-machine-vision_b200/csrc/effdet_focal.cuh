@@ -9,18 +9,21 @@ __device__ __forceinline__ float el_lg2(float x) { float y; asm("lg2.approx.ftz.
 __device__ __forceinline__ float el_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float el_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+// The library is built with -fmad=false (decision paths must round every operation separately), so the fused multiply-adds
+// of this continuous-valued loss are written out: 21 instructions per element instead of 28, 4 of them MUFU.
 template <bool G15 = false>
 __device__ __forceinline__ float el_focal(float y, float x, float alpha, float gamma, float ls) {
   // focal_loss.py:36-52
   const float e = el_ex2(-1.4426950408889634f * fabsf(x));   // exp(-|x|)
   const float r = el_rcp(1.0f + e);
-  const float p = (x >= 0.0f) ? r : e * r;          // sigmoid(x)
-  const float p_t = y * p + (1.0f - y) * (1.0f - p);
-  const float af = y * alpha + (1.0f - y) * (1.0f - alpha);
-  const float q = fmaxf(1.0f - p_t, 0.0f);
+  const float p = (x >= 0.0f) ? r : e * r;                    // sigmoid(x)
+  // 1 - p_t with p_t = y p + (1 - y)(1 - p):  p + y (1 - 2p)
+  const float q = fmaxf(__fmaf_rn(y, __fmaf_rn(-2.0f, p, 1.0f), p), 0.0f);
+  const float af = __fmaf_rn(y, 2.0f * alpha - 1.0f, 1.0f - alpha);   // y alpha + (1 - y)(1 - alpha); the constants fold per kernel
   const float mod = (G15 || gamma == 1.5f) ? q * el_sqrt(q) : __powf(q, gamma);
-  const float ys = y * (1.0f - ls) + 0.5f * ls;
-  const float ce = fmaxf(x, 0.0f) - x * ys - 0.6931471805599453f * el_lg2(r);  // log1p(exp(-|x|)) = -log(1/(1+e))
+  const float ys = __fmaf_rn(y, 1.0f - ls, 0.5f * ls);
+  // sigmoid_cross_entropy_with_logits: max(x,0) - x ys + log1p(exp(-|x|)), and log1p(e) = -log(1 / (1 + e))
+  const float ce = __fmaf_rn(-0.6931471805599453f, el_lg2(r), __fmaf_rn(-x, ys, fmaxf(x, 0.0f)));
   return af * mod * ce;
 }
 

@@ -215,8 +215,8 @@ __global__ void __launch_bounds__(EL_THREADS) focal_box_grad_kernel(ElGradParams
   const float bs = 50.0f / (4.0f * npos);
   if (p.cls_grad[l]) {
     const unsigned long long nv = p.cls_vec[l];
-#pragma unroll 2
     const int32_t* __restrict__ ci = p.cls_index[l];
+#pragma unroll 2
     for (unsigned long long i = (unsigned long long)cta * EL_THREADS + threadIdx.x; i < nv; i += stride) {
       const float4 x = __ldcs(p.cls_pred[l] + i);
       float4 y;

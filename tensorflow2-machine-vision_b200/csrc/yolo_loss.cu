@@ -534,212 +534,6 @@ __global__ void __launch_bounds__(YL_ICHUNK, YL_IMINB) yolo_loss_ignore_kernel(Y
   }
 }
 
-// K4b', the pipelined form of the ignore kernel for predictions in device memory (16-byte aligned, records of >= 8 floats):
-// a persistent grid (8 CTAs of 4 warps per SM); every WARP owns chunks of 32 consecutive records of one (level, image) and
-// is a pipeline of its own — the two 16-byte loads and the obj flag of its NEXT chunk are in flight while it filters, drains
-// and accumulates the current one, the queue of surviving (record, GT) pairs is per warp (slots from ballots, no atomics),
-// and nothing inside the loop needs a CTA barrier.  Same arithmetic as K4b (the filter and the exact tests are shared
-// code), so the ignore mask is bit-identical; the object-loss partials are per (CTA, level).
-#define YL_PIPE_CTAS_PER_SM 8
-#define YL_PIPE_QCAP 96
-
-struct YlPipe {
-  int chunks_per_img[YL_LEVELS];   // 32-record chunks per image of each level
-  long long chunk_base[YL_LEVELS + 1];
-  double* partials;                // [n_pipe_cta][YL_LEVELS]
-  int n_pipe_cta;
-};
-
-template <int MINB>
-__global__ void __launch_bounds__(YL_ICHUNK, MINB) yolo_loss_ignore_pipe_kernel(YlParams p, YlPipe pp) {
-  __shared__ float4 s_t[YL_ICHUNK];
-  __shared__ uint32_t s_q[YL_ICHUNK / 32][YL_PIPE_QCAP];
-  __shared__ uint32_t s_hit[YL_ICHUNK / 32];
-  __shared__ double s_acc[YL_ICHUNK / 32][YL_LEVELS];
-  if ((int)blockIdx.x >= pp.n_pipe_cta) {  // block-uniform: the trailing CTAs take the per-object terms
-    __shared__ double s_tacc[YL_ICHUNK / 32][3];
-    yl_terms_body(p, blockIdx.x - pp.n_pipe_cta, s_tacc);
-    return;
-  }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long n_chunks = pp.chunk_base[YL_LEVELS];
-  const long long gwarp = (long long)blockIdx.x * (YL_ICHUNK / 32) + warp;
-  const long long wstride = (long long)pp.n_pipe_cta * (YL_ICHUNK / 32);
-  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
-  float4* my_t = s_t + warp * 32;
-  uint32_t* my_q = s_q[warp];
-
-  // (level, image, first record) of a chunk, and the raw loads of this lane's record
-  auto locate = [&](long long c, int& l, int& img, int& rin0) {
-    l = 0;
-#pragma unroll
-    for (int k = 1; k < YL_LEVELS; ++k) if (c >= pp.chunk_base[k]) l = k;
-    const int r = (int)(c - pp.chunk_base[l]);
-    img = r / pp.chunks_per_img[l];
-    rin0 = (r - img * pp.chunks_per_img[l]) * 32;
-  };
-  auto fetch = [&](long long c, float4& lo, float4& hi, float& obj) {
-    lo = make_float4(0.f, 0.f, 0.f, 0.f); hi = lo; obj = 0.f;
-    if (c >= n_chunks) return;
-    int l, img, rin0;
-    locate(c, l, img, rin0);
-    const int rpi = p.lv.rec_per_img[l];
-    const int rin = rin0 + lane;
-    if (rin >= rpi) return;
-    const size_t f0 = ((size_t)img * rpi + rin) * p.RF;
-    lo = __ldcg(reinterpret_cast<const float4*>(p.lv.y_pred[l]) + (f0 >> 2));
-    hi = __ldcg(reinterpret_cast<const float4*>(p.lv.y_pred[l]) + (f0 >> 2) + 1);
-    if (p.obj_bits) {
-      const int bit = p.lv.anchor_base[l] + rin;
-      obj = ((__ldg(p.obj_bits + (size_t)img * p.bits_words + (bit >> 5)) >> (bit & 31)) & 1u) ? 1.0f : 0.0f;
-    } else {
-      obj = p.obj_compact[(size_t)img * p.n_img + p.lv.anchor_base[l] + rin];
-    }
-  };
-
-  float4 lo, hi;
-  float obj;
-  fetch(gwarp, lo, hi, obj);
-  for (long long c = gwarp; c < n_chunks; c += wstride) {
-    float4 nlo, nhi;
-    float nobj;
-    fetch(c + wstride, nlo, nhi, nobj);   // the next chunk travels while this one is processed
-    int l, img, rin0;
-    locate(c, l, img, rin0);
-    const int rpi = p.lv.rec_per_img[l];
-    const int rin = rin0 + lane;
-    const bool active = rin < rpi;
-    const int n_gt = p.gt_count[img * YL_LEVELS + l];
-    const float4* gbox = p.gt_box + (size_t)img * p.n_img + p.lv.anchor_base[l];
-    const float4* gaux = p.gt_aux + (size_t)img * p.n_img + p.lv.anchor_base[l];
-    const int W = p.lv.w[l], H = p.lv.h[l];
-    float tx = 0.f, ty = 0.f, tw = 0.f, th = 0.f, pobj = 0.f;
-    if (active) {
-      // the record starts 0..3 floats into lo: rotate the 8 loaded floats left by sh with two select stages
-      const int sh = (int)((((size_t)img * rpi + rin) * p.RF) & 3);
-      const bool s1 = sh & 1, s2 = sh & 2;
-      const float a0 = s1 ? lo.y : lo.x, a1 = s1 ? lo.z : lo.y, a2 = s1 ? lo.w : lo.z, a3 = s1 ? hi.x : lo.w;
-      const float a4 = s1 ? hi.y : hi.x, a5 = s1 ? hi.z : hi.y, a6 = s1 ? hi.w : hi.z;
-      tx = s2 ? a2 : a0; ty = s2 ? a3 : a1; tw = s2 ? a4 : a2; th = s2 ? a5 : a3; pobj = s2 ? a6 : a4;
-    }
-    bool hit = false;  // some GT with metric >= thr (or NaN)
-    if (n_gt > 0) {    // warp-uniform
-      my_t[lane] = make_float4(tx, ty, tw, th);
-      if (lane == 0) s_hit[warp] = 0u;
-      __syncwarp();
-      // ---------------- phase 1 (the filter of K4b, per warp) ----------------
-      const int cell = yl_fastdiv(rin, p.magic_a);
-      const int a = min(rin - cell * p.A, 7);
-      const int gy = yl_fastdiv(cell, p.lv.magic_w[l]);
-      const int gx = cell - gy * W;
-      const bool filter_ok = p.thr >= 0.5f;
-      const bool nice = active && filter_ok && (tw >= p.tmin_w[l][a]) && (tw <= 4.0f) && (th >= p.tmin_h[l][a]) &&
-                        (th <= 4.0f) && (tx == tx) && (ty == ty);
-      const float sp = tw + th + p.logk[l][a];
-      const float invW = 1.0f / (float)W, invH = 1.0f / (float)H;
-      float fx0 = 0.f, fy0 = 0.f, fx1 = 0.f, fy1 = 0.f, farea = 0.f;
-      bool fast_ok = false;
-      if (nice) {
-        const float ex = __expf(-fabsf(tx)), ey = __expf(-fabsf(ty));
-        const float rx = __fdividef(1.0f, 1.0f + ex), ry = __fdividef(1.0f, 1.0f + ey);
-        const float fx = ((tx >= 0.0f ? rx : ex * rx) + (float)gx) * invW, fy = ((ty >= 0.0f ? ry : ey * ry) + (float)gy) * invH;
-        const float fw = __expf(tw) * __fdividef(p.lv.anc_w[l][a], p.img_w), fh = __expf(th) * __fdividef(p.lv.anc_h[l][a], p.img_h);
-        fx0 = fx - 0.5f * fw; fx1 = fx + 0.5f * fw; fy0 = fy - 0.5f * fh; fy1 = fy + 0.5f * fh;
-        farea = fw * fh;
-        fast_ok = (fw <= 2.0f) && (fh <= 2.0f);
-      }
-      const float thr_lo = p.thr - YL_IOU_EPS;
-      const float cx0 = (float)gx * invW - YL_CELL_MARGIN, cx1 = (float)(gx + 1) * invW + YL_CELL_MARGIN;
-      const float cy0 = (float)gy * invH - YL_CELL_MARGIN, cy1 = (float)(gy + 1) * invH + YL_CELL_MARGIN;
-      const uint32_t act = __ballot_sync(0xffffffffu, active);
-      float ux0 = 0.f, ux1 = 0.f, uy0 = 0.f, uy1 = 0.f;
-      if (act) {
-        const int first = __ffs(act) - 1, last = 31 - __clz(act);
-        const float f_x0 = __shfl_sync(0xffffffffu, cx0, first), f_y0 = __shfl_sync(0xffffffffu, cy0, first);
-        const float l_x1 = __shfl_sync(0xffffffffu, cx1, last), l_y1 = __shfl_sync(0xffffffffu, cy1, last);
-        const int gyf = __shfl_sync(0xffffffffu, gy, first), gyl = __shfl_sync(0xffffffffu, gy, last);
-        uy0 = f_y0; uy1 = l_y1;
-        ux0 = (gyf == gyl) ? f_x0 : -1.0f;
-        ux1 = (gyf == gyl) ? l_x1 : 2.0f;
-      }
-      const bool any_rough = __any_sync(0xffffffffu, active && !nice);
-      const float lo_k = p.log_thr - YL_LOG_MARGIN, hi_k = -p.log_thr + YL_LOG_MARGIN;
-      int nq = 0;   // warp-uniform queue length
-      for (int j0 = 0; j0 < n_gt; j0 += 32) {
-        const int j = j0 + lane;
-        bool relevant = false;
-        if (j < n_gt) {
-          const float4 cg = __ldg(gbox + j);
-          relevant = any_rough || (__ldg(gaux + j).w == 0.0f) || !((ux1 < cg.x) || (cg.z < ux0) || (uy1 < cg.y) || (cg.w < uy0));
-        }
-        uint32_t mask = __ballot_sync(0xffffffffu, relevant);
-        while (mask) {
-          const int g = j0 + __ffs(mask) - 1;
-          mask &= mask - 1u;
-          const float4 cg = __ldg(gbox + g);
-          const float4 xg = __ldg(gaux + g);  // area, atan term, log(area), regular flag
-          const float iw = fminf(fx1, cg.z) - fmaxf(fx0, cg.x), ih = fminf(fy1, cg.w) - fmaxf(fy0, cg.y);
-          const float inter = iw * ih;
-          const bool cell_rej = (cx1 < cg.x) | (cg.z < cx0) | (cy1 < cg.y) | (cg.w < cy0);
-          const bool win_rej = (sp < xg.z + lo_k) | (sp > xg.z + hi_k);
-          const bool dis_rej = (iw < -1e-5f) | (ih < -1e-5f);
-          const bool iou_rej = fast_ok & (iw >= YL_IOU_FLOOR) & (ih >= YL_IOU_FLOOR) & (inter < thr_lo * (farea + xg.x - inter));
-          const bool rejected = nice & (xg.w != 0.0f) & (cell_rej | win_rej | dis_rej | iou_rej);
-          const bool push = active & !hit & !rejected;
-          const uint32_t pm = __ballot_sync(0xffffffffu, push);
-          if (pm == 0u) continue;
-          if (nq + __popc(pm) <= YL_PIPE_QCAP) {
-            if (push) my_q[nq + __popc(pm & ((1u << lane) - 1u))] = ((uint32_t)lane << 24) | (uint32_t)g;
-            nq += __popc(pm);
-          } else if (push) {  // queue full: exact test now (opaque asm: keep the decode out of the filter loop, see K4b)
-            float otx = tx, oty = ty, otw = tw, oth = th;
-            asm volatile("" : "+f"(otx), "+f"(oty), "+f"(otw), "+f"(oth));
-            if (yl_pair_hits(p, l, rin, otx, oty, otw, oth, cg, xg)) hit = true;
-          }
-        }
-      }
-      const uint32_t hit_now = __ballot_sync(0xffffffffu, hit);
-      if (lane == 0 && hit_now) s_hit[warp] = hit_now;
-      __syncwarp();
-      // ---------------- phase 2: drain, one pair per lane ----------------
-      for (int qi = lane; qi < nq; qi += 32) {
-        const uint32_t e = my_q[qi];
-        const int r = (int)(e >> 24), g = (int)(e & 0xffffffu);
-        if ((s_hit[warp] >> r) & 1u) continue;  // already decided (benign race: only skips work)
-        const float4 t = my_t[r];
-        if (yl_pair_hits(p, l, rin0 + r, t.x, t.y, t.z, t.w, __ldg(gbox + g), __ldg(gaux + g))) atomicOr(&s_hit[warp], 1u << r);
-      }
-      __syncwarp();
-      hit = (s_hit[warp] >> lane) & 1u;
-      __syncwarp();   // s_hit / my_t / my_q are rewritten by the next chunk
-    }
-    // ---------------- phase 3 ----------------
-    float e = 0.f;
-    if (active) {
-      const float bc = yl_fast_bce(obj, pobj);
-      const float ign = hit ? 0.0f : 1.0f;
-      if (p.out_ignore) p.out_ignore[(size_t)img * p.n_img + p.lv.anchor_base[l] + rin] = hit ? 0 : 1;
-      e = obj * bc + (1.0f - obj) * bc * ign;  // tyu:114
-      if (p.conf_grad) {
-        const float ex = __expf(-fabsf(pobj));
-        const float rr = 1.0f / (1.0f + ex);
-        const float sg = pobj >= 0.0f ? rr : ex * rr;
-        p.conf_grad[(size_t)p.B * p.lv.anchor_base[l] + (size_t)img * rpi + rin] = (sg - obj) * (obj + (1.0f - obj) * ign) * p.inv_div;
-      }
-    }
-    e = warp_sum(e);  // 32 fp32 terms; everything above is fp64
-    if (l == 0) acc0 += (double)e; else if (l == 1) acc1 += (double)e; else acc2 += (double)e;
-    lo = nlo; hi = nhi; obj = nobj;
-  }
-  if (lane == 0) { s_acc[warp][0] = acc0; s_acc[warp][1] = acc1; s_acc[warp][2] = acc2; }
-  __syncthreads();
-  if (threadIdx.x < YL_LEVELS) {
-    double sum = 0;
-    for (int i = 0; i < YL_ICHUNK / 32; ++i) sum += s_acc[i][threadIdx.x];
-    pp.partials[(size_t)blockIdx.x * YL_LEVELS + threadIdx.x] = sum;
-  }
-}
-
 // K4c: YL_FIN_CTAS CTAs each reduce an interleaved share of the per-CTA partials in fp64 (fixed assignment, fixed
 // order); the CTA that takes the last ticket adds the YL_FIN_CTAS slices in index order and writes parts / loss.
 // Deterministic run to run, and shorter than a single CTA walking all partials (shapes measured in DESIGN.md section 9).
@@ -756,7 +550,6 @@ struct YlFinalize {
   float batch_divisor; float* parts; float* loss;
   double* slices;          // [YL_FIN_CTAS][12]
   unsigned int* ticket;    // zero on entry; reset by the last CTA
-  int pipe_ctas;           // > 0: `partials` is [pipe_ctas][3] (pipelined ignore kernel) instead of one value per K4b CTA
   B200Exchange xchg;       // data parallel: the 12 terms are summed over the ranks inside this kernel (world 1: no-op)
   int publish_only;        // 1: store this rank's terms into the peers' mailboxes and return (b200_yolo_loss_collect_peer finishes)
 };
@@ -770,12 +563,8 @@ __global__ void __launch_bounds__(YL_FIN_THREADS) yolo_loss_finalize_kernel(YlFi
   const int t0 = blockIdx.x * YL_FIN_THREADS + (int)threadIdx.x, stride = YL_FIN_CTAS * YL_FIN_THREADS;
 #pragma unroll
   for (int l = 0; l < 3; ++l) {
-    if (f.pipe_ctas > 0) {
-      for (int c = t0; c < f.pipe_ctas; c += stride) acc[l * 4 + 2] += f.partials[(size_t)c * YL_LEVELS + l];
-    } else {
 #pragma unroll 4
-      for (int c = f.cta_base[l] + t0; c < f.cta_base[l + 1]; c += stride) acc[l * 4 + 2] += f.partials[c];
-    }
+    for (int c = f.cta_base[l] + t0; c < f.cta_base[l + 1]; c += stride) acc[l * 4 + 2] += f.partials[c];
     for (int c = f.obj_cta_base[l] + t0; c < f.obj_cta_base[l + 1]; c += stride) {
       acc[l * 4 + 0] += f.partials_obj[(size_t)c * 3 + 0];
       acc[l * 4 + 1] += f.partials_obj[(size_t)c * 3 + 1];
@@ -1021,7 +810,7 @@ static YlWs yl_layout(const int32_t hw[6], int B, int A, int* n_img_out, YlLevel
   w.obj = o; o = b200_align_up(o + sizeof(float) * (size_t)B * n_img, 256);
   w.gt = o; o = b200_align_up(o + sizeof(float4) * (size_t)B * n_img, 256);
   w.gtl = o; o = b200_align_up(o + sizeof(float4) * (size_t)B * n_img, 256);
-  w.part = o; o = b200_align_up(o + sizeof(double) * YL_LEVELS * (size_t)cta, 256);  // K4b: one per CTA; K4b': [pipe CTAs <= cta][levels]
+  w.part = o; o = b200_align_up(o + sizeof(double) * (size_t)cta, 256);
   w.part_obj = o; o = b200_align_up(o + sizeof(double) * 3 * (size_t)YL_LEVELS * B * YL_TERM_SPLIT, 256);
   w.cgrad = o; o = b200_align_up(o + sizeof(float) * (size_t)B * n_img, 256);
   w.oidx = o; o = b200_align_up(o + sizeof(int32_t) * (size_t)B * n_img, 256);
@@ -1137,9 +926,6 @@ static int yolo_loss_impl(const float* const y_true[3], const float* const y_pre
     yolo_loss_gtprep_kernel<<<YL_LEVELS * B, 128, 0, stream>>>(p);
     B200_LAUNCH_CHECK();
   }
-  YlPipe pipe;
-  pipe.n_pipe_cta = 0;
-  bool use_pipe = false;
   if (stages & 4) {
     // predictions in pinned host memory are read in place over PCIe: one request per record instead of two
     cudaPointerAttributes attr;
@@ -1147,29 +933,7 @@ static int yolo_loss_impl(const float* const y_true[3], const float* const y_pre
     if (cudaPointerGetAttributes(&attr, y_pred[YL_LEVELS - 1]) == cudaSuccess) host_pred = attr.type == cudaMemoryTypeHost;
     else (void)cudaGetLastError();
     const int grid = YL_LEVELS * B * YL_TERM_SPLIT + ws.n_cta;
-    bool aligned16 = true;
-    for (int l = 0; l < YL_LEVELS; ++l) aligned16 &= (reinterpret_cast<uintptr_t>(y_pred[l]) & 15) == 0;
-    use_pipe = !host_pred && aligned16 && p.RF >= 8 && !getenv("B200_YL_NO_PIPE");
-    if (use_pipe) {
-      long long cb = 0;
-      for (int l = 0; l < YL_LEVELS; ++l) {
-        pipe.chunks_per_img[l] = (p.lv.rec_per_img[l] + 31) / 32;
-        pipe.chunk_base[l] = cb;
-        cb += (long long)pipe.chunks_per_img[l] * B;
-      }
-      pipe.chunk_base[YL_LEVELS] = cb;
-      long long want = (cb + YL_ICHUNK / 32 - 1) / (YL_ICHUNK / 32);
-      const char* mb = getenv("B200_YL_PIPE_MINB");   // tuning hook: resident CTAs per SM the kernel is compiled for (8 | 6 | 5)
-      const int minb = mb ? atoi(mb) : YL_PIPE_CTAS_PER_SM;
-      const long long cap = (long long)b200_sm_count() * (minb == 6 ? 6 : minb == 5 ? 5 : 8);
-      pipe.n_pipe_cta = (int)(want < cap ? want : cap);
-      if (pipe.n_pipe_cta > ws.n_cta) pipe.n_pipe_cta = ws.n_cta;   // the partials array holds [n_cta][levels] doubles
-      pipe.partials = p.partials;
-      const int pgrid = pipe.n_pipe_cta + YL_LEVELS * B * YL_TERM_SPLIT;
-      if (minb == 6) yolo_loss_ignore_pipe_kernel<6><<<pgrid, YL_ICHUNK, 0, stream>>>(p, pipe);
-      else if (minb == 5) yolo_loss_ignore_pipe_kernel<5><<<pgrid, YL_ICHUNK, 0, stream>>>(p, pipe);
-      else yolo_loss_ignore_pipe_kernel<8><<<pgrid, YL_ICHUNK, 0, stream>>>(p, pipe);
-    } else if (host_pred) yolo_loss_ignore_kernel<true><<<grid, YL_ICHUNK, 0, stream>>>(p);
+    if (host_pred) yolo_loss_ignore_kernel<true><<<grid, YL_ICHUNK, 0, stream>>>(p);
     else yolo_loss_ignore_kernel<false><<<grid, YL_ICHUNK, 0, stream>>>(p);
     B200_LAUNCH_CHECK();
   }
@@ -1181,7 +945,6 @@ static int yolo_loss_impl(const float* const y_true[3], const float* const y_pre
   f.slices = reinterpret_cast<double*>(wsb + ws.fin);
   f.ticket = reinterpret_cast<unsigned int*>(wsb + ws.cnt) + (size_t)B * YL_LEVELS;
   f.publish_only = publish_only;
-  f.pipe_ctas = use_pipe ? pipe.n_pipe_cta : 0;
   if (xchg) f.xchg = *xchg;
   else { f.xchg.rank = 0; f.xchg.world = 1; for (int r = 0; r < B200_XCHG_MAX_WORLD; ++r) f.xchg.mailbox[r] = nullptr; }
   yolo_loss_finalize_kernel<<<YL_FIN_CTAS, YL_FIN_THREADS, 0, stream>>>(f);
