@@ -358,9 +358,10 @@ def headline_c2(b, line):
     world, rank, dev = b.world, b.rank, b.dev
     batch, image = args.batch or 64, 608
     anc = synth.yolo_anchors().astype(F)
-    rng = np.random.default_rng(SEED + 2 + 1000 * rank)
-    heads_h = synth.yolo_heads(rng, batch, image)
-    boxes_h, classes_h, off_h = synth.gt_batch(rng, batch, (image, image), max_boxes=100)
+    # weak scaling: every rank gets the same AMOUNT of work — the ground truth of the per-GPU batch is the same draw on every
+    # rank (box counts and geometry decide the loss kernels' work), the head tensors are rank-specific
+    heads_h = synth.yolo_heads(np.random.default_rng(SEED + 2 + 1000 * rank), batch, image)
+    boxes_h, classes_h, off_h = synth.gt_batch(np.random.default_rng(SEED + 2), batch, (image, image), max_boxes=100)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     heads_p = [pin(h) for h in heads_h]
     boxes_p, classes_p, off_p = pin(boxes_h), pin(classes_h), pin(off_h)
@@ -444,7 +445,7 @@ def headline_c2(b, line):
                    "what": "each window = exactly --steps steps between barrier + synchronize, CUDA events, max over ranks; "
                            "value / ms_per_step are the median window"},
         "config": {"workload": WHAT["c2"], "image": image, "per_gpu_batch": batch, "global_batch": global_batch,
-                   "classes": 80, "anchors_per_cell": 3, "gt_boxes_per_image": "U{1..100}",
+                   "classes": 80, "anchors_per_cell": 3, "gt_boxes_per_image": "U{1..100} (the same draw on every rank; heads differ per rank)",
                    "parallelism": "dp%d (images sharded; one 12-float all-reduce per step: %s)" % (world, b.exchange_kind),
                    "launch": "launch by launch" if dev_step is raw else (
                        "CUDA graph replay of the step up to the publish half of the exchange; the collect half of step i runs on a second "
