@@ -62,7 +62,8 @@ def parse():
     ap.add_argument("--c5-global-batch", type=int, default=512, help="global batch of configs.c5 (512 = BASELINE configs[4])")
     ap.add_argument("--cpu-sample", type=int, default=0, help="images per CPU-baseline run (0 = 16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl", "torch"], help="transport of the loss all-reduce (N > 1)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl", "torch", "local"],
+                    help="transport of the loss all-reduce (N > 1); local = no exchange at all (diagnostic: isolates its cost)")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: keep the whole exchange inside the step's finalize kernel (no second stream)")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every step launch by launch instead of replaying CUDA graphs")
@@ -257,6 +258,8 @@ class Bench(object):
                 self.exchange_kind = "b200_allreduce_loss: ncclAllReduce issued by the library on the step's stream"
             if kind == "torch":
                 self.exchange_kind = "torch.distributed all_reduce behind the step (outside the CUDA graph)"
+            if kind == "local":
+                self.exchange_kind = "NONE (diagnostic run: every rank keeps its local loss)"
         self.peaks = {}
         try:
             self.peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -378,7 +381,7 @@ def headline_c2(b, line):
     def step(heads, boxes, classes, off):
         """One step on this rank's images: target assignment + loss, the 12 terms summed over the ranks."""
         gen.GetTargetsBatch(classes, boxes, off, out=y_true)
-        if in_graph or world == 1:
+        if in_graph or world == 1 or args.exchange == "local":
             return tyu._loss_call(y_true, heads, (image, image), anc, 0.5, "ciou", 0, batch_divisor=global_batch,
                                   workspace=ws, exchange=b.exchange)
         loss, parts = tyu._loss_call(y_true, heads, (image, image), anc, 0.5, "ciou", 0, batch_divisor=global_batch,
@@ -394,7 +397,7 @@ def headline_c2(b, line):
         b.barrier()
     peer = b.exchange is not None and hasattr(b.exchange, "mailboxes")
     overlapped = False
-    if args.no_graph or (world > 1 and not in_graph):
+    if args.no_graph or (world > 1 and not in_graph and args.exchange != "local"):
         dev_step = raw
     elif world > 1 and peer and not args.no_overlap:
         # The step's graph ends with the PUBLISH half of the exchange (peer stores, no wait); the collect half of step i

@@ -731,7 +731,8 @@ extern "C" int b200_effdet_assign_targets_indexed(int num_levels, const int32_t*
 //   * box decode from the head offsets and the anchor table (anchors.py:245-274) -> the dense decoded tensor,
 //   * Huber box loss + positive count (box_loss.py:17-29), and
 //   * the append of every non-background anchor to its image's candidate list (anchors.py:179-189).
-// WITH_LOSS = false is the same stream without targets: convert_outputs_boxes + the filter of convert_outputs_one.
+// (Without targets — convert_outputs_boxes + convert_outputs_one alone — the per-warp bulk-copy filter above is the faster
+// stream and takes the decode along: b200_effdet_decode_postprocess.)
 #define EFU_TILE 64      // anchors per tile
 #define EFU_THREADS 256
 #ifndef EFU_INFLIGHT
@@ -1073,8 +1074,8 @@ static int efu_impl(bool with_loss, int num_levels, const int32_t* hw, int A, co
     B200_CUDA(cudaFuncSetAttribute(effdet_stream_kernel<WL, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     effdet_stream_kernel<WL, G><<<grid, EFU_THREADS, smem, stream>>>(p);                                                  \
   } while (0)
-  if (!with_loss) EFU_LAUNCH(false, false);
-  else if (gamma == 1.5f) EFU_LAUNCH(true, true);
+  B200_REQUIRE(with_loss, B200_ERR_BAD_ARG, "%s: the CTA-tiled stream needs targets (the target-free pass is the bulk-copy filter)", who);
+  if (gamma == 1.5f) EFU_LAUNCH(true, true);
   else EFU_LAUNCH(true, false);
 #undef EFU_LAUNCH
   B200_LAUNCH_CHECK();

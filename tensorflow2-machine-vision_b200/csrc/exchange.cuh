@@ -4,10 +4,10 @@
 //
 // B200-first form: no separate collective launch.  Every rank owns a small "mailbox" in its HBM that its peers map
 // through CUDA IPC (NVLink 5 / NVSwitch peer stores).  The last CTA of the loss-finalize kernel
-//   1. stores its n <= 32 partial terms into slot [epoch % 4][rank] of EVERY rank's mailbox (plain peer stores),
-//   2. fences (system scope) and release-stores the epoch number into the slot's flag,
-//   3. acquire-spins on the `world` flags of its OWN mailbox (local HBM, no link traffic while waiting),
-//   4. adds the `world` payloads in rank order — the same order on every rank, so every rank gets the same bits.
+//   1. lane r stores the n <= 32 partial terms into slot [epoch % 4][rank] of rank r's mailbox (plain peer stores) and
+//   2. release-stores the epoch number into that slot's flag (the release orders the lane's own stores: no wider fence),
+//   3. lane r acquire-spins on rank r's flag in its OWN mailbox (local HBM, no link traffic while waiting),
+//   4. the warp adds the `world` payloads in rank order — the same order on every rank, so every rank gets the same bits.
 // Four slot sets are used round robin.  Fused form: a rank can be at most one exchange ahead of its slowest peer (it
 // needs that peer's flag of epoch e to leave epoch e), so a set is never overwritten while somebody still reads it.
 // Split form (publish now, collect later on another stream): rule "publish(f) is ordered after this rank's own
@@ -58,7 +58,9 @@ __device__ __forceinline__ unsigned long long xchg_globaltimer() {
 // the header; both advance by one per exchange.  The caller orders publish(f) after its own collect(f - 2) (stream /
 // event order; see the slot-set argument at the top); the fused form below is trivially safe.
 //
-// publish: one value per lane (lanes >= n pass anything) into slot [epoch % 4][rank] of every rank's mailbox.
+// publish: one value per lane (lanes >= n pass anything).  Lane r (< world) is the courier to rank r: it receives the n
+// values by shuffles, stores them into slot [epoch % 4][rank] of rank r's mailbox and release-stores the flag behind them
+// — the release of a thread orders that thread's own earlier stores, so no CTA- or system-wide fence is needed.
 template <typename T>
 __device__ __forceinline__ void xchg_publish_warp(const B200Exchange& x, T v, int n) {
   const int lane = threadIdx.x & 31;
@@ -67,21 +69,18 @@ __device__ __forceinline__ void xchg_publish_warp(const B200Exchange& x, T v, in
   if (lane == 0) epoch = *reinterpret_cast<volatile unsigned long long*>(&hdr->pub_epoch) + 1ull;
   epoch = __shfl_sync(0xffffffffu, epoch, 0);
   const unsigned par = (unsigned)(epoch % B200_XCHG_SLOT_SETS);
-  if (lane < n) {
-    for (int r = 0; r < x.world; ++r) {   // own mailbox too: the sum then reads all ranks the same way
-      volatile T* dst = reinterpret_cast<volatile T*>(xchg_slot(x.mailbox[r], par, x.rank));
-      dst[lane] = v;
-    }
+  unsigned char* slot = lane < x.world ? xchg_slot(x.mailbox[lane], par, x.rank) : nullptr;   // own mailbox too
+  for (int i = 0; i < n; ++i) {
+    const T vi = __shfl_sync(0xffffffffu, v, i);
+    if (slot) reinterpret_cast<volatile T*>(slot)[i] = vi;
   }
-  __threadfence_system();
-  __syncwarp();
-  if (lane < x.world)
-    xchg_st_release_sys(reinterpret_cast<unsigned long long*>(xchg_slot(x.mailbox[lane], par, x.rank) + 8 * B200_XCHG_MAX_VALUES), epoch);
+  if (slot) xchg_st_release_sys(reinterpret_cast<unsigned long long*>(slot + 8 * B200_XCHG_MAX_VALUES), epoch);
   if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(&hdr->pub_epoch) = epoch;
 }
 
-// collect: waits for every rank's flag of the next epoch in the LOCAL mailbox (no link traffic while waiting) and adds the
-// payloads in rank order — the same order on every rank.  Returns the sum on lanes < n.
+// collect: lane r (< world) acquire-spins on rank r's flag of the next epoch in the LOCAL mailbox (no link traffic while
+// waiting); the warp barrier then carries the happens-before edge to the lanes that add the payloads — in rank order, the
+// same order on every rank.  Returns the sum on lanes < n.
 template <typename T>
 __device__ __forceinline__ T xchg_collect_warp(const B200Exchange& x, int n) {
   const int lane = threadIdx.x & 31;
@@ -97,11 +96,9 @@ __device__ __forceinline__ T xchg_collect_warp(const B200Exchange& x, int n) {
     const unsigned long long t0 = xchg_globaltimer();
     while (xchg_ld_acquire_sys(flag) < epoch) {
       if (xchg_globaltimer() - t0 > B200_XCHG_TIMEOUT_NS) { ok = false; break; }
-      __nanosleep(64);
     }
   }
-  ok = __all_sync(0xffffffffu, ok);
-  __threadfence_system();
+  ok = __all_sync(0xffffffffu, ok);   // also the barrier that orders the payload reads below behind every lane's acquire
   T acc = (T)0;
   if (lane < n) {
     for (int r = 0; r < x.world; ++r) {
