@@ -62,9 +62,9 @@ def parse():
     ap.add_argument("--c5-global-batch", type=int, default=512, help="global batch of configs.c5 (512 = BASELINE configs[4])")
     ap.add_argument("--cpu-sample", type=int, default=0, help="images per CPU-baseline run (0 = 16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl", "torch", "local"],
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl", "torch", "local", "peer-idle"],
                     help="transport of the loss all-reduce (N > 1); local = no exchange at all (diagnostic: isolates its cost)")
-    ap.add_argument("--no-overlap", action="store_true", help="N > 1: keep the whole exchange inside the step's finalize kernel (no second stream)")
+    ap.add_argument("--overlap", action="store_true", help="N > 1: split the exchange (publish in the step, collect on a second stream under the next step)")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every step launch by launch instead of replaying CUDA graphs")
     ap.add_argument("--only-step", action="store_true", help="skip phase timing / e2e / cpu baseline / parity (profiling runs)")
@@ -260,6 +260,9 @@ class Bench(object):
                 self.exchange_kind = "torch.distributed all_reduce behind the step (outside the CUDA graph)"
             if kind == "local":
                 self.exchange_kind = "NONE (diagnostic run: every rank keeps its local loss)"
+            if kind == "peer-idle":   # diagnostic: peer mappings exist (CUDA IPC, peer access enabled) but the step never uses them
+                self.idle_exchange = runtime.PeerExchange()
+                self.exchange_kind = "NONE (diagnostic run: peer mailboxes mapped but unused)"
         self.peaks = {}
         try:
             self.peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -381,7 +384,7 @@ def headline_c2(b, line):
     def step(heads, boxes, classes, off):
         """One step on this rank's images: target assignment + loss, the 12 terms summed over the ranks."""
         gen.GetTargetsBatch(classes, boxes, off, out=y_true)
-        if in_graph or world == 1 or args.exchange == "local":
+        if in_graph or world == 1 or args.exchange in ("local", "peer-idle"):
             return tyu._loss_call(y_true, heads, (image, image), anc, 0.5, "ciou", 0, batch_divisor=global_batch,
                                   workspace=ws, exchange=b.exchange)
         loss, parts = tyu._loss_call(y_true, heads, (image, image), anc, 0.5, "ciou", 0, batch_divisor=global_batch,
@@ -397,9 +400,9 @@ def headline_c2(b, line):
         b.barrier()
     peer = b.exchange is not None and hasattr(b.exchange, "mailboxes")
     overlapped = False
-    if args.no_graph or (world > 1 and not in_graph and args.exchange != "local"):
+    if args.no_graph or (world > 1 and not in_graph and args.exchange not in ("local", "peer-idle")):
         dev_step = raw
-    elif world > 1 and peer and not args.no_overlap:
+    elif world > 1 and peer and args.overlap:
         # The step's graph ends with the PUBLISH half of the exchange (peer stores, no wait); the collect half of step i
         # runs on a second stream under the kernels of step i+1.  Two graphs with their own result buffers alternate; the
         # graph of step i waits for the collect of step i-2 (the rule of the four slot sets, csrc/exchange.cuh).

@@ -67,6 +67,10 @@ struct YlParams {
   const uint32_t* obj_bits;   // [B, bits_words]
   int bits_words;
   int32_t* gt_count;    // [B, 3]
+  // split form of the ignore pass (K4b-lean + K4b-exact): records whose filter leaves a (record, GT) pair undecided
+  uint32_t* pend_queue;            // [B * n_img] global record ids (img * n_img + anchor_base[l] + rin)
+  unsigned int* pend_count;        // number of queued records
+  unsigned long long* obj_fixed;   // [3] object-loss terms of the queued records, 2^-32 fixed point (order-independent sum)
   double* partials;     // [n_cta]      object_loss partial of each ignore-kernel CTA
   double* partials_obj; // [3*B*YL_TERM_SPLIT,3] xy, wh, cls partials of each terms-kernel CTA (level-major)
 };
@@ -534,6 +538,196 @@ __global__ void __launch_bounds__(YL_ICHUNK, YL_IMINB) yolo_loss_ignore_kernel(Y
   }
 }
 
+// ---- split form of K4b for predictions in device memory (the default there) ---------------------------------------
+// The filter of K4b rejects all but a few thousand (record, GT) pairs per batch; the exact decode + exact metric those few
+// need is what makes K4b a 64-register kernel (8 CTAs per SM, ~45 % of the warp slots).  Here the stream is split:
+//   K4b-lean   the same loads, the same decode-free / approximate-IoU rejects, BCE of every DECIDED record (no surviving
+//              pair => ignore = 1); a record with a surviving pair is only queued (one global id per record).  No
+//              shared-memory queue, no exact code: far fewer registers, no mid-kernel CTA barriers.
+//   K4b-exact  a warp per queued record: the exact test (yl_pair_hits, with its own exact rejects) against EVERY ground
+//              truth of the record's (image, level), lanes <-> GTs; writes the record's ignore bit / gradient and adds its
+//              object-loss term to a 2^-32 fixed-point accumulator (integer atomics: the sum is order independent, so
+//              the loss stays bit-reproducible).
+// A rejected pair is provably below the threshold, so "some surviving pair hits" == "some GT hits":
+// the ignore mask is bit-identical to K4b's.
+#define YL_FIXED_ONE 4294967296.0  // 2^32
+
+template <int MINB>
+__global__ void __launch_bounds__(YL_ICHUNK, MINB) yolo_loss_ignore_lean_kernel(YlParams p) {
+  __shared__ double s_acc[YL_ICHUNK / 32];
+  const int n_term_cta = YL_LEVELS * p.B * YL_TERM_SPLIT;
+  const int n_icta = (int)gridDim.x - n_term_cta;
+  if ((int)blockIdx.x >= n_icta) {  // block-uniform
+    __shared__ double s_tacc[YL_ICHUNK / 32][3];
+    yl_terms_body(p, blockIdx.x - n_icta, s_tacc);
+    return;
+  }
+  const int icta = blockIdx.x;
+  int l, img, chunk;
+  yl_locate(p.lv, icta, l, img, chunk);
+  const int rpi = p.lv.rec_per_img[l];
+  const int rin = chunk * YL_ICHUNK + (int)threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool active = rin < rpi;
+  const int n_gt = p.gt_count[img * YL_LEVELS + l];
+  const float4* gbox = p.gt_box + (size_t)img * p.n_img + p.lv.anchor_base[l];
+  const float4* gaux = p.gt_aux + (size_t)img * p.n_img + p.lv.anchor_base[l];
+  const int W = p.lv.w[l], H = p.lv.h[l];
+  float obj = 0.f, tx = 0.f, ty = 0.f, tw = 0.f, th = 0.f, pobj = 0.f;
+  if (active) {
+    if (p.obj_bits) {
+      const int bit = p.lv.anchor_base[l] + rin;
+      obj = ((__ldg(p.obj_bits + (size_t)img * p.bits_words + (bit >> 5)) >> (bit & 31)) & 1u) ? 1.0f : 0.0f;
+    } else {
+      obj = p.obj_compact[(size_t)img * p.n_img + p.lv.anchor_base[l] + rin];
+    }
+    const size_t f0 = ((size_t)img * rpi + rin) * p.RF;
+    const float4 lo = __ldcg(reinterpret_cast<const float4*>(p.lv.y_pred[l]) + (f0 >> 2));
+    const float4 hi = __ldcg(reinterpret_cast<const float4*>(p.lv.y_pred[l]) + (f0 >> 2) + 1);
+    const int sh = (int)(f0 & 3);
+    const bool s1 = sh & 1, s2 = sh & 2;
+    const float a0 = s1 ? lo.y : lo.x, a1 = s1 ? lo.z : lo.y, a2 = s1 ? lo.w : lo.z, a3 = s1 ? hi.x : lo.w;
+    const float a4 = s1 ? hi.y : hi.x, a5 = s1 ? hi.z : hi.y, a6 = s1 ? hi.w : hi.z;
+    tx = s2 ? a2 : a0; ty = s2 ? a3 : a1; tw = s2 ? a4 : a2; th = s2 ? a5 : a3; pobj = s2 ? a6 : a4;
+  }
+  bool pending = false;  // some (record, GT) pair survives the rejects: K4b-exact decides
+  if (n_gt > 0) {        // block-uniform
+    const int cell = yl_fastdiv(rin, p.magic_a);
+    const int a = min(rin - cell * p.A, 7);
+    const int gy = yl_fastdiv(cell, p.lv.magic_w[l]);
+    const int gx = cell - gy * W;
+    const bool filter_ok = p.thr >= 0.5f;
+    const bool nice = active && filter_ok && (tw >= p.tmin_w[l][a]) && (tw <= 4.0f) && (th >= p.tmin_h[l][a]) &&
+                      (th <= 4.0f) && (tx == tx) && (ty == ty);
+    const float sp = tw + th + p.logk[l][a];
+    const float invW = 1.0f / (float)W, invH = 1.0f / (float)H;
+    float fx0 = 0.f, fy0 = 0.f, fx1 = 0.f, fy1 = 0.f, farea = 0.f;
+    bool fast_ok = false;
+    if (nice) {
+      const float ex = __expf(-fabsf(tx)), ey = __expf(-fabsf(ty));
+      const float rx = __fdividef(1.0f, 1.0f + ex), ry = __fdividef(1.0f, 1.0f + ey);
+      const float fx = ((tx >= 0.0f ? rx : ex * rx) + (float)gx) * invW, fy = ((ty >= 0.0f ? ry : ey * ry) + (float)gy) * invH;
+      const float fw = __expf(tw) * __fdividef(p.lv.anc_w[l][a], p.img_w), fh = __expf(th) * __fdividef(p.lv.anc_h[l][a], p.img_h);
+      fx0 = fx - 0.5f * fw; fx1 = fx + 0.5f * fw; fy0 = fy - 0.5f * fh; fy1 = fy + 0.5f * fh;
+      farea = fw * fh;
+      fast_ok = (fw <= 2.0f) && (fh <= 2.0f);
+    }
+    const float thr_lo = p.thr - YL_IOU_EPS;
+    const float cx0 = (float)gx * invW - YL_CELL_MARGIN, cx1 = (float)(gx + 1) * invW + YL_CELL_MARGIN;
+    const float cy0 = (float)gy * invH - YL_CELL_MARGIN, cy1 = (float)(gy + 1) * invH + YL_CELL_MARGIN;
+    const uint32_t act = __ballot_sync(0xffffffffu, active);
+    float ux0 = 0.f, ux1 = 0.f, uy0 = 0.f, uy1 = 0.f;
+    if (act) {
+      const int first = __ffs(act) - 1, last = 31 - __clz(act);
+      const float f_x0 = __shfl_sync(0xffffffffu, cx0, first), f_y0 = __shfl_sync(0xffffffffu, cy0, first);
+      const float l_x1 = __shfl_sync(0xffffffffu, cx1, last), l_y1 = __shfl_sync(0xffffffffu, cy1, last);
+      const int gyf = __shfl_sync(0xffffffffu, gy, first), gyl = __shfl_sync(0xffffffffu, gy, last);
+      uy0 = f_y0; uy1 = l_y1;
+      ux0 = (gyf == gyl) ? f_x0 : -1.0f;
+      ux1 = (gyf == gyl) ? l_x1 : 2.0f;
+    }
+    const bool any_rough = __any_sync(0xffffffffu, active && !nice);
+    const float lo_k = p.log_thr - YL_LOG_MARGIN, hi_k = -p.log_thr + YL_LOG_MARGIN;
+    for (int j0 = 0; j0 < n_gt; j0 += 32) {
+      const int j = j0 + lane;
+      bool relevant = false;
+      if (j < n_gt) {
+        const float4 cg = __ldg(gbox + j);
+        relevant = any_rough || (__ldg(gaux + j).w == 0.0f) || !((ux1 < cg.x) || (cg.z < ux0) || (uy1 < cg.y) || (cg.w < uy0));
+      }
+      uint32_t mask = __ballot_sync(0xffffffffu, relevant);
+      while (mask) {
+        const int g = j0 + __ffs(mask) - 1;
+        mask &= mask - 1u;
+        const float4 cg = __ldg(gbox + g);
+        const float4 xg = __ldg(gaux + g);  // area, atan term, log(area), regular flag
+        const float iw = fminf(fx1, cg.z) - fmaxf(fx0, cg.x), ih = fminf(fy1, cg.w) - fmaxf(fy0, cg.y);
+        const float inter = iw * ih;
+        const bool cell_rej = (cx1 < cg.x) | (cg.z < cx0) | (cy1 < cg.y) | (cg.w < cy0);
+        const bool win_rej = (sp < xg.z + lo_k) | (sp > xg.z + hi_k);
+        const bool dis_rej = (iw < -1e-5f) | (ih < -1e-5f);
+        const bool iou_rej = fast_ok & (iw >= YL_IOU_FLOOR) & (ih >= YL_IOU_FLOOR) & (inter < thr_lo * (farea + xg.x - inter));
+        const bool rejected = nice & (xg.w != 0.0f) & (cell_rej | win_rej | dis_rej | iou_rej);
+        pending |= active & !rejected;
+      }
+    }
+  }
+  // queue the undecided records (warp-aggregated append), account for the decided ones
+  {
+    const uint32_t pm = __ballot_sync(0xffffffffu, pending);
+    if (pm) {
+      unsigned int base = 0;
+      if (lane == 0) base = atomicAdd(p.pend_count, (unsigned int)__popc(pm));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (pending) p.pend_queue[base + __popc(pm & ((1u << lane) - 1u))] = (uint32_t)((size_t)img * p.n_img + p.lv.anchor_base[l] + rin);
+    }
+  }
+  float e = 0.f;
+  if (active && !pending) {
+    const float bc = yl_fast_bce(obj, pobj);
+    if (p.out_ignore) p.out_ignore[(size_t)img * p.n_img + p.lv.anchor_base[l] + rin] = 1;
+    e = obj * bc + (1.0f - obj) * bc;  // tyu:114 with ignore = 1
+    if (p.conf_grad) {
+      const float ex = __expf(-fabsf(pobj));
+      const float rr = 1.0f / (1.0f + ex);
+      const float sg = pobj >= 0.0f ? rr : ex * rr;
+      p.conf_grad[(size_t)p.B * p.lv.anchor_base[l] + (size_t)img * rpi + rin] = (sg - obj) * p.inv_div;   // obj + (1 - obj) * 1 = 1
+    }
+  }
+  e = warp_sum(e);  // 32 fp32 terms; the cross-warp and cross-CTA sums are fp64
+  if (lane == 0) s_acc[warp] = (double)e;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sum = 0;
+    for (int i = 0; i < YL_ICHUNK / 32; ++i) sum += s_acc[i];
+    p.partials[icta] = sum;
+  }
+}
+
+__global__ void __launch_bounds__(128) yolo_loss_ignore_exact_kernel(YlParams p) {
+  const int lane = threadIdx.x & 31;
+  const unsigned int n = *p.pend_count;
+  const unsigned int nwarps = gridDim.x * (blockDim.x >> 5);
+  for (unsigned int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < n; q += nwarps) {
+    const uint32_t id = p.pend_queue[q];
+    const int img = (int)(id / (uint32_t)p.n_img);
+    const int ain = (int)(id - (uint32_t)img * (uint32_t)p.n_img);
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < YL_LEVELS; ++k) if (ain >= p.lv.anchor_base[k]) l = k;
+    const int rin = ain - p.lv.anchor_base[l];
+    const int rpi = p.lv.rec_per_img[l];
+    const float* rec = p.lv.y_pred[l] + ((size_t)img * rpi + rin) * p.RF;
+    const float tx = __ldg(rec), ty = __ldg(rec + 1), tw = __ldg(rec + 2), th = __ldg(rec + 3), pobj = __ldg(rec + 4);
+    float obj;
+    if (p.obj_bits) obj = ((__ldg(p.obj_bits + (size_t)img * p.bits_words + (ain >> 5)) >> (ain & 31)) & 1u) ? 1.0f : 0.0f;
+    else obj = p.obj_compact[(size_t)img * p.n_img + ain];
+    const int n_gt = p.gt_count[img * YL_LEVELS + l];
+    const float4* gbox = p.gt_box + (size_t)img * p.n_img + p.lv.anchor_base[l];
+    const float4* gaux = p.gt_aux + (size_t)img * p.n_img + p.lv.anchor_base[l];
+    bool hit = false;
+    for (int g0 = 0; g0 < n_gt && !hit; g0 += 32) {   // lanes <-> ground-truth boxes
+      const int g = g0 + lane;
+      bool h = false;
+      if (g < n_gt) h = yl_pair_hits(p, l, rin, tx, ty, tw, th, __ldg(gbox + g), __ldg(gaux + g));
+      hit = __any_sync(0xffffffffu, h);
+    }
+    if (lane == 0) {
+      const float bc = yl_fast_bce(obj, pobj);
+      const float ign = hit ? 0.0f : 1.0f;
+      if (p.out_ignore) p.out_ignore[(size_t)img * p.n_img + ain] = hit ? 0 : 1;
+      const float e = obj * bc + (1.0f - obj) * bc * ign;  // tyu:114
+      atomicAdd(p.obj_fixed + l, (unsigned long long)((double)e * YL_FIXED_ONE + 0.5));
+      if (p.conf_grad) {
+        const float ex = __expf(-fabsf(pobj));
+        const float rr = 1.0f / (1.0f + ex);
+        const float sg = pobj >= 0.0f ? rr : ex * rr;
+        p.conf_grad[(size_t)p.B * p.lv.anchor_base[l] + (size_t)img * rpi + rin] = (sg - obj) * (obj + (1.0f - obj) * ign) * p.inv_div;
+      }
+    }
+  }
+}
+
 // K4c: YL_FIN_CTAS CTAs each reduce an interleaved share of the per-CTA partials in fp64 (fixed assignment, fixed
 // order); the CTA that takes the last ticket adds the YL_FIN_CTAS slices in index order and writes parts / loss.
 // Deterministic run to run, and shorter than a single CTA walking all partials (shapes measured in DESIGN.md section 9).
@@ -551,6 +745,7 @@ struct YlFinalize {
   double* slices;          // [YL_FIN_CTAS][12]
   unsigned int* ticket;    // zero on entry; reset by the last CTA
   B200Exchange xchg;       // data parallel: the 12 terms are summed over the ranks inside this kernel (world 1: no-op)
+  const unsigned long long* obj_fixed;  // [3] or null: object-loss terms of the records K4b-exact decided (2^-32 fixed point)
   int publish_only;        // 1: store this rank's terms into the peers' mailboxes and return (b200_yolo_loss_collect_peer finishes)
 };
 
@@ -594,6 +789,7 @@ __global__ void __launch_bounds__(YL_FIN_THREADS) yolo_loss_finalize_kernel(YlFi
     if (lane < 12) {
       double s = 0.0;
       for (int g = 0; g < YL_FIN_CTAS; ++g) s += __ldcg(f.slices + g * 12 + lane);
+      if (f.obj_fixed && (lane & 3) == 2) s += (double)__ldcg(f.obj_fixed + (lane >> 2)) * (1.0 / YL_FIXED_ONE);
       v = DM_DIV((float)s, f.batch_divisor);  // reduce_sum(...) / batch_size_float, tyu:120-123
     }
     // data parallel: batch_divisor is the GLOBAL batch, so the per-rank terms simply add up; the sum runs over
@@ -783,7 +979,7 @@ __global__ void __launch_bounds__(128) yolo_loss_assign_sparse_kernel(YtParams t
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-struct YlWs { size_t obj, gt, gtl, cnt, part, part_obj, cgrad, oidx, fin, total; int n_cta, n_cta_obj; };
+struct YlWs { size_t obj, gt, gtl, cnt, cnt_bytes, part, part_obj, cgrad, oidx, fin, pend, total; int n_cta, n_cta_obj; };
 
 static YlWs yl_layout(const int32_t hw[6], int B, int A, int* n_img_out, YlLevels* lv) {
   YlWs w;
@@ -806,7 +1002,9 @@ static YlWs yl_layout(const int32_t hw[6], int B, int A, int* n_img_out, YlLevel
   w.n_cta = cta;
   w.n_cta_obj = octa;
   size_t o = 0;
-  w.cnt = o; o = b200_align_up(o + sizeof(int32_t) * ((size_t)B * YL_LEVELS + 1), 256);  // + the finalize ticket
+  // zeroed per call: object counts [B,3], the finalize ticket, the pending-record count (+ pad to 8), 3 fixed-point sums
+  w.cnt_bytes = b200_align_up(sizeof(int32_t) * ((size_t)B * YL_LEVELS + 2), 8) + 3 * sizeof(unsigned long long);
+  w.cnt = o; o = b200_align_up(o + w.cnt_bytes, 256);
   w.obj = o; o = b200_align_up(o + sizeof(float) * (size_t)B * n_img, 256);
   w.gt = o; o = b200_align_up(o + sizeof(float4) * (size_t)B * n_img, 256);
   w.gtl = o; o = b200_align_up(o + sizeof(float4) * (size_t)B * n_img, 256);
@@ -815,6 +1013,7 @@ static YlWs yl_layout(const int32_t hw[6], int B, int A, int* n_img_out, YlLevel
   w.cgrad = o; o = b200_align_up(o + sizeof(float) * (size_t)B * n_img, 256);
   w.oidx = o; o = b200_align_up(o + sizeof(int32_t) * (size_t)B * n_img, 256);
   w.fin = o; o = b200_align_up(o + sizeof(double) * 12 * YL_FIN_CTAS, 256);
+  w.pend = o; o = b200_align_up(o + sizeof(uint32_t) * (size_t)B * n_img, 256);
   w.total = o;
   return w;
 }
@@ -899,7 +1098,10 @@ static int yolo_loss_impl(const float* const y_true[3], const float* const y_pre
   p.gt_count = reinterpret_cast<int32_t*>(wsb + ws.cnt);
   p.partials = reinterpret_cast<double*>(wsb + ws.part);
   p.partials_obj = reinterpret_cast<double*>(wsb + ws.part_obj);
-  if (stages & 1) B200_CUDA(cudaMemsetAsync(wsb + ws.cnt, 0, sizeof(int32_t) * ((size_t)B * YL_LEVELS + 1), stream));
+  if (stages & 1) B200_CUDA(cudaMemsetAsync(wsb + ws.cnt, 0, ws.cnt_bytes, stream));
+  p.pend_queue = reinterpret_cast<uint32_t*>(wsb + ws.pend);
+  p.pend_count = reinterpret_cast<unsigned int*>(wsb + ws.cnt) + (size_t)B * YL_LEVELS + 1;
+  p.obj_fixed = reinterpret_cast<unsigned long long*>(wsb + ws.cnt + b200_align_up(sizeof(int32_t) * ((size_t)B * YL_LEVELS + 2), 8));
   p.sp_t = nullptr; p.sp_cls = nullptr; p.obj_bits = nullptr; p.bits_words = 0;
   if (sparse) {
     B200_REQUIRE(sparse->total_boxes >= 0 && sparse->offsets && sparse->assign_anchors_wh_host, B200_ERR_BAD_ARG, "b200_yolo_loss_from_boxes: null box arrays");
@@ -926,6 +1128,7 @@ static int yolo_loss_impl(const float* const y_true[3], const float* const y_pre
     yolo_loss_gtprep_kernel<<<YL_LEVELS * B, 128, 0, stream>>>(p);
     B200_LAUNCH_CHECK();
   }
+  bool use_split = false;
   if (stages & 4) {
     // predictions in pinned host memory are read in place over PCIe: one request per record instead of two
     cudaPointerAttributes attr;
@@ -933,7 +1136,21 @@ static int yolo_loss_impl(const float* const y_true[3], const float* const y_pre
     if (cudaPointerGetAttributes(&attr, y_pred[YL_LEVELS - 1]) == cudaSuccess) host_pred = attr.type == cudaMemoryTypeHost;
     else (void)cudaGetLastError();
     const int grid = YL_LEVELS * B * YL_TERM_SPLIT + ws.n_cta;
-    if (host_pred) yolo_loss_ignore_kernel<true><<<grid, YL_ICHUNK, 0, stream>>>(p);
+    bool aligned16 = true;
+    for (int l = 0; l < YL_LEVELS; ++l) aligned16 &= (reinterpret_cast<uintptr_t>(y_pred[l]) & 15) == 0;
+    const char* split_env = getenv("B200_YL_SPLIT");   // tuning hook: 0 = the single-kernel form, 8/10/12/16 = CTAs per SM of K4b-lean
+    const int split = split_env ? atoi(split_env) : 12;
+    use_split = !host_pred && aligned16 && p.RF >= 8 && split > 0;
+    if (use_split) {
+      // the queue counter and the fixed-point sums start from zero for THIS pass (the stage hook may repeat it)
+      B200_CUDA(cudaMemsetAsync(p.pend_count, 0, (size_t)(reinterpret_cast<unsigned char*>(p.obj_fixed + 3) - reinterpret_cast<unsigned char*>(p.pend_count)), stream));
+      if (split >= 16) yolo_loss_ignore_lean_kernel<16><<<grid, YL_ICHUNK, 0, stream>>>(p);
+      else if (split >= 12) yolo_loss_ignore_lean_kernel<12><<<grid, YL_ICHUNK, 0, stream>>>(p);
+      else if (split >= 10) yolo_loss_ignore_lean_kernel<10><<<grid, YL_ICHUNK, 0, stream>>>(p);
+      else yolo_loss_ignore_lean_kernel<8><<<grid, YL_ICHUNK, 0, stream>>>(p);
+      B200_LAUNCH_CHECK();
+      yolo_loss_ignore_exact_kernel<<<2 * b200_sm_count(), 128, 0, stream>>>(p);
+    } else if (host_pred) yolo_loss_ignore_kernel<true><<<grid, YL_ICHUNK, 0, stream>>>(p);
     else yolo_loss_ignore_kernel<false><<<grid, YL_ICHUNK, 0, stream>>>(p);
     B200_LAUNCH_CHECK();
   }
@@ -945,6 +1162,7 @@ static int yolo_loss_impl(const float* const y_true[3], const float* const y_pre
   f.slices = reinterpret_cast<double*>(wsb + ws.fin);
   f.ticket = reinterpret_cast<unsigned int*>(wsb + ws.cnt) + (size_t)B * YL_LEVELS;
   f.publish_only = publish_only;
+  f.obj_fixed = p.obj_fixed;   // zero unless K4b-exact ran
   if (xchg) f.xchg = *xchg;
   else { f.xchg.rank = 0; f.xchg.world = 1; for (int r = 0; r < B200_XCHG_MAX_WORLD; ++r) f.xchg.mailbox[r] = nullptr; }
   yolo_loss_finalize_kernel<<<YL_FIN_CTAS, YL_FIN_THREADS, 0, stream>>>(f);
