@@ -64,7 +64,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl", "torch", "local", "peer-idle"],
                     help="transport of the loss all-reduce (N > 1); local = no exchange at all (diagnostic: isolates its cost)")
-    ap.add_argument("--overlap", action="store_true", help="N > 1: split the exchange (publish in the step, collect on a second stream under the next step)")
+    ap.add_argument("--fused-exchange", action="store_true", help="N > 1: keep the exchange inside the step's finalize kernel (one graph, no second stream; ~6 us per step slower)")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every step launch by launch instead of replaying CUDA graphs")
     ap.add_argument("--only-step", action="store_true", help="skip phase timing / e2e / cpu baseline / parity (profiling runs)")
@@ -402,36 +402,40 @@ def headline_c2(b, line):
     overlapped = False
     if args.no_graph or (world > 1 and not in_graph and args.exchange not in ("local", "peer-idle")):
         dev_step = raw
-    elif world > 1 and peer and args.overlap:
-        # The step's graph ends with the PUBLISH half of the exchange (peer stores, no wait); the collect half of step i
-        # runs on a second stream under the kernels of step i+1.  Two graphs with their own result buffers alternate; the
-        # graph of step i waits for the collect of step i-2 (the rule of the four slot sets, csrc/exchange.cuh).
+    elif world > 1 and peer and not args.fused_exchange:
+        # The step's graph ends with this rank's 12 terms (already divided by the global batch); the exchange — ONE one-warp
+        # kernel over the NVLink mailboxes (publish + collect, b200_allreduce_loss_peer) and the 12-term fold — runs on a
+        # second stream under the kernels of the next step.  Remote stores inside the step's last kernel would cost the
+        # step ~6 us (measured: the kernel cannot retire before its peer writes are acknowledged); on the side stream they
+        # cost the step nothing.  Two graphs with their own result buffers alternate; the graph of step i waits for the
+        # exchange of step i-2.
         overlapped = True
         comm = torch.cuda.Stream()
-        res = [dict(parts=torch.empty((3, 4), dtype=torch.float32, device=dev), loss=torch.zeros((), dtype=torch.float32, device=dev), done=None) for _ in range(2)]
 
-        def pub_step():
+        def local_step():
             gen.GetTargetsBatch(classes_d, boxes_d, off_d, out=y_true)
             return tyu._loss_call(y_true, heads_d, (image, image), anc, 0.5, "ciou", 0, batch_divisor=global_batch, workspace=ws,
-                                  exchange=b.exchange, defer_collect=True)
-        graphs = [b.runtime.capture(pub_step, warmup=0), b.runtime.capture(pub_step, warmup=0)]
+                                  return_parts=True)
+        graphs = [b.runtime.capture(local_step), b.runtime.capture(local_step)]
+        done = [None, None]
         counter = [0]
 
         def dev_step():
             k = counter[0] & 1
             counter[0] += 1
             main = torch.cuda.current_stream()
-            if res[k]["done"] is not None:
-                main.wait_event(res[k]["done"])
-            graphs[k]()
+            if done[k] is not None:
+                main.wait_event(done[k])
+            loss_k, parts_k = graphs[k]()
             ready = torch.cuda.Event()
             ready.record(main)
             with torch.cuda.stream(comm):
                 comm.wait_event(ready)
-                b.exchange.collect_yolo(res[k]["parts"], res[k]["loss"])
-                res[k]["done"] = torch.cuda.Event()
-                res[k]["done"].record(comm)
-            return res[k]["loss"]
+                b.exchange.allreduce_(parts_k)
+                b.lib.b200_yolo_loss_combine(parts_k.data_ptr(), loss_k.data_ptr(), comm.cuda_stream)
+                done[k] = torch.cuda.Event()
+                done[k].record(comm)
+            return loss_k
         b.tail_hooks.append(lambda: torch.cuda.current_stream().wait_stream(comm))
     else:
         dev_step = b.runtime.capture(raw)
@@ -454,8 +458,8 @@ def headline_c2(b, line):
                    "classes": 80, "anchors_per_cell": 3, "gt_boxes_per_image": "U{1..100} (the same draw on every rank; heads differ per rank)",
                    "parallelism": "dp%d (images sharded; one 12-float all-reduce per step: %s)" % (world, b.exchange_kind),
                    "launch": "launch by launch" if dev_step is raw else (
-                       "CUDA graph replay of the step up to the publish half of the exchange; the collect half of step i runs on a second "
-                       "stream under step i+1" if overlapped else "CUDA graph replay of the whole step (exchange included)"),
+                       "CUDA graph replay of the step; the exchange of step i (one one-warp peer-mailbox kernel) runs on a second stream "
+                       "under step i+1" if overlapped else "CUDA graph replay of the whole step (exchange included)"),
                    "l2": "inputs larger than L2 (y_pred %.0f MB + y_true %.0f MB per step vs 126 MB L2)" % (n_fill * 4 / 1e6, n_fill * 4 / 1e6)},
         "loss": loss_val, "clocks": clocks,
         "gpu_launches": 6 * args.steps * len(windows),

@@ -291,22 +291,26 @@ __device__ __forceinline__ int yl_fastdiv(int n, uint32_t magic) {
 #define YL_IMINB 8   // 64 registers: no spills; 10 (48 registers) spills and is 5 us slower
 #endif
 
-__device__ __forceinline__ bool yl_pair_hits(const YlParams& p, int l, int rin, float tx, float ty, float tw, float th,
-                                             const float4 c, const float4 x) {
+// exact decode of a record (tyu:57,61: xy = (sigmoid(t)+grid)/grid_wh ; wh = exp(t)*anchor/image_wh, no inf guard, Q7)
+__device__ __forceinline__ BoxT yl_decode_record(const YlParams& p, int l, int rin, float tx, float ty, float tw, float th) {
   const int W = p.lv.w[l], H = p.lv.h[l];
   const int cell = yl_fastdiv(rin, p.magic_a);
   const int a = min(rin - cell * p.A, 7);
   const int gy = yl_fastdiv(cell, p.lv.magic_w[l]);
   const int gx = cell - gy * W;
-  // tyu:57,61: xy = (sigmoid(t)+grid)/grid_wh ; wh = exp(t)*anchor/image_wh (no inf guard here, Q7)
   const float x_ = DM_DIV(DM_ADD(dm_sigmoidf(tx), (float)gx), (float)W);
   const float y_ = DM_DIV(DM_ADD(dm_sigmoidf(ty), (float)gy), (float)H);
   const float w_ = DM_DIV(DM_MUL(dm_expf(tw), p.lv.anc_w[l][a]), p.img_w);
   const float h_ = DM_DIV(DM_MUL(dm_expf(th), p.lv.anc_h[l][a]), p.img_h);
   const float hx_ = DM_DIV(w_, 2.0f), hy_ = DM_DIV(h_, 2.0f);
-  BoxT pb = bm_prep(DM_SUB(x_, hx_), DM_SUB(y_, hy_), DM_ADD(x_, hx_), DM_ADD(y_, hy_), B200_METRIC_YOLO_IOU);
+  return bm_prep(DM_SUB(x_, hx_), DM_SUB(y_, hy_), DM_ADD(x_, hx_), DM_ADD(y_, hy_), B200_METRIC_YOLO_IOU);
+}
+
+// exact test of a decoded record against one prepared ground-truth box (c = corners, x = area, atan term, log area,
+// regular flag): metric >= thr, or NaN (tf.reduce_max propagates NaN and NaN < thr is False)
+__device__ __forceinline__ bool yl_box_hits(const YlParams& p, BoxT pb, bool pb_regular, const float4 c, const float4 x) {
   BoxT gb; gb.c0 = c.x; gb.c1 = c.y; gb.c2 = c.z; gb.c3 = c.w; gb.area = x.x; gb.at = x.y;
-  if (x.w != 0.0f && p.thr > 0.0f && yl_regular(pb)) {
+  if (x.w != 0.0f && p.thr > 0.0f && pb_regular) {
     // exact rejects for regular pairs: no overlap, or areas further apart than thr allows (iou <= min/max)
     if ((pb.c2 <= c.x) || (c.z <= pb.c0) || (pb.c3 <= c.y) || (c.w <= pb.c1)) return false;
     if (fminf(pb.area, x.x) < 0.99f * p.thr * fmaxf(pb.area, x.x)) return false;
@@ -314,7 +318,13 @@ __device__ __forceinline__ bool yl_pair_hits(const YlParams& p, int l, int rin, 
   if (p.metric == B200_METRIC_YOLO_CIOU) pb.at = dm_atanf(DM_DIV(DM_SUB(pb.c2, pb.c0), DM_SUB(pb.c3, pb.c1)));
   if (bm_surely_below(pb, gb, p.metric, p.thr)) return false;
   const float mm = bm_metric(pb, gb, p.metric);
-  return (mm >= p.thr) || (mm != mm);  // NaN propagates through tf.reduce_max: best < thr is False
+  return (mm >= p.thr) || (mm != mm);
+}
+
+__device__ __forceinline__ bool yl_pair_hits(const YlParams& p, int l, int rin, float tx, float ty, float tw, float th,
+                                             const float4 c, const float4 x) {
+  const BoxT pb = yl_decode_record(p, l, rin, tx, ty, tw, th);
+  return yl_box_hits(p, pb, yl_regular(pb), c, x);
 }
 
 // PAIRED selects how the five logits of a record are fetched (see the load section): two lanes per record and one
@@ -705,11 +715,15 @@ __global__ void __launch_bounds__(128) yolo_loss_ignore_exact_kernel(YlParams p)
     const int n_gt = p.gt_count[img * YL_LEVELS + l];
     const float4* gbox = p.gt_box + (size_t)img * p.n_img + p.lv.anchor_base[l];
     const float4* gaux = p.gt_aux + (size_t)img * p.n_img + p.lv.anchor_base[l];
+    // the record is decoded once (every lane the same values), then lanes <-> ground-truth boxes: the exact no-overlap /
+    // area-ratio rejects dispose of almost all of them before a metric is evaluated
+    const BoxT pb = yl_decode_record(p, l, rin, tx, ty, tw, th);
+    const bool pb_regular = yl_regular(pb);
     bool hit = false;
-    for (int g0 = 0; g0 < n_gt && !hit; g0 += 32) {   // lanes <-> ground-truth boxes
+    for (int g0 = 0; g0 < n_gt && !hit; g0 += 32) {
       const int g = g0 + lane;
       bool h = false;
-      if (g < n_gt) h = yl_pair_hits(p, l, rin, tx, ty, tw, th, __ldg(gbox + g), __ldg(gaux + g));
+      if (g < n_gt) h = yl_box_hits(p, pb, pb_regular, __ldg(gbox + g), __ldg(gaux + g));
       hit = __any_sync(0xffffffffu, h);
     }
     if (lane == 0) {
@@ -717,7 +731,9 @@ __global__ void __launch_bounds__(128) yolo_loss_ignore_exact_kernel(YlParams p)
       const float ign = hit ? 0.0f : 1.0f;
       if (p.out_ignore) p.out_ignore[(size_t)img * p.n_img + ain] = hit ? 0 : 1;
       const float e = obj * bc + (1.0f - obj) * bc * ign;  // tyu:114
-      atomicAdd(p.obj_fixed + l, (unsigned long long)((double)e * YL_FIXED_ONE + 0.5));
+      // non-finite terms (NaN / inf logits) cannot be carried in fixed point: they poison the sum through the top bit pattern
+      if (e == e && e < 1.0e9f) atomicAdd(p.obj_fixed + l, (unsigned long long)((double)e * YL_FIXED_ONE + 0.5));
+      else atomicOr(p.obj_fixed + l, 0x8000000000000000ull);
       if (p.conf_grad) {
         const float ex = __expf(-fabsf(pobj));
         const float rr = 1.0f / (1.0f + ex);
@@ -789,7 +805,10 @@ __global__ void __launch_bounds__(YL_FIN_THREADS) yolo_loss_finalize_kernel(YlFi
     if (lane < 12) {
       double s = 0.0;
       for (int g = 0; g < YL_FIN_CTAS; ++g) s += __ldcg(f.slices + g * 12 + lane);
-      if (f.obj_fixed && (lane & 3) == 2) s += (double)__ldcg(f.obj_fixed + (lane >> 2)) * (1.0 / YL_FIXED_ONE);
+      if (f.obj_fixed && (lane & 3) == 2) {
+        const unsigned long long fx = __ldcg(f.obj_fixed + (lane >> 2));
+        s += (fx >> 63) ? (double)__longlong_as_double(0x7ff8000000000000ll) : (double)fx * (1.0 / YL_FIXED_ONE);   // top bit = a non-finite term
+      }
       v = DM_DIV((float)s, f.batch_divisor);  // reduce_sum(...) / batch_size_float, tyu:120-123
     }
     // data parallel: batch_divisor is the GLOBAL batch, so the per-rank terms simply add up; the sum runs over
@@ -1138,8 +1157,11 @@ static int yolo_loss_impl(const float* const y_true[3], const float* const y_pre
     const int grid = YL_LEVELS * B * YL_TERM_SPLIT + ws.n_cta;
     bool aligned16 = true;
     for (int l = 0; l < YL_LEVELS; ++l) aligned16 &= (reinterpret_cast<uintptr_t>(y_pred[l]) & 15) == 0;
-    const char* split_env = getenv("B200_YL_SPLIT");   // tuning hook: 0 = the single-kernel form, 8/10/12/16 = CTAs per SM of K4b-lean
-    const int split = split_env ? atoi(split_env) : 12;
+    // B200_YL_SPLIT = 8/10/12/16 selects the split form (CTAs per SM K4b-lean is compiled for); default: the single kernel.
+    // Measured at 608x608 batch 64: K4b 71 us; K4b-lean 53.7 us (48 registers, 10 CTAs per SM) + K4b-exact 15.6 us for the
+    // ~12 k undecided records = 69 us, step 196.5 vs 199.3 us — inside 1.5 %, not worth a second launch by default.
+    const char* split_env = getenv("B200_YL_SPLIT");
+    const int split = split_env ? atoi(split_env) : 0;
     use_split = !host_pred && aligned16 && p.RF >= 8 && split > 0;
     if (use_split) {
       // the queue counter and the fixed-point sums start from zero for THIS pass (the stage hook may repeat it)
@@ -1149,7 +1171,12 @@ static int yolo_loss_impl(const float* const y_true[3], const float* const y_pre
       else if (split >= 10) yolo_loss_ignore_lean_kernel<10><<<grid, YL_ICHUNK, 0, stream>>>(p);
       else yolo_loss_ignore_lean_kernel<8><<<grid, YL_ICHUNK, 0, stream>>>(p);
       B200_LAUNCH_CHECK();
-      yolo_loss_ignore_exact_kernel<<<2 * b200_sm_count(), 128, 0, stream>>>(p);
+      {  // a warp per queued record; the count lives on the device, so the grid is sized for the usual few thousand records
+        // (more are covered by the warps' stride loop) — surplus warps read the count and leave
+        const char* xg = getenv("B200_YL_EXACT_CTAS");
+        const int ctas = xg ? atoi(xg) : 1024;
+        yolo_loss_ignore_exact_kernel<<<ctas > 0 ? ctas : 1024, 128, 0, stream>>>(p);
+      }
     } else if (host_pred) yolo_loss_ignore_kernel<true><<<grid, YL_ICHUNK, 0, stream>>>(p);
     else yolo_loss_ignore_kernel<false><<<grid, YL_ICHUNK, 0, stream>>>(p);
     B200_LAUNCH_CHECK();

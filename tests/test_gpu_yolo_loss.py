@@ -316,3 +316,51 @@ def test_get_loss_gradient_matches_oracle(lib, cuda, image, batch, iou_type):
         # structure: non-object records carry a gradient only in the conf channel
         nobj = y_true[l][..., 4] == 0
         assert np.count_nonzero(np.delete(g[nobj], 4, axis=-1)) == 0
+
+
+def test_split_ignore_pass_is_bit_identical(lib, cuda, monkeypatch):
+    """The split form of the ignore pass (B200_YL_SPLIT: K4b-lean streams and filters, K4b-exact resolves the undecided
+    records) must give the ignore mask of the single kernel bit for bit and the same loss (the undecided records' terms go
+    through a 2^-32 fixed-point sum)."""
+    import torch
+    from tfmv_b200 import synth
+    from tfmv_b200.ai_models.datasets.coco_dataset import DataGenerator
+    from tfmv_b200.ai_models.utils.tf_yolo_utils import _loss_call
+    rng = np.random.default_rng(77)
+    image, batch = 256, 5
+    anc = synth.yolo_anchors().astype(F)
+    heads = [torch.from_numpy(h).to(cuda) for h in synth.yolo_heads(rng, batch, image)]
+    # plant predictions on their targets so that the mask has zeros, and one NaN logit
+    boxes, classes, off = synth.gt_batch(rng, batch, (image, image), max_boxes=40)
+    gen = DataGenerator(80, anc / F(image), (image, image))
+    y_true = gen.GetTargetsBatch(classes, boxes, off)
+    for l in range(3):
+        yt = y_true[l]
+        hp = heads[l].view(yt.shape)
+        m = yt[..., 4] > 0
+        g = yt.shape[1]
+        idx = m.nonzero()
+        for b, yy, xx, a in idx.tolist()[::2]:
+            t = yt[b, yy, xx, a]
+            fx = min(max(float(t[0]) * g - xx, 1e-3), 1 - 1e-3)
+            fy = min(max(float(t[1]) * g - yy, 1e-3), 1 - 1e-3)
+            hp[b, yy, xx, a, 0] = float(np.log(fx / (1 - fx)))
+            hp[b, yy, xx, a, 1] = float(np.log(fy / (1 - fy)))
+            hp[b, yy, xx, a, 2] = float(np.log(max(float(t[2]) * image / anc[l][a][0], 1e-6)))
+            hp[b, yy, xx, a, 3] = float(np.log(max(float(t[3]) * image / anc[l][a][1], 1e-6)))
+    n_img = sum(int(t.shape[1] * t.shape[2] * 3) for t in y_true)
+    out = {}
+    for mode in ("0", "10", "16"):
+        monkeypatch.setenv("B200_YL_SPLIT", mode)
+        ign = torch.zeros((batch, n_img), dtype=torch.uint8, device=cuda)
+        loss, parts = _loss_call(y_true, heads, (image, image), anc, 0.5, "ciou", 0, return_parts=True, ignore_out=ign)
+        out[mode] = (float(loss), parts.cpu().numpy(), ign.cpu().numpy())
+    assert out["0"][2].min() == 0 and out["0"][2].max() == 1          # the mask has both values
+    for mode in ("10", "16"):
+        assert np.array_equal(out[mode][2], out["0"][2]), mode
+        assert abs(out[mode][0] - out["0"][0]) <= 2e-6 * abs(out["0"][0]), (mode, out[mode][0], out["0"][0])
+    # a NaN logit reaches the loss in both forms
+    heads[2].view(y_true[2].shape)[0, 1, 1, 0, 4] = float("nan")
+    for mode in ("0", "10"):
+        monkeypatch.setenv("B200_YL_SPLIT", mode)
+        assert np.isnan(float(_loss_call(y_true, heads, (image, image), anc, 0.5, "ciou", 0))), mode
