@@ -64,6 +64,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl", "torch", "local", "peer-idle"],
                     help="transport of the loss all-reduce (N > 1); local = no exchange at all (diagnostic: isolates its cost)")
+    ap.add_argument("--graph-steps", type=int, default=4, help="consecutive steps captured in one CUDA graph (must divide --steps; 1 = one graph per step)")
     ap.add_argument("--fused-exchange", action="store_true", help="N > 1: keep the exchange inside the step's finalize kernel (one graph, no second stream; ~6 us per step slower)")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every step launch by launch instead of replaying CUDA graphs")
@@ -287,14 +288,14 @@ class Bench(object):
             self.dist.barrier()
             self.torch.cuda.synchronize()
 
-    def window(self, fn, steps):
+    def window(self, fn, steps, unit=1):
         """EXACTLY `steps` calls of fn bracketed by barrier + synchronize on both sides, CUDA events on the launching
         stream, max over ranks.  Returns milliseconds for the window."""
         torch = self.torch
         self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
+        for _ in range(steps // unit):   # one call of fn = `unit` steps (a CUDA graph of several consecutive steps)
             fn()
         for hook in self.tail_hooks:   # side streams whose work belongs to the timed region join before the stop event
             hook()
@@ -308,11 +309,11 @@ class Bench(object):
         self.barrier()
         return ms
 
-    def timed(self, fn, steps, warmup, repeats=1):
+    def timed(self, fn, steps, warmup, repeats=1, unit=1):
         """Warm-up, then `repeats` windows of `steps` steps.  Returns (median ms per step, per-window ms-per-step list)."""
-        for _ in range(max(warmup, 3)):
+        for _ in range((max(warmup, 3) + unit - 1) // unit):
             fn()
-        per = [self.window(fn, steps) / steps for _ in range(max(1, repeats))]
+        per = [self.window(fn, steps, unit) / steps for _ in range(max(1, repeats))]
         return statistics.median(per), per
 
     def wrap(self, fn):
@@ -400,46 +401,43 @@ def headline_c2(b, line):
         b.barrier()
     peer = b.exchange is not None and hasattr(b.exchange, "mailboxes")
     overlapped = False
+    unit = 1   # steps per call of dev_step
     if args.no_graph or (world > 1 and not in_graph and args.exchange not in ("local", "peer-idle")):
         dev_step = raw
-    elif world > 1 and peer and not args.fused_exchange:
-        # The step's graph ends with this rank's 12 terms (already divided by the global batch); the exchange — ONE one-warp
-        # kernel over the NVLink mailboxes (publish + collect, b200_allreduce_loss_peer) and the 12-term fold — runs on a
-        # second stream under the kernels of the next step.  Remote stores inside the step's last kernel would cost the
-        # step ~6 us (measured: the kernel cannot retire before its peer writes are acknowledged); on the side stream they
-        # cost the step nothing.  Two graphs with their own result buffers alternate; the graph of step i waits for the
-        # exchange of step i-2.
-        overlapped = True
-        comm = torch.cuda.Stream()
+    elif (world == 1 or (peer and not args.fused_exchange)) and args.graph_steps > 1 and args.steps % args.graph_steps == 0:
+        # ONE CUDA graph holds `graph_steps` consecutive steps.  At N > 1 every step's graph section ends with this rank's 12
+        # terms (already divided by the global batch); its exchange — one one-warp kernel over the NVLink mailboxes
+        # (b200_allreduce_loss_peer: publish + collect) plus the 12-term fold — is a side branch of the graph that runs under
+        # the kernels of the following step and joins at the end of the graph.  (Remote stores inside the step's last kernel
+        # cost the step ~6 us — the kernel cannot retire before its peer writes are acknowledged; host-side event hand-offs
+        # between per-step graphs cost ~4 us; a branch inside the graph costs neither.)
+        unit = args.graph_steps
+        overlapped = world > 1
+        side = torch.cuda.Stream()
 
-        def local_step():
-            gen.GetTargetsBatch(classes_d, boxes_d, off_d, out=y_true)
-            return tyu._loss_call(y_true, heads_d, (image, image), anc, 0.5, "ciou", 0, batch_divisor=global_batch, workspace=ws,
-                                  return_parts=True)
-        graphs = [b.runtime.capture(local_step), b.runtime.capture(local_step)]
-        done = [None, None]
-        counter = [0]
+        keep = []   # every sub-step's result tensors stay referenced: the side branch still reads them when the next one starts
 
-        def dev_step():
-            k = counter[0] & 1
-            counter[0] += 1
+        def multi_step():
             main = torch.cuda.current_stream()
-            if done[k] is not None:
-                main.wait_event(done[k])
-            loss_k, parts_k = graphs[k]()
-            ready = torch.cuda.Event()
-            ready.record(main)
-            with torch.cuda.stream(comm):
-                comm.wait_event(ready)
-                b.exchange.allreduce_(parts_k)
-                b.lib.b200_yolo_loss_combine(parts_k.data_ptr(), loss_k.data_ptr(), comm.cuda_stream)
-                done[k] = torch.cuda.Event()
-                done[k].record(comm)
-            return loss_k
-        b.tail_hooks.append(lambda: torch.cuda.current_stream().wait_stream(comm))
+            loss = None
+            del keep[:]
+            for _ in range(unit):
+                gen.GetTargetsBatch(classes_d, boxes_d, off_d, out=y_true)
+                loss, parts = tyu._loss_call(y_true, heads_d, (image, image), anc, 0.5, "ciou", 0, batch_divisor=global_batch,
+                                             workspace=ws, return_parts=True)
+                keep.append((loss, parts))
+                if world > 1:
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        b.exchange.allreduce_(parts)
+                        b.lib.b200_yolo_loss_combine(parts.data_ptr(), loss.data_ptr(), side.cuda_stream)
+            if world > 1:
+                main.wait_stream(side)
+            return loss
+        dev_step = b.runtime.capture(multi_step)
     else:
         dev_step = b.runtime.capture(raw)
-    ms_dev, windows = b.timed(dev_step, args.steps, args.warmup, args.repeats)
+    ms_dev, windows = b.timed(dev_step, args.steps, args.warmup, args.repeats, unit=unit)
     last = dev_step()
     torch.cuda.synchronize()
     loss_val = float(last.item())
@@ -458,12 +456,14 @@ def headline_c2(b, line):
                    "classes": 80, "anchors_per_cell": 3, "gt_boxes_per_image": "U{1..100} (the same draw on every rank; heads differ per rank)",
                    "parallelism": "dp%d (images sharded; one 12-float all-reduce per step: %s)" % (world, b.exchange_kind),
                    "launch": "launch by launch" if dev_step is raw else (
-                       "CUDA graph replay of the step; the exchange of step i (one one-warp peer-mailbox kernel) runs on a second stream "
-                       "under step i+1" if overlapped else "CUDA graph replay of the whole step (exchange included)"),
+                       ("one CUDA graph per %d consecutive steps" % unit if unit > 1 else "one CUDA graph per step") + (
+                           "; the exchange of step i (a one-warp peer-mailbox kernel) is a side branch of the graph under step i+1" if overlapped
+                           else ("; exchange inside the finalize kernel" if world > 1 else ""))),
                    "l2": "inputs larger than L2 (y_pred %.0f MB + y_true %.0f MB per step vs 126 MB L2)" % (n_fill * 4 / 1e6, n_fill * 4 / 1e6)},
         "loss": loss_val, "clocks": clocks,
-        "gpu_launches": 6 * args.steps * len(windows),
-        "gpu_launches_note": "6 kernels per step (fill, scatter, scan, gtprep, ignore+terms, finalize incl. the exchange)",
+        "gpu_launches": (6 + (2 if overlapped else 0)) * args.steps * len(windows),
+        "gpu_launches_note": "6 kernels per step (fill, scatter, scan, gtprep, ignore+terms, finalize)" + (
+            " + exchange and fold kernels on the side branch" if overlapped else ""),
     })
     if b.exchange is not None and hasattr(b.exchange, "status"):
         ep, err = b.exchange.status()
