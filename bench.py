@@ -49,6 +49,12 @@ WHAT = {
 }
 
 
+def auto_graph_steps(steps, want):
+    if want > 0:
+        return want if steps % want == 0 else 1
+    return max(d for d in range(1, 33) if steps % d == 0)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -64,12 +70,14 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl", "torch", "local", "peer-idle"],
                     help="transport of the loss all-reduce (N > 1); local = no exchange at all (diagnostic: isolates its cost)")
-    ap.add_argument("--graph-steps", type=int, default=4, help="consecutive steps captured in one CUDA graph (must divide --steps; 1 = one graph per step)")
+    ap.add_argument("--graph-steps", type=int, default=0, help="consecutive steps captured in one CUDA graph (0 = the largest divisor of --steps up to 32; 1 = one graph per step)")
     ap.add_argument("--fused-exchange", action="store_true", help="N > 1: keep the exchange inside the step's finalize kernel (one graph, no second stream; ~6 us per step slower)")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every step launch by launch instead of replaying CUDA graphs")
     ap.add_argument("--only-step", action="store_true", help="skip phase timing / e2e / cpu baseline / parity (profiling runs)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    args.graph_steps = auto_graph_steps(args.steps, args.graph_steps)
+    return args
 
 
 # ------------------------------------------------------------------------------------------------
