@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) effdet_nms_pivot_kernel(NmsPre
   extern __shared__ __align__(16) unsigned char pre_smem[];
   nms_pivot_body(p, pre_smem);
 }
-__global__ void __launch_bounds__(512) effdet_nms_pregather_kernel(NmsPreselectParams p) { nms_pregather_body(p); }
+__global__ void __launch_bounds__(256) effdet_nms_pregather_kernel(NmsPreselectParams p) { nms_pregather_body(p); }
 
 // The NMS tail shared by b200_effdet_postprocess and the fused entry points: (large segments) pivot + multi-CTA
 // pre-gather of the first window, then one CTA per image.
@@ -560,9 +560,9 @@ static int ef_launch_nms(const EfFilterParams& fp, const EfWs& ws, unsigned char
     // large segments: several CTAs per image gather the first NMS window so the single NMS CTA does not have to
     // scan hundreds of thousands of scores alone
     NmsPreselectParams pp;
-    int slices = (4 * b200_sm_count() + num_images - 1) / num_images;
+    int slices = (5 * b200_sm_count() + num_images - 1) / num_images;   // ~5 CTAs of 256 threads (46 registers) per SM: one wave
     if (slices < 1) slices = 1;
-    if (slices > 32) slices = 32;
+    if (slices > 64) slices = 64;
     pp.scores = fp.cand_score; pp.order_id = fp.cand_aidx; pp.counts = fp.counts; pp.stride = n_img; pp.slices = slices;
     pp.use_score_thr = 1; pp.score_thr = score_thr;
     pp.keys = reinterpret_cast<unsigned long long*>(wsb + ws.pre_keys);
@@ -573,7 +573,7 @@ static int ef_launch_nms(const EfFilterParams& fp, const EfWs& ws, unsigned char
     B200_CUDA(cudaFuncSetAttribute(effdet_nms_pivot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NMS_PIVOT_SMEM));
     effdet_nms_pivot_kernel<<<num_images, NMS_THREADS, NMS_PIVOT_SMEM, stream>>>(pp);
     B200_LAUNCH_CHECK();
-    effdet_nms_pregather_kernel<<<num_images * slices, 512, 0, stream>>>(pp);
+    effdet_nms_pregather_kernel<<<num_images * slices, 256, 0, stream>>>(pp);
     B200_LAUNCH_CHECK();
     np.pre_keys = pp.keys; np.pre_pos = pp.pos; np.pre_count = pp.count; np.pre_elig = pp.eligible; np.pre_khi = pp.khi;
   }

@@ -757,7 +757,13 @@ static __device__ void nms_pivot_body(const NmsPreselectParams& p, unsigned char
 
 // `slices` CTAs per segment: each scans its slice (4 independent loads in flight per thread) and appends the eligible
 // keys below the pivot to the segment's window in global memory with warp-aggregated atomics.
+#define NMS_PG_STAGE 1024   // selected keys a CTA stages in shared memory before its single append to the segment's list
+#define NMS_PG_LOADS 8      // independent loads of each array a thread keeps in flight
+
 static __device__ void nms_pregather_body(const NmsPreselectParams& p) {
+  __shared__ unsigned long long s_keys[NMS_PG_STAGE];
+  __shared__ uint32_t s_pos[NMS_PG_STAGE];
+  __shared__ int s_n, s_el, s_base;
   const int tid = threadIdx.x, lane = tid & 31;
   const int seg = blockIdx.x / p.slices, slice = blockIdx.x - seg * p.slices;
   const int n = p.counts[seg];
@@ -765,43 +771,50 @@ static __device__ void nms_pregather_body(const NmsPreselectParams& p) {
   const uint32_t* oid_base = p.order_id ? p.order_id + (size_t)seg * p.stride : nullptr;
   const unsigned long long khi = p.khi[seg];
   const int lo = (int)(((long long)slice * n) / p.slices), hi = (int)(((long long)(slice + 1) * n) / p.slices);
+  if (tid == 0) { s_n = 0; s_el = 0; }
+  __syncthreads();
   int my_el = 0;
   const int T = blockDim.x;
-  for (int i0 = lo; i0 < hi; i0 += 4 * T) {
-    float sv[4]; uint32_t ov[4];
+  for (int i0 = lo; i0 < hi; i0 += NMS_PG_LOADS * T) {
+    float sv[NMS_PG_LOADS]; uint32_t ov[NMS_PG_LOADS];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < NMS_PG_LOADS; ++u) {
       const int i = i0 + u * T + tid;
       sv[u] = (i < hi) ? scores[i] : 0.0f;
       ov[u] = (i < hi) ? (oid_base ? oid_base[i] : (uint32_t)i) : 0u;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < NMS_PG_LOADS; ++u) {
       const int i = i0 + u * T + tid;
-      bool take = false;
-      unsigned long long K = 0ull;
       if (i < hi && !(p.use_score_thr && (sv[u] < p.score_thr))) {
-        K = ((unsigned long long)nms_dkey(sv[u]) << 32) | ov[u];
+        const unsigned long long K = ((unsigned long long)nms_dkey(sv[u]) << 32) | ov[u];
         ++my_el;
-        take = (khi == ~0ull) || (K < khi);
-      }
-      const uint32_t bal = __ballot_sync(0xffffffffu, take);
-      if (bal) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&p.count[seg], __popc(bal));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (take) {
-          const int slot = base + __popc(bal & ((1u << lane) - 1u));
-          if (slot < NMS_PRE_CAP) {
-            p.keys[(size_t)seg * NMS_PRE_CAP + slot] = K;
-            p.pos[(size_t)seg * NMS_PRE_CAP + slot] = (uint32_t)i;
+        if ((khi == ~0ull) || (K < khi)) {
+          // staged in shared memory (an atomic there returns in a few cycles; a global one per hit stalled the warp for a
+          // round trip); the rare overflow goes straight to the list
+          const int slot = atomicAdd(&s_n, 1);
+          if (slot < NMS_PG_STAGE) { s_keys[slot] = K; s_pos[slot] = (uint32_t)i; }
+          else {
+            const int g = atomicAdd(&p.count[seg], 1);
+            if (g < NMS_PRE_CAP) { p.keys[(size_t)seg * NMS_PRE_CAP + g] = K; p.pos[(size_t)seg * NMS_PRE_CAP + g] = (uint32_t)i; }
           }
         }
       }
     }
   }
   my_el = warp_sum_i(my_el);
-  if (lane == 0 && my_el) atomicAdd(&p.eligible[seg], my_el);
+  if (lane == 0 && my_el) atomicAdd(&s_el, my_el);
+  __syncthreads();
+  const int staged = min(s_n, NMS_PG_STAGE);
+  if (tid == 0) {
+    s_base = staged ? atomicAdd(&p.count[seg], staged) : 0;
+    if (s_el) atomicAdd(&p.eligible[seg], s_el);
+  }
+  __syncthreads();
+  for (int t = tid; t < staged; t += T) {
+    const int g = s_base + t;
+    if (g < NMS_PRE_CAP) { p.keys[(size_t)seg * NMS_PRE_CAP + g] = s_keys[t]; p.pos[(size_t)seg * NMS_PRE_CAP + g] = s_pos[t]; }
+  }
 }
 
 // runs CALL(METRIC) with the runtime metric as a compile-time constant
