@@ -275,6 +275,15 @@ class Anchors(object):
       if tb[l].shape != rel[l].shape or tc[l].shape != cl[l].shape or tm[l].numel() != rel[l].numel() // 4:
         raise ValueError('target shapes of level %d differ from the predictions (dense one-hot class targets expected)' % l)
     dev = cl[0].device
+    if C > 128:
+      # the one-pass stream stages 64-anchor tiles of logits and targets in shared memory (classes_num <= 128): wider heads
+      # take the separate calls — same results, the logits are read twice
+      from ..efficientdet_net_train import get_loss
+      res = get_loss(tb, tc, tm, rel, cl, alpha, gamma, delta, exchange=exchange, return_parts=True)
+      dec = self.convert_outputs_boxes(rel)
+      out = self.convert_outputs_batch(dec, cl, max_output_size=K, iou_threshold=iou_threshold, score_threshold=score_threshold,
+                                       iou_type=iou_type, with_indices=with_indices)
+      return (res[0], tuple(dec), out, res[1], res[2]) if return_parts else (res[0], tuple(dec), out)
     dec = [torch.empty_like(t) for t in rel]
     out = self._post_outputs(B, K, dev, with_indices)
     sums = torch.empty((2 * L + 1,), dtype=torch.float64, device=dev)
