@@ -324,7 +324,6 @@ struct YoloFinalizeParams {
   const float* cand_score; const int32_t* cand_cls; const float* cand_conf;
   const uint32_t* cand_aidx; const int32_t* counts; const uint32_t* bitmap; int bitmap_words;
   int32_t* nms_pos;  // [B, max_out] scratch
-  long long* row_rec; // [B, max_out] scratch: (level << 56) | record index of every emitted row, -1 for unused rows
   // outputs, all [B, max_out, ...]
   float* out_boxes; int32_t* out_cls; float* out_score; float* out_classes; float* out_conf;
   int32_t* out_sel_idx; int32_t* out_sel_anchor; int32_t* out_count;
@@ -401,50 +400,32 @@ __global__ void __launch_bounds__(THREADS, NMS_THREADS / THREADS) yolo_nms_final
       const uint32_t wv = p.bitmap[(size_t)img * p.bitmap_words + (a >> 5)];
       p.out_sel_idx[obase + k] = (int32_t)(wprefix[a >> 5] + __popc(wv & ((1u << (a & 31u)) - 1u)));
     }
-    if (p.out_classes) {   // where the class-row kernel finds the record: one load there instead of count -> pos -> anchor
-      int l = 0;
-#pragma unroll
-      for (int j = 1; j < YD_MAX_LEVELS; ++j) if ((int)a >= p.lv.anchor_base[j]) l = j;
-      p.row_rec[obase + k] = ((long long)l << 56) | ((long long)img * p.lv.rec_per_img[l] + ((int)a - p.lv.anchor_base[l]));
-    }
   }
-  if (p.out_classes)
-    for (int k = kept + (int)threadIdx.x; k < p.cfg.max_out; k += blockDim.x) p.row_rec[obase + k] = -1;
 }
 
-// sigmoid(classes) rows of the selected boxes, read back from the head tensors (tyu:140,265).  A separate launch so that
-// the B*max_out*C deterministic sigmoids spread over the whole GPU instead of serialising inside the per-image NMS CTAs
-// (folding them into the NMS CTA was measured: 52.7 -> 77.9 us at batch 1).  A warp takes YC_ROWS rows at a time: their
-// record codes, then all their logits, are in flight together (two dependent round trips per YC_ROWS rows).
-#define YC_ROWS 4
+// sigmoid(classes) rows of the selected boxes, read back from the head tensors (tyu:140,265).  A separate launch
+// so the B*max_out*C sigmoids spread over the whole GPU instead of serialising inside the per-image NMS CTAs.
 __global__ void __launch_bounds__(256) yolo_classes_kernel(YoloFinalizeParams p) {
   const int lane = threadIdx.x & 31;
-  const long long rows = (long long)p.B * p.cfg.max_out;
-  const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * YC_ROWS;
-  if (row0 >= rows) return;
-  long long code[YC_ROWS];
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // row = img * max_out + k
+  if (row >= p.B * p.cfg.max_out) return;
+  const int img = row / p.cfg.max_out, k = row - img * p.cfg.max_out;
+  if (k >= p.out_count[img]) return;
+  const size_t cbase = (size_t)img * p.n_img;
+  const uint32_t a = p.cand_aidx[cbase + p.nms_pos[(size_t)img * p.cfg.max_out + k]];
+  int l = 0;
 #pragma unroll
-  for (int r = 0; r < YC_ROWS; ++r) code[r] = (row0 + r < rows) ? __ldg(p.row_rec + row0 + r) : -1;
-  float x[YC_ROWS][4];
+  for (int j = 1; j < YD_MAX_LEVELS; ++j) if ((int)a >= p.lv.anchor_base[j]) l = j;
+  const long long rec = (long long)img * p.lv.rec_per_img[l] + ((int)a - p.lv.anchor_base[l]);
+  const float* src = p.lv.head[l] + rec * p.RF + 5;
+  float* dst = p.out_classes + (size_t)row * p.C;
+  // the (cold) logits of up to 128 classes are fetched before the first sigmoid starts
+  float x[4];
 #pragma unroll
-  for (int r = 0; r < YC_ROWS; ++r) {
-    const int l = code[r] < 0 ? 0 : (int)(code[r] >> 56);
-    const float* src = p.lv.head[l] + (code[r] & 0x00ffffffffffffffll) * p.RF + 5;
+  for (int j = 0; j < 4; ++j) x[j] = (lane + 32 * j < p.C) ? __ldg(src + lane + 32 * j) : 0.0f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) x[r][j] = (code[r] >= 0 && lane + 32 * j < p.C) ? __ldg(src + lane + 32 * j) : 0.0f;
-  }
-#pragma unroll
-  for (int r = 0; r < YC_ROWS; ++r) {
-    if (code[r] < 0) continue;
-    float* dst = p.out_classes + (size_t)(row0 + r) * p.C;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) if (lane + 32 * j < p.C) dst[lane + 32 * j] = dm_sigmoidf(x[r][j]);
-    if (p.C > 128) {
-      const int l = (int)(code[r] >> 56);
-      const float* src = p.lv.head[l] + (code[r] & 0x00ffffffffffffffll) * p.RF + 5;
-      for (int c = lane + 128; c < p.C; c += 32) dst[c] = dm_sigmoidf(__ldg(src + c));
-    }
-  }
+  for (int j = 0; j < 4; ++j) if (lane + 32 * j < p.C) dst[lane + 32 * j] = dm_sigmoidf(x[j]);
+  for (int c = lane + 128; c < p.C; c += 32) dst[c] = dm_sigmoidf(__ldg(src + c));
 }
 
 // ---- dense decode for the stand-alone GetBoxes shim ---------------------------------------------
@@ -504,7 +485,7 @@ static int fill_levels(YoloLevels& lv, const float* const heads[3], const int32_
 }
 
 struct YoloWs {
-  size_t counts, bitmap, box, score, cls, conf, aidx, pos, rec, total;
+  size_t counts, bitmap, box, score, cls, conf, aidx, pos, total;
   int bitmap_words;
 };
 static YoloWs yolo_ws_layout(int B, int n_img, int max_out) {
@@ -519,7 +500,6 @@ static YoloWs yolo_ws_layout(int B, int n_img, int max_out) {
   w.conf = o; o = b200_align_up(o + sizeof(float) * (size_t)B * n_img, 256);
   w.aidx = o; o = b200_align_up(o + sizeof(uint32_t) * (size_t)B * n_img, 256);
   w.pos = o; o = b200_align_up(o + sizeof(int32_t) * (size_t)B * max_out, 256);
-  w.rec = o; o = b200_align_up(o + sizeof(long long) * (size_t)B * max_out, 256);
   w.total = o;
   return w;
 }
@@ -600,7 +580,6 @@ extern "C" int b200_yolo_decode_nms(const float* const heads[3], const int32_t h
   fp.cand_box = dp.cand_box; fp.cand_score = dp.cand_score; fp.cand_cls = dp.cand_cls; fp.cand_conf = dp.cand_conf;
   fp.cand_aidx = dp.cand_aidx; fp.counts = dp.counts; fp.bitmap = dp.bitmap; fp.bitmap_words = ws.bitmap_words;
   fp.nms_pos = reinterpret_cast<int32_t*>(wsb + ws.pos);
-  fp.row_rec = reinterpret_cast<long long*>(wsb + ws.rec);
   fp.out_boxes = out_boxes; fp.out_cls = out_class_id; fp.out_score = out_score; fp.out_classes = out_classes;
   fp.out_conf = out_conf; fp.out_sel_idx = out_sel_idx; fp.out_sel_anchor = out_sel_anchor; fp.out_count = out_count;
   // one 1024-thread CTA per SM gives the lowest latency; batches that need more than one wave use 512-thread CTAs,
@@ -622,7 +601,7 @@ extern "C" int b200_yolo_decode_nms(const float* const heads[3], const int32_t h
   B200_LAUNCH_CHECK();
   if (out_classes) {
     const long long rows = (long long)B * max_out;
-    yolo_classes_kernel<<<(int)((rows + 8 * YC_ROWS - 1) / (8 * YC_ROWS)), 256, 0, stream>>>(fp);
+    yolo_classes_kernel<<<(int)((rows + 7) / 8), 256, 0, stream>>>(fp);
     B200_LAUNCH_CHECK();
   }
   return B200_OK;
