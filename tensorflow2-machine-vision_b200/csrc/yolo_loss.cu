@@ -694,11 +694,11 @@ __global__ void __launch_bounds__(YL_ICHUNK, MINB) yolo_loss_ignore_lean_kernel(
   }
 }
 
-__global__ void __launch_bounds__(128) yolo_loss_ignore_exact_kernel(YlParams p) {
+// the exact pass over the queued records: a warp per record, `gwarp` of `nwarps` warps
+__device__ __forceinline__ void yl_exact_pass(const YlParams& p, unsigned int gwarp, unsigned int nwarps) {
   const int lane = threadIdx.x & 31;
   const unsigned int n = *p.pend_count;
-  const unsigned int nwarps = gridDim.x * (blockDim.x >> 5);
-  for (unsigned int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < n; q += nwarps) {
+  for (unsigned int q = gwarp; q < n; q += nwarps) {
     const uint32_t id = p.pend_queue[q];
     const int img = (int)(id / (uint32_t)p.n_img);
     const int ain = (int)(id - (uint32_t)img * (uint32_t)p.n_img);
@@ -744,6 +744,10 @@ __global__ void __launch_bounds__(128) yolo_loss_ignore_exact_kernel(YlParams p)
   }
 }
 
+__global__ void __launch_bounds__(128) yolo_loss_ignore_exact_kernel(YlParams p) {
+  yl_exact_pass(p, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), gridDim.x * (blockDim.x >> 5));
+}
+
 // K4c: YL_FIN_CTAS CTAs each reduce an interleaved share of the per-CTA partials in fp64 (fixed assignment, fixed
 // order); the CTA that takes the last ticket adds the YL_FIN_CTAS slices in index order and writes parts / loss.
 // Deterministic run to run, and shorter than a single CTA walking all partials (shapes measured in DESIGN.md section 9).
@@ -765,9 +769,19 @@ struct YlFinalize {
   int publish_only;        // 1: store this rank's terms into the peers' mailboxes and return (b200_yolo_loss_collect_peer finishes)
 };
 
-__global__ void __launch_bounds__(YL_FIN_THREADS) yolo_loss_finalize_kernel(YlFinalize f) {
+// With `exact` (split form of the ignore pass) the launch is wider than YL_FIN_CTAS: every CTA first resolves its share of
+// the queued records (K4b-exact inside this launch: no third kernel on the step's critical path), the first YL_FIN_CTAS
+// CTAs also reduce their slices, and the ticket counts ALL CTAs.
+__global__ void __launch_bounds__(YL_FIN_THREADS) yolo_loss_finalize_kernel(YlFinalize f, YlParams p, int exact) {
   __shared__ double s_red[YL_FIN_THREADS / 32][12];
   __shared__ bool s_last;
+  if (exact) yl_exact_pass(p, blockIdx.x * (YL_FIN_THREADS / 32) + (threadIdx.x >> 5), gridDim.x * (YL_FIN_THREADS / 32));
+  if ((int)blockIdx.x >= YL_FIN_CTAS) {   // block-uniform: exact-pass-only CTAs just take a ticket
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); s_last = (atomicAdd(f.ticket, 1u) == gridDim.x - 1); }
+    __syncthreads();
+    if (!s_last) return;
+  } else {
   double acc[12];
 #pragma unroll
   for (int i = 0; i < 12; ++i) acc[i] = 0.0;
@@ -782,11 +796,11 @@ __global__ void __launch_bounds__(YL_FIN_THREADS) yolo_loss_finalize_kernel(YlFi
       acc[l * 4 + 3] += f.partials_obj[(size_t)c * 3 + 2];
     }
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < 12; ++i) {
     double v = warp_sum_d(acc[i]);
-    if (lane == 0) s_red[warp][i] = v;
+    if (lane_ == 0) s_red[warp_][i] = v;
   }
   __syncthreads();
   if (threadIdx.x < 12) {
@@ -796,10 +810,12 @@ __global__ void __launch_bounds__(YL_FIN_THREADS) yolo_loss_finalize_kernel(YlFi
     __threadfence();
   }
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(f.ticket, 1u) == YL_FIN_CTAS - 1);
+  if (threadIdx.x == 0) { __threadfence(); s_last = (atomicAdd(f.ticket, 1u) == gridDim.x - 1); }
   __syncthreads();
   if (!s_last) return;
+  }
   __threadfence();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (warp == 0) {
     float v = 0.0f;
     if (lane < 12) {
@@ -1157,25 +1173,23 @@ static int yolo_loss_impl(const float* const y_true[3], const float* const y_pre
     const int grid = YL_LEVELS * B * YL_TERM_SPLIT + ws.n_cta;
     bool aligned16 = true;
     for (int l = 0; l < YL_LEVELS; ++l) aligned16 &= (reinterpret_cast<uintptr_t>(y_pred[l]) & 15) == 0;
-    // B200_YL_SPLIT = 8/10/12/16 selects the split form (CTAs per SM K4b-lean is compiled for); default: the single kernel.
-    // Measured at 608x608 batch 64: K4b 71 us; K4b-lean 53.7 us (48 registers, 10 CTAs per SM) + K4b-exact 15.6 us for the
-    // ~12 k undecided records = 69 us, step 196.5 vs 199.3 us — inside 1.5 %, not worth a second launch by default.
+    // B200_YL_SPLIT = 0 selects the single kernel K4b, 8/10/12/16 the split form (CTAs per SM K4b-lean is compiled for;
+    // default 10).  Measured at 608x608 batch 64: K4b 71 us; K4b-lean 53.7 us (48 registers, 10 CTAs per SM); the exact pass
+    // over the ~12 k undecided records costs 15.6 us as a launch of its own and rides in the widened finalize launch instead.
     const char* split_env = getenv("B200_YL_SPLIT");
-    const int split = split_env ? atoi(split_env) : 0;
+    const int split = split_env ? atoi(split_env) : 10;
     use_split = !host_pred && aligned16 && p.RF >= 8 && split > 0;
     if (use_split) {
-      // the queue counter and the fixed-point sums start from zero for THIS pass (the stage hook may repeat it)
-      B200_CUDA(cudaMemsetAsync(p.pend_count, 0, (size_t)(reinterpret_cast<unsigned char*>(p.obj_fixed + 3) - reinterpret_cast<unsigned char*>(p.pend_count)), stream));
+      // the queue counter and the fixed-point sums are zeroed with the object counts (stage 1); the stage hook may run this
+      // pass on its own, repeatedly
+      if (!(stages & 1)) B200_CUDA(cudaMemsetAsync(p.pend_count, 0, (size_t)(reinterpret_cast<unsigned char*>(p.obj_fixed + 3) - reinterpret_cast<unsigned char*>(p.pend_count)), stream));
       if (split >= 16) yolo_loss_ignore_lean_kernel<16><<<grid, YL_ICHUNK, 0, stream>>>(p);
       else if (split >= 12) yolo_loss_ignore_lean_kernel<12><<<grid, YL_ICHUNK, 0, stream>>>(p);
       else if (split >= 10) yolo_loss_ignore_lean_kernel<10><<<grid, YL_ICHUNK, 0, stream>>>(p);
       else yolo_loss_ignore_lean_kernel<8><<<grid, YL_ICHUNK, 0, stream>>>(p);
-      B200_LAUNCH_CHECK();
-      {  // a warp per queued record; the count lives on the device, so the grid is sized for the usual few thousand records
-        // (more are covered by the warps' stride loop) — surplus warps read the count and leave
-        const char* xg = getenv("B200_YL_EXACT_CTAS");
-        const int ctas = xg ? atoi(xg) : 1024;
-        yolo_loss_ignore_exact_kernel<<<ctas > 0 ? ctas : 1024, 128, 0, stream>>>(p);
+      if (!(stages & 8)) {   // no finalize in this call: the exact pass as a launch of its own (the finalize launch carries it otherwise)
+        B200_LAUNCH_CHECK();
+        yolo_loss_ignore_exact_kernel<<<1024, 128, 0, stream>>>(p);
       }
     } else if (host_pred) yolo_loss_ignore_kernel<true><<<grid, YL_ICHUNK, 0, stream>>>(p);
     else yolo_loss_ignore_kernel<false><<<grid, YL_ICHUNK, 0, stream>>>(p);
@@ -1192,7 +1206,13 @@ static int yolo_loss_impl(const float* const y_true[3], const float* const y_pre
   f.obj_fixed = p.obj_fixed;   // zero unless K4b-exact ran
   if (xchg) f.xchg = *xchg;
   else { f.xchg.rank = 0; f.xchg.world = 1; for (int r = 0; r < B200_XCHG_MAX_WORLD; ++r) f.xchg.mailbox[r] = nullptr; }
-  yolo_loss_finalize_kernel<<<YL_FIN_CTAS, YL_FIN_THREADS, 0, stream>>>(f);
+  {
+    // split form: the finalize launch is widened and resolves the queued records first (default 4 CTAs per SM)
+    const char* fx = getenv("B200_YL_FINX_CTAS");
+    int wide = fx ? atoi(fx) : 4 * b200_sm_count();
+    if (wide < YL_FIN_CTAS) wide = YL_FIN_CTAS;
+    yolo_loss_finalize_kernel<<<use_split ? wide : YL_FIN_CTAS, YL_FIN_THREADS, 0, stream>>>(f, p, use_split ? 1 : 0);
+  }
   B200_LAUNCH_CHECK();
   if (out_grad) {
     YlGradDense g;
