@@ -67,6 +67,8 @@ struct YlParams {
   const uint32_t* obj_bits;   // [B, bits_words]
   int bits_words;
   int32_t* gt_count;    // [B, 3]
+  int scan_reverse;           // scan CTAs walk y_true from its end: the part GetTargets wrote last is still in L2
+  unsigned int* scan_ticket;  // [B, 3] scan CTAs done per (image, level): the last one prepares that GT list (null: K4a' runs as a launch)
   // split form of the ignore pass (K4b-lean + K4b-exact): records whose filter leaves a (record, GT) pair undecided
   uint32_t* pend_queue;            // [B * n_img] global record ids (img * n_img + anchor_base[l] + rin)
   unsigned int* pend_count;        // number of queued records
@@ -96,17 +98,64 @@ __device__ __forceinline__ bool yl_regular(const BoxT& b) {
 #endif
 #define YL_OBJ_CHUNK (YL_CHUNK * YL_OBJ_PER_THREAD)
 
+#define YL_SORT_CAP 2048
+__device__ __forceinline__ void yl_gtprep_body(const YlParams& p, int l, int img, int* s_idx) {
+  const int nthr = blockDim.x;
+  const int rpi = p.lv.rec_per_img[l];
+  const float* yt = p.sp_t ? nullptr : p.lv.y_true[l] + ((size_t)img * rpi) * p.RF;
+  const int n = __ldcg(&p.gt_count[img * YL_LEVELS + l]);
+  const size_t gbase = (size_t)img * p.n_img + p.lv.anchor_base[l];
+  // The scan kernel appended the object records with atomics, i.e. in a run-dependent order; the xy / wh / class terms
+  // are summed in list order (fp64, then one fp32 cast), so the list is put into ascending record order first: the
+  // loss is then bit-reproducible run to run (lists longer than YL_SORT_CAP keep the atomic order).  The sparse-target
+  // path builds its list in box order already.
+  if (!p.sp_t && n > 1 && n <= YL_SORT_CAP) {
+    for (int k = threadIdx.x; k < n; k += nthr) s_idx[k] = __ldcg(&p.obj_index[gbase + k]);
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += nthr) {
+      const int mine = s_idx[k];
+      int rank = 0;
+      for (int j = 0; j < n; ++j) rank += (s_idx[j] < mine) ? 1 : 0;  // record indices are unique
+      p.obj_index[gbase + rank] = mine;
+    }
+    __syncthreads();
+  }
+  for (int k = threadIdx.x; k < n; k += nthr) {
+    float tx, ty, tw, th;
+    if (p.sp_t) {
+      const float4 v = p.sp_t[gbase + k];
+      tx = v.x; ty = v.y; tw = v.z; th = v.w;
+    } else {
+      const float* t = yt + (size_t)__ldcg(&p.obj_index[gbase + k]) * p.RF;
+      tx = __ldg(t); ty = __ldg(t + 1); tw = __ldg(t + 2); th = __ldg(t + 3);
+    }
+    const float hx = DM_DIV(tw, 2.0f), hy = DM_DIV(th, 2.0f);
+    BoxT g = bm_prep(DM_SUB(tx, hx), DM_SUB(ty, hy), DM_ADD(tx, hx), DM_ADD(ty, hy), p.metric);
+    p.gt_box[gbase + k] = make_float4(g.c0, g.c1, g.c2, g.c3);
+    p.gt_aux[gbase + k] = make_float4(g.area, g.at, dm_logf(g.area), yl_regular(g) ? 1.0f : 0.0f);
+  }
+}
+
+__global__ void __launch_bounds__(128) yolo_loss_gtprep_kernel(YlParams p) {
+  __shared__ int s_idx[YL_SORT_CAP];
+  const int l = blockIdx.x / p.B;
+  yl_gtprep_body(p, l, blockIdx.x - l * p.B, s_idx);
+}
+
 // K4a: pure stream over the obj channel.  Objects (obj != 0) are appended to the (image, level) object list in
 // obj_index; their terms are computed by the next kernel, when the memory system is no longer saturated by the scan
 // (doing it here cost a second DRAM round trip per CTA behind everyone else's scan loads: 42 us vs 30 + 4).
 __global__ void __launch_bounds__(YL_CHUNK) yolo_loss_scan_kernel(YlParams p) {
   __shared__ int s_list[YL_OBJ_CHUNK];
+  __shared__ int s_idx[YL_SORT_CAP];
   __shared__ int s_n, s_base;
+  __shared__ bool s_last;
   // same (level, image, chunk) decomposition as the ignore kernel but with larger chunks
   int l = 0;
+  const int bid = p.scan_reverse ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
 #pragma unroll
-  for (int k = 1; k < YL_LEVELS; ++k) if ((int)blockIdx.x >= p.lv.obj_cta_base[k]) l = k;
-  const int rcta = blockIdx.x - p.lv.obj_cta_base[l];
+  for (int k = 1; k < YL_LEVELS; ++k) if (bid >= p.lv.obj_cta_base[k]) l = k;
+  const int rcta = bid - p.lv.obj_cta_base[l];
   const int img = rcta / p.lv.obj_chunks_per_img[l];
   const int chunk = rcta - img * p.lv.obj_chunks_per_img[l];
   const int rpi = p.lv.rec_per_img[l];
@@ -129,54 +178,27 @@ __global__ void __launch_bounds__(YL_CHUNK) yolo_loss_scan_kernel(YlParams p) {
   }
   __syncthreads();
   const int n = s_n;
-  if (n == 0) return;
-  if (threadIdx.x == 0) s_base = atomicAdd(&p.gt_count[img * YL_LEVELS + l], n);
+  if (n > 0) {   // block-uniform
+    if (threadIdx.x == 0) s_base = atomicAdd(&p.gt_count[img * YL_LEVELS + l], n);
+    __syncthreads();
+    int32_t* dst = p.obj_index + (size_t)img * p.n_img + p.lv.anchor_base[l] + s_base;
+    for (int i = threadIdx.x; i < n; i += YL_CHUNK) dst[i] = s_list[i];
+  }
+  if (!p.scan_ticket) return;
+  // K4a' without a launch: the last CTA of this (image, level) to finish prepares its GT list
   __syncthreads();
-  int32_t* dst = p.obj_index + (size_t)img * p.n_img + p.lv.anchor_base[l] + s_base;
-  for (int i = threadIdx.x; i < n; i += YL_CHUNK) dst[i] = s_list[i];
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(&p.scan_ticket[img * YL_LEVELS + l], 1u) == (unsigned)p.lv.obj_chunks_per_img[l] - 1u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  yl_gtprep_body(p, l, img, s_idx);
 }
 
 // K4a': one thread per object: the prepared GT box of the ignore mask (corners of (t_xy, t_wh), tyu:68-71; area,
 // atan(w/h), log area, "regular" flag).  One CTA per (level, image).
-#define YL_SORT_CAP 2048
-__global__ void __launch_bounds__(128) yolo_loss_gtprep_kernel(YlParams p) {
-  __shared__ int s_idx[YL_SORT_CAP];
-  const int l = blockIdx.x / p.B, img = blockIdx.x - l * p.B;
-  const int rpi = p.lv.rec_per_img[l];
-  const float* yt = p.sp_t ? nullptr : p.lv.y_true[l] + ((size_t)img * rpi) * p.RF;
-  const int n = p.gt_count[img * YL_LEVELS + l];
-  const size_t gbase = (size_t)img * p.n_img + p.lv.anchor_base[l];
-  // The scan kernel appended the object records with atomics, i.e. in a run-dependent order; the xy / wh / class terms
-  // are summed in list order (fp64, then one fp32 cast), so the list is put into ascending record order first: the
-  // loss is then bit-reproducible run to run (lists longer than YL_SORT_CAP keep the atomic order).  The sparse-target
-  // path builds its list in box order already.
-  if (!p.sp_t && n > 1 && n <= YL_SORT_CAP) {
-    for (int k = threadIdx.x; k < n; k += 128) s_idx[k] = p.obj_index[gbase + k];
-    __syncthreads();
-    for (int k = threadIdx.x; k < n; k += 128) {
-      const int mine = s_idx[k];
-      int rank = 0;
-      for (int j = 0; j < n; ++j) rank += (s_idx[j] < mine) ? 1 : 0;  // record indices are unique
-      p.obj_index[gbase + rank] = mine;
-    }
-    __syncthreads();
-  }
-  for (int k = threadIdx.x; k < n; k += 128) {
-    float tx, ty, tw, th;
-    if (p.sp_t) {
-      const float4 v = p.sp_t[gbase + k];
-      tx = v.x; ty = v.y; tw = v.z; th = v.w;
-    } else {
-      const float* t = yt + (size_t)p.obj_index[gbase + k] * p.RF;
-      tx = __ldg(t); ty = __ldg(t + 1); tw = __ldg(t + 2); th = __ldg(t + 3);
-    }
-    const float hx = DM_DIV(tw, 2.0f), hy = DM_DIV(th, 2.0f);
-    BoxT g = bm_prep(DM_SUB(tx, hx), DM_SUB(ty, hy), DM_ADD(tx, hx), DM_ADD(ty, hy), p.metric);
-    p.gt_box[gbase + k] = make_float4(g.c0, g.c1, g.c2, g.c3);
-    p.gt_aux[gbase + k] = make_float4(g.area, g.at, dm_logf(g.area), yl_regular(g) ? 1.0f : 0.0f);
-  }
-}
-
 // A warp per object record: xy / wh / class terms (tyu:107-118).  Runs as the trailing 3*B*YL_TERM_SPLIT CTAs of the
 // ignore kernel's grid (two dependent DRAM round trips and ~600 serial instructions per object: hidden under the
 // ignore pass instead of sitting on the critical path).  CTA (l, img, s) takes objects k = s*4 + warp, stepping by
@@ -1038,7 +1060,7 @@ static YlWs yl_layout(const int32_t hw[6], int B, int A, int* n_img_out, YlLevel
   w.n_cta_obj = octa;
   size_t o = 0;
   // zeroed per call: object counts [B,3], the finalize ticket, the pending-record count (+ pad to 8), 3 fixed-point sums
-  w.cnt_bytes = b200_align_up(sizeof(int32_t) * ((size_t)B * YL_LEVELS + 2), 8) + 3 * sizeof(unsigned long long);
+  w.cnt_bytes = b200_align_up(sizeof(int32_t) * ((size_t)B * YL_LEVELS + 2), 8) + 3 * sizeof(unsigned long long) + sizeof(unsigned int) * (size_t)B * YL_LEVELS;
   w.cnt = o; o = b200_align_up(o + w.cnt_bytes, 256);
   w.obj = o; o = b200_align_up(o + sizeof(float) * (size_t)B * n_img, 256);
   w.gt = o; o = b200_align_up(o + sizeof(float4) * (size_t)B * n_img, 256);
@@ -1137,6 +1159,9 @@ static int yolo_loss_impl(const float* const y_true[3], const float* const y_pre
   p.pend_queue = reinterpret_cast<uint32_t*>(wsb + ws.pend);
   p.pend_count = reinterpret_cast<unsigned int*>(wsb + ws.cnt) + (size_t)B * YL_LEVELS + 1;
   p.obj_fixed = reinterpret_cast<unsigned long long*>(wsb + ws.cnt + b200_align_up(sizeof(int32_t) * ((size_t)B * YL_LEVELS + 2), 8));
+  // full dense call: the scan's last CTA per (image, level) prepares the GT list (stage hooks keep K4a' as its own launch)
+  { const char* e = getenv("B200_YL_SCAN_REV"); p.scan_reverse = e ? atoi(e) : 1; }
+  p.scan_ticket = (!sparse && (stages & 3) == 3 && !getenv("B200_YL_GTPREP_LAUNCH")) ? reinterpret_cast<unsigned int*>(p.obj_fixed + 3) : nullptr;
   p.sp_t = nullptr; p.sp_cls = nullptr; p.obj_bits = nullptr; p.bits_words = 0;
   if (sparse) {
     B200_REQUIRE(sparse->total_boxes >= 0 && sparse->offsets && sparse->assign_anchors_wh_host, B200_ERR_BAD_ARG, "b200_yolo_loss_from_boxes: null box arrays");
@@ -1159,7 +1184,7 @@ static int yolo_loss_impl(const float* const y_true[3], const float* const y_pre
     yolo_loss_scan_kernel<<<ws.n_cta_obj, YL_CHUNK, 0, stream>>>(p);
     B200_LAUNCH_CHECK();
   }
-  if (stages & 2) {
+  if ((stages & 2) && !p.scan_ticket) {
     yolo_loss_gtprep_kernel<<<YL_LEVELS * B, 128, 0, stream>>>(p);
     B200_LAUNCH_CHECK();
   }
