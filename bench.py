@@ -469,8 +469,8 @@ def headline_c2(b, line):
                            else ("; exchange inside the finalize kernel" if world > 1 else ""))),
                    "l2": "inputs larger than L2 (y_pred %.0f MB + y_true %.0f MB per step vs 126 MB L2)" % (n_fill * 4 / 1e6, n_fill * 4 / 1e6)},
         "loss": loss_val, "clocks": clocks,
-        "gpu_launches": (6 + (2 if overlapped else 0)) * args.steps * len(windows),
-        "gpu_launches_note": "6 kernels per step (fill, scatter, scan, gtprep, ignore+terms, finalize)" + (
+        "gpu_launches": (5 + (2 if overlapped else 0)) * args.steps * len(windows),
+        "gpu_launches_note": "5 kernels per step (fill, scatter, scan + GT prep, ignore-lean + object terms, finalize + exact ignore pass)" + (
             " + exchange and fold kernels on the side branch" if overlapped else ""),
     })
     if b.exchange is not None and hasattr(b.exchange, "status"):
@@ -506,9 +506,8 @@ def headline_c2(b, line):
     for name, fn, nbytes in (
             ("fill_zero_multi_kernel", ph_fill, n_fill * 4),
             ("yolo_scatter_targets_kernel", ph_scatter, int(boxes_d.shape[0]) * (16 + 4 + 340)),
-            ("yolo_loss_scan_kernel", ph_loss_stage(1), n_fill * 4),
-            ("yolo_loss_gtprep_kernel", ph_loss_stage(2), int(boxes_d.shape[0]) * (16 + 32)),
-            ("yolo_loss_ignore_kernel", ph_loss_stage(4), n_fill * 4),
+            ("yolo_loss_scan_kernel", ph_loss_stage(3), n_fill * 4),          # its last CTAs prepare the GT lists
+            ("yolo_loss_ignore_lean_kernel", ph_loss_stage(4), n_fill * 4),   # stage 4 alone: + the exact pass as its own launch
             ("yolo_loss_finalize_kernel", ph_loss_stage(8), n_rec // 128 * 8)):
         if name == "yolo_loss_finalize_kernel" and world > 1:
             continue   # stage 8 alone would exchange on one rank only; its time is in the step

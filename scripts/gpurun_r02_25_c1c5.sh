@@ -1,0 +1,12 @@
+#!/bin/bash
+# c1 (batch 1 latency + batch 256) and c5 (512 and 64 per GPU) after an NMS change: step times + parity flags
+cd $GRAFT_REPO_ROOT
+show() { python -c "
+import sys,json
+d=json.loads(sys.stdin.read())
+for k,v in d.get('configs',{}).items():
+    print(k, 'ms', round(v.get('ms_per_step',0),4), 'value', round(v.get('value',0)), 'b1', (v.get('batch1') or {}).get('latency_us'), 'frac_dense', round((v.get('roofline') or {}).get('frac_dense',0),3), 'parity', v.get('parity'))
+"; }
+python bench.py --only c1 --no-cpu-baseline 2>/dev/null | show
+python bench.py --only c5 --no-cpu-baseline 2>/dev/null | show
+python bench.py --only c5 --c5-global-batch 64 --no-cpu-baseline 2>/dev/null | show

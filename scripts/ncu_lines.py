@@ -1,13 +1,14 @@
 #!/usr/bin/env python
 """Aggregates the stall samples of an ncu report by CUDA source line (needs -lineinfo and --import-source on).
-  python scripts/ncu_lines.py report.ncu-rep [top_n]"""
+  python scripts/ncu_lines.py report.ncu-rep [top_n [kernel_regex]]"""
 import csv
 import subprocess
 import sys
 
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
+kern = ["--kernel-name", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []   # optional: only launches of this kernel
+txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"] + kern, capture_output=True, text=True).stdout
 rows = list(csv.reader(txt.splitlines()))
 hdr = None
 agg = {}

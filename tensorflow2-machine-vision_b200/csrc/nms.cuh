@@ -29,6 +29,15 @@
 #include "boxmath.cuh"
 #include "common.cuh"
 
+#ifdef NMS_TRACE   // tuning builds only: SM-clock time stamps of the phases of block 0 (read back by b200_debug_nms_trace)
+static __device__ long long g_nms_trace[64 + 4 * 32];
+#define NMS_T(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_nms_trace[i] = clock64(); } while (0)
+#define NMS_TW(k) do { if ((threadIdx.x & 31) == 0 && blockIdx.x == 0) g_nms_trace[64 + (k) * 32 + (threadIdx.x >> 5)] = clock64(); } while (0)
+#else
+#define NMS_T(i) do { } while (0)
+#define NMS_TW(k) do { } while (0)
+#endif
+
 #define NMS_THREADS 1024
 #define NMS_CHUNK 1024
 #define NMS_WINDOW 4096
@@ -125,6 +134,7 @@ __device__ __forceinline__ void nms_bitonic(unsigned long long* sK, uint32_t* sP
 }
 
 #define NMS_BINS 2048
+#define NMS_KC 8   // keys a thread keeps in registers for the selection passes of a small segment
 
 // bucket of a descending-score key inside [dmin, dmax]: monotone non-decreasing in d (int->float rounding, the
 // multiplication by a positive constant and the truncation all are), so bucket(a) < bucket(b) implies a < b
@@ -186,20 +196,27 @@ __device__ __forceinline__ int nms_block_scan_bins(int* hist, uint32_t* red, int
 // Exact ascending order of keys[0..n) (n <= NMS_WINDOW, 64-bit keys in shared memory; ties by position) as an index array:
 // ord[r] = position of the r-th smallest key.  bins: 2 * NMS_BINS ints of scratch (ord may alias its first half),
 // nxt: n ints of scratch, red: 96 uint32.  Cost: a handful of barriers and O(chain length) per key.
+// With have_range the caller supplies mn <= every key's high word and an estimate mx of the largest one (keys above mx all
+// fall into the last bucket — still monotone, so the order stays exact) and the range pass with its two barriers is skipped.
 template <int THREADS>
 __device__ __forceinline__ void nms_bucket_order(const unsigned long long* keys, int n, int* bins, int* nxt, uint32_t* red,
-                                                 unsigned short* ord) {
+                                                 unsigned short* ord, bool have_range = false, uint32_t mn_in = 0u,
+                                                 uint32_t mx_in = 0u) {
   constexpr int PER = NMS_WINDOW / THREADS;
   int* hist = bins;
   int* head = bins + NMS_BINS;
   uint32_t mn = 0xffffffffu, mx = 0u;
   int dummy = 0;
-  for (int t = threadIdx.x; t < n; t += THREADS) {
-    const uint32_t d = (uint32_t)(keys[t] >> 32);
-    mn = min(mn, d); mx = max(mx, d);
+  if (!have_range) {
+    for (int t = threadIdx.x; t < n; t += THREADS) {
+      const uint32_t d = (uint32_t)(keys[t] >> 32);
+      mn = min(mn, d); mx = max(mx, d);
+    }
   }
   for (int b = threadIdx.x; b < NMS_BINS; b += THREADS) { hist[b] = 0; head[b] = -1; }
-  nms_block_minmaxsum<THREADS>(mn, mx, dummy, red);   // its barriers also publish the cleared bins
+  if (have_range) { mn = mn_in; mx = mx_in < mn_in ? mn_in : mx_in; __syncthreads(); }
+  else nms_block_minmaxsum<THREADS>(mn, mx, dummy, red);   // its barriers also publish the cleared bins
+  NMS_T(16);
   const float scale = nms_bin_scale(mn, mx);
   for (int t = threadIdx.x; t < n; t += THREADS) {
     const int b = nms_bin((uint32_t)(keys[t] >> 32), mn, scale);
@@ -207,7 +224,9 @@ __device__ __forceinline__ void nms_bucket_order(const unsigned long long* keys,
     nxt[t] = atomicExch(&head[b], t);
   }
   __syncthreads();
+  NMS_T(17);
   nms_block_scan_bins<THREADS>(hist, red, 0, nullptr);
+  NMS_T(18);
   int dst[PER];
 #pragma unroll
   for (int u = 0; u < PER; ++u) {
@@ -225,6 +244,7 @@ __device__ __forceinline__ void nms_bucket_order(const unsigned long long* keys,
     }
   }
   __syncthreads();   // every chain walk is finished: the bins may be overwritten by ord
+  NMS_T(19);
 #pragma unroll
   for (int u = 0; u < PER; ++u) {
     const int t = (int)threadIdx.x + u * THREADS;
@@ -238,6 +258,7 @@ __device__ __forceinline__ void nms_bucket_order(const unsigned long long* keys,
 // How a candidate's box is obtained when it enters the window: by default a read of seg.boxes; a caller may decode
 // it on demand instead (YOLO: only the few hundred candidates NMS actually looks at are ever decoded).
 struct NmsLoadDirect {
+  static constexpr bool kKeyCache = false;   // register cache of a small segment's keys (16 registers): opt-in per caller
   __device__ __forceinline__ float4 operator()(const NmsSegment& seg, uint32_t pos) const {
     return __ldg(reinterpret_cast<const float4*>(seg.boxes) + pos);
   }
@@ -281,6 +302,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
 
   if (tid < 256) sHead[tid] = -1;
   const int n = seg.n;
+  NMS_T(0);
   // window size goal: enough candidates to emit max_out boxes when little is suppressed, small enough that the
   // bitonic sort of the window (the dominant cost of a lightly suppressed image) stays cheap
   const int target = nms_window_target(cfg.max_out, n);
@@ -310,7 +332,33 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
     }
     // one sweep over the source: body(i, K) for every eligible key that is left; four independent loads in flight per
     // thread (a plain strided loop serialises on the L2 latency: 48 dependent round trips per pass at 49 k candidates)
+    // A segment of at most NMS_KC keys per thread is read ONCE: the keys stay in registers for the range, histogram and
+    // gather passes (three L2 / L1 round trips per pass otherwise — at 5 k candidates the passes are pure latency).
+    const bool small_seg = BoxLoad::kKeyCache && !use_pre && src_n <= NMS_KC * THREADS;
+    unsigned long long Kc[NMS_KC];
+    uint32_t kc_ok = 0u;
+    if (small_seg) {
+      float sv[NMS_KC];
+      uint32_t ov[NMS_KC];
+#pragma unroll
+      for (int u = 0; u < NMS_KC; ++u) {
+        const int i = tid + u * THREADS;
+        sv[u] = (i < src_n) ? seg.scores[i] : 0.0f;
+        ov[u] = (i < src_n && seg.order_id) ? seg.order_id[i] : (uint32_t)i;
+      }
+#pragma unroll
+      for (int u = 0; u < NMS_KC; ++u) {
+        const int i = tid + u * THREADS;
+        Kc[u] = ((unsigned long long)nms_dkey(sv[u]) << 32) | ov[u];
+        if ((i < src_n) && !(cfg.use_score_thr && (sv[u] < cfg.score_thr)) && (Kc[u] >= klo)) kc_ok |= 1u << u;
+      }
+    }
     auto for_each_key = [&](auto&& body) {
+      if (small_seg) {
+#pragma unroll
+        for (int u = 0; u < NMS_KC; ++u) if ((kc_ok >> u) & 1u) body(tid + u * THREADS, Kc[u]);
+        return;
+      }
       for (int i0 = tid; i0 < src_n; i0 += 4 * THREADS) {
         unsigned long long K[4];
         bool ok[4];
@@ -341,6 +389,8 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
         for (int u = 0; u < 4; ++u) if (ok[u]) body(i0 + u * THREADS, K[u]);
       }
     };
+    bool win_range = false;           // range of the gathered window's keys, known from the selection passes
+    uint32_t win_mn = 0u, win_mx = 0u;
     {
       // G1: range and number of the eligible keys that are left
       uint32_t dmin = 0xffffffffu, dmax = 0u;
@@ -350,6 +400,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
         ++n_el; dmin = min(dmin, d); dmax = max(dmax, d);
       });
       nms_block_minmaxsum<THREADS>(dmin, dmax, n_el, sRed);
+      NMS_T(1);
       if (n_el == 0) { exhausted = true; break; }
       const float scale = nms_bin_scale(dmin, dmax);
       int cut = NMS_BINS - 1;
@@ -359,7 +410,9 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
         __syncthreads();
         for_each_key([&](int, unsigned long long K) { atomicAdd(&sBins[nms_bin((uint32_t)(K >> 32), dmin, scale)], 1); });
         __syncthreads();
+        NMS_T(2);
         nms_block_scan_bins<THREADS>(sBins, sRed, target, &sScalar[3]);
+        NMS_T(3);
         cut = sScalar[3];
         const int upto = (cut + 1 < NMS_BINS) ? sBins[cut + 1] : n_el;   // keys in buckets 0..cut
         fallback = upto > NMS_WINDOW;   // one bucket alone overflows the window (masses of near-equal scores)
@@ -374,12 +427,22 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
         __syncthreads();
         for_each_key([&](int i, unsigned long long K) {
           if (nms_bin((uint32_t)(K >> 32), dmin, scale) > cut) return;
-          const int slot = atomicAdd(&sScalar[0], 1);
+          const uint32_t grp = __activemask();   // one atomic per group of lanes that arrive together
+          const int leader = __ffs(grp) - 1;
+          int slot = 0;
+          if (lane == leader) slot = atomicAdd(&sScalar[0], __popc(grp));
+          slot = __shfl_sync(grp, slot, leader) + __popc(grp & ((1u << lane) - 1u));
           sK[slot] = K; sPos[slot] = use_pre ? pre->pos[i] : (uint32_t)i;
         });
         __syncthreads();
         n_win = sScalar[0];
+        NMS_T(4);
         gathered = true;
+        win_range = true; win_mn = dmin; win_mx = dmax;
+        if (cut < NMS_BINS - 1) {       // keys of buckets 0..cut lie below dmin + (cut + 1) / scale (an estimate is enough)
+          const float lim = (float)(cut + 1) / scale;
+          if (lim < (float)(dmax - dmin)) win_mx = dmin + (uint32_t)lim + 1u;
+        }
         // the window holds everything that is left only if nothing was cut here AND the pre-gathered list was complete
         const bool complete = (n_win >= n_el) && (!use_pre || *pre->count >= *pre->eligible);
         if (!complete) khi = 1ull;   // placeholder: the real bound (largest key of the window + 1) is set after ordering
@@ -467,7 +530,8 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
       for (int t = tid; t < n_win; t += THREADS) sOrd[t] = (unsigned short)t;
       __syncthreads();
     } else {
-      nms_bucket_order<THREADS>(sK, n_win, sBins, sNext, sRed, sOrd);
+      nms_bucket_order<THREADS>(sK, n_win, sBins, sNext, sRed, sOrd, win_range, win_mn, win_mx);
+      NMS_T(5);
       if (khi == 1ull) khi = sK[sOrd[n_win - 1]] + 1ull;   // everything not gathered has a larger key (bucket > cut)
     }
 
@@ -486,6 +550,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
       }
       if (tid < 2) sSupp[tid] = 0u;
       __syncthreads();
+      NMS_T(6);
       if (mode == B200_NMS_BY_CLASS) {
         // ---- per-class NMS: classes never interact, so the chunk is split by class bucket and every bucket is resolved
         // by its own warp (greedy in rank order inside the bucket); the survivors are then emitted in global rank order.
@@ -512,6 +577,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
         }
         for (int i = tid; i < 32 * 256 / 2; i += THREADS) reinterpret_cast<uint32_t*>(sTab)[i] = 0u;
         __syncthreads();
+        NMS_T(7);
         // (2) stable split by bucket: 32-candidate blocks in rank order; intra-block rank by match_any, block counts in sTab
         const int n_blk = (n_chunk + 31) >> 5;
         for (int blk = warp; blk < n_blk; blk += NW) {
@@ -548,9 +614,66 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
           if (ct < n_chunk) sMem[sBase[bucket] + sTab[blk * 256 + bucket] + __popc(peers & ((1u << lane) - 1u))] = (unsigned short)ct;
         }
         __syncthreads();
-        // (3) a warp per bucket: greedy in rank order; state lives in shared memory (sAlive), broadcast reads of box i
-        for (int b = warp; b < 256; b += NW) {
+        NMS_T(8);
+        // (3) inside a bucket: every member tests itself against the better-ranked members of its bucket in parallel (a thread
+        // per member; bit i of its 64-bit word = "member i of my bucket, same class, suppresses me"), then one thread per
+        // bucket walks its members in rank order with the alive set in a register: member t stays iff it was alive and no
+        // ALIVE better-ranked member suppresses it — the same greedy recurrence, ~m dependent ALU steps instead of m warp
+        // rounds of shared-memory traffic (the warp-per-bucket loop took 14 us of the 36 us of a 416x416 image: 10 members
+        // per class on average, three buckets per warp, the slowest warp decides).  Buckets above 64 members keep that loop.
+        unsigned long long* sBy = reinterpret_cast<unsigned long long*>(sAlive + NMS_CHUNK);   // [NMS_CHUNK], bucket-major like sMem
+        NMS_TW(0);
+        // four lanes per member share its better-ranked bucket mates (i = sub, sub + 4, ...): the depth of the pass is a
+        // quarter of the largest bucket instead of the whole of it; the next mate's box is fetched while the current test runs
+        for (int q0 = 0; q0 < n_chunk; q0 += THREADS / 4) {
+          const int q = q0 + (tid >> 2), sub = tid & 3;
+          unsigned long long by = 0ull;
+          if (q < n_chunk) {
+            const int cj = sMem[q];
+            const int cls_j = cCl[cj];
+            const int base = sBase[(uint32_t)cls_j & 255u];
+            const int pj = q - base;
+            if (sub < pj && sBase[((uint32_t)cls_j & 255u) + 1] - base <= 64) {
+              BoxT bj; bj.c0 = cC0[cj]; bj.c1 = cC1[cj]; bj.c2 = cC2[cj]; bj.c3 = cC3[cj]; bj.area = cAr[cj]; bj.at = cAt[cj];
+              int ci = sMem[base + sub];
+              BoxT bi; bi.c0 = cC0[ci]; bi.c1 = cC1[ci]; bi.c2 = cC2[ci]; bi.c3 = cC3[ci]; bi.area = cAr[ci]; bi.at = cAt[ci];
+              int cls_i = cCl[ci];
+              for (int i = sub; i < pj; i += 4) {
+                BoxT bn = bi; int cls_n = cls_i;
+                if (i + 4 < pj) {
+                  const int cn = sMem[base + i + 4];
+                  bn.c0 = cC0[cn]; bn.c1 = cC1[cn]; bn.c2 = cC2[cn]; bn.c3 = cC3[cn]; bn.area = cAr[cn]; bn.at = cAt[cn];
+                  cls_n = cCl[cn];
+                }
+                // classes sharing a bucket (ids 256 apart) do not interact
+                if (cls_i == cls_j && nms_suppresses<METRIC>(bi, cls_j, bj, cls_j, mode, thr)) by |= 1ull << i;
+                bi = bn; cls_i = cls_n;
+              }
+            }
+          }
+          uint32_t lo32 = (uint32_t)by, hi32 = (uint32_t)(by >> 32);
+          lo32 |= __shfl_xor_sync(0xffffffffu, lo32, 1); hi32 |= __shfl_xor_sync(0xffffffffu, hi32, 1);
+          lo32 |= __shfl_xor_sync(0xffffffffu, lo32, 2); hi32 |= __shfl_xor_sync(0xffffffffu, hi32, 2);
+          if (q < n_chunk && sub == 0) sBy[q] = ((unsigned long long)hi32 << 32) | lo32;
+        }
+        NMS_TW(1);
+        __syncthreads();
+        NMS_TW(2);
+        for (int b = tid; b < 256; b += THREADS) {
           const int base = sBase[b], m = sBase[b + 1] - base;
+          if (m < 2 || m > 64) continue;
+          unsigned long long alive = 0ull;
+#pragma unroll 4
+          for (int t = 0; t < m; ++t) {                  // read-only walk: nothing is stored until the set is final
+            const bool a = sAlive[sMem[base + t]] && !(sBy[base + t] & alive);
+            alive |= (unsigned long long)a << t;
+          }
+          for (int t = 0; t < m; ++t)
+            if (!((alive >> t) & 1ull)) sAlive[sMem[base + t]] = 0;
+        }
+        for (int b = warp; b < 256; b += NW) {   // oversized buckets: a warp per bucket, greedy in rank order, state in sAlive
+          const int base = sBase[b], m = sBase[b + 1] - base;
+          if (m <= 64) continue;                         // warp-uniform
           for (int i = 0; i + 1 < m; ++i) {
             const int ci = sMem[base + i];
             if (!sAlive[ci]) continue;                   // warp-uniform
@@ -558,14 +681,16 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
             const int cls_i = cCl[ci];
             for (int j = i + 1 + lane; j < m; j += 32) {
               const int cj = sMem[base + j];
-              if (!sAlive[cj] || cCl[cj] != cls_i) continue;   // classes sharing a bucket (ids 256 apart) do not interact
+              if (!sAlive[cj] || cCl[cj] != cls_i) continue;
               BoxT bj; bj.c0 = cC0[cj]; bj.c1 = cC1[cj]; bj.c2 = cC2[cj]; bj.c3 = cC3[cj]; bj.area = cAr[cj]; bj.at = cAt[cj];
               if (nms_suppresses<METRIC>(bi, cls_i, bj, cls_i, mode, thr)) sAlive[cj] = 0;
             }
             __syncwarp();
           }
         }
+        NMS_TW(3);
         __syncthreads();
+        NMS_T(9);
         // (4) emit the survivors in rank order, up to the cap
         for (int c0 = 0; c0 < n_chunk && n_kept < cfg.max_out; c0 += THREADS) {
           const int ct = c0 + tid;
@@ -573,6 +698,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
           const uint32_t bal = __ballot_sync(0xffffffffu, a);
           if (lane == 0) sRed[warp] = (uint32_t)__popc(bal);
           __syncthreads();
+          NMS_T(14);
           int before = 0, total = 0;
 #pragma unroll
           for (int w = 0; w < NW; ++w) { const int t = (int)sRed[w]; if (w < warp) before += t; total += t; }
@@ -584,8 +710,10 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
             kNext[slot] = atomicExch(&sHead[(uint32_t)cCl[ct] & 255u], slot);
           }
           n_kept = min(cfg.max_out, n_kept + total);
+          NMS_T(15);
           __syncthreads();
         }
+        NMS_T(10);
         continue;
       }
       const int n_tiles = (n_chunk + 63) >> 6;

@@ -332,6 +332,7 @@ struct YoloFinalizeParams {
 // Decode-on-demand for NMS: candidate `pos` of the image -> its record in the head tensor -> decode_box; the result is
 // written back to the candidate store so that the emitted rows can be copied out afterwards.
 struct YoloLazyBox {
+  static constexpr bool kKeyCache = true;   // a 416x416 image has ~5 k candidates: its selection passes run from registers
   const YoloLevels* lv;
   int img, A, RF;
   float4* cand_box;  // this image's slice
@@ -355,6 +356,7 @@ struct YoloLazyBox {
 template <int METRIC, int THREADS>
 __global__ void __launch_bounds__(THREADS, NMS_THREADS / THREADS) yolo_nms_finalize_kernel(YoloFinalizeParams p) {
   extern __shared__ __align__(16) unsigned char nms_smem[];
+  NMS_T(13);
   const int img = blockIdx.x;
   const size_t cbase = (size_t)img * p.n_img;
   NmsSegment seg;
@@ -368,6 +370,7 @@ __global__ void __launch_bounds__(THREADS, NMS_THREADS / THREADS) yolo_nms_final
   lazy.lv = &p.lv; lazy.img = img; lazy.A = p.A; lazy.RF = p.RF; lazy.cand_box = p.cand_box + cbase;
   const int kept = nms_run_segment<METRIC, YoloLazyBox, THREADS>(seg, p.cfg, pos, nms_smem, nullptr, lazy);
   __syncthreads();
+  NMS_T(11);
   if (threadIdx.x == 0) p.out_count[img] = kept;
   const size_t obase = (size_t)img * p.cfg.max_out;
   // rank of an anchor index among the image's candidates = its position in the reference's compacted list
@@ -401,7 +404,14 @@ __global__ void __launch_bounds__(THREADS, NMS_THREADS / THREADS) yolo_nms_final
       p.out_sel_idx[obase + k] = (int32_t)(wprefix[a >> 5] + __popc(wv & ((1u << (a & 31u)) - 1u)));
     }
   }
+  NMS_T(12);
 }
+
+#ifdef NMS_TRACE
+extern "C" int b200_debug_nms_trace(long long* out_host64) {
+  return cudaMemcpyFromSymbol(out_host64, g_nms_trace, sizeof(long long) * (64 + 4 * 32)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 // sigmoid(classes) rows of the selected boxes, read back from the head tensors (tyu:140,265).  A separate launch
 // so the B*max_out*C sigmoids spread over the whole GPU instead of serialising inside the per-image NMS CTAs.
