@@ -559,9 +559,16 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
         unsigned short* sTab = reinterpret_cast<unsigned short*>(sK);          // [32 blocks][256 buckets] counts -> offsets
         unsigned short* sMem = sTab + 32 * 256;                                 // [NMS_CHUNK] members, bucket-major, rank order
         int* sBase = reinterpret_cast<int*>(sMem + NMS_CHUNK);                  // [257] bucket starts
-        unsigned char* sAlive = reinterpret_cast<unsigned char*>(sBase + 260);  // [NMS_CHUNK]
+        unsigned char* sAlive = reinterpret_cast<unsigned char*>(sBase + 260);  // [NMS_CHUNK] not suppressed by an earlier chunk / window
+        unsigned long long* sSet = reinterpret_cast<unsigned long long*>(sAlive + NMS_CHUNK);  // [256] per bucket: alive members (bit = position)
+        int* sPB = reinterpret_cast<int*>(sSet + 256);                           // [257] pair-index starts of the buckets
+        unsigned short* sQ = reinterpret_cast<unsigned short*>(sPB + 260);       // [NMS_CHUNK] candidate -> its slot in sMem
+        unsigned long long* sBy = sS + NMS_SAMPLES / 2;   // [NMS_CHUNK] per member: which better-ranked bucket mates suppress it (sOrd holds the first half of sS)
+        static_assert(32 * 256 * 2 + NMS_CHUNK * 2 + 260 * 4 + NMS_CHUNK + 256 * 8 + 260 * 4 + NMS_CHUNK * 2 <= NMS_WINDOW * 8, "per-class scratch exceeds the key window");
+        static_assert(NMS_WINDOW * 2 <= NMS_SAMPLES * 4 && NMS_CHUNK * 8 <= NMS_SAMPLES * 4, "sOrd / sBy do not fit the sample array");
         constexpr int NW = THREADS / 32;
-        // (1) against the boxes kept by earlier chunks / windows; clear the count table
+        constexpr int BUCKET_MAX = 64;   // buckets up to this size are resolved from suppression words, larger ones by the warp loop
+        // (1) against the boxes kept by earlier chunks / windows; clear the count table and the suppression words
         for (int ct = tid; ct < n_chunk; ct += THREADS) {
           bool supp = false;
           if (n_kept > 0) {
@@ -574,8 +581,10 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
             }
           }
           sAlive[ct] = supp ? 0 : 1;
+          sBy[ct] = 0ull;
         }
         for (int i = tid; i < 32 * 256 / 2; i += THREADS) reinterpret_cast<uint32_t*>(sTab)[i] = 0u;
+        for (int i = tid; i < 256; i += THREADS) sSet[i] = 0ull;
         __syncthreads();
         NMS_T(7);
         // (2) stable split by bucket: 32-candidate blocks in rank order; intra-block rank by match_any, block counts in sTab
@@ -593,87 +602,102 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
           sBase[b + 1] = run;
         }
         __syncthreads();
-        if (warp == 0) {   // bucket starts: exclusive prefix of the 256 totals
-          int v[8], local = 0;
+        if (warp == 0) {   // bucket starts: exclusive prefix of the 256 totals; pair-index starts: the same over m (m - 1) / 2
+          int v[8], pv[8], local = 0, plocal = 0;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) { v[k] = sBase[lane * 8 + k + 1]; local += v[k]; }
-          int incl = local;
+          for (int k = 0; k < 8; ++k) {
+            v[k] = sBase[lane * 8 + k + 1]; local += v[k];
+            pv[k] = (v[k] <= BUCKET_MAX) ? (v[k] * (v[k] - 1)) >> 1 : 0; plocal += pv[k];
+          }
+          int incl = local, pincl = plocal;
 #pragma unroll
-          for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-          int run = incl - local;
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o), pt = __shfl_up_sync(0xffffffffu, pincl, o);
+            if (lane >= o) { incl += t; pincl += pt; }
+          }
+          int run = incl - local, prun = pincl - plocal;
           __syncwarp();
 #pragma unroll
-          for (int k = 0; k < 8; ++k) { sBase[lane * 8 + k] = run; run += v[k]; }
-          if (lane == 31) sBase[256] = run;
+          for (int k = 0; k < 8; ++k) { sBase[lane * 8 + k] = run; run += v[k]; sPB[lane * 8 + k] = prun; prun += pv[k]; }
+          if (lane == 31) { sBase[256] = run; sPB[256] = prun; }
         }
         __syncthreads();
         for (int blk = warp; blk < n_blk; blk += NW) {
           const int ct = (blk << 5) + lane;
           const uint32_t bucket = ct < n_chunk ? ((uint32_t)cCl[ct] & 255u) : 0xffffu;
           const uint32_t peers = __match_any_sync(0xffffffffu, bucket);
-          if (ct < n_chunk) sMem[sBase[bucket] + sTab[blk * 256 + bucket] + __popc(peers & ((1u << lane) - 1u))] = (unsigned short)ct;
+          if (ct < n_chunk) {
+            const int base = sBase[bucket];
+            const int pos = sTab[blk * 256 + bucket] + __popc(peers & ((1u << lane) - 1u));
+            sMem[base + pos] = (unsigned short)ct;
+            sQ[ct] = (unsigned short)(base + pos);
+            if (sAlive[ct] && pos < BUCKET_MAX) atomicOr(&sSet[bucket], 1ull << pos);   // (only read for buckets <= BUCKET_MAX)
+          }
         }
         __syncthreads();
         NMS_T(8);
-        // (3) inside a bucket: every member tests itself against the better-ranked members of its bucket in parallel (a thread
-        // per member; bit i of its 64-bit word = "member i of my bucket, same class, suppresses me"), then one thread per
-        // bucket walks its members in rank order with the alive set in a register: member t stays iff it was alive and no
-        // ALIVE better-ranked member suppresses it — the same greedy recurrence, ~m dependent ALU steps instead of m warp
-        // rounds of shared-memory traffic (the warp-per-bucket loop took 14 us of the 36 us of a 416x416 image: 10 members
-        // per class on average, three buckets per warp, the slowest warp decides).  Buckets above 64 members keep that loop.
-        unsigned long long* sBy = reinterpret_cast<unsigned long long*>(sAlive + NMS_CHUNK);   // [NMS_CHUNK], bucket-major like sMem
+        // (3) inside a bucket.  The pairs (i < j) of all buckets form one flat index space (bucket starts in sPB, a triangle
+        // inside a bucket): every thread tests an equal share of them and ORs bit i into member j's word when i (same class)
+        // suppresses j.  Then one thread per bucket walks its members in rank order with the alive set in a register: member
+        // t stays iff it was alive and no ALIVE better-ranked mate suppresses it — the greedy recurrence itself, ~5 dependent
+        // ALU steps per member.  (A warp per bucket walking shared-memory state took 14 us of the 36 us of a 416x416 image —
+        // 10 members per class, three buckets per warp, the slowest warp decides; a thread per member 5 us.)
         NMS_TW(0);
-        // four lanes per member share its better-ranked bucket mates (i = sub, sub + 4, ...): the depth of the pass is a
-        // quarter of the largest bucket instead of the whole of it; the next mate's box is fetched while the current test runs
-        for (int q0 = 0; q0 < n_chunk; q0 += THREADS / 4) {
-          const int q = q0 + (tid >> 2), sub = tid & 3;
-          unsigned long long by = 0ull;
-          if (q < n_chunk) {
-            const int cj = sMem[q];
-            const int cls_j = cCl[cj];
-            const int base = sBase[(uint32_t)cls_j & 255u];
-            const int pj = q - base;
-            if (sub < pj && sBase[((uint32_t)cls_j & 255u) + 1] - base <= 64) {
-              BoxT bj; bj.c0 = cC0[cj]; bj.c1 = cC1[cj]; bj.c2 = cC2[cj]; bj.c3 = cC3[cj]; bj.area = cAr[cj]; bj.at = cAt[cj];
-              int ci = sMem[base + sub];
-              BoxT bi; bi.c0 = cC0[ci]; bi.c1 = cC1[ci]; bi.c2 = cC2[ci]; bi.c3 = cC3[ci]; bi.area = cAr[ci]; bi.at = cAt[ci];
-              int cls_i = cCl[ci];
-              for (int i = sub; i < pj; i += 4) {
-                BoxT bn = bi; int cls_n = cls_i;
-                if (i + 4 < pj) {
-                  const int cn = sMem[base + i + 4];
-                  bn.c0 = cC0[cn]; bn.c1 = cC1[cn]; bn.c2 = cC2[cn]; bn.c3 = cC3[cn]; bn.area = cAr[cn]; bn.at = cAt[cn];
-                  cls_n = cCl[cn];
+        {
+          const int P = sPB[256];
+          const int per = (P + THREADS - 1) / THREADS;
+          int e = tid * per;
+          const int e_end = min(P, e + per);
+          if (e < e_end) {
+            int lo = 0, hi = 256;                          // sPB[lo] <= e < sPB[hi]
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sPB[mid] <= e) lo = mid; else hi = mid; }
+            int bkt = lo, base = sBase[bkt], m = sBase[bkt + 1] - base;
+            const int r = e - sPB[bkt];
+            int j = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)r)) * 0.5f);
+            while ((j * (j - 1)) >> 1 > r) --j;
+            while (((j + 1) * j) >> 1 <= r) ++j;
+            int i = r - ((j * (j - 1)) >> 1);
+            int cj = sMem[base + j];
+            BoxT bj; bj.c0 = cC0[cj]; bj.c1 = cC1[cj]; bj.c2 = cC2[cj]; bj.c3 = cC3[cj]; bj.area = cAr[cj]; bj.at = cAt[cj];
+            int cls_j = cCl[cj];
+            for (;;) {
+              const int ci = sMem[base + i];
+              if (cCl[ci] == cls_j) {                      // classes sharing a bucket (ids 256 apart) do not interact
+                BoxT bi; bi.c0 = cC0[ci]; bi.c1 = cC1[ci]; bi.c2 = cC2[ci]; bi.c3 = cC3[ci]; bi.area = cAr[ci]; bi.at = cAt[ci];
+                if (nms_suppresses<METRIC>(bi, cls_j, bj, cls_j, mode, thr)) atomicOr(&sBy[base + j], 1ull << i);
+              }
+              if (++e >= e_end) break;
+              if (++i == j) {
+                i = 0;
+                if (++j == m) {                            // next bucket that has pairs (exists: e < P)
+                  do { ++bkt; base = sBase[bkt]; m = sBase[bkt + 1] - base; } while (m < 2 || m > BUCKET_MAX);
+                  j = 1;
                 }
-                // classes sharing a bucket (ids 256 apart) do not interact
-                if (cls_i == cls_j && nms_suppresses<METRIC>(bi, cls_j, bj, cls_j, mode, thr)) by |= 1ull << i;
-                bi = bn; cls_i = cls_n;
+                cj = sMem[base + j];
+                bj.c0 = cC0[cj]; bj.c1 = cC1[cj]; bj.c2 = cC2[cj]; bj.c3 = cC3[cj]; bj.area = cAr[cj]; bj.at = cAt[cj];
+                cls_j = cCl[cj];
               }
             }
           }
-          uint32_t lo32 = (uint32_t)by, hi32 = (uint32_t)(by >> 32);
-          lo32 |= __shfl_xor_sync(0xffffffffu, lo32, 1); hi32 |= __shfl_xor_sync(0xffffffffu, hi32, 1);
-          lo32 |= __shfl_xor_sync(0xffffffffu, lo32, 2); hi32 |= __shfl_xor_sync(0xffffffffu, hi32, 2);
-          if (q < n_chunk && sub == 0) sBy[q] = ((unsigned long long)hi32 << 32) | lo32;
         }
         NMS_TW(1);
         __syncthreads();
         NMS_TW(2);
         for (int b = tid; b < 256; b += THREADS) {
           const int base = sBase[b], m = sBase[b + 1] - base;
-          if (m < 2 || m > 64) continue;
+          if (m < 2 || m > BUCKET_MAX) continue;
+          const unsigned long long a0 = sSet[b];
           unsigned long long alive = 0ull;
 #pragma unroll 4
-          for (int t = 0; t < m; ++t) {                  // read-only walk: nothing is stored until the set is final
-            const bool a = sAlive[sMem[base + t]] && !(sBy[base + t] & alive);
+          for (int t = 0; t < m; ++t) {
+            const bool a = ((a0 >> t) & 1ull) && !(sBy[base + t] & alive);
             alive |= (unsigned long long)a << t;
           }
-          for (int t = 0; t < m; ++t)
-            if (!((alive >> t) & 1ull)) sAlive[sMem[base + t]] = 0;
+          sSet[b] = alive;
         }
         for (int b = warp; b < 256; b += NW) {   // oversized buckets: a warp per bucket, greedy in rank order, state in sAlive
           const int base = sBase[b], m = sBase[b + 1] - base;
-          if (m <= 64) continue;                         // warp-uniform
+          if (m <= BUCKET_MAX) continue;                 // warp-uniform
           for (int i = 0; i + 1 < m; ++i) {
             const int ci = sMem[base + i];
             if (!sAlive[ci]) continue;                   // warp-uniform
@@ -694,7 +718,12 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
         // (4) emit the survivors in rank order, up to the cap
         for (int c0 = 0; c0 < n_chunk && n_kept < cfg.max_out; c0 += THREADS) {
           const int ct = c0 + tid;
-          const bool a = ct < n_chunk && sAlive[ct];
+          bool a = false;
+          if (ct < n_chunk) {
+            const uint32_t bucket = (uint32_t)cCl[ct] & 255u;
+            const int base = sBase[bucket];
+            a = (sBase[bucket + 1] - base <= BUCKET_MAX) ? ((sSet[bucket] >> ((int)sQ[ct] - base)) & 1ull) != 0ull : sAlive[ct] != 0;
+          }
           const uint32_t bal = __ballot_sync(0xffffffffu, a);
           if (lane == 0) sRed[warp] = (uint32_t)__popc(bal);
           __syncthreads();
