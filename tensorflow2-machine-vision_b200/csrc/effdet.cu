@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) effdet_nms_finalize_kernel(EfF
     pre.keys = p.pre_keys + (size_t)img * NMS_PRE_CAP; pre.pos = p.pre_pos + (size_t)img * NMS_PRE_CAP;
     pre.count = p.pre_count + img; pre.eligible = p.pre_elig + img; pre.khi = p.pre_khi + img;
   }
-  const int kept = nms_run_segment<METRIC>(seg, p.cfg, pos, nms_smem, p.pre_keys ? &pre : nullptr);
+  const int kept = nms_run_segment<METRIC, NmsLoadDirectAgnostic>(seg, p.cfg, pos, nms_smem, p.pre_keys ? &pre : nullptr);
   __syncthreads();
   if (threadIdx.x == 0) p.out_count[img] = kept;
   const size_t obase = (size_t)img * p.cfg.max_out;

@@ -259,9 +259,15 @@ __device__ __forceinline__ void nms_bucket_order(const unsigned long long* keys,
 // it on demand instead (YOLO: only the few hundred candidates NMS actually looks at are ever decoded).
 struct NmsLoadDirect {
   static constexpr bool kKeyCache = false;   // register cache of a small segment's keys (16 registers): opt-in per caller
+  static constexpr int kMode = -1;           // -1: NmsConfig::mode decides at run time; else the caller's only mode (the other
+                                             // mode's code — and its registers — are not compiled into that kernel)
   __device__ __forceinline__ float4 operator()(const NmsSegment& seg, uint32_t pos) const {
     return __ldg(reinterpret_cast<const float4*>(seg.boxes) + pos);
   }
+};
+
+struct NmsLoadDirectAgnostic : NmsLoadDirect {   // callers that only ever run class-agnostic NMS (EfficientDet)
+  static constexpr int kMode = B200_NMS_AGNOSTIC;
 };
 
 // THREADS = CTA size (a multiple of 64, <= NMS_THREADS): 1024 for the lowest per-image latency; 512 lets two CTAs
@@ -272,7 +278,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const int mode = cfg.mode;
+  const int mode = BoxLoad::kMode >= 0 ? BoxLoad::kMode : cfg.mode;
   const float thr = cfg.iou_thr;
 
   unsigned long long* sK = reinterpret_cast<unsigned long long*>(smem_raw);  // [NMS_WINDOW]
@@ -597,8 +603,11 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
         }
         __syncthreads();
         for (int b = tid; b < 256; b += THREADS) {   // per bucket: exclusive prefix over the blocks, total into sBase[b + 1]
-          int run = 0;
-          for (int blk = 0; blk < n_blk; ++blk) { const int t = sTab[blk * 256 + b]; sTab[blk * 256 + b] = (unsigned short)run; run += t; }
+          int t[NMS_CHUNK / 32], run = 0;              // all counts are loaded before the first store (independent loads)
+#pragma unroll
+          for (int blk = 0; blk < NMS_CHUNK / 32; ++blk) t[blk] = (blk < n_blk) ? (int)sTab[blk * 256 + b] : 0;
+#pragma unroll
+          for (int blk = 0; blk < NMS_CHUNK / 32; ++blk) { if (blk < n_blk) sTab[blk * 256 + b] = (unsigned short)run; run += t[blk]; }
           sBase[b + 1] = run;
         }
         __syncthreads();
@@ -683,7 +692,8 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
         NMS_TW(1);
         __syncthreads();
         NMS_TW(2);
-        for (int b = tid; b < 256; b += THREADS) {
+        // (buckets spread over all warps: a warp waits for the largest of its buckets)
+        for (int b = tid / (THREADS / 256); b < 256 && tid % (THREADS / 256) == 0; b += 256) {
           const int base = sBase[b], m = sBase[b + 1] - base;
           if (m < 2 || m > BUCKET_MAX) continue;
           const unsigned long long a0 = sSet[b];

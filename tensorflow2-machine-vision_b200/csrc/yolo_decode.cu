@@ -333,6 +333,7 @@ struct YoloFinalizeParams {
 // written back to the candidate store so that the emitted rows can be copied out afterwards.
 struct YoloLazyBox {
   static constexpr bool kKeyCache = true;   // a 416x416 image has ~5 k candidates: its selection passes run from registers
+  static constexpr int kMode = B200_NMS_BY_CLASS;
   const YoloLevels* lv;
   int img, A, RF;
   float4* cand_box;  // this image's slice

@@ -142,6 +142,27 @@ def test_nms_yolo_family_matches_oracle(lib, cuda, iou_type, case):
     assert got.tolist() == want.tolist()
 
 
+@pytest.mark.parametrize("iou_type", ["iou", "ciou"])
+@pytest.mark.parametrize("n,cluster,max_out", [(900, 60, 500), (2600, 90, 700), (6000, 200, 500)])
+def test_nms_by_class_mixed_bucket_sizes_and_shared_buckets(lib, cuda, iou_type, n, cluster, max_out):
+    """Per-class NMS resolves class buckets (class id & 255) two ways: buckets of up to 64 members from pairwise suppression
+    words, larger ones by a warp loop.  Skewed class frequencies put both kinds — and single-member buckets — into one chunk;
+    class ids 256 apart share a bucket and must not interact."""
+    from oracle import yolo as oy
+    from tfmv_b200.ai_models.utils.tf_iou_utils import GetIOUNMSByClasses
+    rng = np.random.default_rng(77 + n)
+    boxes = _rand_boxes(rng, n, cluster=cluster)
+    scores = rng.random(n, dtype=F)
+    scores[rng.integers(0, n, n // 4)] = F(0.5)   # exact ties
+    ids = np.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 17, 256, 257, 258 + 256, 300, 1 + 512, 40, 41, 42, 43], dtype=np.int32)
+    prob = np.array([30, 20, 10, 5, 3, 2, 2, 2, 2, 2, 1, 6, 5, 2, 1, 4, 1, 1, 0.5, 0.5])
+    classes = ids[rng.choice(len(ids), n, p=prob / prob.sum())].astype(np.int32)
+    want = oy.get_iou_nms_by_classes(boxes, scores, classes, max_out, 0.45, iou_type)
+    got = GetIOUNMSByClasses(_t(boxes, cuda), _t(scores, cuda), _t(classes, cuda), max_out, 0.45, iou_type).cpu().numpy()
+    assert got.tolist() == want.tolist()
+    assert 0 < len(want) <= max_out
+
+
 @pytest.mark.parametrize("iou_type", ["iou", "giou", "diou", "ciou"])
 @pytest.mark.parametrize("n,cluster,max_out,sthr", [(1, 0, 200, None), (300, 30, 200, 0.2), (4000, 300, 200, 1e-4),
                                                       (20000, 0, 200, 1e-4), (2000, 3, 200, -5.0)])
