@@ -192,7 +192,7 @@ class Anchors(object):
       'boxes': torch.empty((n, K, 4), dtype=torch.float32, device=dev),
       'classes_id': torch.empty((n, K), dtype=torch.int64, device=dev),
       'scores': torch.empty((n, K), dtype=torch.float32, device=dev),
-      'count': torch.zeros((n,), dtype=torch.int32, device=dev),
+      'count': torch.empty((n,), dtype=torch.int32, device=dev),   # written for every image by the NMS kernel
     }
     if with_indices:
       out['sel_idx'] = torch.empty((n, K), dtype=torch.int32, device=dev)
@@ -214,7 +214,7 @@ class Anchors(object):
       'boxes': torch.empty((n, K, 4), dtype=torch.float32, device=dev),
       'classes_id': torch.empty((n, K), dtype=torch.int64, device=dev),
       'scores': torch.empty((n, K), dtype=torch.float32, device=dev),
-      'count': torch.zeros((n,), dtype=torch.int32, device=dev),
+      'count': torch.empty((n,), dtype=torch.int32, device=dev),   # written for every image by the NMS kernel
     }
     if with_indices:
       out['sel_idx'] = torch.empty((n, K), dtype=torch.int32, device=dev)

@@ -122,7 +122,7 @@ def GetNMSBoxesBatch(y1, y2, y3, anchors_wh, image_wh, classes_num,
     'classes_id': torch.empty((B, K), dtype=torch.int32, device=dev),
     'scores': torch.empty((B, K), dtype=torch.float32, device=dev),
     'confidence': torch.empty((B, K, 1), dtype=torch.float32, device=dev),
-    'count': torch.zeros((B,), dtype=torch.int32, device=dev),
+    'count': torch.empty((B,), dtype=torch.int32, device=dev),   # written for every image by the NMS kernel
   }
   if with_classes:
     out['classes'] = torch.empty((B, K, C), dtype=torch.float32, device=dev)

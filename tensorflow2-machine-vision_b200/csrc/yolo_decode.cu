@@ -399,6 +399,7 @@ __global__ void __launch_bounds__(THREADS, NMS_THREADS / THREADS) yolo_nms_final
     p.out_score[obase + k] = p.cand_score[cbase + q];
     p.out_conf[obase + k] = dm_sigmoidf(p.cand_conf[cbase + q]);
     const uint32_t a = p.cand_aidx[cbase + q];
+    pos[k] = (int32_t)a;   // from here on the scratch row holds flat anchor indices: yolo_classes_kernel needs no candidate lookup
     if (p.out_sel_anchor) p.out_sel_anchor[obase + k] = (int32_t)a;
     if (p.out_sel_idx && p.bitmap) {
       const uint32_t wv = p.bitmap[(size_t)img * p.bitmap_words + (a >> 5)];
@@ -421,9 +422,9 @@ __global__ void __launch_bounds__(256) yolo_classes_kernel(YoloFinalizeParams p)
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // row = img * max_out + k
   if (row >= p.B * p.cfg.max_out) return;
   const int img = row / p.cfg.max_out, k = row - img * p.cfg.max_out;
-  if (k >= p.out_count[img]) return;
-  const size_t cbase = (size_t)img * p.n_img;
-  const uint32_t a = p.cand_aidx[cbase + p.nms_pos[(size_t)img * p.cfg.max_out + k]];
+  // flat anchor index, left by the NMS kernel; fetched together with the count (rows past the count hold stale values)
+  const uint32_t a = (uint32_t)__ldcg(p.nms_pos + (size_t)img * p.cfg.max_out + k);
+  if (k >= __ldcg(p.out_count + img)) return;
   int l = 0;
 #pragma unroll
   for (int j = 1; j < YD_MAX_LEVELS; ++j) if ((int)a >= p.lv.anchor_base[j]) l = j;
@@ -574,6 +575,8 @@ extern "C" int b200_yolo_decode_nms(const float* const heads[3], const int32_t h
   const uint32_t slab = 128u * (uint32_t)dp.RF;
   int warps = 16;  // one tile in flight per warp; the warps of an SM overlap each other's loads
   while (warps > 1 && (size_t)warps * YD_STAGES * slab + 256 > 200 * 1024) warps >>= 1;
+  // a single image has fewer tiles than the GPU has warp slots: spread them (one warp per scheduler finishes its tile sooner)
+  while (warps > 2 && dp.lv.tile_base[YD_MAX_LEVELS] <= (long long)(warps / 2) * b200_sm_count()) warps >>= 1;
   B200_REQUIRE((size_t)warps * YD_STAGES * slab + 256 <= 220 * 1024, B200_ERR_UNSUPPORTED, "b200_yolo_decode_nms: record too large (C=%d)", C);
   const size_t smem1 = (size_t)warps * YD_STAGES * slab + sizeof(uint64_t) * warps * YD_STAGES + 16;
   B200_CUDA(cudaFuncSetAttribute(yolo_decode_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
