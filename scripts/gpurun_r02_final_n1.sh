@@ -24,7 +24,7 @@ python bench.py --only c5 --c5-global-batch 64 --no-cpu-baseline > gpurun_out/r0
 # ncu --set full of the headline's dominant kernel and of the EfficientDet stream
 A="--only c2 --only-step --no-graph --steps 3 --warmup 3 --repeats 1"
 python bench.py $A > gpurun_out/plain_c2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:yolo_loss_ignore_kernel -s 4 -c 1 -o gpurun_out/r02_prof_ignore_final -f python bench.py $A > gpurun_out/ncu_full_c2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'yolo_loss_ignore_lean_kernel|yolo_loss_scan_kernel|yolo_loss_finalize_kernel|yolo_scatter_targets_kernel|fill_zero_multi' -s 15 -c 5 -o gpurun_out/r02_prof_c2_step -f python bench.py $A > gpurun_out/ncu_full_c2.log 2>&1
 A="--only c3 --only-step --no-graph --steps 3 --warmup 3 --repeats 1 --config-repeats 1"
 python bench.py $A > gpurun_out/plain_c3.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:effdet_stream_kernel -s 3 -c 1 -o gpurun_out/r02_prof_stream_final -f python bench.py $A > gpurun_out/ncu_full_c3.log 2>&1

@@ -237,6 +237,7 @@ struct EfFinalizeParams {
 template <int METRIC>
 __global__ void __launch_bounds__(NMS_THREADS, 1) effdet_nms_finalize_kernel(EfFinalizeParams p) {
   extern __shared__ __align__(16) unsigned char nms_smem[];
+  NMS_T(13);
   const int img = blockIdx.x;
   const size_t cbase = (size_t)img * p.n_img;
   NmsSegment seg;
@@ -253,6 +254,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) effdet_nms_finalize_kernel(EfF
   }
   const int kept = nms_run_segment<METRIC, NmsLoadDirectAgnostic>(seg, p.cfg, pos, nms_smem, p.pre_keys ? &pre : nullptr);
   __syncthreads();
+  NMS_T(11);
   if (threadIdx.x == 0) p.out_count[img] = kept;
   const size_t obase = (size_t)img * p.cfg.max_out;
   uint32_t* wprefix = reinterpret_cast<uint32_t*>(nms_smem);
@@ -282,7 +284,14 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) effdet_nms_finalize_kernel(EfF
       p.out_sel_idx[obase + k] = (int32_t)(wprefix[a >> 5] + __popc(wv & ((1u << (a & 31u)) - 1u)));
     }
   }
+  NMS_T(12);
 }
+
+#ifdef NMS_TRACE
+extern "C" int b200_debug_nms_trace_effdet(long long* out_host64) {
+  return cudaMemcpyFromSymbol(out_host64, g_nms_trace, sizeof(long long) * (64 + 4 * 32)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 // ---- target assignment (anc:91-138) ------------------------------------------------------------------
 struct EfAssignParams {

@@ -33,7 +33,9 @@
 static __device__ long long g_nms_trace[64 + 4 * 32];
 #define NMS_T(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_nms_trace[i] = clock64(); } while (0)
 #define NMS_TW(k) do { if ((threadIdx.x & 31) == 0 && blockIdx.x == 0) g_nms_trace[64 + (k) * 32 + (threadIdx.x >> 5)] = clock64(); } while (0)
+#define NMS_TA(i, t_prev) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long now_ = clock64(); g_nms_trace[i] += now_ - (t_prev); (t_prev) = now_; } } while (0)
 #else
+#define NMS_TA(i, t_prev) do { } while (0)
 #define NMS_T(i) do { } while (0)
 #define NMS_TW(k) do { } while (0)
 #endif
@@ -106,7 +108,13 @@ __device__ __forceinline__ bool nms_suppresses(const BoxT& kept, int kept_cls, c
     if (bm_surely_below(kept, cand, METRIC, thr)) return false;
     return bm_metric(kept, cand, METRIC) >= thr;
   }
+#ifdef NMS_TRACE
+  if (blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&g_nms_trace[30]), 1ull);
+#endif
   if (bm_surely_below(kept, cand, METRIC, thr)) return false;
+#ifdef NMS_TRACE
+  if (blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&g_nms_trace[31]), 1ull);
+#endif
   return !(bm_metric(kept, cand, METRIC) < thr);
 }
 
@@ -135,12 +143,16 @@ __device__ __forceinline__ void nms_bitonic(unsigned long long* sK, uint32_t* sP
 
 #define NMS_BINS 2048
 #define NMS_KC 8   // keys a thread keeps in registers for the selection passes of a small segment
+#ifndef NMS_LOADS
+#define NMS_LOADS 4   // independent loads a thread keeps in flight in a selection pass over a large segment (8: no faster, spills)
+#endif
 
 // bucket of a descending-score key inside [dmin, dmax]: monotone non-decreasing in d (int->float rounding, the
 // multiplication by a positive constant and the truncation all are), so bucket(a) < bucket(b) implies a < b
+// (keys below dmin fall into bucket 0, keys above dmax into the last one: dmin / dmax may be estimates from a sample)
 __device__ __forceinline__ int nms_bin(uint32_t d, uint32_t dmin, float scale) {
-  const int b = (int)((float)(d - dmin) * scale);
-  return b < NMS_BINS - 1 ? b : NMS_BINS - 1;
+  const int b = (int)((float)(d - dmin) * scale);   // the conversion saturates
+  return d <= dmin ? 0 : (b < NMS_BINS - 1 ? b : NMS_BINS - 1);
 }
 __device__ __forceinline__ float nms_bin_scale(uint32_t dmin, uint32_t dmax) {
   return (float)NMS_BINS / ((float)(dmax - dmin) + 1.0f);
@@ -336,7 +348,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
       if (e == 0) { exhausted = true; break; }
       if (c >= 1 && c <= NMS_PRE_CAP) { use_pre = true; src_n = c; }
     }
-    // one sweep over the source: body(i, K) for every eligible key that is left; four independent loads in flight per
+    // one sweep over the source: body(i, K) for every eligible key that is left; NMS_LOADS independent loads in flight per
     // thread (a plain strided loop serialises on the L2 latency: 48 dependent round trips per pass at 49 k candidates)
     // A segment of at most NMS_KC keys per thread is read ONCE: the keys stay in registers for the range, histogram and
     // gather passes (three L2 / L1 round trips per pass otherwise — at 5 k candidates the passes are pure latency).
@@ -365,60 +377,81 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
         for (int u = 0; u < NMS_KC; ++u) if ((kc_ok >> u) & 1u) body(tid + u * THREADS, Kc[u]);
         return;
       }
-      for (int i0 = tid; i0 < src_n; i0 += 4 * THREADS) {
-        unsigned long long K[4];
-        bool ok[4];
+      for (int i0 = tid; i0 < src_n; i0 += NMS_LOADS * THREADS) {
+        unsigned long long K[NMS_LOADS];
+        bool ok[NMS_LOADS];
         if (use_pre) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < NMS_LOADS; ++u) {
             const int i = i0 + u * THREADS;
             ok[u] = i < src_n;
             K[u] = ok[u] ? pre->keys[i] : 0ull;
           }
         } else {
-          float sv[4];
-          uint32_t ov[4];
+          float sv[NMS_LOADS];
+          uint32_t ov[NMS_LOADS];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < NMS_LOADS; ++u) {
             const int i = i0 + u * THREADS;
             sv[u] = (i < src_n) ? seg.scores[i] : 0.0f;
             ov[u] = (i < src_n && seg.order_id) ? seg.order_id[i] : (uint32_t)i;
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < NMS_LOADS; ++u) {
             const int i = i0 + u * THREADS;
             K[u] = ((unsigned long long)nms_dkey(sv[u]) << 32) | ov[u];
             ok[u] = (i < src_n) && !(cfg.use_score_thr && (sv[u] < cfg.score_thr)) && (K[u] >= klo);
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) if (ok[u]) body(i0 + u * THREADS, K[u]);
+        for (int u = 0; u < NMS_LOADS; ++u) if (ok[u]) body(i0 + u * THREADS, K[u]);
       }
     };
     bool win_range = false;           // range of the gathered window's keys, known from the selection passes
     uint32_t win_mn = 0u, win_mx = 0u;
     {
-      // G1: range and number of the eligible keys that are left
+      // G1: range and number of the eligible keys that are left.  A large source is only SAMPLED for its range (one key per
+      // thread): the buckets stay monotone whatever the bounds are (nms_bin clamps), so the cut below is still exact — keys
+      // better than the best sample merely share bucket 0 — and the count comes out of the histogram pass.  One full pass
+      // over the scores less (12 of the 35 us the three passes cost at 49 k candidates).
       uint32_t dmin = 0xffffffffu, dmax = 0u;
       int n_el = 0;
-      for_each_key([&](int, unsigned long long K) {
-        const uint32_t d = (uint32_t)(K >> 32);
-        ++n_el; dmin = min(dmin, d); dmax = max(dmax, d);
-      });
-      nms_block_minmaxsum<THREADS>(dmin, dmax, n_el, sRed);
+      bool sampled = !small_seg && src_n > 2 * NMS_WINDOW;
+      if (sampled) {
+        const int i = (int)(((long long)tid * src_n) / THREADS);
+        unsigned long long K;
+        bool ok;
+        if (use_pre) { K = pre->keys[i]; ok = true; }
+        else {
+          const float sv = seg.scores[i];
+          K = ((unsigned long long)nms_dkey(sv) << 32) | (seg.order_id ? seg.order_id[i] : (uint32_t)i);
+          ok = !(cfg.use_score_thr && (sv < cfg.score_thr)) && (K >= klo);
+        }
+        if (ok) { n_el = 1; dmin = dmax = (uint32_t)(K >> 32); }
+        nms_block_minmaxsum<THREADS>(dmin, dmax, n_el, sRed);
+        if (n_el < 16) { sampled = false; dmin = 0xffffffffu; dmax = 0u; n_el = 0; }   // too few eligible samples: count properly
+      }
+      if (!sampled) {
+        for_each_key([&](int, unsigned long long K) {
+          const uint32_t d = (uint32_t)(K >> 32);
+          ++n_el; dmin = min(dmin, d); dmax = max(dmax, d);
+        });
+        nms_block_minmaxsum<THREADS>(dmin, dmax, n_el, sRed);
+        if (n_el == 0) { exhausted = true; break; }
+      }
       NMS_T(1);
-      if (n_el == 0) { exhausted = true; break; }
       const float scale = nms_bin_scale(dmin, dmax);
       int cut = NMS_BINS - 1;
-      if (n_el > NMS_WINDOW) {
+      if (sampled || n_el > NMS_WINDOW) {
         // G2: histogram of the buckets; G3: the bucket where the cumulative count reaches the target
         for (int b = tid; b < NMS_BINS; b += THREADS) sBins[b] = 0;
         __syncthreads();
         for_each_key([&](int, unsigned long long K) { atomicAdd(&sBins[nms_bin((uint32_t)(K >> 32), dmin, scale)], 1); });
         __syncthreads();
         NMS_T(2);
-        nms_block_scan_bins<THREADS>(sBins, sRed, target, &sScalar[3]);
+        const int total = nms_block_scan_bins<THREADS>(sBins, sRed, target, &sScalar[3]);
         NMS_T(3);
+        if (sampled) n_el = total;      // (>= 16: the samples are among them)
         cut = sScalar[3];
         const int upto = (cut + 1 < NMS_BINS) ? sBins[cut + 1] : n_el;   // keys in buckets 0..cut
         fallback = upto > NMS_WINDOW;   // one bucket alone overflows the window (masses of near-equal scores)
@@ -444,7 +477,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
         n_win = sScalar[0];
         NMS_T(4);
         gathered = true;
-        win_range = true; win_mn = dmin; win_mx = dmax;
+        win_range = !sampled; win_mn = dmin; win_mx = dmax;   // (a sampled range would pile the best keys into one ordering bucket)
         if (cut < NMS_BINS - 1) {       // keys of buckets 0..cut lie below dmin + (cut + 1) / scale (an estimate is enough)
           const float lim = (float)(cut + 1) / scale;
           if (lim < (float)(dmax - dmin)) win_mx = dmin + (uint32_t)lim + 1u;
@@ -756,8 +789,18 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
         continue;
       }
       const int n_tiles = (n_chunk + 63) >> 6;
+#ifdef NMS_TRACE
+      if (tid == 0 && blockIdx.x == 0) g_nms_trace[21] = 0;
+#endif
       for (int T = 0; T < n_tiles && n_kept < cfg.max_out; ++T) {
+#ifdef NMS_TRACE
+        if (tid == 0 && blockIdx.x == 0) g_nms_trace[21] += 1;   // tiles consumed
+#endif
         const int t0 = T << 6;
+#ifdef NMS_TRACE
+        long long t_ph = clock64();
+        if (tid == 0 && blockIdx.x == 0 && T == 0) { g_nms_trace[24] = g_nms_trace[25] = g_nms_trace[26] = g_nms_trace[27] = 0; }
+#endif
         // phase 1: tile candidates vs the kept list.  warp w: candidates 32*(w&1)..+31, kept indices (w>>1) + (THREADS/64) j
         {
           const int c = ((warp & 1) << 5) + lane;
@@ -788,6 +831,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
         __syncthreads();
         unsigned long long tile_alive = ~((unsigned long long)sSupp[0] | ((unsigned long long)sSupp[1] << 32));
         if (n_chunk - t0 < 64) tile_alive &= (1ull << (n_chunk - t0)) - 1ull;
+        NMS_TA(24, t_ph);
         // phase 2: intra-tile mask via ballots: warp w owns rows (2048/THREADS) w ... (2 rows at 1024 threads)
 #pragma unroll
         for (int rr = 0; rr < 2048 / THREADS; ++rr) {
@@ -815,32 +859,44 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
           if (lane == 0) sMask[r] = (unsigned long long)bits[0] | ((unsigned long long)bits[1] << 32);
         }
         __syncthreads();
-        // one-warp sweep
+        NMS_TA(25, t_ph);
+        // one-warp sweep.  lane <-> columns lane and lane + 32: the warp first transposes the 64 x 64 bit matrix (64 broadcast
+        // reads; by = the better-ranked rows that suppress the column), then iterates  kept' = alive & ~any(by & kept)  from
+        // kept = alive until nothing changes.  The greedy solution is the unique fixed point and position j is final after
+        // j + 1 rounds at the latest — in practice after the length of the longest suppression chain (2-4 rounds), where a
+        // single thread walking the kept rows paid one dependent shared-memory read per emitted box (1.8 us per tile).
         if (warp == 0) {
           const unsigned long long m0 = ((tile_alive >> lane) & 1ull) ? (sMask[lane] & tile_alive) : 0ull;
           const unsigned long long m1 = ((tile_alive >> (lane + 32)) & 1ull) ? (sMask[lane + 32] & tile_alive) : 0ull;
           const bool any = __any_sync(0xffffffffu, (m0 | m1) != 0ull);
           unsigned long long keptmask = tile_alive;
           const int room = cfg.max_out - n_kept;
+          if (any) {
+            uint32_t by0_lo = 0u, by0_hi = 0u, by1_lo = 0u, by1_hi = 0u;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const unsigned long long ra = sMask[i], rb = sMask[i + 32];   // rows of dead candidates are all zero (phase 2)
+              by0_lo |= (((uint32_t)ra >> lane) & 1u) << i;
+              by1_lo |= (((uint32_t)(ra >> 32) >> lane) & 1u) << i;
+              by0_hi |= (((uint32_t)rb >> lane) & 1u) << i;
+              by1_hi |= (((uint32_t)(rb >> 32) >> lane) & 1u) << i;
+            }
+            const unsigned long long by0 = ((unsigned long long)by0_hi << 32) | by0_lo, by1 = ((unsigned long long)by1_hi << 32) | by1_lo;
+            const bool a0 = (tile_alive >> lane) & 1ull, a1 = (tile_alive >> (lane + 32)) & 1ull;
+            for (;;) {
+              const uint32_t k0 = __ballot_sync(0xffffffffu, a0 && !(by0 & keptmask));
+              const uint32_t k1 = __ballot_sync(0xffffffffu, a1 && !(by1 & keptmask));
+              const unsigned long long next = ((unsigned long long)k1 << 32) | k0;
+              if (next == keptmask) break;
+              keptmask = next;
+            }
+          }
           if (lane == 0) {
-            if (any) {
-              unsigned long long rem = tile_alive;
-              keptmask = 0ull;
-              int nk = 0;
-              while (rem && nk < room) {
-                const int i = __ffsll((long long)rem) - 1;
-                keptmask |= (1ull << i);
-                ++nk;
-                rem &= ~(1ull << i);
-                rem &= ~sMask[i];
-              }
-            } else {
-              int nk = __popcll(keptmask);
-              while (nk > room) {  // keep only the first `room` alive candidates
-                const int hi = 63 - __clzll((long long)keptmask);
-                keptmask &= ~(1ull << hi);
-                --nk;
-              }
+            int nk = __popcll(keptmask);
+            while (nk > room) {  // keep only the first `room` of them
+              const int hi = 63 - __clzll((long long)keptmask);
+              keptmask &= ~(1ull << hi);
+              --nk;
             }
             *sKeptMask = keptmask;
             sScalar[2] = __popcll(keptmask);
@@ -850,6 +906,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
         __syncthreads();
         const unsigned long long keptmask = *sKeptMask;
         const int nk = sScalar[2];
+        NMS_TA(26, t_ph);
         // emit: append to the kept list
         if (tid < 64 && ((keptmask >> tid) & 1ull)) {
           const int gi = t0 + tid;
@@ -860,10 +917,15 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
           if (mode == B200_NMS_BY_CLASS) kNext[slot] = atomicExch(&sHead[(uint32_t)cCl[gi] & 255u], slot);
         }
         n_kept += nk;
+        NMS_TA(27, t_ph);
         __syncthreads();
       }
       __syncthreads();
+      NMS_T(20);
     }
+#ifdef NMS_TRACE
+    if (tid == 0 && blockIdx.x == 0) g_nms_trace[22] += 1;   // windows
+#endif
     if (khi == ~0ull) exhausted = true;
     klo = khi;
     __syncthreads();

@@ -2,7 +2,7 @@
 // Yolov4Loss.call (losses/yolo_loss.py:85-159).
 //
 // The reference materialises ~20 (H,W,A,n_gt) broadcast temporaries per image inside a tf.while_loop; here
-// the loss is four launches over the dense NHWC tensors, touching only the sectors the arithmetic needs:
+// the loss is three to four launches over the dense NHWC tensors, touching only the sectors the arithmetic needs:
 //
 //  K4a yolo_loss_scan_kernel     one CTA per 1024 consecutive anchor records of one (level, image): reads the obj
 //      channel of y_true (one 32-byte sector per 340-byte record), stores it to a compact per-anchor array and appends
@@ -14,6 +14,11 @@
 //      the exact decode (tyu:57-75) and exact metric (iou / diou / ciou, tiu:5-65), and accumulates
 //      object_loss = obj*bce + (1-obj)*bce*ignore (tyu:111-114).  The trailing CTAs of its grid instead take a warp per
 //      object and produce the xy, wh and class terms (tyu:107-118) from the full y_true / y_pred records.
+//      Default (device-resident, 16-byte aligned y_pred, records of >= 8 floats): the pass is SPLIT.  K4b-lean
+//      (yolo_loss_ignore_lean_kernel, 48 registers, 10 CTAs per SM) streams, applies the rejects and only QUEUES the records
+//      that some GT might still hit (~1 % of them); K4b-exact resolves the queue (a warp per record) at the head of the
+//      widened K4c launch, its object-loss terms in 2^-32 fixed point so that the sum does not depend on the order.
+//      The launches of a dense call are then K4a (whose last CTA per (image, level) also does K4a'), K4b-lean, K4c.
 //  K4c yolo_loss_finalize_kernel  fixed-order fp64 reduction of the per-CTA partials -> parts[3][4] / batch,
 //      loss = sum_l ((xy+wh)+obj)+cls in fp32 in the reference's order (tyu:120-125).  Deterministic run to run (the object lists are
 //      put into ascending record order by K4a' before anything is summed over them).
