@@ -417,9 +417,14 @@ extern "C" int b200_debug_nms_trace(long long* out_host64) {
 
 // sigmoid(classes) rows of the selected boxes, read back from the head tensors (tyu:140,265).  A separate launch
 // so the B*max_out*C sigmoids spread over the whole GPU instead of serialising inside the per-image NMS CTAs.
+// LPR lanes per row: the kernel is bound by the issue of the deterministic sigmoid (~60 instructions), so the lanes that
+// idle in a row's last round are the cost — 80 classes on 32 lanes waste one round in six, on 16 lanes (two rows per
+// warp) none.
+template <int LPR>
 __global__ void __launch_bounds__(256) yolo_classes_kernel(YoloFinalizeParams p) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // row = img * max_out + k
+  constexpr int RPW = 32 / LPR, NJ = 128 / LPR;
+  const int sub = threadIdx.x & (LPR - 1);
+  const int row = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + ((threadIdx.x & 31) / LPR);  // row = img * max_out + k
   if (row >= p.B * p.cfg.max_out) return;
   const int img = row / p.cfg.max_out, k = row - img * p.cfg.max_out;
   // flat anchor index, left by the NMS kernel; fetched together with the count (rows past the count hold stale values)
@@ -432,12 +437,12 @@ __global__ void __launch_bounds__(256) yolo_classes_kernel(YoloFinalizeParams p)
   const float* src = p.lv.head[l] + rec * p.RF + 5;
   float* dst = p.out_classes + (size_t)row * p.C;
   // the (cold) logits of up to 128 classes are fetched before the first sigmoid starts
-  float x[4];
+  float x[NJ];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) x[j] = (lane + 32 * j < p.C) ? __ldg(src + lane + 32 * j) : 0.0f;
+  for (int j = 0; j < NJ; ++j) x[j] = (sub + LPR * j < p.C) ? __ldg(src + sub + LPR * j) : 0.0f;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) if (lane + 32 * j < p.C) dst[lane + 32 * j] = dm_sigmoidf(x[j]);
-  for (int c = lane + 128; c < p.C; c += 32) dst[c] = dm_sigmoidf(__ldg(src + c));
+  for (int j = 0; j < NJ; ++j) if (sub + LPR * j < p.C) dst[sub + LPR * j] = dm_sigmoidf(x[j]);
+  for (int c = sub + 128; c < p.C; c += LPR) dst[c] = dm_sigmoidf(__ldg(src + c));
 }
 
 // ---- dense decode for the stand-alone GetBoxes shim ---------------------------------------------
@@ -615,7 +620,9 @@ extern "C" int b200_yolo_decode_nms(const float* const heads[3], const int32_t h
   B200_LAUNCH_CHECK();
   if (out_classes) {
     const long long rows = (long long)B * max_out;
-    yolo_classes_kernel<<<(int)((rows + 7) / 8), 256, 0, stream>>>(fp);
+    // half a warp per row when that leaves fewer idle lanes in the last round (80 classes: 5 x 16 against 3 x 32)
+    if (((C + 15) / 16) * 16 < ((C + 31) / 32) * 32) yolo_classes_kernel<16><<<(int)((rows + 15) / 16), 256, 0, stream>>>(fp);
+    else yolo_classes_kernel<32><<<(int)((rows + 7) / 8), 256, 0, stream>>>(fp);
     B200_LAUNCH_CHECK();
   }
   return B200_OK;
