@@ -49,6 +49,7 @@ struct YoloDecodeParams {
   int32_t* counts;     // [B]
   uint32_t* bitmap;    // [B, bitmap_words] or nullptr
   int bitmap_words;
+  int early_issue;     // refill a warp's slab before its append (atomic + stores) instead of after it
 };
 
 // ---- mbarrier / bulk-copy PTX -----------------------------------------------------------------
@@ -290,6 +291,13 @@ __global__ void __launch_bounds__(512, 1) yolo_decode_filter_kernel(YoloDecodePa
         aidx = (uint32_t)(p.lv.anchor_base[l] + rin);
       }
     }
+    // Every lane is done reading the slab: refill it NOW, so that the copy of the next tile is in flight during the append
+    // below (an atomic round trip to L2 plus the stores — 9 % of the warp's cycle when the copy was issued after it).
+    if (p.early_issue) {
+      __syncwarp();
+      if (t_issue < n_tiles) issue(t_issue, stage);
+      t_issue += gstride;
+    }
     // warp-aggregated append, one atomic per (warp, image)
     uint32_t todo = __ballot_sync(0xffffffffu, pass);
     while (todo) {
@@ -309,9 +317,11 @@ __global__ void __launch_bounds__(512, 1) yolo_decode_filter_kernel(YoloDecodePa
       }
       todo &= ~grp;
     }
-    __syncwarp();  // every lane is done reading the slab before it is refilled
-    if (t_issue < n_tiles) issue(t_issue, stage);
-    t_issue += gstride;
+    if (!p.early_issue) {
+      __syncwarp();  // every lane is done reading the slab before it is refilled
+      if (t_issue < n_tiles) issue(t_issue, stage);
+      t_issue += gstride;
+    }
     if (++stage == YD_STAGES) { stage = 0; phase ^= 1u; }
   }
 }
@@ -589,6 +599,11 @@ extern "C" int b200_yolo_decode_nms(const float* const heads[3], const int32_t h
   long long want = (n_tiles + warps - 1) / warps;
   int grid = (int)(want < (long long)b200_sm_count() ? want : (long long)b200_sm_count());
   if (grid < 1) grid = 1;
+  // Refilling a warp's slab before its append keeps one more copy in flight: -3 % for the call on its own at any size, and
+  // for the fused evaluation step at 512 images; at 64 images per GPU the same step is 3 % SLOWER with it (the filter then
+  // takes DRAM bandwidth from the loss chain that shares the GPU, and that chain is the longer one there).  Long streams
+  // (>= 32 tiles per warp) refill early, short ones late; B200_YD_EARLY_ISSUE=0/1 overrides (measurements only).
+  { const char* e = getenv("B200_YD_EARLY_ISSUE"); dp.early_issue = e ? atoi(e) : (n_tiles >= 32ll * grid * warps ? 1 : 0); }
   yolo_decode_filter_kernel<<<grid, warps * 32, smem1, stream>>>(dp);
   B200_LAUNCH_CHECK();
 
