@@ -167,21 +167,28 @@ __global__ void __launch_bounds__(256, 1) effdet_filter_kernel(EfFilterParams p)
     float score = 0.f;
     uint32_t aidx = 0;
     float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool fused_decode = p.rel[l] != nullptr;   // block-uniform
+    int rin = 0, mi = 0;
+    long long grec = 0;
+    float m = 0.f;
+    float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (lane < nrec) {
       const long long rec = rec0 + lane;
       const int api = p.lv.anc_per_img[l];
       const long long total = (long long)p.NB * api;
-      int rin;
       if (total < 0x7fffffffLL) { img = (int)((uint32_t)rec / (uint32_t)api); rin = (int)((uint32_t)rec - (uint32_t)img * (uint32_t)api); }
       else { img = (int)(rec / api); rin = (int)(rec - (long long)img * api); }
-      const long long grec = (long long)(p.B0 + img) * api + rin;
-      const bool fused_decode = p.rel[l] != nullptr;   // block-uniform
-      float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      grec = (long long)(p.B0 + img) * api + rin;
       if (fused_decode) r4 = __ldcs(p.rel[l] + grec);   // issued before the class scan: coalesced, 16 bytes per lane
       // tf.math.argmax: first maximal index; reduce_max: the maximum (anc:172-174)
-      float m = r[0];
-      int mi = 0;
+      m = r[0];
       for (int c = 1; c < C; ++c) { const float v = r[c]; if (v > m) { m = v; mi = c; } }
+    }
+    // the class scan was the last read of the slab: its refill is in flight during the decode and the append below
+    __syncwarp();
+    if (t_issue < n_tiles) issue(t_issue, stage);
+    t_issue += gstride;
+    if (lane < nrec) {
       if (fused_decode) {
         // convert_outputs_boxes (_boxes_decoder, anc:245-274) for every anchor: the dense decoded tensor is an output
         int y, x, an_i;
@@ -216,9 +223,6 @@ __global__ void __launch_bounds__(256, 1) effdet_filter_kernel(EfFilterParams p)
       }
       todo &= ~grp;
     }
-    __syncwarp();
-    if (t_issue < n_tiles) issue(t_issue, stage);
-    t_issue += gstride;
     if (++stage == EF_STAGES) { stage = 0; phase ^= 1u; }
   }
 }
