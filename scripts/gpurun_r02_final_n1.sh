@@ -29,3 +29,12 @@ A="--only c3 --only-step --no-graph --steps 3 --warmup 3 --repeats 1 --config-re
 python bench.py $A > gpurun_out/plain_c3.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:effdet_stream_kernel -s 3 -c 1 -o gpurun_out/r02_prof_stream_final -f python bench.py $A > gpurun_out/ncu_full_c3.log 2>&1
 echo done
+A="--only c4 --only-step --no-graph --steps 3 --warmup 3 --repeats 1 --config-repeats 1"
+python bench.py $A > gpurun_out/plain_c4.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'effdet_filter_kernel|effdet_nms_finalize_kernel' -s 6 -c 2 -o gpurun_out/r02_prof_c4_final -f python bench.py $A > gpurun_out/ncu_full_c4.log 2>&1
+A="--only c1 --only-step --no-graph --steps 3 --warmup 3 --repeats 1 --config-repeats 1"
+python bench.py $A > gpurun_out/plain_c1.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'yolo_nms_finalize_kernel|yolo_decode_filter_kernel|yolo_classes_kernel' -s 9 -c 3 -o gpurun_out/r02_prof_c1_final -f python bench.py $A > gpurun_out/ncu_full_c1.log 2>&1
+python scripts/run_one.py c1_b1 6 > gpurun_out/plain_c1b1.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'yolo_nms_finalize_kernel' -s 3 -c 1 -o gpurun_out/r02_prof_c1b1_final -f python scripts/run_one.py c1_b1 6 > gpurun_out/ncu_full_c1b1.log 2>&1
+echo done2

@@ -273,6 +273,9 @@ struct NmsLoadDirect {
   static constexpr bool kKeyCache = false;   // register cache of a small segment's keys (16 registers): opt-in per caller
   static constexpr int kMode = -1;           // -1: NmsConfig::mode decides at run time; else the caller's only mode (the other
                                              // mode's code — and its registers — are not compiled into that kernel)
+  static constexpr bool kSampleRange = true; // large segments: bucket range from a sample instead of a full pass (compiled out for
+                                             // the YOLO kernels: their segments are small, and the mere presence of the path cost
+                                             // the single-image kernel 2.6 us, measured)
   __device__ __forceinline__ float4 operator()(const NmsSegment& seg, uint32_t pos) const {
     return __ldg(reinterpret_cast<const float4*>(seg.boxes) + pos);
   }
@@ -416,7 +419,7 @@ static __device__ int nms_run_segment(const NmsSegment& seg, const NmsConfig& cf
       // over the scores less (12 of the 35 us the three passes cost at 49 k candidates).
       uint32_t dmin = 0xffffffffu, dmax = 0u;
       int n_el = 0;
-      bool sampled = !small_seg && src_n > 2 * NMS_WINDOW;
+      bool sampled = BoxLoad::kSampleRange && !small_seg && src_n > 2 * NMS_WINDOW;
       if (sampled) {
         const int i = (int)(((long long)tid * src_n) / THREADS);
         unsigned long long K;

@@ -195,6 +195,7 @@ __device__ __forceinline__ Decoded decode_box(float tx, float ty, float tw, floa
   return d;
 }
 
+template <bool EARLY>   // EARLY: a warp refills its slab before its append (atomic + stores) instead of after it
 __global__ void __launch_bounds__(512, 1) yolo_decode_filter_kernel(YoloDecodeParams p) {
   extern __shared__ __align__(128) unsigned char yd_smem[];
   const int lane = threadIdx.x & 31;
@@ -293,7 +294,7 @@ __global__ void __launch_bounds__(512, 1) yolo_decode_filter_kernel(YoloDecodePa
     }
     // Every lane is done reading the slab: refill it NOW, so that the copy of the next tile is in flight during the append
     // below (an atomic round trip to L2 plus the stores — 9 % of the warp's cycle when the copy was issued after it).
-    if (p.early_issue) {
+    if (EARLY) {
       __syncwarp();
       if (t_issue < n_tiles) issue(t_issue, stage);
       t_issue += gstride;
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(512, 1) yolo_decode_filter_kernel(YoloDecodePa
       }
       todo &= ~grp;
     }
-    if (!p.early_issue) {
+    if (!EARLY) {
       __syncwarp();  // every lane is done reading the slab before it is refilled
       if (t_issue < n_tiles) issue(t_issue, stage);
       t_issue += gstride;
@@ -344,6 +345,7 @@ struct YoloFinalizeParams {
 struct YoloLazyBox {
   static constexpr bool kKeyCache = true;   // a 416x416 image has ~5 k candidates: its selection passes run from registers
   static constexpr int kMode = B200_NMS_BY_CLASS;
+  static constexpr bool kSampleRange = false;
   const YoloLevels* lv;
   int img, A, RF;
   float4* cand_box;  // this image's slice
@@ -594,7 +596,7 @@ extern "C" int b200_yolo_decode_nms(const float* const heads[3], const int32_t h
   while (warps > 2 && dp.lv.tile_base[YD_MAX_LEVELS] <= (long long)(warps / 2) * b200_sm_count()) warps >>= 1;
   B200_REQUIRE((size_t)warps * YD_STAGES * slab + 256 <= 220 * 1024, B200_ERR_UNSUPPORTED, "b200_yolo_decode_nms: record too large (C=%d)", C);
   const size_t smem1 = (size_t)warps * YD_STAGES * slab + sizeof(uint64_t) * warps * YD_STAGES + 16;
-  B200_CUDA(cudaFuncSetAttribute(yolo_decode_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+
   const long long n_tiles = dp.lv.tile_base[YD_MAX_LEVELS];
   long long want = (n_tiles + warps - 1) / warps;
   int grid = (int)(want < (long long)b200_sm_count() ? want : (long long)b200_sm_count());
@@ -604,7 +606,13 @@ extern "C" int b200_yolo_decode_nms(const float* const heads[3], const int32_t h
   // takes DRAM bandwidth from the loss chain that shares the GPU, and that chain is the longer one there).  Long streams
   // (>= 32 tiles per warp) refill early, short ones late; B200_YD_EARLY_ISSUE=0/1 overrides (measurements only).
   { const char* e = getenv("B200_YD_EARLY_ISSUE"); dp.early_issue = e ? atoi(e) : (n_tiles >= 32ll * grid * warps ? 1 : 0); }
-  yolo_decode_filter_kernel<<<grid, warps * 32, smem1, stream>>>(dp);
+  if (dp.early_issue) {
+    B200_CUDA(cudaFuncSetAttribute(yolo_decode_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    yolo_decode_filter_kernel<true><<<grid, warps * 32, smem1, stream>>>(dp);
+  } else {
+    B200_CUDA(cudaFuncSetAttribute(yolo_decode_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    yolo_decode_filter_kernel<false><<<grid, warps * 32, smem1, stream>>>(dp);
+  }
   B200_LAUNCH_CHECK();
 
   YoloFinalizeParams fp;
@@ -636,7 +644,8 @@ extern "C" int b200_yolo_decode_nms(const float* const heads[3], const int32_t h
   if (out_classes) {
     const long long rows = (long long)B * max_out;
     // half a warp per row when that leaves fewer idle lanes in the last round (80 classes: 5 x 16 against 3 x 32)
-    if (((C + 15) / 16) * 16 < ((C + 31) / 32) * 32) yolo_classes_kernel<16><<<(int)((rows + 15) / 16), 256, 0, stream>>>(fp);
+    // (a few hundred rows are latency-bound: a full warp per row has the shorter chain)
+    if (rows >= 16384 && ((C + 15) / 16) * 16 < ((C + 31) / 32) * 32) yolo_classes_kernel<16><<<(int)((rows + 15) / 16), 256, 0, stream>>>(fp);
     else yolo_classes_kernel<32><<<(int)((rows + 7) / 8), 256, 0, stream>>>(fp);
     B200_LAUNCH_CHECK();
   }
