@@ -1,6 +1,6 @@
 """Randomised campaign for GetNMSBoxes (run by hand on a GPU box; not collected by pytest).
 
-    python tests/stress/decode_nms_campaign.py [cases] [first_seed]
+    python tests/stress/decode_nms_campaign.py [cases] [first_seed] [seconds]
 
 Random image sizes, batch sizes, thresholds and metrics; logits of several spreads (saturating sigmoids, exp overflow
 -> box dropped), conf logits planted right around logit(conf_thr), class logits with near-ties inside and outside the
@@ -66,15 +66,21 @@ def main():
     import torch
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     first = int(sys.argv[2]) if len(sys.argv) > 2 else 5000
+    budget = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0   # optional wall-clock budget in seconds
+    import time
+    t_start, done = time.time(), 0
     dev = torch.device("cuda:0")
     bad = emitted = 0
     for seed in range(first, first + n):
+        if budget and time.time() - t_start > budget:
+            break
+        done += 1
         try:
             emitted += one_case(seed, dev)
         except AssertionError as e:
             bad += 1
             print("MISMATCH seed %d: %s" % (seed, str(e)[:200]), flush=True)
-    print("cases %d  emitted boxes %d  failing cases %d" % (n, emitted, bad))
+    print("cases %d  emitted boxes %d  failing cases %d" % (done, emitted, bad))
     return 1 if bad else 0
 
 

@@ -1,6 +1,6 @@
 """Randomised campaign for the EfficientDet utilities (run by hand on a GPU box; not collected by pytest).
 
-    python tests/stress/effdet_campaign.py [cases] [first_seed]
+    python tests/stress/effdet_campaign.py [cases] [first_seed] [seconds]
 
 Random anchor configurations (levels, scales, aspect ratios, image sizes incl. rectangular), batch sizes and class
 counts.  Post-processing: logits with exact ties between anchors, ties across classes, planted duplicates (heavy
@@ -100,15 +100,21 @@ def main():
     import torch
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 100
     first = int(sys.argv[2]) if len(sys.argv) > 2 else 12000
+    budget = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0   # optional wall-clock budget in seconds
+    import time
+    t_start, done = time.time(), 0
     dev = torch.device("cuda:0")
     bad = emitted = 0
     for seed in range(first, first + n):
+        if budget and time.time() - t_start > budget:
+            break
+        done += 1
         try:
             emitted += one_case(seed, dev)
         except AssertionError as e:
             bad += 1
             print("MISMATCH seed %d: %s" % (seed, str(e)[:200]), flush=True)
-    print("cases %d  emitted boxes %d  failing cases %d" % (n, emitted, bad))
+    print("cases %d  emitted boxes %d  failing cases %d" % (done, emitted, bad))
     return 1 if bad else 0
 
 

@@ -1,6 +1,6 @@
 """Randomised campaign for the ignore mask of GetLoss (run by hand on a GPU box; not collected by pytest).
 
-    python tests/stress/ignore_mask_campaign.py [cases] [first_seed]
+    python tests/stress/ignore_mask_campaign.py [cases] [first_seed] [seconds]
 
 Every case draws an image size, a threshold >= 0.5 (the regime of the decode-free and approximate-IoU rejects,
 DESIGN.md §6), a metric, a logit spread and a ground-truth set that includes very small boxes, plants predictions
@@ -72,16 +72,22 @@ def main():
     import torch
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     first = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+    budget = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0   # optional wall-clock budget in seconds
+    import time
+    t_start, done = time.time(), 0
     dev = torch.device("cuda:0")
     total_bad = zeros = planted = 0
     for seed in range(first, first + n):
+        if budget and time.time() - t_start > budget:
+            break
+        done += 1
         bad, z, pl, cfg = one_case(seed, dev)
         total_bad += bad
         zeros += z
         planted += pl
         if bad:
             print("MISMATCH seed %d: %d bits, case %r" % (seed, bad, cfg), flush=True)
-    print("cases %d  planted predictions %d  ignore-mask zeros %d  mismatching bits %d" % (n, planted, zeros, total_bad))
+    print("cases %d  planted predictions %d  ignore-mask zeros %d  mismatching bits %d" % (done, planted, zeros, total_bad))
     return 1 if total_bad else 0
 
 
