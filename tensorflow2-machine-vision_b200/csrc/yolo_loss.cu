@@ -721,12 +721,17 @@ __global__ void __launch_bounds__(YL_ICHUNK, MINB) yolo_loss_ignore_lean_kernel(
   }
 }
 
-// the exact pass over the queued records: a warp per record, `gwarp` of `nwarps` warps
+// the exact pass over the queued records: HALF a warp per record (two records in flight per warp: the pass is a chain of
+// dependent loads per record — queue entry, record, GT list — so it is bound by how many records are in flight, not by
+// lanes: an (image, level) has ~17 GTs on average, one or two rounds of 16), `gwarp` of `nwarps` warps
 __device__ __forceinline__ void yl_exact_pass(const YlParams& p, unsigned int gwarp, unsigned int nwarps) {
   const int lane = threadIdx.x & 31;
+  const int half = lane >> 4, sub = lane & 15;
   const unsigned int n = *p.pend_count;
-  for (unsigned int q = gwarp; q < n; q += nwarps) {
-    const uint32_t id = p.pend_queue[q];
+  for (unsigned int q0 = gwarp * 2u; q0 < n; q0 += nwarps * 2u) {   // warp-uniform trip count
+    const unsigned int q = q0 + (unsigned int)half;
+    const bool valid = q < n;
+    const uint32_t id = valid ? p.pend_queue[q] : 0u;
     const int img = (int)(id / (uint32_t)p.n_img);
     const int ain = (int)(id - (uint32_t)img * (uint32_t)p.n_img);
     int l = 0;
@@ -739,21 +744,24 @@ __device__ __forceinline__ void yl_exact_pass(const YlParams& p, unsigned int gw
     float obj;
     if (p.obj_bits) obj = ((__ldg(p.obj_bits + (size_t)img * p.bits_words + (ain >> 5)) >> (ain & 31)) & 1u) ? 1.0f : 0.0f;
     else obj = p.obj_compact[(size_t)img * p.n_img + ain];
-    const int n_gt = p.gt_count[img * YL_LEVELS + l];
+    const int n_gt = valid ? p.gt_count[img * YL_LEVELS + l] : 0;
     const float4* gbox = p.gt_box + (size_t)img * p.n_img + p.lv.anchor_base[l];
     const float4* gaux = p.gt_aux + (size_t)img * p.n_img + p.lv.anchor_base[l];
-    // the record is decoded once (every lane the same values), then lanes <-> ground-truth boxes: the exact no-overlap /
-    // area-ratio rejects dispose of almost all of them before a metric is evaluated
+    // the record is decoded once (every lane of the half the same values), then lanes <-> ground-truth boxes: the exact
+    // no-overlap / area-ratio rejects dispose of almost all of them before a metric is evaluated
     const BoxT pb = yl_decode_record(p, l, rin, tx, ty, tw, th);
     const bool pb_regular = yl_regular(pb);
     bool hit = false;
-    for (int g0 = 0; g0 < n_gt && !hit; g0 += 32) {
-      const int g = g0 + lane;
+    for (int g0 = 0;; g0 += 16) {
+      const bool more = g0 < n_gt && !hit;
+      if (!__any_sync(0xffffffffu, more)) break;
+      const int g = g0 + sub;
       bool h = false;
-      if (g < n_gt) h = yl_box_hits(p, pb, pb_regular, __ldg(gbox + g), __ldg(gaux + g));
-      hit = __any_sync(0xffffffffu, h);
+      if (more && g < n_gt) h = yl_box_hits(p, pb, pb_regular, __ldg(gbox + g), __ldg(gaux + g));
+      const uint32_t bal = __ballot_sync(0xffffffffu, h);
+      hit = hit || ((bal >> (16 * half)) & 0xffffu) != 0u;
     }
-    if (lane == 0) {
+    if (valid && sub == 0) {
       const float bc = yl_fast_bce(obj, pobj);
       const float ign = hit ? 0.0f : 1.0f;
       if (p.out_ignore) p.out_ignore[(size_t)img * p.n_img + ain] = hit ? 0 : 1;
