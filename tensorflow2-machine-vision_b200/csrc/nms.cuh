@@ -18,11 +18,20 @@
 //      order of its members as an index array.  (The sampled-pivot + bitonic path of round 1 — 66 + 78 barrier stages
 //      — is kept only as the fallback for a bucket that alone overflows the window, e.g. thousands of equal scores.)
 //      Segments with <= 4096 candidates are gathered whole;
-//   2. the sorted window is consumed lazily in tiles of 64 candidates: a tile is first tested against every box
-//      emitted so far (kept list in shared memory; 64 x n_kept pairs spread over the 1024 threads), then resolved
-//      internally with a 64x64 ballot bitmask and a one-warp sweep (skipped when the tile has no internal
-//      conflict).  Only as many tiles as are needed to emit max_out boxes are touched, so the work is
-//      O(emitted^2) and independent of the window size.
+//      Segments of at most 8 keys per thread whose caller opts in (YOLO) read their scores once and run the passes
+//      from registers; segments above 8192 keys take the bucket range from one sample per thread (the buckets are
+//      monotone whatever the bounds, so the cut stays exact) and the count from the histogram pass;
+//   2. class-agnostic mode: the sorted window is consumed lazily in tiles of 64 candidates: a tile is first tested
+//      against every box emitted so far (kept list in shared memory; 64 x n_kept pairs spread over the 1024 threads),
+//      then resolved internally with a 64x64 ballot bitmask and a one-warp fixed-point sweep (skipped when the tile has
+//      no internal conflict).  Only as many tiles as are needed to emit max_out boxes are touched, so the work is
+//      O(emitted^2) and independent of the window size;
+//   3. per-class mode: a chunk of 1024 ranked candidates is split stably by class bucket; all pairs (i < j) of all
+//      buckets form one flat index space that the threads share equally (bit i of member j's word = "i suppresses
+//      j"), one thread per bucket then walks its members in rank order with the alive set in a register, and the
+//      survivors are emitted in rank order.
+// Every pair test starts with bm_surely_below (boxmath.cuh): no overlap, or IoU clearly below the threshold by a
+// division-free comparison — the full metric (2-4 IEEE divisions) runs for ~1 pair in 3000 on dense heads.
 // The metric is a template parameter so each instantiation carries one metric's code (the 7-way runtime switch
 // inlined at three call sites was 150 KB of SASS and did not fit the instruction cache).
 #pragma once
