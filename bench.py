@@ -556,6 +556,36 @@ def headline_c2(b, line):
         line["sparse_target_fusion"] = {"what": "GetLossFromBoxes: assignment + loss from the box lists, no dense y_true (API extension, SURVEY 8f N3)",
                                         "value": global_batch / (ms_f / 1e3), "unit": "images/s", "ms_per_step": ms_f,
                                         "loss_rel_diff": abs(floss - loss_val) / abs(loss_val)}
+        # the reference's own execution model: DataGenerator.GetTargets runs in tf.data workers UNDER the previous train step
+        # (datasets/coco_dataset.py:328).  Same calls, same fresh dense y_true per batch, two target buffers: GetTargets of batch
+        # i + 1 on a side stream while GetLoss of batch i runs (the first GetTargets of every graph is not overlapped)
+        gsteps = args.graph_steps if (not args.no_graph and args.steps % args.graph_steps == 0) else 1
+        yt2 = [y_true, tuple(torch.empty_like(t) for t in y_true)]
+        pside = torch.cuda.Stream()
+        pkeep = []
+
+        def pipelined():
+            main = torch.cuda.current_stream()
+            del pkeep[:]
+            gen.GetTargetsBatch(classes_d, boxes_d, off_d, out=yt2[0])
+            loss = None
+            for i in range(gsteps):
+                if i + 1 < gsteps:
+                    pside.wait_stream(main)            # loss i - 1 has released the buffer that targets i + 1 overwrite
+                    with torch.cuda.stream(pside):
+                        gen.GetTargetsBatch(classes_d, boxes_d, off_d, out=yt2[(i + 1) % 2])
+                loss = tyu._loss_call(yt2[i % 2], heads_d, (image, image), anc, 0.5, "ciou", 0, batch_divisor=global_batch, workspace=ws)
+                pkeep.append(loss)
+                main.wait_stream(pside)                # loss i + 1 needs targets i + 1
+            return loss
+        pipelined()
+        torch.cuda.synchronize()
+        plfn = b.wrap(pipelined)
+        ms_pl, _ = b.timed(plfn, args.steps, 3, 5, unit=gsteps)
+        plloss = float(plfn().item())
+        line["pipelined_targets"] = {"what": "GetTargets of batch i+1 on a second stream under GetLoss of batch i (what tf.data does for the reference), "
+                                             "two dense target buffers, %d consecutive steps per graph" % gsteps,
+                                     "value": global_batch / (ms_pl / 1e3), "unit": "images/s", "ms_per_step": ms_pl, "loss_equal": plloss == loss_val}
     # ---- end to end through the public API with HOST buffers ----
     e2e_steps = max(3, min(args.steps, 10))
     call = lambda hp, bx, cl, of: float(step(hp, bx, cl, of).item())
