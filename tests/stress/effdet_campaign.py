@@ -50,8 +50,9 @@ def one_case(seed, dev):
         k = rng.integers(0, n, max(1, n // 16))
         flat[k, :] = F(0.5)                                    # ties across classes -> background
         rflat = rel[l].reshape(-1, 4)
-        k = rng.integers(0, n - 1, max(1, n // 6))
-        rflat[k + 1] = rflat[k]                                # neighbouring anchors predicting (almost) the same box
+        if n > 1:                                              # (a 1x1 level with one anchor and one image has no neighbour)
+            k = rng.integers(0, n - 1, max(1, n // 6))
+            rflat[k + 1] = rflat[k]                            # neighbouring anchors predicting (almost) the same box
     dec_w = o.convert_outputs_boxes(rel)
     dec = a.convert_outputs_boxes([d(r) for r in rel])
     for x, y in zip(dec, dec_w):
